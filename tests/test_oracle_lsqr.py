@@ -1,0 +1,120 @@
+"""Oracle vs the reference's LSQR / sparse-matrix known answers
+(src/tests/tests_lsqr.f90, src/tests/tests_sparse_matrix.f90)."""
+import numpy as np
+
+from conftest import TOL, comparable
+
+
+def _build(oracle, rows, ncols):
+    m = oracle.SparseMatrix(len(rows), ncols, len(rows) * ncols)
+    for r in rows:
+        for i, v in enumerate(r):
+            m.add(v, i + 1)
+        m.new_row()
+    m.finalize()
+    return m
+
+
+def test_lsqr_determined(oracle):
+    # tests_lsqr.f90:71-122
+    n = 1440
+    m = _build(oracle, [[float(j)] * n for j in range(1, n + 1)], n)
+    b = np.array([float(j * n) for j in range(1, n + 1)])
+    x, hist, it = oracle.lsqr_solve(100, 1e-13, 0.0, m, b)
+    assert all(comparable(v, 1.0, TOL) for v in x)
+
+
+def test_lsqr_overdetermined_1(oracle):
+    # tests_lsqr.f90:144-218
+    nrows = 1000
+    bb = (1.0, -3.0, 0.0)
+    rows, rhs = [], []
+    for i in range(1, nrows + 1):
+        xi = float(i) / float(nrows)
+        rows.append([xi ** 0, xi ** 1, xi ** 2])
+        rhs.append(bb[0] + bb[1] * xi + bb[2] * xi ** 2)
+    m = _build(oracle, rows, 3)
+    x, hist, it = oracle.lsqr_solve(100, 1e-14, 0.0, m, np.array(rhs))
+    assert comparable(x[0], bb[0], TOL)
+    assert comparable(x[1], bb[1], TOL)
+    assert abs(x[2]) < TOL
+
+
+def test_lsqr_overdetermined_2(oracle):
+    # tests_lsqr.f90:227-351 (Wunsch 5x3), single-precision matrix tolerance 1e-2
+    a = [[1.2550, 1.6731, -1.3927], [0.4891, 0.0943, -0.7829], [-0.1755, 1.8612, 1.0972],
+         [0.4189, 0.2469, -0.5990], [-0.2900, 0.7677, 0.8188]]
+    b = np.array([0.3511, -1.6710, 6.838, -0.8843, 3.7018])
+    m = _build(oracle, a, 3)
+    x, hist, it = oracle.lsqr_solve(100, 1e-13, 0.0, m, b)
+    # the reference compares against single-precision literals 157.611 etc.
+    assert abs(x[0] - np.float32(157.611)) < 1e-2
+    assert abs(x[1] + np.float32(38.0747)) < 1e-2
+    assert abs(x[2] - np.float32(96.0291)) < 1e-2
+
+
+def test_lsqr_underdetermined_1(oracle):
+    # tests_lsqr.f90:366-447 -- min-norm solution (0, 1, 1), |x1| < 1e-15 absolute.
+    m = _build(oracle, [[1.0, 1.0, 0.0], [2.0, 1.0, -1.0]], 3)
+    x, hist, it = oracle.lsqr_solve(100, 1e-13, 0.0, m, np.array([1.0, 0.0]))
+    assert abs(x[0]) < 1e-15
+    assert comparable(x[1], 1.0, TOL)
+    assert comparable(x[2], 1.0, TOL)
+
+
+def test_lsqr_underdetermined_2(oracle):
+    # tests_lsqr.f90:461-518
+    m = _build(oracle, [[0.25] * 4], 4)
+    x, hist, it = oracle.lsqr_solve(100, 1e-14, 0.0, m, np.array([1.0]))
+    assert all(comparable(v, 1.0, TOL) for v in x)
+
+
+def test_lsqr_underdetermined_3(oracle):
+    # tests_lsqr.f90:532-624
+    m = _build(oracle, [[1.0, 1.0, 1.0, 1.0], [1.0, -1.0, -1.0, 1.0]], 4)
+    x, hist, it = oracle.lsqr_solve(100, 1e-14, 0.0, m, np.array([1.0, -1.0]))
+    for got, want in zip(x, (0.0, 0.5, 0.5, 0.0)):
+        assert comparable(got, want, TOL)
+
+
+def test_normalize_columns(oracle):
+    # tests_sparse_matrix.f90:39-113
+    ncolumns, nrows = 10, 30
+    A = np.zeros((nrows, ncolumns))
+    counter = 0
+    for j in range(nrows):
+        for i in range(ncolumns):
+            counter += 1
+            A[j, i] = float(counter) if (i + 1) <= ncolumns // 2 else 0.0
+    m = _build(oracle, A.tolist(), ncolumns)
+    assert m.nel == nrows * (ncolumns // 2)          # zero values are not stored (:219)
+    cn = m.normalize_columns()
+    for i in range(ncolumns):
+        assert comparable(cn[i], np.linalg.norm(A[:, i]), TOL)
+        vi = np.zeros(ncolumns)
+        vi[i] = 1.0
+        col = m.mult_vector(vi)
+        want = 1.0 if np.linalg.norm(A[:, i]) != 0 else 0.0
+        assert comparable(np.linalg.norm(col), want, TOL)
+
+
+def test_sensit_variant_equals_plain_when_no_constraints(oracle):
+    # lsqr_solve_sensit (lsqr_solver2.F90:47) with an all-empty constraint matrix and no wavelet
+    # must walk the same iterates as lsqr_solve (:321).
+    rng = np.random.default_rng(7)
+    nrows, ncols = 12, 20
+    A = rng.standard_normal((nrows, ncols))
+    m = _build(oracle, A.tolist(), ncols)
+    Cm = oracle.SparseMatrix(5, ncols, 1, 5)
+    Cm.add_empty_rows(5)
+    Cm.finalize()
+    b = rng.standard_normal(nrows)
+    x1, h1, it1 = oracle.lsqr_solve(30, 1e-13, 0.0, m, b)
+    x2, h2, it2 = oracle.lsqr_solve_sensit(30, 1e-13, 0.0, 0.0, m, Cm, np.concatenate([b, np.zeros(5)]),
+                                           ncols // 2, ncols // 2, 1, 1, 1, 0, True)
+    assert it1 == it2
+    # v = -beta v + (S^T u) is associated differently in the two routines (:236 vs :414): residuals
+    # agree to rounding until convergence noise takes over.
+    big = h1 > 1e-9
+    np.testing.assert_allclose(h1[big], h2[big], rtol=1e-6)
+    np.testing.assert_allclose(x1, x2, rtol=1e-9, atol=1e-12)
