@@ -1,0 +1,155 @@
+/*
+ * tfx.h -- C ABI of libtfx: the B200-native replacement for the Tomofast-x inversion hot path.
+ *
+ * The reference (TOMOFAST/Tomofast-x, Fortran 2008 + MPI) has no plugin/FFI interface; the drop-in
+ * boundary is the set of Fortran MODULE interfaces used by problem_joint_gravmag.F90 and
+ * joint_inverse_problem.F90.  Every entry point below replaces one module procedure and cites it
+ * (paths relative to the reference checkout).  fortran/ holds same-named ISO_C_BINDING shim modules
+ * that forward to these symbols; INTEGRATION.md shows how a maintainer wires them in.
+ *
+ * Conventions
+ *  - plain C types only; all indices crossing the ABI are 1-BASED like the reference's.
+ *  - vectors are real(8) (CUSTOM_REAL = 8), matrix values real(4) (MATRIX_PRECISION = 4),
+ *    src/global_typedefs.F90:39-45.
+ *  - vector arguments may be HOST pointers (copied to/from the device inside the call) or DEVICE
+ *    pointers (used in place); the library detects which with cudaPointerGetAttributes.
+ *  - every function returns 0 on success; otherwise a negative code and tfx_last_error() holds the
+ *    message the reference would have passed to exit_MPI (src/utils/mpi_tools.F90:30-54).
+ *  - one process drives one GPU (one MPI rank per GPU); calls are synchronous for the caller.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef TFX_H
+#define TFX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tfx_matrix tfx_matrix;   /* replaces type(t_sparse_matrix), sparse_matrix.f90:31-98 */
+
+/* ---- runtime --------------------------------------------------------------------------------- */
+int         tfx_version(void);
+const char *tfx_last_error(void);
+/* Selects the GPU of this rank (device < 0: LOCAL_RANK env or 0) and creates the stream.
+ * Replaces nothing in the reference (MPI_Init stays in program_tomofastx.F90:56). */
+int         tfx_init(int device);
+int         tfx_finalize(void);
+int         tfx_device_synchronize(void);
+/* Number of GPU kernels launched by the library so far (bench.py's gpu_launches). */
+uint64_t    tfx_launch_count(void);
+/* Options: "dense_detect" (1: finalize() turns an uncompressed CSR into the dense block). */
+int         tfx_set_option(const char *name, int value);
+
+/* ---- communicator: stands in for MPI_COMM_WORLD on the solver's reductions ---------------------
+ * lsqr_solver2.F90:214 (MPI_Allreduce of u) and :514 (scalar Allreduce) become ncclAllReduce.
+ * Rank 0 creates the id, the host application broadcasts the 128 bytes (MPI_Bcast in the Fortran
+ * shim, torch.distributed in the Python host), every rank calls tfx_comm_init. */
+int tfx_comm_unique_id(char id[128]);
+int tfx_comm_init(int nranks, int rank, const char id[128]);
+int tfx_comm_finalize(void);
+int tfx_comm_allreduce_sum(double *buf, int64_t count);            /* host or device pointer */
+
+/* ---- module sparse_matrix (src/inversion/sparse_matrix.f90) ----------------------------------- */
+int tfx_sparse_matrix_initialize(tfx_matrix **m, int32_t nl, int32_t ncolumns, int64_t nnz,
+                                 int32_t myrank, int32_t nl_empty);             /* :105-130 */
+int tfx_sparse_matrix_destroy(tfx_matrix *m);
+int tfx_sparse_matrix_reset(tfx_matrix *m);                                    /* :135-151 */
+int tfx_sparse_matrix_finalize(tfx_matrix *m, int32_t myrank);                 /* :157-208 (+ device upload) */
+int tfx_sparse_matrix_add(tfx_matrix *m, double value, int32_t column, int32_t myrank);      /* :213-229 */
+int tfx_sparse_matrix_add_row(tfx_matrix *m, int32_t nel_add, const float *values,
+                              const int32_t *columns, int32_t myrank);         /* :234-249 */
+int tfx_sparse_matrix_new_row(tfx_matrix *m, int32_t myrank);                  /* :254-276 */
+int tfx_sparse_matrix_add_empty_rows(tfx_matrix *m, int32_t nrows, int32_t myrank);          /* :281-293 */
+int tfx_sparse_matrix_mult_vector(tfx_matrix *m, const double *x, double *b);  /* :298-307 */
+int tfx_sparse_matrix_add_mult_vector(tfx_matrix *m, const double *x, double *b);            /* :313-329 */
+int tfx_sparse_matrix_part_mult_vector(tfx_matrix *m, int32_t nelements, const double *x, int32_t ndata,
+                                       double *b, int32_t line_start, int32_t param_shift,
+                                       int32_t myrank);                        /* :335-367 */
+int tfx_sparse_matrix_trans_mult_vector(tfx_matrix *m, const double *x, double *b);          /* :373-382 */
+int tfx_sparse_matrix_add_trans_mult_vector(tfx_matrix *m, const double *x, double *b);      /* :388-405 */
+int32_t tfx_sparse_matrix_get_total_row_number(const tfx_matrix *m);           /* :448-453 */
+int32_t tfx_sparse_matrix_get_current_row_number(const tfx_matrix *m);         /* :458-463 */
+int32_t tfx_sparse_matrix_get_ncolumns(const tfx_matrix *m);                   /* :468-473 */
+int64_t tfx_sparse_matrix_get_number_elements(const tfx_matrix *m);            /* :478-483 */
+int64_t tfx_sparse_matrix_get_nnz(const tfx_matrix *m);                        /* :488-493 */
+/* Bulk constructor from arrays in the reference's storage (1-based ija/ijl/rowptr); finalized. */
+int tfx_sparse_matrix_from_arrays(tfx_matrix **m, int32_t nl, int32_t ncolumns, int32_t nl_nonempty,
+                                  int64_t nel, const float *sa, const int32_t *ija, const int64_t *ijl,
+                                  const int32_t *rowptr);
+/* 0: compressed-segment (CSR + CSR of the transpose); 1: dense column-major block. */
+int tfx_sparse_matrix_storage_kind(const tfx_matrix *m);
+/* Copies the device-resident matrix back in the reference's CSR storage (for tests / file writers).
+ * Pass NULL arrays to query sizes only. */
+int tfx_sparse_matrix_export(tfx_matrix *m, int64_t *nel, int32_t *nl_nonempty, float *sa, int32_t *ija,
+                             int64_t *ijl, int32_t *rowptr);
+
+/* ---- module wavelet_transform (src/utils/wavelet_transform.F90) -------------------------------- */
+int tfx_forward_wavelet(double *s, int32_t n1, int32_t n2, int32_t n3, int32_t wavelet_type);   /* :37-51 */
+int tfx_inverse_wavelet(double *s, int32_t n1, int32_t n2, int32_t n3, int32_t wavelet_type);   /* :56-70 */
+int tfx_Haar3D(double *s, int32_t n1, int32_t n2, int32_t n3);                                  /* :75-153 */
+int tfx_iHaar3D(double *s, int32_t n1, int32_t n2, int32_t n3);                                 /* :158-236 */
+int tfx_DaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3);                                /* :243-367 */
+int tfx_iDaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3);                               /* :374-498 */
+/* module wavelet_utils: apply_wavelet_transform (src/inversion/wavelet_utils.F90:37-72), nbproc = 1:
+ * v(nelements, ncomponents, nproblems), model_full is not needed (no gather). */
+int tfx_apply_wavelet_transform(int32_t nelements, int32_t nx, int32_t ny, int32_t nz, int32_t ncomponents,
+                                double *v, int32_t fwd, int32_t compression_type, int32_t nproblems,
+                                const int32_t *solve_problem, int32_t myrank, int32_t nbproc);
+
+/* ---- module lsqr_solver (src/inversion/lsqr_solver2.F90) --------------------------------------- */
+int tfx_lsqr_solve(int32_t nlines, int32_t nelements, int32_t niter, double rmin, double gamma,
+                   tfx_matrix *matrix, double *u, double *x, int32_t myrank);                    /* :321-473 */
+int tfx_lsqr_solve_sensit(int32_t nlines, int32_t ncolumns, int32_t niter, double rmin, double gamma,
+                          double target_misfit, tfx_matrix *matrix_sensit, tfx_matrix *matrix_cons,
+                          double *u, double *x, const int32_t solve_problem[2], int32_t nelements,
+                          int32_t nx, int32_t ny, int32_t nz, int32_t ncomponents,
+                          int32_t compression_type, int32_t wavelet_domain, double *memory,
+                          int32_t myrank, int32_t nbproc);                                       /* :47-308 */
+/* Diagnostics of the last solve: r = phibar/b1 after every executed iteration (the reference only
+ * prints the final one, :302-306), number of executed iterations, 1 if the fused single-sweep path
+ * ran. r_hist may be NULL. */
+int tfx_lsqr_last_history(double *r_hist, int32_t capacity, int32_t *iters, int32_t *fused);
+
+/* ---- module sensitivity_gravmag (src/forward/gravmag/sensitivity_gravmag.F90) ------------------ */
+typedef struct tfx_sensit_params {
+  int32_t problem_type;        /* 1 gravity, 2 magnetic (select type at :126-137)                    */
+  int32_t nx, ny, nz;          /* full grid                                                          */
+  int32_t ndata;               /* number of stations                                                 */
+  int32_t ndata_components;    /* par%ndata_components                                               */
+  int32_t nmodel_components;   /* par%nmodel_components                                              */
+  int32_t data_type;           /* gravity: 1 gz, 2 gradiometry (zz only with 1 data component)       */
+  int32_t compression_type;    /* 0 none, 1 Haar, 2 Daubechies D4                                    */
+  double  compression_rate;    /* :64-77                                                             */
+  double  problem_weight;      /* ipar%problem_weight(problem)                                       */
+  double  mi, md, theta, intensity;   /* magnetic field (magnetic_field.f90:64-110)                  */
+  int32_t cell0, ncells_local; /* 0-based first local cell and count (column slab of this rank);
+                                  compression requires the full grid on every rank                   */
+  int32_t param_shift;         /* column shift of this problem inside the joint matrix (:685-686)    */
+  int32_t ncolumns;            /* total columns of matrix_sensit (2*ncomp*nelements, jip.F90:213)    */
+} tfx_sensit_params;
+
+/* calculate_and_write_sensit (:82-410) + read_sensitivity_kernel (:648-883) without the disk round
+ * trip: evaluates the kernels on the GPU, applies column weight / wavelet / threshold / real(4)
+ * rounding / problem*data weight exactly in the reference's order and leaves the finalized matrix
+ * on the device. grid arrays hold the FULL grid (nx*ny*nz cells); column_weight_full(nx*ny*nz);
+ * data_weight(ndata_components, ndata). Outputs (may be NULL): sensit_nnz(nx*ny*nz) per-column
+ * counts (:267,293), comp_error (:350), nnz_total. */
+int tfx_calculate_sensit(tfx_matrix **matrix_sensit, const tfx_sensit_params *par,
+                         const double *X1, const double *X2, const double *Y1, const double *Y2,
+                         const double *Z1, const double *Z2,
+                         const double *data_X, const double *data_Y, const double *data_Z,
+                         const double *column_weight_full, const double *data_weight,
+                         int32_t *sensit_nnz, double *comp_error, int64_t *nnz_total);
+
+/* One raw sensitivity line per station (no weighting), for kernel parity tests:
+ * lines(ncells, nmodel_components, ndata_components, ndata_batch) Fortran order. */
+int tfx_sensit_lines(const tfx_sensit_params *par, const double *X1, const double *X2, const double *Y1,
+                     const double *Y2, const double *Z1, const double *Z2, int32_t ndata_batch,
+                     const double *data_X, const double *data_Y, const double *data_Z, double *lines);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFX_H */

@@ -2,7 +2,7 @@
 (src/tests/tests_lsqr.f90, src/tests/tests_sparse_matrix.f90)."""
 import numpy as np
 
-from conftest import TOL, comparable
+from tests.conftest import TOL, comparable
 
 
 def _build(oracle, rows, ncols):

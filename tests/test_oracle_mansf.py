@@ -1,0 +1,29 @@
+"""Oracle-only run of config A (Parfile_mansf_slice) on the CPU: pins the restatement against the
+surveyor's sanity figures (SURVEY.md section 8c / BASELINE.md section 5 -- NOT reference output; the
+reference ships no golden outputs for Parfile runs, so end-to-end parity is otherwise unpinned)."""
+import numpy as np
+import pytest
+
+from tests import mansf
+
+
+@pytest.fixture(scope="module")
+def inv(oracle):
+    cfg = mansf.Config()
+    return mansf.Inversion(mansf.OracleBackend(oracle), cfg, oracle.admm_iterate)
+
+
+def test_assembly_figures(inv):
+    cfg = inv.cfg
+    assert cfg.nel_compressed == 1228                       # int(0.15 * 8192)
+    assert inv.S.nel == 314368                              # 256 x 1228, no ties
+    assert abs(inv.comp_error - 2.154e-3) < 2e-5            # compression error r
+    assert abs(np.linalg.norm(inv.d_obs) - 2.4011e-4) < 2e-8
+
+
+def test_first_major_iteration_residuals(inv):
+    b, x, hist = inv.step()
+    assert len(hist) == 100                                 # every solve runs the full 100 iterations
+    assert np.allclose(hist[:3], [0.2475, 0.1003, 0.0585], atol=6e-4)
+    assert abs(hist[-1] - 8.78e-3) < 2e-4
+    assert abs(inv.costs[-1] - 3.03e-4) < 2e-5              # relative data cost after major iteration 1

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import TOL, comparable
+from tests.conftest import TOL, comparable
 
 
 def test_wavelet_calculate_data(oracle):

@@ -1,0 +1,383 @@
+"""tomofast-x_b200 -- Python host mirror of the reference's module interfaces over libtfx (C ABI).
+
+The compute path is hand-written sm_100a CUDA inside libtfx.so (tomofast-x_b200/csrc); this module
+only binds include/tfx.h with ctypes and mirrors the reference's names and argument meaning:
+
+    reference (Fortran)                         here
+    ------------------------------------------  ----------------------------------------------
+    type(t_sparse_matrix) + bound procedures    SparseMatrix (sparse_matrix.f90:31-405)
+    forward_wavelet / inverse_wavelet           forward_wavelet / inverse_wavelet (wavelet_transform.F90:37-70)
+    lsqr_solve / lsqr_solve_sensit              lsqr_solve / lsqr_solve_sensit (lsqr_solver2.F90:47,321)
+    calculate_and_write_sensit + read_...       calculate_sensit (sensitivity_gravmag.F90:82,648)
+
+There is NO CPU fallback: every compute call fails loudly (TfxError) when libtfx.so or a CUDA device
+is missing. The directory name contains a hyphen; import it as `tomofastx_b200` (alias module at
+the repository root).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtfx.so")
+_lib = None
+
+
+class TfxError(RuntimeError):
+    """Raised where the reference would call exit_MPI (src/utils/mpi_tools.F90:30-54)."""
+
+
+def build(force=False, verbose=False):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_tfx_build", os.path.join(_HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force, verbose=verbose)
+
+
+class SensitParams(C.Structure):
+    """struct tfx_sensit_params (include/tfx.h)."""
+    _fields_ = [("problem_type", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+                ("ndata", C.c_int32), ("ndata_components", C.c_int32), ("nmodel_components", C.c_int32),
+                ("data_type", C.c_int32), ("compression_type", C.c_int32), ("compression_rate", C.c_double),
+                ("problem_weight", C.c_double), ("mi", C.c_double), ("md", C.c_double), ("theta", C.c_double),
+                ("intensity", C.c_double), ("cell0", C.c_int32), ("ncells_local", C.c_int32),
+                ("param_shift", C.c_int32), ("ncolumns", C.c_int32)]
+
+
+def lib():
+    """Loads libtfx.so; raises TfxError if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TfxError("libtfx.so is missing: run `python tomofast-x_b200/build.py` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    L.tfx_last_error.restype = C.c_char_p
+    L.tfx_launch_count.restype = C.c_uint64
+    L.tfx_init.argtypes = [C.c_int]
+    L.tfx_set_option.argtypes = [C.c_char_p, C.c_int]
+    L.tfx_comm_unique_id.argtypes = [C.c_char_p]
+    L.tfx_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
+    L.tfx_comm_allreduce_sum.argtypes = [vp, i64]
+    L.tfx_sparse_matrix_initialize.argtypes = [C.POINTER(vp), i32, i32, i64, i32, i32]
+    L.tfx_sparse_matrix_destroy.argtypes = [vp]
+    L.tfx_sparse_matrix_reset.argtypes = [vp]
+    L.tfx_sparse_matrix_finalize.argtypes = [vp, i32]
+    L.tfx_sparse_matrix_add.argtypes = [vp, dbl, i32, i32]
+    L.tfx_sparse_matrix_add_row.argtypes = [vp, i32, vp, vp, i32]
+    L.tfx_sparse_matrix_new_row.argtypes = [vp, i32]
+    L.tfx_sparse_matrix_add_empty_rows.argtypes = [vp, i32, i32]
+    for n in ("mult_vector", "add_mult_vector", "trans_mult_vector", "add_trans_mult_vector"):
+        getattr(L, "tfx_sparse_matrix_" + n).argtypes = [vp, vp, vp]
+    L.tfx_sparse_matrix_part_mult_vector.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32]
+    for n in ("get_total_row_number", "get_current_row_number", "get_ncolumns"):
+        getattr(L, "tfx_sparse_matrix_" + n).argtypes = [vp]
+        getattr(L, "tfx_sparse_matrix_" + n).restype = i32
+    for n in ("get_number_elements", "get_nnz"):
+        getattr(L, "tfx_sparse_matrix_" + n).argtypes = [vp]
+        getattr(L, "tfx_sparse_matrix_" + n).restype = i64
+    L.tfx_sparse_matrix_from_arrays.argtypes = [C.POINTER(vp), i32, i32, i32, i64, vp, vp, vp, vp]
+    L.tfx_sparse_matrix_storage_kind.argtypes = [vp]
+    L.tfx_sparse_matrix_export.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), vp, vp, vp, vp]
+    for n in ("tfx_forward_wavelet", "tfx_inverse_wavelet"):
+        getattr(L, n).argtypes = [vp, i32, i32, i32, i32]
+    for n in ("tfx_Haar3D", "tfx_iHaar3D", "tfx_DaubD43D", "tfx_iDaubD43D"):
+        getattr(L, n).argtypes = [vp, i32, i32, i32]
+    L.tfx_apply_wavelet_transform.argtypes = [i32, i32, i32, i32, i32, vp, i32, i32, i32, vp, i32, i32]
+    L.tfx_lsqr_solve.argtypes = [i32, i32, i32, dbl, dbl, vp, vp, vp, i32]
+    L.tfx_lsqr_solve_sensit.argtypes = [i32, i32, i32, dbl, dbl, dbl, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
+                                        i32, i32, C.POINTER(dbl), i32, i32]
+    L.tfx_lsqr_last_history.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.tfx_calculate_sensit.argtypes = [C.POINTER(vp), C.POINTER(SensitParams)] + [vp] * 11 + [vp, C.POINTER(dbl),
+                                                                                              C.POINTER(i64)]
+    L.tfx_sensit_lines.argtypes = [C.POINTER(SensitParams)] + [vp] * 6 + [i32] + [vp] * 4
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise TfxError(lib().tfx_last_error().decode("utf-8", "replace") + " (code %d)" % rc)
+
+
+def init(device=-1):
+    _check(lib().tfx_init(int(device)))
+
+
+def launch_count():
+    return int(lib().tfx_launch_count())
+
+
+def set_option(name, value):
+    _check(lib().tfx_set_option(name.encode(), int(value)))
+
+
+def synchronize():
+    _check(lib().tfx_device_synchronize())
+
+
+def _ptr(a):
+    """Host numpy array, torch CUDA tensor or raw int device pointer -> void*."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if isinstance(a, int):
+        return a
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError("unsupported vector type %r" % type(a))
+
+
+def _f64(a):
+    if isinstance(a, np.ndarray):
+        return np.ascontiguousarray(a, dtype=np.float64)
+    if hasattr(a, "data_ptr"):
+        return a
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+class SparseMatrix:
+    """t_sparse_matrix (src/inversion/sparse_matrix.f90:31-98); indices are 1-based like the reference's."""
+
+    def __init__(self, nl=None, ncolumns=None, nnz=None, myrank=0, nl_empty=0, _handle=None):
+        self._h = C.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+            return
+        _check(lib().tfx_sparse_matrix_initialize(C.byref(self._h), nl, ncolumns, nnz, myrank, nl_empty))
+
+    @classmethod
+    def from_arrays(cls, nl, ncolumns, sa, ija, ijl, rowptr):
+        sa = np.ascontiguousarray(sa, dtype=np.float32)
+        ija = np.ascontiguousarray(ija, dtype=np.int32)
+        ijl = np.ascontiguousarray(ijl, dtype=np.int64)
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        h = C.c_void_p()
+        _check(lib().tfx_sparse_matrix_from_arrays(C.byref(h), nl, ncolumns, len(rowptr), len(sa), sa.ctypes.data,
+                                                   ija.ctypes.data, ijl.ctypes.data, rowptr.ctypes.data))
+        return cls(_handle=h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().tfx_sparse_matrix_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(lib().tfx_sparse_matrix_reset(self._h))
+
+    def finalize(self, myrank=0):
+        _check(lib().tfx_sparse_matrix_finalize(self._h, myrank))
+
+    def add(self, value, column, myrank=0):
+        _check(lib().tfx_sparse_matrix_add(self._h, float(value), int(column), myrank))
+
+    def add_row(self, values, columns, myrank=0):
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        columns = np.ascontiguousarray(columns, dtype=np.int32)
+        _check(lib().tfx_sparse_matrix_add_row(self._h, len(values), values.ctypes.data, columns.ctypes.data, myrank))
+
+    def new_row(self, myrank=0):
+        _check(lib().tfx_sparse_matrix_new_row(self._h, myrank))
+
+    def add_empty_rows(self, nrows, myrank=0):
+        _check(lib().tfx_sparse_matrix_add_empty_rows(self._h, int(nrows), myrank))
+
+    def get_total_row_number(self):
+        return lib().tfx_sparse_matrix_get_total_row_number(self._h)
+
+    def get_current_row_number(self):
+        return lib().tfx_sparse_matrix_get_current_row_number(self._h)
+
+    def get_ncolumns(self):
+        return lib().tfx_sparse_matrix_get_ncolumns(self._h)
+
+    def get_number_elements(self):
+        return lib().tfx_sparse_matrix_get_number_elements(self._h)
+
+    def get_nnz(self):
+        return lib().tfx_sparse_matrix_get_nnz(self._h)
+
+    def storage_kind(self):
+        return lib().tfx_sparse_matrix_storage_kind(self._h)
+
+    def _prod(self, fn, x, b, nin, nout):
+        x = _f64(x)
+        if b is None:
+            b = np.zeros(nout)
+        _check(fn(self._h, _ptr(x), _ptr(b)))
+        return b
+
+    def mult_vector(self, x, b=None):
+        return self._prod(lib().tfx_sparse_matrix_mult_vector, x, b, self.get_ncolumns(), self.get_total_row_number())
+
+    def add_mult_vector(self, x, b):
+        return self._prod(lib().tfx_sparse_matrix_add_mult_vector, x, b, 0, 0)
+
+    def trans_mult_vector(self, x, b=None):
+        return self._prod(lib().tfx_sparse_matrix_trans_mult_vector, x, b, self.get_total_row_number(), self.get_ncolumns())
+
+    def add_trans_mult_vector(self, x, b):
+        return self._prod(lib().tfx_sparse_matrix_add_trans_mult_vector, x, b, 0, 0)
+
+    def part_mult_vector(self, x, ndata, line_start, param_shift, b=None, myrank=0):
+        x = _f64(x)
+        nel = x.size if isinstance(x, np.ndarray) else x.numel()
+        if b is None:
+            b = np.zeros(ndata)
+        _check(lib().tfx_sparse_matrix_part_mult_vector(self._h, nel, _ptr(x), ndata, _ptr(b), line_start, param_shift,
+                                                        myrank))
+        return b
+
+    def export(self):
+        """(sa, ija, ijl, rowptr) in the reference's storage (1-based)."""
+        nel, nne = C.c_int64(0), C.c_int32(0)
+        _check(lib().tfx_sparse_matrix_export(self._h, C.byref(nel), C.byref(nne), None, None, None, None))
+        sa = np.zeros(max(nel.value, 1), dtype=np.float32)
+        ija = np.zeros(max(nel.value, 1), dtype=np.int32)
+        ijl = np.zeros(nne.value + 1, dtype=np.int64)
+        rowptr = np.zeros(max(nne.value, 1), dtype=np.int32)
+        _check(lib().tfx_sparse_matrix_export(self._h, C.byref(nel), C.byref(nne), sa.ctypes.data, ija.ctypes.data,
+                                              ijl.ctypes.data, rowptr.ctypes.data))
+        return sa[:nel.value], ija[:nel.value], ijl, rowptr[:nne.value]
+
+
+def _wavelet(fn, s, n1, n2, n3, *extra):
+    if isinstance(s, np.ndarray):
+        assert s.dtype == np.float64 and s.flags["C_CONTIGUOUS"] and s.size == n1 * n2 * n3
+    _check(fn(_ptr(s), n1, n2, n3, *extra))
+    return s
+
+
+def forward_wavelet(s, n1, n2, n3, wavelet_type):
+    """In place on s (flattened Fortran-order volume s(n1,n2,n3)); host array or device tensor."""
+    return _wavelet(lib().tfx_forward_wavelet, s, n1, n2, n3, wavelet_type)
+
+
+def inverse_wavelet(s, n1, n2, n3, wavelet_type):
+    return _wavelet(lib().tfx_inverse_wavelet, s, n1, n2, n3, wavelet_type)
+
+
+def Haar3D(s, n1, n2, n3):
+    return _wavelet(lib().tfx_Haar3D, s, n1, n2, n3)
+
+
+def iHaar3D(s, n1, n2, n3):
+    return _wavelet(lib().tfx_iHaar3D, s, n1, n2, n3)
+
+
+def DaubD43D(s, n1, n2, n3):
+    return _wavelet(lib().tfx_DaubD43D, s, n1, n2, n3)
+
+
+def iDaubD43D(s, n1, n2, n3):
+    return _wavelet(lib().tfx_iDaubD43D, s, n1, n2, n3)
+
+
+def apply_wavelet_transform(nelements, nx, ny, nz, ncomponents, v, fwd, compression_type, nproblems, solve_problem,
+                            myrank=0, nbproc=1):
+    sp = np.ascontiguousarray(solve_problem, dtype=np.int32)
+    _check(lib().tfx_apply_wavelet_transform(nelements, nx, ny, nz, ncomponents, _ptr(v), int(bool(fwd)),
+                                             compression_type, nproblems, sp.ctypes.data, myrank, nbproc))
+    return v
+
+
+def last_history():
+    """(r_history, iters, fused) of the last solve."""
+    it, fused = C.c_int32(0), C.c_int32(0)
+    _check(lib().tfx_lsqr_last_history(None, 0, C.byref(it), C.byref(fused)))
+    h = np.zeros(max(it.value, 1))
+    _check(lib().tfx_lsqr_last_history(h.ctypes.data, it.value, C.byref(it), C.byref(fused)))
+    return h[:it.value], it.value, bool(fused.value)
+
+
+def lsqr_solve(nlines, nelements, niter, rmin, gamma, matrix, u, x, myrank=0):
+    """lsqr_solve (lsqr_solver2.F90:321): u (rhs) is overwritten, x receives the solution."""
+    _check(lib().tfx_lsqr_solve(nlines, nelements, niter, rmin, gamma, matrix._h, _ptr(u), _ptr(x), myrank))
+    return x
+
+
+def lsqr_solve_sensit(nlines, ncolumns, niter, rmin, gamma, target_misfit, matrix_sensit, matrix_cons, u, x,
+                      SOLVE_PROBLEM, nelements, nx, ny, nz, ncomponents, compression_type, WAVELET_DOMAIN,
+                      myrank=0, nbproc=1):
+    """lsqr_solve_sensit (lsqr_solver2.F90:47). Returns `memory` like the reference's out argument."""
+    sp = np.ascontiguousarray([int(bool(s)) for s in SOLVE_PROBLEM], dtype=np.int32)
+    mem = C.c_double(0.0)
+    _check(lib().tfx_lsqr_solve_sensit(nlines, ncolumns, niter, rmin, gamma, target_misfit, matrix_sensit._h,
+                                       matrix_cons._h if matrix_cons is not None else None, _ptr(u), _ptr(x),
+                                       sp.ctypes.data, nelements, nx, ny, nz, ncomponents, compression_type,
+                                       int(bool(WAVELET_DOMAIN)), C.byref(mem), myrank, nbproc))
+    return mem.value
+
+
+def _grid_ptrs(grid):
+    arrs = [np.ascontiguousarray(g, dtype=np.float64) for g in grid]
+    return arrs, [a.ctypes.data for a in arrs]
+
+
+def calculate_sensit(par, grid, data_xyz, column_weight_full, data_weight):
+    """calculate_and_write_sensit + read_sensitivity_kernel on the device (no disk round trip).
+    Returns (SparseMatrix, sensit_nnz, comp_error, nnz_total)."""
+    arrs, gp = _grid_ptrs(grid)
+    dx, dy, dz = (np.ascontiguousarray(a, dtype=np.float64) for a in data_xyz)
+    cw = np.ascontiguousarray(column_weight_full, dtype=np.float64)
+    dw = np.ascontiguousarray(data_weight, dtype=np.float64)
+    n = par.nx * par.ny * par.nz
+    assert cw.size == n and dw.size == par.ndata * par.ndata_components and dx.size == par.ndata
+    nnz_col = np.zeros(n, dtype=np.int32)
+    cerr, tot = C.c_double(0.0), C.c_int64(0)
+    h = C.c_void_p()
+    _check(lib().tfx_calculate_sensit(C.byref(h), C.byref(par), *gp, dx.ctypes.data, dy.ctypes.data, dz.ctypes.data,
+                                      cw.ctypes.data, dw.ctypes.data, nnz_col.ctypes.data, C.byref(cerr),
+                                      C.byref(tot)))
+    return SparseMatrix(_handle=h), nnz_col, cerr.value, tot.value
+
+
+def sensit_lines(par, grid, data_xyz):
+    """Raw kernel lines, numpy shape (ndata, ndata_components, nmodel_components, ncells)."""
+    arrs, gp = _grid_ptrs(grid)
+    dx, dy, dz = (np.ascontiguousarray(a, dtype=np.float64) for a in data_xyz)
+    n = par.nx * par.ny * par.nz
+    out = np.zeros((dx.size, par.ndata_components, par.nmodel_components, n))
+    _check(lib().tfx_sensit_lines(C.byref(par), *gp, dx.size, dx.ctypes.data, dy.ctypes.data, dz.ctypes.data,
+                                  out.ctypes.data))
+    return out
+
+
+# ---- communicator (one rank per GPU) ----------------------------------------------------------------
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(lib().tfx_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(nranks, rank, uid):
+    _check(lib().tfx_comm_init(nranks, rank, uid))
+
+
+def comm_finalize():
+    _check(lib().tfx_comm_finalize())
+
+
+def comm_allreduce_sum(buf, count):
+    _check(lib().tfx_comm_allreduce_sum(_ptr(buf), int(count)))
+
+
+# ---- partitioning helpers (src/utils/parallel_tools.f90:46-86) ----------------------------------------
+def calculate_nelements_at_cpu(nelements_total, myrank, nbproc):
+    """Even split with the remainder on the first ranks (parallel_tools.f90:46-63)."""
+    n = nelements_total // nbproc
+    if myrank + 1 <= nelements_total - n * nbproc:
+        n += 1
+    return n
+
+
+def get_nsmaller(nelements_total, myrank, nbproc):
+    """Number of elements on ranks below myrank for the even split (parallel_tools.f90:68-86)."""
+    return sum(calculate_nelements_at_cpu(nelements_total, r, nbproc) for r in range(myrank))

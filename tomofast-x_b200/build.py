@@ -1,0 +1,66 @@
+"""Builds libtfx.so (hand-written sm_100a CUDA + the C ABI of include/tfx.h) in-tree with nvcc.
+
+    python tomofast-x_b200/build.py [--force] [--verbose]
+
+nvcc cross-compiles without a GPU. The library has no link-time dependency besides the CUDA
+runtime (NCCL is dlopen'ed on demand), so it loads on a CPU-only box for the symbol checks.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libtfx.so")
+SOURCES = ["api.cu", "wavelet.cu", "csr.cu", "dense.cu", "lsqr.cu", "assembly.cu", "sensit.cu", "comm.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+         "--expt-extended-lambda", "-Xcudafe", "--diag_suppress=177"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "tfx.h"))
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    procs = []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            cmd = [_nvcc()] + ARCH + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write("nvcc failed for %s:\n%s\n" % (src, out))
+        elif verbose and out.strip():
+            print("---- %s\n%s" % (src, out))
+    if failed:
+        raise RuntimeError("libtfx build failed")
+    if force or procs or _stale(LIB, objs):
+        cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

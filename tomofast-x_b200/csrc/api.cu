@@ -1,0 +1,584 @@
+// api.cu -- the C ABI (include/tfx.h), the t_sparse_matrix replacement and the runtime context.
+#include "../../include/tfx.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "matrix.h"
+
+namespace tfx {
+
+// ---------------------------------------------------------------------------------------------
+// context / errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int g_opt_dense_detect = 1;
+
+void set_error(const std::string &msg) { g_err = msg; }
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+Context &ctx() {
+  static Context c;
+  return c;
+}
+
+static int init_device(int device) {
+  Context &c = ctx();
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(-1, "libtfx: no CUDA device available (there is no CPU fallback)");
+  }
+  if (device < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    device = lr ? atoi(lr) % ndev : 0;
+  }
+  if (device >= ndev) return fail(-2, "libtfx: device index out of range");
+  if (c.ready && c.device == device) return 0;
+  TFX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TFX_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(-3, std::string("libtfx is built for sm_100a (B200); found ") + prop.name);
+  c.device = device;
+  c.num_sms = prop.multiProcessorCount;
+  if (!c.stream) TFX_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  c.ready = true;
+  return 0;
+}
+
+int ensure_init() {
+  if (ctx().ready) return 0;
+  return init_device(-1);
+}
+
+int VecIO::bind(double *ptr, size_t count, bool copy_in) {
+  n = count;
+  if (is_device_ptr(ptr)) {
+    dev = ptr;
+    host = nullptr;
+    return 0;
+  }
+  host = ptr;
+  TFX_TRY(own.alloc(count));
+  dev = own.p;
+  if (copy_in && count) TFX_CUDA(cudaMemcpyAsync(dev, host, count * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+  return 0;
+}
+int VecIO::copy_back() {
+  if (host && n) {
+    TFX_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+    TFX_CUDA(cudaStreamSynchronize(ctx().stream));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Matrix: device mirror
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(DevBuf<T> &d, const std::vector<T> &h) {
+  TFX_TRY(d.alloc(h.size()));
+  if (!h.empty()) TFX_CUDA(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+  return 0;
+}
+
+int matrix_upload(Matrix &m, bool allow_dense) {
+  TFX_TRY(ensure_init());
+  const int32_t ns = m.nl_nonempty;
+  const int64_t nel = m.nel;
+  // ---- forward CSR (0-based)
+  std::vector<int64_t> ptr((size_t)ns + 1);
+  for (int32_t i = 0; i <= ns; ++i) ptr[i] = m.ijl[i] - 1;
+  std::vector<int32_t> idx((size_t)nel), segmap((size_t)ns);
+  for (int64_t k = 0; k < nel; ++k) idx[k] = m.ija[k] - 1;
+  for (int32_t i = 0; i < ns; ++i) segmap[i] = m.rowptr[i] - 1;
+  SegMatrix &f = m.fwd;
+  f.nnz = nel; f.nseg = ns; f.nout = m.nl; f.nin = m.ncolumns;
+  TFX_TRY(upload(f.ptr, ptr));
+  TFX_TRY(upload(f.idx, idx));
+  std::vector<float> val(m.sa.begin(), m.sa.begin() + nel);
+  TFX_TRY(upload(f.val, val));
+  TFX_TRY(upload(f.segmap, segmap));
+  TFX_TRY(seg_build_items(f, ptr.data()));
+
+  // ---- CSR of the transpose: counting sort by column, stable in stored-row order, so that the
+  // entries of a column appear in the order add_trans_mult_vector visits them (sparse_matrix.f90:397-403).
+  std::vector<int64_t> cnt((size_t)m.ncolumns + 1, 0);
+  for (int64_t k = 0; k < nel; ++k) cnt[idx[k] + 1]++;
+  std::vector<int32_t> tmap;
+  std::vector<int64_t> tptr;
+  std::vector<int64_t> start((size_t)m.ncolumns, 0);
+  tptr.push_back(0);
+  {
+    int64_t run = 0;
+    for (int32_t j = 0; j < m.ncolumns; ++j) {
+      start[j] = run;
+      if (cnt[j + 1] > 0) {
+        tmap.push_back(j);
+        run += cnt[j + 1];
+        tptr.push_back(run);
+      }
+    }
+  }
+  std::vector<int32_t> tidx((size_t)nel);
+  std::vector<float> tval((size_t)nel);
+  for (int32_t i = 0; i < ns; ++i) {
+    const int32_t row = segmap[i];
+    for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k) {
+      const int64_t pos = start[idx[k]]++;
+      tidx[pos] = row;
+      tval[pos] = val[k];
+    }
+  }
+  SegMatrix &t = m.trn;
+  t.nnz = nel; t.nseg = (int32_t)tmap.size(); t.nout = m.ncolumns; t.nin = m.nl;
+  TFX_TRY(upload(t.ptr, tptr));
+  TFX_TRY(upload(t.idx, tidx));
+  TFX_TRY(upload(t.val, tval));
+  TFX_TRY(upload(t.segmap, tmap));
+  TFX_TRY(seg_build_items(t, tptr.data()));
+  m.has_seg = true;
+
+  // ---- dense block detection: every row present, same contiguous column range (the uncompressed
+  // kernel, sensitivity_gravmag.F90:288-295, possibly shifted by param_shift).
+  m.has_dense = false;
+  if (allow_dense && g_opt_dense_detect && ns == m.nl && ns >= 1 && ns <= kDenseMaxRows && nel > 0) {
+    const int64_t W = ptr[1] - ptr[0];
+    bool ok = W > 0 && W * (int64_t)ns == nel;
+    const int32_t c0 = ok ? idx[0] : 0;
+    for (int32_t i = 0; ok && i < ns; ++i) {
+      if (ptr[i + 1] - ptr[i] != W) { ok = false; break; }
+      for (int64_t k = 0; k < W; ++k)
+        if (idx[ptr[i] + k] != c0 + (int32_t)k) { ok = false; break; }
+    }
+    if (ok) {
+      DenseCM &d = m.dense;
+      d.nrows = ns; d.ncols = (int32_t)W; d.col0 = c0; d.ld = ((int64_t)ns + 3) / 4 * 4; d.grid = 0;
+      std::vector<float> cm((size_t)d.ld * (size_t)W, 0.0f);
+      for (int32_t i = 0; i < ns; ++i)
+        for (int64_t k = 0; k < W; ++k) cm[(size_t)k * d.ld + i] = val[ptr[i] + k];
+      TFX_TRY(upload(d.val, cm));
+      m.has_dense = true;
+      m.dense_row0 = 0;
+    }
+  }
+  TFX_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Builder (mirrors sparse_matrix.f90 line by line in behaviour, including the error texts)
+// ---------------------------------------------------------------------------------------------
+static int builder_guard(const Matrix &m) {
+  if (m.device_only) return fail(-10, "sparse_matrix: this matrix was assembled on the device and cannot be modified");
+  return 0;
+}
+
+}  // namespace tfx
+
+using namespace tfx;
+
+extern "C" {
+
+int tfx_version(void) { return 100; }
+const char *tfx_last_error(void) { return g_err.c_str(); }
+int tfx_init(int device) { return init_device(device); }
+int tfx_finalize(void) {
+  comm_finalize();
+  return 0;
+}
+int tfx_device_synchronize(void) {
+  TFX_TRY(ensure_init());
+  TFX_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+uint64_t tfx_launch_count(void) { return ctx().launches; }
+int tfx_set_option(const char *name, int value) {
+  if (name && strcmp(name, "dense_detect") == 0) {
+    g_opt_dense_detect = value;
+    return 0;
+  }
+  return fail(-4, std::string("unknown option: ") + (name ? name : "(null)"));
+}
+
+// ---- communicator -------------------------------------------------------------------------------
+int tfx_comm_unique_id(char id[128]) { return comm_unique_id(id); }
+int tfx_comm_init(int nranks, int rank, const char id[128]) { return comm_init(nranks, rank, id); }
+int tfx_comm_finalize(void) { return comm_finalize(); }
+int tfx_comm_allreduce_sum(double *buf, int64_t count) {
+  TFX_TRY(ensure_init());
+  VecIO v;
+  TFX_TRY(v.bind(buf, (size_t)count, true));
+  TFX_TRY(comm_allreduce_sum(v.dev, (size_t)count, ctx().stream));
+  TFX_TRY(v.copy_back());
+  TFX_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+// ---- sparse_matrix ------------------------------------------------------------------------------
+int tfx_sparse_matrix_initialize(tfx_matrix **out, int32_t nl, int32_t ncolumns, int64_t nnz, int32_t myrank,
+                                 int32_t nl_empty) {
+  (void)myrank;
+  if (!out) return fail(-11, "sparse_matrix_initialize: null handle");
+  if (nnz < 0 || nl < 0) return fail(-12, "Wrong sizes in sparse_matrix_allocate_arrays!");
+  tfx_matrix *h = new tfx_matrix();
+  Matrix &m = h->m;
+  m.nl = nl; m.ncolumns = ncolumns; m.nnz = nnz;
+  m.nl_nonempty_allocated = nl - nl_empty;
+  if (m.nl_nonempty_allocated < 0) m.nl_nonempty_allocated = 0;
+  m.ijl.assign((size_t)m.nl_nonempty_allocated + 1, 0);
+  m.rowptr.assign((size_t)std::max(1, m.nl_nonempty_allocated), 0);
+  // sa/ija grow on demand up to nnz (the reference allocates nnz up front; the bound is enforced in add()).
+  *out = h;
+  return 0;
+}
+
+int tfx_sparse_matrix_destroy(tfx_matrix *h) {
+  delete h;
+  return 0;
+}
+
+int tfx_sparse_matrix_reset(tfx_matrix *h) {
+  Matrix &m = h->m;
+  TFX_TRY(builder_guard(m));
+  m.nl_current = 0; m.nl_current_all = 0; m.nel = 0; m.nel_last = 0; m.nl_nonempty = 0;
+  m.sa.clear(); m.ija.clear();
+  std::fill(m.ijl.begin(), m.ijl.end(), 0);
+  std::fill(m.rowptr.begin(), m.rowptr.end(), 0);
+  m.finalized = false; m.has_seg = false; m.has_dense = false;
+  return 0;
+}
+
+int tfx_sparse_matrix_add(tfx_matrix *h, double value, int32_t column, int32_t myrank) {
+  (void)myrank;
+  Matrix &m = h->m;
+  TFX_TRY(builder_guard(m));
+  if (value == 0.0) return 0;                      // "Do not add zero values to a sparse matrix."
+  if (m.nel >= m.nnz) return fail(-13, "Error in total number of elements in sparse_matrix_add!");
+  m.sa.push_back((float)value);                    // real(value, MATRIX_PRECISION)
+  m.ija.push_back(column);
+  m.nel += 1;
+  return 0;
+}
+
+int tfx_sparse_matrix_add_row(tfx_matrix *h, int32_t nel_add, const float *values, const int32_t *columns,
+                              int32_t myrank) {
+  (void)myrank;
+  Matrix &m = h->m;
+  TFX_TRY(builder_guard(m));
+  if (m.nel + nel_add > m.nnz) return fail(-14, "Error in total number of elements in sparse_matrix_add_row!");
+  m.sa.insert(m.sa.end(), values, values + nel_add);
+  m.ija.insert(m.ija.end(), columns, columns + nel_add);
+  m.nel += nel_add;
+  return 0;
+}
+
+int tfx_sparse_matrix_new_row(tfx_matrix *h, int32_t myrank) {
+  (void)myrank;
+  Matrix &m = h->m;
+  TFX_TRY(builder_guard(m));
+  if (m.nl_current >= m.nl_nonempty_allocated)
+    return fail(-15, "Error in number of rows in sparse_matrix_new_row!\nnl_current=" + std::to_string(m.nl_current) +
+                         "\nnl=" + std::to_string(m.nl));
+  m.nl_current_all += 1;
+  if (m.nel > m.nel_last) {                        // only non-empty rows are stored
+    m.nl_current += 1;
+    m.ijl[m.nl_current - 1] = m.nel_last + 1;
+    m.rowptr[m.nl_current - 1] = m.nl_current_all;
+    m.nel_last = m.nel;
+  }
+  return 0;
+}
+
+int tfx_sparse_matrix_add_empty_rows(tfx_matrix *h, int32_t nrows, int32_t myrank) {
+  (void)myrank;
+  Matrix &m = h->m;
+  TFX_TRY(builder_guard(m));
+  m.nl_current_all += nrows;
+  return 0;
+}
+
+int tfx_sparse_matrix_finalize(tfx_matrix *h, int32_t myrank) {
+  (void)myrank;
+  Matrix &m = h->m;
+  if (m.device_only) return 0;
+  if (m.nl_current_all != m.nl)
+    return fail(-16, "Error in total number of rows in sparse_matrix_finalize!\nnl_current=" +
+                         std::to_string(m.nl_current) + "\nnl=" + std::to_string(m.nl));
+  if (m.nel_last != m.nel)
+    return fail(-17, "Elements were added to the matrix after calling new_row() and before calling finalize()!");
+  m.ijl[m.nl_current] = m.nel + 1;
+  m.nl_nonempty = m.nl_current;
+  // validate(), sparse_matrix.f90:188-208
+  for (int32_t i = 0; i < m.nl_nonempty; ++i)
+    for (int64_t k = m.ijl[i]; k <= m.ijl[i + 1] - 1; ++k) {
+      if (k < 1 || k > m.nnz) return fail(-18, "Sparse matrix element-index validation failed!");
+      const int32_t j = m.ija[k - 1];
+      if (j < 1 || j > m.ncolumns) return fail(-19, "Sparse matrix column-index validation failed!");
+    }
+  TFX_TRY(matrix_upload(m, true));
+  m.finalized = true;
+  return 0;
+}
+
+int tfx_sparse_matrix_from_arrays(tfx_matrix **out, int32_t nl, int32_t ncolumns, int32_t nl_nonempty, int64_t nel,
+                                  const float *sa, const int32_t *ija, const int64_t *ijl, const int32_t *rowptr) {
+  TFX_TRY(tfx_sparse_matrix_initialize(out, nl, ncolumns, nel, 0, nl - nl_nonempty));
+  Matrix &m = (*out)->m;
+  m.sa.assign(sa, sa + nel);
+  m.ija.assign(ija, ija + nel);
+  for (int32_t i = 0; i <= nl_nonempty; ++i) m.ijl[i] = ijl[i];
+  for (int32_t i = 0; i < nl_nonempty; ++i) m.rowptr[i] = rowptr[i];
+  m.nel = m.nel_last = nel;
+  m.nl_current = nl_nonempty;
+  m.nl_current_all = nl;
+  int rc = tfx_sparse_matrix_finalize(*out, 0);
+  if (rc != 0) {
+    delete *out;
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int32_t tfx_sparse_matrix_get_total_row_number(const tfx_matrix *h) { return h->m.nl; }
+int32_t tfx_sparse_matrix_get_current_row_number(const tfx_matrix *h) { return h->m.nl_current_all; }
+int32_t tfx_sparse_matrix_get_ncolumns(const tfx_matrix *h) { return h->m.ncolumns; }
+int64_t tfx_sparse_matrix_get_number_elements(const tfx_matrix *h) { return h->m.nel; }
+int64_t tfx_sparse_matrix_get_nnz(const tfx_matrix *h) { return h->m.nnz; }
+int tfx_sparse_matrix_storage_kind(const tfx_matrix *h) { return h->m.has_dense ? 1 : 0; }
+
+// Products. kind: 0 forward, 1 transposed.
+static int product(Matrix &m, const double *x, double *b, bool accumulate, bool transposed) {
+  TFX_TRY(ensure_init());
+  if (!m.finalized) return fail(-20, "sparse_matrix: product called before finalize()");
+  cudaStream_t st = ctx().stream;
+  const size_t nin = transposed ? m.nl : m.ncolumns, nout = transposed ? m.ncolumns : m.nl;
+  VecIO vx, vb;
+  TFX_TRY(vx.bind(const_cast<double *>(x), nin, true));
+  TFX_TRY(vb.bind(b, nout, accumulate));
+  if (m.has_seg) {
+    SegMatrix &s = transposed ? m.trn : m.fwd;
+    TFX_TRY(seg_spmv(s, vx.dev, vb.dev, accumulate, 0, (int32_t)nout, 0, nullptr, st));
+  } else if (m.has_dense) {
+    // device-assembled dense block: run the one-product modes of the sweep kernel
+    DevBuf<double> tmp;
+    if (transposed) {
+      TFX_TRY(tmp.alloc(nout));
+      TFX_CUDA(cudaMemsetAsync(tmp.p, 0, nout * 8, st));
+      TFX_TRY(dense_sweep(m.dense, DENSE_T_ONLY, vx.dev + m.dense_row0, nullptr, nullptr, tmp.p, nullptr, nullptr, nullptr, nullptr, st));
+    } else {
+      TFX_TRY(tmp.alloc(nout));
+      TFX_CUDA(cudaMemsetAsync(tmp.p, 0, nout * 8, st));
+      TFX_TRY(dense_sweep(m.dense, DENSE_F_ONLY, nullptr, vx.dev, nullptr, nullptr, nullptr, tmp.p + m.dense_row0, nullptr, nullptr, st));
+    }
+    // b = (accumulate ? b : 0) + tmp  -- tiny axpy through thrust-free path: reuse cudaMemcpy when !accumulate
+    if (!accumulate) {
+      TFX_CUDA(cudaMemcpyAsync(vb.dev, tmp.p, nout * 8, cudaMemcpyDeviceToDevice, st));
+    } else {
+      TFX_TRY(vec_add_inplace(vb.dev, tmp.p, nout, st));
+    }
+    TFX_CUDA(cudaStreamSynchronize(st));
+  } else {
+    return fail(-21, "sparse_matrix: no device representation");
+  }
+  TFX_TRY(vb.copy_back());
+  TFX_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int tfx_sparse_matrix_mult_vector(tfx_matrix *h, const double *x, double *b) { return product(h->m, x, b, false, false); }
+int tfx_sparse_matrix_add_mult_vector(tfx_matrix *h, const double *x, double *b) { return product(h->m, x, b, true, false); }
+int tfx_sparse_matrix_trans_mult_vector(tfx_matrix *h, const double *x, double *b) { return product(h->m, x, b, false, true); }
+int tfx_sparse_matrix_add_trans_mult_vector(tfx_matrix *h, const double *x, double *b) { return product(h->m, x, b, true, true); }
+
+int tfx_sparse_matrix_part_mult_vector(tfx_matrix *h, int32_t nelements, const double *x, int32_t ndata, double *b,
+                                       int32_t line_start, int32_t param_shift, int32_t myrank) {
+  (void)myrank;
+  Matrix &m = h->m;
+  TFX_TRY(ensure_init());
+  if (!m.finalized) return fail(-20, "sparse_matrix: product called before finalize()");
+  const int32_t line_end = line_start + ndata - 1;
+  if (line_start < 1 || line_start > m.nl_current_all || line_end < 1 || line_end > m.nl_current_all)
+    return fail(-22, "Wrong line index in sparse_matrix_part_mult_vector!");
+  cudaStream_t st = ctx().stream;
+  VecIO vx, vb;
+  TFX_TRY(vx.bind(const_cast<double *>(x), (size_t)nelements, true));
+  TFX_TRY(vb.bind(b, (size_t)ndata, false));
+  if (m.has_seg) {
+    TFX_TRY(seg_spmv(m.fwd, vx.dev, vb.dev, false, line_start - 1, line_end, param_shift, nullptr, st));
+  } else if (m.has_dense) {
+    // dense block covers rows [dense_row0, dense_row0 + nrows) and columns [col0, col0 + ncols):
+    // x(ija - param_shift) -> element col0 + c - param_shift of x.
+    if (line_start - 1 != m.dense_row0 || ndata != m.dense.nrows || m.dense.col0 < param_shift ||
+        m.dense.col0 - param_shift + m.dense.ncols > nelements)
+      return fail(-23, "part_mult_vector: requested part does not match the device-resident dense block");
+    DenseCM &d = m.dense;
+    const int32_t saved = d.col0;
+    d.col0 = saved - param_shift;
+    int rc = dense_sweep(d, DENSE_F_ONLY, nullptr, vx.dev, nullptr, nullptr, nullptr, vb.dev, nullptr, nullptr, st);
+    d.col0 = saved;
+    TFX_TRY(rc);
+  } else {
+    return fail(-21, "sparse_matrix: no device representation");
+  }
+  TFX_TRY(vb.copy_back());
+  TFX_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int tfx_sparse_matrix_export(tfx_matrix *h, int64_t *nel, int32_t *nl_nonempty, float *sa, int32_t *ija, int64_t *ijl,
+                             int32_t *rowptr) {
+  Matrix &m = h->m;
+  if (!m.device_only) {
+    if (nel) *nel = m.nel;
+    if (nl_nonempty) *nl_nonempty = m.nl_nonempty;
+    if (sa) memcpy(sa, m.sa.data(), (size_t)m.nel * 4);
+    if (ija) memcpy(ija, m.ija.data(), (size_t)m.nel * 4);
+    if (ijl) memcpy(ijl, m.ijl.data(), ((size_t)m.nl_nonempty + 1) * 8);
+    if (rowptr) memcpy(rowptr, m.rowptr.data(), (size_t)m.nl_nonempty * 4);
+    return 0;
+  }
+  TFX_TRY(ensure_init());
+  if (m.has_seg) {
+    const SegMatrix &f = m.fwd;
+    if (nel) *nel = f.nnz;
+    if (nl_nonempty) *nl_nonempty = f.nseg;
+    if (sa) TFX_CUDA(cudaMemcpy(sa, f.val.p, (size_t)f.nnz * 4, cudaMemcpyDeviceToHost));
+    if (ija) {
+      TFX_CUDA(cudaMemcpy(ija, f.idx.p, (size_t)f.nnz * 4, cudaMemcpyDeviceToHost));
+      for (int64_t k = 0; k < f.nnz; ++k) ija[k] += 1;
+    }
+    if (ijl) {
+      TFX_CUDA(cudaMemcpy(ijl, f.ptr.p, ((size_t)f.nseg + 1) * 8, cudaMemcpyDeviceToHost));
+      for (int32_t i = 0; i <= f.nseg; ++i) ijl[i] += 1;
+    }
+    if (rowptr) {
+      TFX_CUDA(cudaMemcpy(rowptr, f.segmap.p, (size_t)f.nseg * 4, cudaMemcpyDeviceToHost));
+      for (int32_t i = 0; i < f.nseg; ++i) rowptr[i] += 1;
+    }
+    return 0;
+  }
+  if (m.has_dense) {
+    const DenseCM &d = m.dense;
+    const int64_t n = (int64_t)d.nrows * d.ncols;
+    if (nel) *nel = n;
+    if (nl_nonempty) *nl_nonempty = d.nrows;
+    if (sa || ija) {
+      std::vector<float> cm((size_t)d.ld * d.ncols);
+      TFX_CUDA(cudaMemcpy(cm.data(), d.val.p, cm.size() * 4, cudaMemcpyDeviceToHost));
+      for (int32_t i = 0; i < d.nrows; ++i)
+        for (int32_t c = 0; c < d.ncols; ++c) {
+          if (sa) sa[(int64_t)i * d.ncols + c] = cm[(size_t)c * d.ld + i];
+          if (ija) ija[(int64_t)i * d.ncols + c] = d.col0 + c + 1;
+        }
+    }
+    if (ijl) for (int32_t i = 0; i <= d.nrows; ++i) ijl[i] = (int64_t)i * d.ncols + 1;
+    if (rowptr) for (int32_t i = 0; i < d.nrows; ++i) rowptr[i] = m.dense_row0 + i + 1;
+    return 0;
+  }
+  return fail(-21, "sparse_matrix: no device representation");
+}
+
+// ---- wavelet_transform --------------------------------------------------------------------------
+static int wavelet_call(double *s, int32_t n1, int32_t n2, int32_t n3, int32_t type, bool fwd) {
+  TFX_TRY(ensure_init());
+  VecIO v;
+  TFX_TRY(v.bind(s, (size_t)n1 * n2 * n3, true));
+  TFX_TRY(wavelet3d_device(v.dev, n1, n2, n3, type, fwd, ctx().stream));
+  TFX_TRY(v.copy_back());
+  TFX_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+int tfx_forward_wavelet(double *s, int32_t n1, int32_t n2, int32_t n3, int32_t t) { return wavelet_call(s, n1, n2, n3, t, true); }
+int tfx_inverse_wavelet(double *s, int32_t n1, int32_t n2, int32_t n3, int32_t t) { return wavelet_call(s, n1, n2, n3, t, false); }
+int tfx_Haar3D(double *s, int32_t n1, int32_t n2, int32_t n3) { return wavelet_call(s, n1, n2, n3, 1, true); }
+int tfx_iHaar3D(double *s, int32_t n1, int32_t n2, int32_t n3) { return wavelet_call(s, n1, n2, n3, 1, false); }
+int tfx_DaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3) { return wavelet_call(s, n1, n2, n3, 2, true); }
+int tfx_iDaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3) { return wavelet_call(s, n1, n2, n3, 2, false); }
+
+int tfx_apply_wavelet_transform(int32_t nelements, int32_t nx, int32_t ny, int32_t nz, int32_t ncomponents, double *v,
+                                int32_t fwd, int32_t compression_type, int32_t nproblems, const int32_t *solve_problem,
+                                int32_t myrank, int32_t nbproc) {
+  (void)myrank;
+  TFX_TRY(ensure_init());
+  if (nbproc != 1 || (int64_t)nx * ny * nz != nelements)
+    return fail(-24, "apply_wavelet_transform: the device path needs the full model on the rank (nbproc = 1)");
+  VecIO io;
+  TFX_TRY(io.bind(v, (size_t)nelements * ncomponents * nproblems, true));
+  for (int i = 0; i < nproblems; ++i) {
+    if (!solve_problem[i]) continue;
+    for (int k = 0; k < ncomponents; ++k)
+      TFX_TRY(wavelet3d_device(io.dev + ((size_t)i * ncomponents + k) * nelements, nx, ny, nz, compression_type, fwd != 0,
+                               ctx().stream));
+  }
+  TFX_TRY(io.copy_back());
+  TFX_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+// ---- lsqr_solver --------------------------------------------------------------------------------
+static LsqrResult g_last;
+
+static int lsqr_call(const LsqrParams &p, tfx_matrix *S, tfx_matrix *C, double *u, double *x) {
+  TFX_TRY(ensure_init());
+  VecIO vu, vx;
+  TFX_TRY(vu.bind(u, (size_t)p.nlines, true));
+  TFX_TRY(vx.bind(x, (size_t)p.ncolumns, false));
+  TFX_TRY(lsqr_run(p, &S->m, C ? &C->m : nullptr, vu.dev, vx.dev, g_last));
+  TFX_TRY(vu.copy_back());   // the reference destroys u (it is the solver's work array)
+  TFX_TRY(vx.copy_back());
+  TFX_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+int tfx_lsqr_solve(int32_t nlines, int32_t nelements, int32_t niter, double rmin, double gamma, tfx_matrix *matrix,
+                   double *u, double *x, int32_t myrank) {
+  LsqrParams p;
+  p.nlines = nlines; p.ncolumns = nelements; p.niter = niter; p.rmin = rmin; p.gamma = gamma;
+  p.single_matrix = true; p.myrank = myrank; p.nelements = nelements;
+  return lsqr_call(p, matrix, nullptr, u, x);
+}
+
+int tfx_lsqr_solve_sensit(int32_t nlines, int32_t ncolumns, int32_t niter, double rmin, double gamma,
+                          double target_misfit, tfx_matrix *matrix_sensit, tfx_matrix *matrix_cons, double *u,
+                          double *x, const int32_t solve_problem[2], int32_t nelements, int32_t nx, int32_t ny,
+                          int32_t nz, int32_t ncomponents, int32_t compression_type, int32_t wavelet_domain,
+                          double *memory, int32_t myrank, int32_t nbproc) {
+  LsqrParams p;
+  p.nlines = nlines; p.ncolumns = ncolumns; p.niter = niter; p.rmin = rmin; p.gamma = gamma;
+  p.target_misfit = target_misfit;
+  p.solve_problem[0] = solve_problem[0]; p.solve_problem[1] = solve_problem[1];
+  p.nelements = nelements; p.nx = nx; p.ny = ny; p.nz = nz; p.ncomponents = ncomponents;
+  p.compression_type = compression_type; p.wavelet_domain = wavelet_domain != 0;
+  p.myrank = myrank; p.nbproc = nbproc;
+  int rc = lsqr_call(p, matrix_sensit, matrix_cons, u, x);
+  if (memory) {
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    *memory = (double)(tot - fr) / (1024.0 * 1024.0 * 1024.0);   // device memory in use [GB] (reference: host PSS)
+  }
+  return rc;
+}
+
+int tfx_lsqr_last_history(double *r_hist, int32_t capacity, int32_t *iters, int32_t *fused) {
+  if (iters) *iters = g_last.iters;
+  if (fused) *fused = g_last.fused ? 1 : 0;
+  if (r_hist) {
+    const int n = std::min<int>(capacity, (int)g_last.history.size());
+    for (int i = 0; i < n; ++i) r_hist[i] = g_last.history[i];
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,339 @@
+// assembly.cu -- forward-kernel evaluation on the device (right rectangular prisms).
+//
+// Replaces graviprism_z / gradiprism_zz (src/forward/gravmag/grav/gravity_field.f90:131-195, :314-364)
+// and magprism / sharmbox (src/forward/gravmag/mag/magnetic_field.f90:118-457) together with the
+// weighting / real(4) rounding steps of calculate_and_write_sensit (sensitivity_gravmag.F90:228,290)
+// and read_sensitivity_kernel (:837-843).
+//
+// This stage is FP64-transcendental bound (8 corners x {sqrt, atan2, 2 log} per cell and station),
+// not memory bound and not a GEMM: tensor cores do not apply. One thread evaluates one
+// (station, cell) pair; stations vary fastest across a warp so that the cell box is a broadcast
+// load and the column-major store of the dense block is coalesced.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <math.h>
+
+#include <algorithm>
+
+namespace tfx {
+
+// PI, src/global_typedefs.F90:52.
+#define TFX_PI 3.1415926535897932385
+
+// graviprism_z for one cell / one station, gravity_field.f90:151-192. Returns gz (without G).
+__device__ __forceinline__ double grav_gz(double x1, double x2, double y1, double y2, double z1, double z2, double xd,
+                                          double yd, double zd, int *err) {
+  const double twopi = 2.0 * TFX_PI;
+  const double XX[2] = {xd - x1, xd - x2};
+  const double YY[2] = {yd - y1, yd - y2};
+  const double ZZ[2] = {zd - z1, zd - z2};
+  double gz = 0.0;
+#pragma unroll
+  for (int K = 0; K < 2; ++K)
+#pragma unroll
+    for (int L = 0; L < 2; ++L)
+#pragma unroll
+      for (int M = 0; M < 2; ++M) {
+        const double dmu = ((K + L + M) & 1) ? 1.0 : -1.0;   // signo(K)*signo(L)*signo(M), signo = (-1, +1)
+        const double Rs =
+            sqrt(__dadd_rn(__dadd_rn(__dmul_rn(XX[K], XX[K]), __dmul_rn(YY[L], YY[L])), __dmul_rn(ZZ[M], ZZ[M])));
+        double arg3 = atan2(__dmul_rn(XX[K], YY[L]), __dmul_rn(ZZ[M], Rs));
+        if (arg3 < 0) arg3 = arg3 + twopi;
+        double arg4 = Rs + XX[K];
+        double arg5 = Rs + YY[L];
+        if (arg4 <= 0.) *err = 1;   // "Data coordinate coincides with model grid boundary (YZ)"
+        if (arg5 <= 0.) *err = 2;   // "... (XZ)"
+        arg4 = log(arg4);
+        arg5 = log(arg5);
+        const double term = __dsub_rn(__dsub_rn(__dmul_rn(ZZ[M], arg3), __dmul_rn(XX[K], arg5)), __dmul_rn(YY[L], arg4));
+        gz = __dadd_rn(gz, __dmul_rn(dmu, term));
+      }
+  return gz;
+}
+
+// gradiprism_zz, gravity_field.f90:331-361.
+__device__ __forceinline__ double grav_gzz(double x1, double x2, double y1, double y2, double z1, double z2, double xd,
+                                           double yd, double zd) {
+  const double twopi = 2.0 * TFX_PI;
+  const double XX[2] = {xd - x1, xd - x2};
+  const double YY[2] = {yd - y1, yd - y2};
+  const double ZZ[2] = {-(zd - z1), -(zd - z2)};
+  double gzz = 0.0;
+#pragma unroll
+  for (int K = 0; K < 2; ++K)
+#pragma unroll
+    for (int L = 0; L < 2; ++L)
+#pragma unroll
+      for (int M = 0; M < 2; ++M) {
+        const double dmu = ((K + L + M) & 1) ? 1.0 : -1.0;
+        const double Rs =
+            sqrt(__dadd_rn(__dadd_rn(__dmul_rn(XX[K], XX[K]), __dmul_rn(YY[L], YY[L])), __dmul_rn(ZZ[M], ZZ[M])));
+        double vzz = -atan2(__dmul_rn(XX[K], YY[L]), __dmul_rn(Rs, ZZ[M]));
+        if (vzz < 0) vzz = vzz + twopi;
+        gzz = __dadd_rn(gzz, __dmul_rn(dmu, vzz));
+      }
+  return gzz;
+}
+
+// G_grav = 6.674e-11 is a single-precision literal in the reference (gravity_field.f90:26).
+__device__ __forceinline__ double g_grav() { return (double)6.674e-11f; }
+
+// ---------------------------------------------------------------------------------------------
+// Dense (no compression) block: S[col*ld + row], one thread per (row, col).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grav_dense_kernel(float *__restrict__ S, long long ld, int nrows, int ncols,
+                                                         int cell0, const double *__restrict__ X1,
+                                                         const double *__restrict__ X2, const double *__restrict__ Y1,
+                                                         const double *__restrict__ Y2, const double *__restrict__ Z1,
+                                                         const double *__restrict__ Z2, const double *__restrict__ xd,
+                                                         const double *__restrict__ yd, const double *__restrict__ zd,
+                                                         const double *__restrict__ cw, const double *__restrict__ dw,
+                                                         double problem_weight, int cols_per_block, int *err) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  const double px = xd[row], py = yd[row], pz = zd[row];
+  // combined_weight = real(problem_weight * data_weight, 4), sensitivity_gravmag.F90:837.
+  const float wgt = (float)(problem_weight * dw[row]);
+  const int cbeg = blockIdx.y * cols_per_block;
+  const int cend = min(ncols, cbeg + cols_per_block);
+  int e = 0;
+  for (int c = cbeg; c < cend; ++c) {
+    const int p = cell0 + c;
+    const double gz = grav_gz(X1[p], X2[p], Y1[p], Y2[p], Z1[p], Z2[p], px, py, pz, &e);
+    const double line = __dmul_rn(__dmul_rn(g_grav(), gz), cw[p]);   // LineZ = G*gz (:192); * column weight (:1051)
+    const float v = __fmul_rn((float)line, wgt);                      // real(.,4) (:290) ; * combined_weight (:842)
+    S[(long long)c * ld + row] = v;
+  }
+  if (e) atomicExch(err, e);
+}
+
+int assemble_grav_dense(DenseCM &S, const GridDev &g, int32_t cell0, int32_t ncells, int32_t ndata,
+                        const double *d_xd, const double *d_yd, const double *d_zd, const double *d_cw,
+                        const double *d_dw, double problem_weight, int *d_err, cudaStream_t st) {
+  S.nrows = ndata;
+  S.ncols = ncells;
+  S.ld = ((int64_t)ndata + 3) / 4 * 4;
+  TFX_TRY(S.val.alloc((size_t)S.ld * (size_t)ncells));
+  if (S.ld != ndata) TFX_CUDA(cudaMemsetAsync(S.val.p, 0, (size_t)S.ld * ncells * sizeof(float), st));
+  const int cols_per_block = 64;
+  dim3 grid((ndata + 255) / 256, (ncells + cols_per_block - 1) / cols_per_block);
+  if (grid.y > 65535) {
+    // chunk the columns over several launches
+    const int per = 65535 * cols_per_block;
+    for (int c0 = 0; c0 < ncells; c0 += per) {
+      const int cn = std::min(per, ncells - c0);
+      dim3 gsub((ndata + 255) / 256, (cn + cols_per_block - 1) / cols_per_block);
+      grav_dense_kernel<<<gsub, 256, 0, st>>>(S.val.p + (long long)c0 * S.ld, S.ld, ndata, cn, cell0 + c0, g.X1.p,
+                                              g.X2.p, g.Y1.p, g.Y2.p, g.Z1.p, g.Z2.p, d_xd, d_yd, d_zd, d_cw, d_dw,
+                                              problem_weight, cols_per_block, d_err);
+      ctx().launches++;
+    }
+  } else {
+    grav_dense_kernel<<<grid, 256, 0, st>>>(S.val.p, S.ld, ndata, ncells, cell0, g.X1.p, g.X2.p, g.Y1.p, g.Y2.p,
+                                            g.Z1.p, g.Z2.p, d_xd, d_yd, d_zd, d_cw, d_dw, problem_weight,
+                                            cols_per_block, d_err);
+    ctx().launches++;
+  }
+  TFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Full lines (one per station) for the compression pipeline: lines[b*n + p].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grav_lines_kernel(double *__restrict__ lines, int n, int nb,
+                                                         const double *__restrict__ X1, const double *__restrict__ X2,
+                                                         const double *__restrict__ Y1, const double *__restrict__ Y2,
+                                                         const double *__restrict__ Z1, const double *__restrict__ Z2,
+                                                         const double *__restrict__ xd, const double *__restrict__ yd,
+                                                         const double *__restrict__ zd, int data_type, int *err) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double x1 = X1[p], x2 = X2[p], y1 = Y1[p], y2 = Y2[p], z1 = Z1[p], z2 = Z2[p];
+  int e = 0;
+  for (int b = blockIdx.y; b < nb; b += gridDim.y) {
+    double v;
+    if (data_type == 1) v = grav_gz(x1, x2, y1, y2, z1, z2, xd[b], yd[b], zd[b], &e);
+    else v = grav_gzz(x1, x2, y1, y2, z1, z2, xd[b], yd[b], zd[b]);
+    lines[(long long)b * n + p] = __dmul_rn(g_grav(), v);
+  }
+  if (e) atomicExch(err, e);
+}
+
+int grav_lines(const GridDev &g, int32_t nb, const double *d_xd, const double *d_yd, const double *d_zd, int data_type,
+               double *d_lines, int *d_err, cudaStream_t st) {
+  dim3 grid((g.n + 255) / 256, std::min(nb, 1024));
+  grav_lines_kernel<<<grid, 256, 0, st>>>(d_lines, g.n, nb, g.X1.p, g.X2.p, g.Y1.p, g.Y2.p, g.Z1.p, g.Z2.p, d_xd,
+                                          d_yd, d_zd, data_type, d_err);
+  ctx().launches++;
+  TFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Magnetic tensor of one prism (Sharma 1966), magnetic_field.f90:321-457, eps = 0.
+// ---------------------------------------------------------------------------------------------
+__device__ void sharmbox_dev(double x0, double y0, double z0, double x1, double y1, double z1, double x2, double y2,
+                             double z2, double tsx[3], double tsy[3], double tsz[3], int *err) {
+  const double rx1 = x1 - x0, rx2 = x2 - x0, ry1 = y1 - y0, ry2 = y2 - y0, rz1 = z1 - z0, rz2 = z2 - z0;
+  if (rx1 == 0. || rx2 == 0.) *err = 11;
+  if (ry1 == 0. || ry2 == 0.) *err = 12;
+  const double rx1sq = __dmul_rn(rx1, rx1), rx2sq = __dmul_rn(rx2, rx2), ry1sq = __dmul_rn(ry1, ry1),
+               ry2sq = __dmul_rn(ry2, ry2), rz1sq = __dmul_rn(rz1, rz1), rz2sq = __dmul_rn(rz2, rz2);
+  // R = ry^2 + rx^2 first, then rz^2 + R (the reference's association, :361-373)
+  double R1 = __dadd_rn(ry2sq, rx2sq), R2 = __dadd_rn(ry2sq, rx1sq), R3 = __dadd_rn(ry1sq, rx2sq),
+         R4 = __dadd_rn(ry1sq, rx1sq);
+  double a1 = sqrt(__dadd_rn(rz2sq, R2)), a2 = sqrt(__dadd_rn(rz2sq, R1)), a3 = sqrt(__dadd_rn(rz1sq, R1)),
+         a4 = sqrt(__dadd_rn(rz1sq, R2)), a5 = sqrt(__dadd_rn(rz2sq, R3)), a6 = sqrt(__dadd_rn(rz2sq, R4)),
+         a7 = sqrt(__dadd_rn(rz1sq, R4)), a8 = sqrt(__dadd_rn(rz1sq, R3));
+  // ts_xx (:376-383)
+  double t = atan2(__dmul_rn(ry1, rz2), __dmul_rn(rx2, a5));
+  t = __dsub_rn(t, atan2(__dmul_rn(ry2, rz2), __dmul_rn(rx2, a2)));
+  t = __dadd_rn(t, atan2(__dmul_rn(ry2, rz1), __dmul_rn(rx2, a3)));
+  t = __dsub_rn(t, atan2(__dmul_rn(ry1, rz1), __dmul_rn(rx2, a8)));
+  t = __dadd_rn(t, atan2(__dmul_rn(ry2, rz2), __dmul_rn(rx1, a1)));
+  t = __dsub_rn(t, atan2(__dmul_rn(ry1, rz2), __dmul_rn(rx1, a6)));
+  t = __dadd_rn(t, atan2(__dmul_rn(ry1, rz1), __dmul_rn(rx1, a7)));
+  t = __dsub_rn(t, atan2(__dmul_rn(ry2, rz1), __dmul_rn(rx1, a4)));
+  tsx[0] = t;
+  // ts_yx (:386-389)
+  t = log(__ddiv_rn(rz2 + a2, rz1 + a3));
+  t = __dsub_rn(t, log(__ddiv_rn(rz2 + a1, rz1 + a4)));
+  t = __dadd_rn(t, log(__ddiv_rn(rz2 + a6, rz1 + a7)));
+  t = __dsub_rn(t, log(__ddiv_rn(rz2 + a5, rz1 + a8)));
+  tsy[0] = t;
+  // ts_yy (:392-399)
+  t = atan2(__dmul_rn(rx1, rz2), __dmul_rn(ry2, a1));
+  t = __dsub_rn(t, atan2(__dmul_rn(rx2, rz2), __dmul_rn(ry2, a2)));
+  t = __dadd_rn(t, atan2(__dmul_rn(rx2, rz1), __dmul_rn(ry2, a3)));
+  t = __dsub_rn(t, atan2(__dmul_rn(rx1, rz1), __dmul_rn(ry2, a4)));
+  t = __dadd_rn(t, atan2(__dmul_rn(rx2, rz2), __dmul_rn(ry1, a5)));
+  t = __dsub_rn(t, atan2(__dmul_rn(rx1, rz2), __dmul_rn(ry1, a6)));
+  t = __dadd_rn(t, atan2(__dmul_rn(rx1, rz1), __dmul_rn(ry1, a7)));
+  t = __dsub_rn(t, atan2(__dmul_rn(rx2, rz1), __dmul_rn(ry1, a8)));
+  tsy[1] = t;
+  // ts_yz (:404-422)
+  R1 = __dadd_rn(ry2sq, rz1sq); R2 = __dadd_rn(ry2sq, rz2sq); R3 = __dadd_rn(ry1sq, rz1sq); R4 = __dadd_rn(ry1sq, rz2sq);
+  a1 = sqrt(__dadd_rn(rx1sq, R1)); a2 = sqrt(__dadd_rn(rx2sq, R1)); a3 = sqrt(__dadd_rn(rx1sq, R2));
+  a4 = sqrt(__dadd_rn(rx2sq, R2)); a5 = sqrt(__dadd_rn(rx1sq, R3)); a6 = sqrt(__dadd_rn(rx2sq, R3));
+  a7 = sqrt(__dadd_rn(rx1sq, R4)); a8 = sqrt(__dadd_rn(rx2sq, R4));
+  t = log(__ddiv_rn(rx1 + a1, rx2 + a2));
+  t = __dsub_rn(t, log(__ddiv_rn(rx1 + a3, rx2 + a4)));
+  t = __dadd_rn(t, log(__ddiv_rn(rx1 + a7, rx2 + a8)));
+  t = __dsub_rn(t, log(__ddiv_rn(rx1 + a5, rx2 + a6)));
+  tsy[2] = t;
+  // ts_xz (:424-442)
+  R1 = __dadd_rn(rx2sq, rz1sq); R2 = __dadd_rn(rx2sq, rz2sq); R3 = __dadd_rn(rx1sq, rz1sq); R4 = __dadd_rn(rx1sq, rz2sq);
+  a1 = sqrt(__dadd_rn(ry1sq, R1)); a2 = sqrt(__dadd_rn(ry2sq, R1)); a3 = sqrt(__dadd_rn(ry1sq, R2));
+  a4 = sqrt(__dadd_rn(ry2sq, R2)); a5 = sqrt(__dadd_rn(ry1sq, R3)); a6 = sqrt(__dadd_rn(ry2sq, R3));
+  a7 = sqrt(__dadd_rn(ry1sq, R4)); a8 = sqrt(__dadd_rn(ry2sq, R4));
+  t = log(__ddiv_rn(ry1 + a1, ry2 + a2));
+  t = __dsub_rn(t, log(__ddiv_rn(ry1 + a3, ry2 + a4)));
+  t = __dadd_rn(t, log(__ddiv_rn(ry1 + a7, ry2 + a8)));
+  t = __dsub_rn(t, log(__ddiv_rn(ry1 + a5, ry2 + a6)));
+  tsx[2] = t;
+  tsz[2] = -1 * (tsx[0] + tsy[1]);   // Gauss (:446)
+  tsz[1] = tsy[2];
+  tsx[1] = tsy[0];
+  tsz[0] = tsx[2];
+}
+
+struct MagPar {
+  double magv[3];
+  double mult;   // intensity (susceptibility model) or mu0*T2nT (magnetisation model), :286-292
+  int nmc, ndc;
+};
+
+// magprism, magnetic_field.f90:135-295.
+__global__ void __launch_bounds__(128) mag_lines_kernel(double *__restrict__ lines, int n, int nb,
+                                                        const double *__restrict__ X1, const double *__restrict__ X2,
+                                                        const double *__restrict__ Y1, const double *__restrict__ Y2,
+                                                        const double *__restrict__ Z1, const double *__restrict__ Z2,
+                                                        const double *__restrict__ xd, const double *__restrict__ yd,
+                                                        const double *__restrict__ zd, MagPar mp, int *err) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double gx1 = X1[p], gx2 = X2[p], gy1 = Y1[p], gy2 = Y2[p], gz1 = Z1[p], gz2 = Z2[p];
+  int e = 0;
+  for (int b = blockIdx.y; b < nb; b += gridDim.y) {
+    const double Xd = xd[b], Yd = yd[b], Zd = zd[b];
+    double tx[3], ty[3], tz[3];
+    if ((gx1 < Xd) && (gx2 > Xd) && (gy1 < Yd) && (gy2 > Yd) && (gz1 < Zd) && (gz2 > Zd)) {
+      // Station inside the cell: six sub-prisms around a small void (:139-224).
+      double width = (double)0.1f;   // single-precision literal in the reference (:144)
+      const double min_clr = fmin(fmin(fmin(fabs(Xd - gx1), fabs(Xd - gx2)), fmin(fabs(Yd - gy1), fabs(Yd - gy2))),
+                                  fmin(fabs(Zd - gz1), fabs(Zd - gz2)));
+      if (width > min_clr) width = 0.5 * min_clr;
+      const double bx1[6] = {gx1, gx1, gx1, Xd + width, Xd - width, Xd - width};
+      const double bx2[6] = {gx2, gx2, Xd - width, gx2, Xd + width, Xd + width};
+      const double by1[6] = {gy1, gy1, gy1, gy1, gy1, Yd + width};
+      const double by2[6] = {gy2, gy2, gy2, gy2, Yd - width, gy2};
+      const double bz1[6] = {gz1, Zd + width, Zd - width, Zd - width, Zd - width, Zd - width};
+      const double bz2[6] = {Zd - width, gz2, Zd + width, Zd + width, Zd + width, Zd + width};
+      for (int q = 0; q < 3; ++q) tx[q] = ty[q] = tz[q] = 0.0;
+      for (int j = 0; j < 6; ++j) {
+        double ax[3], ay[3], az[3];
+        sharmbox_dev(Xd, Yd, Zd, bx1[j], by1[j], bz1[j], bx2[j], by2[j], bz2[j], ax, ay, az, &e);
+        for (int q = 0; q < 3; ++q) {
+          tx[q] = __dadd_rn(tx[q], ax[q]);
+          ty[q] = __dadd_rn(ty[q], ay[q]);
+          tz[q] = __dadd_rn(tz[q], az[q]);
+        }
+      }
+    } else {
+      sharmbox_dev(Xd, Yd, Zd, gx1, gy1, gz1, gx2, gy2, gz2, tx, ty, tz, &e);
+    }
+    const double fourpi = 4.0 * TFX_PI;
+    double *out = lines + (long long)b * mp.ndc * mp.nmc * n;   // (p, k, d) Fortran order per station
+#define OUT(k, d) out[((long long)(d)*mp.nmc + (k)) * n + p]
+#define FIN(x) __ddiv_rn(__dmul_rn(mp.mult, (x)), fourpi)
+#define DOT3(a) __dadd_rn(__dadd_rn(__dmul_rn(a[0], mp.magv[0]), __dmul_rn(a[1], mp.magv[1])), __dmul_rn(a[2], mp.magv[2]))
+    if (mp.nmc == 1) {
+      const double mx = DOT3(tx), my = DOT3(ty), mz = DOT3(tz);
+      if (mp.ndc == 1) {
+        OUT(0, 0) = FIN(__dadd_rn(__dadd_rn(__dmul_rn(mx, mp.magv[0]), __dmul_rn(my, mp.magv[1])), __dmul_rn(mz, mp.magv[2])));
+      } else {
+        OUT(0, 0) = FIN(mx); OUT(0, 1) = FIN(my); OUT(0, 2) = FIN(mz);
+      }
+    } else {
+      for (int k = 0; k < 3; ++k) {
+        if (mp.ndc == 1) {
+          OUT(k, 0) = FIN(__dadd_rn(__dadd_rn(__dmul_rn(tx[k], mp.magv[0]), __dmul_rn(ty[k], mp.magv[1])), __dmul_rn(tz[k], mp.magv[2])));
+        } else {
+          OUT(k, 0) = FIN(tx[k]); OUT(k, 1) = FIN(ty[k]); OUT(k, 2) = FIN(tz[k]);
+        }
+      }
+    }
+#undef OUT
+#undef FIN
+#undef DOT3
+  }
+  if (e) atomicExch(err, e);
+}
+
+int mag_lines(const GridDev &g, int32_t nb, const double *d_xd, const double *d_yd, const double *d_zd, int nmc, int ndc,
+              double mi, double md, double theta, double intensity, double *d_lines, int *d_err, cudaStream_t st) {
+  if (!((nmc == 1 || nmc == 3) && (ndc == 1 || ndc == 3)))
+    return fail(-40, "Wrong number of model/data components in magnetic_field_magprism!");
+  MagPar mp;
+  // dircos, magnetic_field.f90:91-110 (host libm; three scalars).
+  const double d2rad = TFX_PI / 180.0;
+  const double decl2 = fmod(450.0 - md, 360.0);
+  const double xincl = mi * d2rad, xdecl = decl2 * d2rad, xazim = theta * d2rad;
+  mp.magv[0] = cos(xincl) * cos(xdecl - xazim);
+  mp.magv[1] = cos(xincl) * sin(xdecl - xazim);
+  mp.magv[2] = sin(xincl);
+  const double mu0 = 4.0 * TFX_PI * 1.e-7, T2nT = 1.e+9;
+  mp.mult = (nmc == 1) ? intensity : (mu0 * T2nT);
+  mp.nmc = nmc;
+  mp.ndc = ndc;
+  dim3 grid((g.n + 127) / 128, std::min(nb, 1024));
+  mag_lines_kernel<<<grid, 128, 0, st>>>(d_lines, g.n, nb, g.X1.p, g.X2.p, g.Y1.p, g.Y2.p, g.Z1.p, g.Z2.p, d_xd, d_yd,
+                                         d_zd, mp, d_err);
+  ctx().launches++;
+  TFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tfx

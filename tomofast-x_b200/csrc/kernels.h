@@ -1,0 +1,106 @@
+// kernels.h -- internal interfaces between the translation units of libtfx.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace tfx {
+
+// ---- wavelet.cu -------------------------------------------------------------------------------
+// In-place 3-D transform of a device-resident Fortran-ordered volume s(n1,n2,n3).
+int wavelet3d_device(double *d_s, int n1, int n2, int n3, int wavelet_type, bool forward, cudaStream_t st);
+
+// ---- csr.cu -----------------------------------------------------------------------------------
+// A compressed-segment matrix view on the device. For the forward product it is the CSR of A
+// (segments = stored rows, idx = column); for the transposed product it is the CSR of A^T
+// (segments = non-empty columns, idx = global row). Long segments are cut into work items of at
+// most kItemLen entries; each item is summed by one warp/CTA in a fixed order and the per-segment
+// partials are added in item order, so every product is run-to-run deterministic.
+struct SegMatrix {
+  int64_t nnz = 0;
+  int32_t nseg = 0;        // stored (non-empty) segments
+  int32_t nout = 0;        // length of the output vector
+  int32_t nin = 0;         // length of the input vector
+  int32_t nitems = 0;
+  int32_t max_items_per_seg = 0;
+  double avg_len = 0.0;
+  DevBuf<int64_t> ptr;     // [nseg+1] 0-based entry offsets
+  DevBuf<int32_t> idx;     // [nnz]    0-based input index
+  DevBuf<float> val;       // [nnz]
+  DevBuf<int32_t> segmap;  // [nseg]   0-based output index of each segment
+  DevBuf<int32_t> item_seg;    // [nitems]
+  DevBuf<int64_t> item_beg;    // [nitems+1] (item i covers [item_beg[i], item_end[i]))
+  DevBuf<int64_t> item_end;    // [nitems]
+  DevBuf<int32_t> seg_item0;   // [nseg+1] first item of each segment
+  DevBuf<double> partial;      // [nitems]
+  bool empty() const { return nnz == 0 || nseg == 0; }
+};
+
+static const int kItemLen = 8192;
+
+// Builds the item table from host copies of ptr (0-based, nseg+1 entries).
+int seg_build_items(SegMatrix &m, const int64_t *h_ptr);
+
+// y[segmap[s] - out_lo] (+)= sum_k val[k] * x[idx[k] - xshift], restricted to segments whose output
+// index lies in [out_lo, out_hi). accumulate == false zeroes y[0 .. out_hi-out_lo) first.
+// `done` (device flag, may be null): kernels exit immediately when *done != 0.
+int seg_spmv(SegMatrix &m, const double *d_x, double *d_y, bool accumulate, int32_t out_lo, int32_t out_hi,
+             int32_t xshift, const int *d_done, cudaStream_t st);
+
+// y += x (device vectors).
+int vec_add_inplace(double *y, const double *x, size_t n, cudaStream_t st);
+
+// ---- dense.cu ---------------------------------------------------------------------------------
+// Uncompressed sensitivity block: column-major f32, column j at base + j*ld (ld % 4 == 0), rows
+// [0, nrows). No column indices are stored (columns are 1..N, sensitivity_gravmag.F90:288-295).
+struct DenseCM {
+  DevBuf<float> val;
+  int64_t ld = 0;
+  int32_t nrows = 0;       // data rows of this block
+  int32_t ncols = 0;       // local columns held by this rank
+  int32_t col0 = 0;        // 0-based position of column 0 inside the solver's column space
+  int32_t grid = 0;        // CTAs of the sweep kernel (== partial buffers)
+  DevBuf<double> partial_q;    // [grid][ld]
+  DevBuf<double> partial_n2;   // [grid]
+  bool empty() const { return nrows == 0 || ncols == 0; }
+};
+
+enum DenseMode { DENSE_FUSED = 0, DENSE_T_ONLY = 1, DENSE_F_ONLY = 2 };
+
+static const int kDenseMaxRows = 10240;  // register-resident u / q: 10 rows per thread x 1024 threads
+
+// One sweep over the block.
+//  FUSED : out[j] = nbeta*v[j] + (S^T u)[j] + g[j];  q += S out;  n2 = |out|^2   (nbeta = *d_nbeta)
+//  T_ONLY: out[j] = (S^T u)[j]
+//  F_ONLY: q += S in  (in = d_v)
+// Vectors v/g/out are indexed in the solver's column space (col0 applied inside). g may be null.
+// q (nrows) and n2 (1) are written (not accumulated) by the trailing reduction kernel.
+int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v, const double *d_g,
+                double *d_out, const double *d_nbeta, double *d_q, double *d_n2, const int *d_done,
+                cudaStream_t st);
+
+// ---- assembly.cu ------------------------------------------------------------------------------
+struct GridDev {
+  int32_t n = 0;
+  DevBuf<double> X1, X2, Y1, Y2, Z1, Z2;
+};
+
+// Fills a dense column-major block with the depth-weighted gravity kernel, reproducing
+// graviprism_z (gravity_field.f90:131-195), apply_column_weight (sensitivity_gravmag.F90:228),
+// the real(4) store (:290) and the real(4) scaling by problem_weight*data_weight (:837-843).
+int assemble_grav_dense(DenseCM &S, const GridDev &g, int32_t cell0, int32_t ncells, int32_t ndata,
+                        const double *d_xd, const double *d_yd, const double *d_zd, const double *d_cw,
+                        const double *d_dw, double problem_weight, int *d_err, cudaStream_t st);
+
+// Computes one gravity sensitivity line (all cells) per data point into d_lines[b*ncells + p].
+int grav_lines(const GridDev &g, int32_t ndata_batch, const double *d_xd, const double *d_yd, const double *d_zd,
+               int data_type, double *d_lines, int *d_err, cudaStream_t st);
+
+// Magnetic tensor lines: d_lines[((b*ndc + d)*nmc + k)*ncells + p] (Fortran sensit_line(p,k,d) per data b).
+int mag_lines(const GridDev &g, int32_t ndata_batch, const double *d_xd, const double *d_yd, const double *d_zd,
+              int nmc, int ndc, double mi, double md, double theta, double intensity, double *d_lines,
+              int *d_err, cudaStream_t st);
+
+}  // namespace tfx

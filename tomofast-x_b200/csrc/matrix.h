@@ -1,0 +1,74 @@
+// matrix.h -- the t_sparse_matrix replacement (host builder + device representations).
+#pragma once
+
+#include <stdint.h>
+
+#include <vector>
+
+#include "kernels.h"
+
+namespace tfx {
+
+// Mirrors t_sparse_matrix (src/inversion/sparse_matrix.f90:31-98). The host-side builder keeps the
+// reference's exact storage (sa real(4), ija int32 1-based, ijl int64 1-based, rowptr int32);
+// finalize() validates it like the reference and mirrors it to the device:
+//   fwd : CSR of A    (forward products, gathers x by column)
+//   trn : CSR of A^T  (transposed products as gathers -- no scatter-add, deterministic)
+//   dense (optional): column-major f32 block when every stored row holds the same contiguous
+//                     column range (the uncompressed kernel), or when assembled on the device.
+struct Matrix {
+  int64_t nnz = 0, nel = 0, nel_last = 0;
+  int32_t nl = 0, nl_nonempty = 0, nl_nonempty_allocated = 0, nl_current = 0, nl_current_all = 0, ncolumns = 0;
+  std::vector<float> sa;
+  std::vector<int32_t> ija;
+  std::vector<int64_t> ijl;
+  std::vector<int32_t> rowptr;
+  bool finalized = false;
+  bool device_only = false;   // assembled on the device: no host arrays, builder calls are errors
+  int tag = 0;
+
+  SegMatrix fwd, trn;
+  bool has_seg = false;
+  DenseCM dense;
+  bool has_dense = false;
+  int32_t dense_row0 = 0;     // 0-based global row of dense row 0
+
+  int64_t device_nnz() const { return has_dense ? (int64_t)dense.nrows * dense.ncols : fwd.nnz; }
+};
+
+int matrix_upload(Matrix &m, bool allow_dense);
+
+// ---- lsqr.cu ----------------------------------------------------------------------------------
+struct LsqrParams {
+  int32_t nlines = 0, ncolumns = 0, niter = 0;
+  double rmin = 0, gamma = 0, target_misfit = 0;
+  int32_t solve_problem[2] = {1, 0};
+  int32_t nelements = 0, nx = 0, ny = 0, nz = 0, ncomponents = 1, compression_type = 0;
+  bool wavelet_domain = true;
+  int32_t myrank = 0, nbproc = 1;
+  bool single_matrix = false;   // lsqr_solve (tests): no constraint matrix, no wavelet
+};
+
+struct LsqrResult {
+  int32_t iters = 0;      // loop bodies executed (the reference prints iter - 1)
+  int32_t status = 0;     // 0 ok, 1: |b| = 0
+  double r = 1.0;
+  bool fused = false;
+  std::vector<double> history;
+};
+
+int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x, LsqrResult &res);
+
+// ---- comm.cu ----------------------------------------------------------------------------------
+int comm_nranks();
+int comm_allreduce_sum(double *d_buf, size_t count, cudaStream_t st);
+int comm_unique_id(char id[128]);
+int comm_init(int nranks, int rank, const char id[128]);
+int comm_finalize();
+
+}  // namespace tfx
+
+// The opaque handle of include/tfx.h.
+struct tfx_matrix {
+  tfx::Matrix m;
+};

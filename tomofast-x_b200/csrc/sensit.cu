@@ -1,0 +1,360 @@
+// sensit.cu -- device-resident sensitivity assembly (module sensitivity_gravmag).
+//
+// Replaces calculate_and_write_sensit (src/forward/gravmag/sensitivity_gravmag.F90:82-410) and
+// read_sensitivity_kernel (:648-883) without the disk round trip. Per data row, in the reference's
+// order: kernel line (graviprism / magprism) -> * column weight (:228) -> [cost_full (:234) ->
+// forward wavelet (:237) -> threshold = (N - nel_compressed)-th smallest |x| (:240-256) -> keep
+// |x| > threshold (strict), columns ascending (:258-272)] -> real(4) (:265/:290) -> * real(problem
+// weight * data weight, 4) in real(4) (:837-843) -> matrix row (idata, d) = model components k
+// concatenated at column shift param_shift + (k-1)*nelements (:759-856).
+#include "../../include/tfx.h"
+
+#include <thrust/copy.h>
+#include <thrust/device_ptr.h>
+#include <thrust/execution_policy.h>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/reduce.h>
+#include <thrust/scan.h>
+#include <thrust/sort.h>
+#include <thrust/transform.h>
+#include <thrust/transform_reduce.h>
+#include <thrust/unique.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "matrix.h"
+
+namespace tfx {
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_apply_cw(double *__restrict__ lines, const double *__restrict__ cw, int64_t n,
+                                                   int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    lines[i] = __dmul_rn(lines[i], cw[i % n]);   // apply_column_weight, sensitivity_gravmag.F90:1042-1054
+}
+
+struct AbsOp {
+  __device__ double operator()(double x) const { return fabs(x); }
+};
+struct SqOp {
+  __device__ double operator()(double x) const { return x * x; }
+};
+struct DiscardedSq {
+  double thr;
+  __device__ double operator()(double x) const { return (fabs(x) > thr) ? 0.0 : x * x; }
+};
+struct KeepPred {
+  const double *line;
+  double thr;
+  __device__ bool operator()(int p) const { return fabs(line[p]) > thr; }
+};
+
+// vals = real(line(col), 4) * wgt (f32 multiply); idx = col + shift; rowid = row; nnz_count[col]++.
+__global__ void __launch_bounds__(256) k_finish_segment(const int32_t *__restrict__ cols, int nel,
+                                                         const double *__restrict__ line, float wgt, int32_t shift,
+                                                         int32_t row, int32_t *__restrict__ idx_out,
+                                                         float *__restrict__ val_out, int32_t *__restrict__ rowid_out,
+                                                         int32_t *__restrict__ nnz_count) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nel; i += gridDim.x * blockDim.x) {
+    const int p = cols[i];
+    idx_out[i] = p + shift;
+    val_out[i] = __fmul_rn((float)line[p], wgt);
+    rowid_out[i] = row;
+    if (nnz_count) atomicAdd(&nnz_count[p], 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_dense_segment(const double *__restrict__ line, int n, float wgt, int32_t shift,
+                                                        int32_t row, int32_t *__restrict__ idx_out,
+                                                        float *__restrict__ val_out, int32_t *__restrict__ rowid_out,
+                                                        int32_t *__restrict__ nnz_count) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    idx_out[p] = p + shift;
+    val_out[p] = __fmul_rn((float)line[p], wgt);
+    rowid_out[p] = row;
+    if (nnz_count) atomicAdd(&nnz_count[p], 1);
+  }
+}
+
+template <typename T>
+int up(DevBuf<T> &d, const T *h, size_t n) {
+  TFX_TRY(d.alloc(n));
+  if (n) TFX_CUDA(cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+  return 0;
+}
+
+int upload_grid(GridDev &g, int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
+                const double *Z1, const double *Z2) {
+  g.n = n;
+  TFX_TRY(up(g.X1, X1, n)); TFX_TRY(up(g.X2, X2, n)); TFX_TRY(up(g.Y1, Y1, n));
+  TFX_TRY(up(g.Y2, Y2, n)); TFX_TRY(up(g.Z1, Z1, n)); TFX_TRY(up(g.Z2, Z2, n));
+  return 0;
+}
+
+int kernel_error(int e) {
+  if (e == 1) return fail(-70, "Data coordinate coincides with model grid boundary (YZ). Adjust the model grid!");
+  if (e == 2) return fail(-70, "Data coordinate coincides with model grid boundary (XZ). Adjust the model grid!");
+  if (e == 11) return fail(-70, "The model grid X-boundary coincides with the data position");
+  if (e == 12) return fail(-70, "The model grid Y-boundary coincides with the data position");
+  return fail(-70, "forward kernel error");
+}
+
+int compute_lines(const tfx_sensit_params &P, const GridDev &g, int nb, const double *dx, const double *dy,
+                  const double *dz, double *d_lines, int *d_err, cudaStream_t st) {
+  if (P.problem_type == 1) {
+    if (P.nmodel_components != 1) return fail(-71, "gravity: nmodel_components must be 1");
+    if (P.data_type == 1 && P.ndata_components == 1) return grav_lines(g, nb, dx, dy, dz, 1, d_lines, d_err, st);
+    if (P.data_type == 2 && P.ndata_components == 1) return grav_lines(g, nb, dx, dy, dz, 2, d_lines, d_err, st);
+    return fail(-72, "gravity: only data_type 1 (gz) and 2 with one component (gzz) are available on the device");
+  }
+  if (P.problem_type == 2)
+    return mag_lines(g, nb, dx, dy, dz, P.nmodel_components, P.ndata_components, P.mi, P.md, P.theta, P.intensity,
+                     d_lines, d_err, st);
+  return fail(-73, "unknown problem_type");
+}
+
+}  // namespace
+
+}  // namespace tfx
+
+using namespace tfx;
+
+extern "C" int tfx_sensit_lines(const tfx_sensit_params *par, const double *X1, const double *X2, const double *Y1,
+                                const double *Y2, const double *Z1, const double *Z2, int32_t nb, const double *data_X,
+                                const double *data_Y, const double *data_Z, double *lines) {
+  TFX_TRY(ensure_init());
+  cudaStream_t st = ctx().stream;
+  const tfx_sensit_params &P = *par;
+  const int32_t N = P.nx * P.ny * P.nz;
+  GridDev g;
+  TFX_TRY(upload_grid(g, N, X1, X2, Y1, Y2, Z1, Z2));
+  DevBuf<double> dx, dy, dz, dl;
+  DevBuf<int> derr;
+  TFX_TRY(up(dx, data_X, nb)); TFX_TRY(up(dy, data_Y, nb)); TFX_TRY(up(dz, data_Z, nb));
+  const size_t per = (size_t)N * P.nmodel_components * P.ndata_components;
+  TFX_TRY(dl.alloc(per * nb));
+  TFX_TRY(derr.alloc(1));
+  TFX_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
+  TFX_TRY(compute_lines(P, g, nb, dx.p, dy.p, dz.p, dl.p, derr.p, st));
+  int e = 0;
+  TFX_CUDA(cudaMemcpyAsync(&e, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaMemcpyAsync(lines, dl.p, per * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  if (e) return kernel_error(e);
+  return 0;
+}
+
+extern "C" int tfx_calculate_sensit(tfx_matrix **out, const tfx_sensit_params *par, const double *X1, const double *X2,
+                                    const double *Y1, const double *Y2, const double *Z1, const double *Z2,
+                                    const double *data_X, const double *data_Y, const double *data_Z,
+                                    const double *column_weight_full, const double *data_weight, int32_t *sensit_nnz,
+                                    double *comp_error, int64_t *nnz_total) {
+  TFX_TRY(ensure_init());
+  Context &c = ctx();
+  cudaStream_t st = c.stream;
+  const tfx_sensit_params &P = *par;
+  if (!out) return fail(-74, "calculate_sensit: null handle");
+  if (P.compression_rate < 0 || P.compression_rate > 1)
+    return fail(-75, "Wrong compression rate! It must be between 0 and 1.");
+  const int64_t N64 = (int64_t)P.nx * P.ny * P.nz;
+  if (N64 <= 0 || N64 > 2000000000LL) return fail(-76, "calculate_sensit: wrong grid size");
+  const int32_t N = (int32_t)N64;
+  const int32_t ndc = P.ndata_components, nmc = P.nmodel_components;
+  // get_nel_compressed, sensitivity_gravmag.F90:64-77
+  const int32_t nel_compressed = (P.compression_type > 0) ? (int32_t)(P.compression_rate * (double)N) : N;
+  const int32_t nl = P.ndata * ndc;
+
+  GridDev g;
+  TFX_TRY(upload_grid(g, N, X1, X2, Y1, Y2, Z1, Z2));
+  DevBuf<double> dx, dy, dz, dcw, ddw;
+  DevBuf<int> derr;
+  TFX_TRY(up(dx, data_X, P.ndata)); TFX_TRY(up(dy, data_Y, P.ndata)); TFX_TRY(up(dz, data_Z, P.ndata));
+  TFX_TRY(up(dcw, column_weight_full, N));
+  TFX_TRY(up(ddw, data_weight, (size_t)P.ndata * ndc));
+  TFX_TRY(derr.alloc(1));
+  TFX_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
+
+  tfx_matrix *h = new tfx_matrix();
+  Matrix &M = h->m;
+  M.device_only = true;
+  M.nl = nl; M.nl_current_all = nl; M.ncolumns = P.ncolumns;
+
+  // ------------------------------------------------------------------ uncompressed gravity: dense block
+  if (P.compression_type == 0 && P.problem_type == 1 && P.data_type == 1 && ndc == 1 && nmc == 1 &&
+      P.ndata <= kDenseMaxRows) {
+    const int32_t ncl = P.ncells_local > 0 ? P.ncells_local : N;
+    if (P.cell0 < 0 || P.cell0 + ncl > N) { delete h; return fail(-77, "calculate_sensit: wrong local cell range"); }
+    int rc = assemble_grav_dense(M.dense, g, P.cell0, ncl, P.ndata, dx.p, dy.p, dz.p, dcw.p, ddw.p, P.problem_weight,
+                                 derr.p, st);
+    if (rc) { delete h; return rc; }
+    int e = 0;
+    TFX_CUDA(cudaMemcpyAsync(&e, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TFX_CUDA(cudaStreamSynchronize(st));
+    if (e) { delete h; return kernel_error(e); }
+    M.dense.col0 = P.param_shift;   // local columns 1..nelements of this rank, shifted for the problem
+    M.has_dense = true; M.dense_row0 = 0;
+    M.nnz = M.nel = (int64_t)P.ndata * ncl;
+    M.nl_nonempty = nl;
+    M.finalized = true;
+    if (sensit_nnz) for (int32_t p = 0; p < N; ++p) sensit_nnz[p] = (p >= P.cell0 && p < P.cell0 + ncl) ? P.ndata : 0;
+    if (comp_error) *comp_error = 0.0;
+    if (nnz_total) *nnz_total = M.nel;
+    *out = h;
+    return 0;
+  }
+
+  // ------------------------------------------------------------------ general row pipeline
+  if (P.cell0 != 0 || (P.ncells_local != 0 && P.ncells_local != N)) {
+    delete h;
+    return fail(-78, "calculate_sensit: the compressed / magnetic pipeline needs the full grid on the rank");
+  }
+  const int64_t nseg_lines = (int64_t)P.ndata * ndc * nmc;
+  const int64_t cap = (int64_t)nel_compressed * nseg_lines;   // upper bound of nnz
+  SegMatrix &F = M.fwd;
+  DevBuf<int32_t> rowid;
+  if (F.idx.alloc((size_t)cap) || F.val.alloc((size_t)cap) || rowid.alloc((size_t)cap)) { delete h; return -101; }
+  DevBuf<int32_t> dnnz, dcols;
+  DevBuf<double> dsorted;
+  if (dnnz.alloc(N) || dcols.alloc(N) || dsorted.alloc(N)) { delete h; return -101; }
+  TFX_CUDA(cudaMemsetAsync(dnnz.p, 0, (size_t)N * 4, st));
+
+  // batch of stations whose lines are resident at once (<= ~1 GiB)
+  const size_t per_station = (size_t)N * nmc * ndc;
+  int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)P.ndata, ((size_t)1 << 27) / per_station));
+  DevBuf<double> dl;
+  if (dl.alloc(per_station * B)) { delete h; return -101; }
+
+  std::vector<int64_t> ptr;       // stored rows only (0-based offsets)
+  std::vector<int32_t> segmap;    // 0-based global row of each stored row
+  std::vector<double> h_dw((size_t)P.ndata * ndc);
+  memcpy(h_dw.data(), data_weight, h_dw.size() * sizeof(double));
+  ptr.push_back(0);
+  int64_t nnz = 0;
+  double err_sum = 0.0;
+  auto pol = thrust::cuda::par.on(st);
+  const int vgrid = c.num_sms * 8;
+
+  for (int32_t b0 = 0; b0 < P.ndata; b0 += B) {
+    const int nb = std::min<int>(B, P.ndata - b0);
+    int rc = compute_lines(P, g, nb, dx.p + b0, dy.p + b0, dz.p + b0, dl.p, derr.p, st);
+    if (rc) { delete h; return rc; }
+    k_apply_cw<<<vgrid, 256, 0, st>>>(dl.p, dcw.p, N, (int64_t)per_station * nb);
+    c.launches++;
+    for (int b = 0; b < nb; ++b) {
+      const int32_t idata = b0 + b;   // 0-based
+      for (int d = 0; d < ndc; ++d) {
+        const int32_t row = idata * ndc + d;
+        const int64_t row_start = nnz;
+        // combined_weight = real(problem_weight * data_weight(d, idata), 4)
+        const float wgt = (float)(P.problem_weight * h_dw[(size_t)idata * ndc + d]);
+        for (int k = 0; k < nmc; ++k) {
+          double *line = dl.p + ((size_t)b * ndc * nmc + (size_t)d * nmc + k) * N;
+          const int32_t shift = P.param_shift + k * N;   // 0-based column = p + shift
+          if (P.compression_type > 0) {
+            thrust::device_ptr<double> L(line), Sd(dsorted.p);
+            const double cost_full = thrust::transform_reduce(pol, L, L + N, SqOp(), 0.0, thrust::plus<double>());
+            rc = wavelet3d_device(line, P.nx, P.ny, P.nz, P.compression_type, true, st);
+            if (rc) { delete h; return rc; }
+            double threshold;
+            if (nel_compressed >= N) {
+              threshold = -1.0;
+            } else {
+              thrust::transform(pol, L, L + N, Sd, AbsOp());
+              thrust::sort(pol, Sd, Sd + N);
+              TFX_CUDA(cudaMemcpyAsync(&threshold, dsorted.p + (N - nel_compressed - 1), sizeof(double),
+                                       cudaMemcpyDeviceToHost, st));
+              TFX_CUDA(cudaStreamSynchronize(st));
+              threshold = fabs(threshold);
+            }
+            if (threshold < 1.e-30) threshold = 1.e-30;
+            thrust::device_ptr<int32_t> Cd(dcols.p);
+            KeepPred pred{line, threshold};
+            auto endp = thrust::copy_if(pol, thrust::counting_iterator<int>(0), thrust::counting_iterator<int>(N), Cd, pred);
+            const int nel = (int)(endp - Cd);
+            if (nel > nel_compressed) { delete h; return fail(-79, "Wrong number of elements in calculate_and_write_sensit!"); }
+            const double cost_disc =
+                thrust::transform_reduce(pol, L, L + N, DiscardedSq{threshold}, 0.0, thrust::plus<double>());
+            err_sum += sqrt(cost_disc / cost_full);   // :283-285
+            if (nel > 0) {
+              k_finish_segment<<<std::min(vgrid, (nel + 255) / 256), 256, 0, st>>>(
+                  dcols.p, nel, line, wgt, shift, row, F.idx.p + nnz, F.val.p + nnz, rowid.p + nnz, dnnz.p);
+              c.launches++;
+            }
+            c.launches += 6;
+            nnz += nel;
+          } else {
+            k_dense_segment<<<std::min(vgrid, (N + 255) / 256), 256, 0, st>>>(line, N, wgt, shift, row, F.idx.p + nnz,
+                                                                             F.val.p + nnz, rowid.p + nnz, dnnz.p);
+            c.launches++;
+            nnz += N;
+          }
+        }
+        if (nnz > row_start) {   // new_row(): only non-empty rows are stored (sparse_matrix.f90:266-274)
+          ptr.push_back(nnz);
+          segmap.push_back(row);
+        }
+      }
+    }
+    int e = 0;
+    TFX_CUDA(cudaMemcpyAsync(&e, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TFX_CUDA(cudaStreamSynchronize(st));
+    if (e) { delete h; return kernel_error(e); }
+  }
+
+  // ---- forward representation
+  F.nnz = nnz; F.nseg = (int32_t)segmap.size(); F.nout = nl; F.nin = P.ncolumns;
+  TFX_TRY(up(F.ptr, ptr.data(), ptr.size()));
+  TFX_TRY(up(F.segmap, segmap.data(), segmap.size()));
+  TFX_TRY(seg_build_items(F, ptr.data()));
+
+  // ---- transpose on the device: stable sort by column keeps the row order inside each column
+  SegMatrix &T = M.trn;
+  T.nnz = nnz; T.nout = P.ncolumns; T.nin = nl;
+  DevBuf<int32_t> keys;
+  TFX_TRY(keys.alloc((size_t)std::max<int64_t>(nnz, 1)));
+  TFX_TRY(T.idx.alloc((size_t)std::max<int64_t>(nnz, 1)));
+  TFX_TRY(T.val.alloc((size_t)std::max<int64_t>(nnz, 1)));
+  std::vector<int64_t> tptr(1, 0);
+  std::vector<int32_t> tmap;
+  if (nnz > 0) {
+    TFX_CUDA(cudaMemcpyAsync(keys.p, F.idx.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaMemcpyAsync(T.idx.p, rowid.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaMemcpyAsync(T.val.p, F.val.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
+    thrust::device_ptr<int32_t> K(keys.p), R(T.idx.p);
+    thrust::device_ptr<float> V(T.val.p);
+    thrust::stable_sort_by_key(pol, K, K + nnz, thrust::make_zip_iterator(thrust::make_tuple(R, V)));
+    DevBuf<int32_t> ucols, ucnt;
+    TFX_TRY(ucols.alloc((size_t)std::min<int64_t>(nnz, P.ncolumns)));
+    TFX_TRY(ucnt.alloc((size_t)std::min<int64_t>(nnz, P.ncolumns)));
+    thrust::device_ptr<int32_t> UC(ucols.p), UN(ucnt.p);
+    auto ends = thrust::reduce_by_key(pol, K, K + nnz, thrust::make_constant_iterator<int32_t>(1), UC, UN);
+    const size_t nu = (size_t)(ends.first - UC);
+    tmap.resize(nu);
+    std::vector<int32_t> cnt(nu);
+    TFX_CUDA(cudaMemcpyAsync(tmap.data(), ucols.p, nu * 4, cudaMemcpyDeviceToHost, st));
+    TFX_CUDA(cudaMemcpyAsync(cnt.data(), ucnt.p, nu * 4, cudaMemcpyDeviceToHost, st));
+    TFX_CUDA(cudaStreamSynchronize(st));
+    tptr.resize(nu + 1);
+    for (size_t i = 0; i < nu; ++i) tptr[i + 1] = tptr[i] + cnt[i];
+    c.launches += 4;
+  }
+  T.nseg = (int32_t)tmap.size();
+  TFX_TRY(up(T.ptr, tptr.data(), tptr.size()));
+  TFX_TRY(up(T.segmap, tmap.data(), tmap.size()));
+  TFX_TRY(seg_build_items(T, tptr.data()));
+
+  M.has_seg = true;
+  M.nnz = M.nel = nnz;
+  M.nl_nonempty = F.nseg;
+  M.finalized = true;
+  if (sensit_nnz) TFX_CUDA(cudaMemcpyAsync(sensit_nnz, dnnz.p, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  if (comp_error) *comp_error = (P.compression_type > 0) ? err_sum / (double)nseg_lines : 0.0;   // :346-353
+  if (nnz_total) *nnz_total = nnz;
+  *out = h;
+  return 0;
+}
