@@ -26,23 +26,54 @@ def test_assembly_matches(pair):
     assert ig.be.nnz_total == 314368
     assert abs(ig.comp_error - io.comp_error) < 1e-9
     assert np.allclose(ig.d_obs, io.d_obs, rtol=1e-7, atol=1e-9 * np.abs(io.d_obs).max())
+    sa_o, ija_o, ijl_o, rp_o = io.S.arrays()
+    sa_g, ija_g, ijl_g, rp_g = ig.S.export()
+    assert np.array_equal(ija_g, ija_o) and np.array_equal(ijl_g, ijl_o) and np.array_equal(rp_g, rp_o)
+    # values: identical except where the f64 value (differing by ~1e-13 rel. through libm) rounds to the
+    # neighbouring real(4)
+    ulp = np.abs(sa_o) * 2.0 ** -23
+    assert np.all(np.abs(sa_g - sa_o) <= ulp)
+    assert np.mean(sa_g != sa_o) < 1e-3
 
 
 def test_teacher_forced_residuals(pair):
+    """r_k of 6 major iterations x 100 LSQR iterations.
+    strict_order (reference summation order): every r_k within 1e-6 relative of the oracle -- the
+    north-star bar. Fast kernels (tree-order sums): LSQR's iterates 13-40 are chaotic under last-bit
+    perturbations (the oracle moves by ~1e-3 there when b is scaled by 1+2e-16), so they are held to the
+    1e-6 bar on the stable iterations (first 10, last 40) and only bounded (5e-2) in the window where the
+    oracle's own perturbation envelope exceeds 1e-6; the solution must agree to 1e-8."""
     cfg, io, ig = pair
-    worst = 0.0
+    # LSQR parity is measured on the SAME matrix: the oracle's CSR is handed to the device through the
+    # reference's own storage (assembly parity is test_assembly_matches' job).
+    Sg = tfx.SparseMatrix.from_arrays(cfg.ndata, cfg.ncolumns, *io.S.arrays())
+    worst_strict = worst_fast = 0.0
     for major in range(6):
-        b = io.build_rhs()                       # oracle state drives both solvers
+        b = io.build_rhs()                       # oracle state drives both solvers (teacher forcing)
         xo, ho = io.be.solve(cfg, io.S, io.C, b)
-        xg, hg = ig.be.solve(cfg, ig.S, ig.C, b)
-        assert len(hg) == len(ho) == cfg.niter
-        rel = np.abs(hg - ho) / ho
-        worst = max(worst, rel.max())
-        assert rel.max() < 1e-6, (major, rel.max())
-        assert np.allclose(xg, xo, rtol=1e-5, atol=1e-7 * np.abs(xo).max())
+        env = np.zeros_like(ho)                  # oracle's own sensitivity to rounding
+        for scale in (1.0 + 2.3e-16, 3.0, 1.0 / 3.0):
+            xp, hp = io.be.solve(cfg, io.S, io.C, b * scale)
+            env = np.maximum(env, np.abs(hp - ho) / ho)
+        tfx.set_option("strict_order", 1)
+        xs, hs = ig.be.solve(cfg, Sg, ig.C, b)
+        tfx.set_option("strict_order", 0)
+        xg, hg = ig.be.solve(cfg, Sg, ig.C, b)
+        assert len(hs) == len(hg) == len(ho) == cfg.niter
+        rel_s = np.abs(hs - ho) / ho
+        rel_f = np.abs(hg - ho) / ho
+        worst_strict = max(worst_strict, rel_s.max())
+        worst_fast = max(worst_fast, rel_f.max())
+        assert rel_s.max() < 1e-6, (major, rel_s.max(), rel_s.argmax())
+        assert np.allclose(xs, xo, rtol=1e-6, atol=1e-9 * np.abs(xo).max())
+        stable = np.r_[0:10, 60:100]
+        assert rel_f[stable].max() < 1e-6, (major, rel_f[stable].max())
+        assert env[10:60].max() > 1e-6            # the oracle itself is not reproducible there
+        assert rel_f[10:60].max() < 5e-2, (major, rel_f.max())
+        assert np.abs(xg - xo).max() < 1e-8 * np.abs(xo).max()
         io.histories.append(ho)
         io.apply(xo)
-    print("worst relative residual difference:", worst)
+    print("worst relative residual difference: strict_order %.3e, fast kernels %.3e" % (worst_strict, worst_fast))
 
 
 def test_free_run_costs(oracle):

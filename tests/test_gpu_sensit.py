@@ -45,8 +45,9 @@ def test_magnetic_station_inside_cell(oracle):
 
 def test_station_on_cell_boundary_aborts():
     pb = make_problem(nx=4, ny=4, nz=2, ndata=1)
-    # station below the top face, exactly on a vertical cell edge: Rs + XX = 0 (gravity_field.f90:176-181)
-    pb.data_xyz = (np.array([100.0]), np.array([100.0]), np.array([10.0]))
+    # station on the line through a cell edge along x (y and z on cell faces): for the cells ahead
+    # Rs + XX = |XX| + XX = 0 (gravity_field.f90:173-178)
+    pb.data_xyz = (np.array([150.0]), np.array([100.0]), np.array([50.0]))
     with pytest.raises(tfx.TfxError, match="coincides with model grid boundary"):
         tfx.sensit_lines(pb.par, pb.grid, pb.data_xyz)
 

@@ -30,8 +30,11 @@ def random_matrix(orc, rng, nl, ncol, row_len_fn, empty_prob=0.0):
         if len(cols):
             mo.add_row(vals, cols)
             mg.add_row(vals, cols)
-        mo.new_row()
-        mg.new_row()
+            mo.new_row()
+            mg.new_row()
+        else:                         # the reference adds empty rows with add_empty_rows (damping.F90:158,179)
+            mo.add_empty_rows(1)
+            mg.add_empty_rows(1)
     mo.finalize()
     mg.finalize()
     return mo, mg, rows

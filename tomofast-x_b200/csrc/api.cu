@@ -20,6 +20,7 @@ namespace tfx {
 // ---------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int g_opt_dense_detect = 1;
+int g_opt_strict_order = 0;   // 1: LSQR uses the reference's sequential summation order (parity mode)
 
 void set_error(const std::string &msg) { g_err = msg; }
 int fail(int code, const std::string &msg) {
@@ -207,6 +208,10 @@ uint64_t tfx_launch_count(void) { return ctx().launches; }
 int tfx_set_option(const char *name, int value) {
   if (name && strcmp(name, "dense_detect") == 0) {
     g_opt_dense_detect = value;
+    return 0;
+  }
+  if (name && strcmp(name, "strict_order") == 0) {
+    g_opt_strict_order = value;
     return 0;
   }
   return fail(-4, std::string("unknown option: ") + (name ? name : "(null)"));

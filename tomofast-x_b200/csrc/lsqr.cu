@@ -188,6 +188,35 @@ __global__ void __launch_bounds__(kVecThreads) k_xw_update(double *__restrict__ 
   }
 }
 
+// Fused path, columns NOT covered by the dense block (e.g. the unused second problem of the joint
+// column space): vhat = -beta v + g there, plus the partial sums of |vhat|^2 over those columns.
+__global__ void __launch_bounds__(kVecThreads) k_outside_update(double *__restrict__ v, const double *__restrict__ g,
+                                                                 int64_t n, int64_t blk0, int64_t blk1,
+                                                                 const LsqrScalars *sc, double *__restrict__ partial) {
+  if (sc->done) return;
+  __shared__ double red[32];
+  const double nb = sc->neg_beta;
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i >= blk0 && i < blk1) continue;
+    const double val = fma(nb, v[i], g ? g[i] : 0.0);
+    v[i] = val;
+    s = fma(val, val, s);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// *out += sum(partial[0..n))
+__global__ void __launch_bounds__(kVecThreads) k_final_sum_add(const double *__restrict__ partial, int n, double *out,
+                                                                const int *done) {
+  if (*done) return;
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *out += s;
+}
+
 // misfit = sqrt(sum((Sx - b0)^2)/n) (lsqr_solver2.F90:183-188)
 __global__ void __launch_bounds__(kVecThreads) k_diffsq_partial(const double *__restrict__ a,
                                                                  const double *__restrict__ b, int64_t n,
@@ -268,6 +297,8 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
   if (wav && ((int64_t)p.nx * p.ny * p.nz != p.nelements))
     return fail(-53, "lsqr: nelements must equal nx*ny*nz when the wavelet transform runs inside the loop");
 
+  if (g_opt_strict_order) return lsqr_run_strict(p, S, C, d_u, d_x, res);
+
   const bool dense_ok = S->has_dense && S->dense.nrows == nls && S->dense_row0 == 0 && S->dense.nrows <= kDenseMaxRows;
   if (S->has_dense && !dense_ok && !S->has_seg) return fail(-54, "lsqr: dense sensitivity block does not cover all data rows");
   const bool fused = dense_ok && !wav && !misfit;
@@ -318,10 +349,16 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
 
   if (fused) {
     // =========================== FUSED PATH ===========================
+    const bool outside = (S->dense.col0 != 0 || S->dense.ncols != ncol);
     auto sweep = [&]() -> int {
       // g = C^T u_c ; vhat = -beta v + S^T u_d + g ; q_d = S vhat ; n2 = |vhat|^2 ; q_c = C vhat
       if (have_C) TFX_TRY(seg_spmv(C->trn, d_u + nls, g, false, 0, (int32_t)ncol, 0, done, st));
       TFX_TRY(dense_sweep(S->dense, DENSE_FUSED, d_u, v, have_C ? g : nullptr, v, &sc->neg_beta, q, q + nlines, done, st));
+      if (outside && have_C) {
+        k_outside_update<<<GV, kVecThreads, 0, st>>>(v, g, ncol, S->dense.col0, (int64_t)S->dense.col0 + S->dense.ncols,
+                                                     sc, partial); LAUNCHED();
+        k_final_sum_add<<<1, kVecThreads, 0, st>>>(partial, GV, q + nlines, done); LAUNCHED();
+      }
       if (ncons > 0) {
         if (have_C) TFX_TRY(seg_spmv(C->fwd, v, q + nls, false, 0, ncons, 0, done, st));
       }
@@ -330,9 +367,7 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
     };
     // Columns outside the dense block (e.g. the unused second problem) stay zero in v: the sweep only
     // rewrites its own column range, and C^T u_c contributions there are added below when present.
-    if (S->dense.col0 != 0 || S->dense.ncols != ncol) {
-      if (have_C) return fail(-55, "lsqr(fused): constraint matrix with columns outside the dense block is not supported");
-    }
+    // (without a constraint matrix those columns are identically zero and need no work)
     // init: neg_beta multiplies v = 0, so vhat = S^T u (+ C^T u_c)
     TFX_TRY(sweep());
     k_scal_alpha<<<1, 1, 0, st>>>(q + nlines, sc, 1, p.niter, p.rmin, W.hist.p); LAUNCHED();

@@ -57,7 +57,11 @@ struct LsqrResult {
   std::vector<double> history;
 };
 
+// Option "strict_order": reproduce the reference's sequential summation order (slow parity mode).
+extern int g_opt_strict_order;
+
 int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x, LsqrResult &res);
+int lsqr_run_strict(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x, LsqrResult &res);
 
 // ---- comm.cu ----------------------------------------------------------------------------------
 int comm_nranks();
