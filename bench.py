@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- LSQR iterations/s on the Tomofast-x inversion hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (libtfx, sm_100a CUDA)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+Workload (config.workload): BASELINE.json configs[1] -- synthetic gravity inversion, 256 x 256 x 64
+cells, 10 000 stations, no compression, assembled ON the device with the gravity prism kernel
+(SURVEY.md section 8d inputs: regular 100 x 100 x 50 m cells, stations on a lattice at z = -0.1, depth
+weighting type 1, one 250 kg/m3 block as true model, Parfile-default model damping 1e-11).
+A "step" is one LSQR iteration of lsqr_solve_sensit: both products with S (and with the damping block),
+the norms and the x/w updates. With N > 1 the SAME problem is column-sharded over the ranks like the
+reference's MPI decomposition (lsqr_solver2.F90:16) -> "scaling": "strong".
+
+value  : iterations/s with u, x and S resident in HBM, timed with CUDA events on the library stream
+         around the iteration loop (max over ranks).
+e2e    : iterations/s through the C ABI call tfx_lsqr_solve_sensit with HOST buffers (pinned): H2D of the
+         right-hand side, the initialisation before the loop, K iterations, D2H of x and u.
+roofline: the fused sweep kernel (dense_sweep_kernel): ALGORITHMIC bytes (4 B per matrix entry read
+         once + the vectors) / mean launch time from CUDA events, against the measured HBM peak.
+cpu_baseline / --impl reference: the oracle port of the reference loops (sparse_matrix.f90:313-405,
+         lsqr_solver2.F90:321-473) on the host cores, column-split over P processes like the reference's
+         MPI ranks, on a bounded column sample of the same matrix shape, scaled linearly in nnz.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "LSQR iterations/sec"
+UNIT = "it/s"
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.FIELDS,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# distributed plumbing (torchrun env); data-path collectives are NCCL inside libtfx
+# ----------------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.td = None
+        if self.world > 1:
+            import torch.distributed as td
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            td.init_process_group(backend="gloo", rank=self.rank, world_size=self.world)
+            self.td = td
+
+    def barrier(self):
+        if self.td:
+            self.td.barrier()
+
+    def bcast_obj(self, obj):
+        if not self.td:
+            return obj
+        box = [obj]
+        self.td.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def max(self, x):
+        if not self.td:
+            return x
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum(self, x):
+        if not self.td:
+            return x
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
+        return float(t[0])
+
+    def finish(self):
+        if self.td:
+            self.td.barrier()
+            self.td.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------
+def workload_name(a):
+    return "synthetic gravity inversion %dx%dx%d cells, %d data, no compression" % (a.nx, a.ny, a.nz, a.ndata)
+
+
+def run_ours(a):
+    import tomofastx_b200 as tfx
+    from tests.synth import depth_weight_type1, regular_grid, station_lattice
+
+    d = Dist()
+    tfx.init(d.local_rank)
+    if d.world > 1:
+        uid = d.bcast_obj(tfx.comm_unique_id() if d.rank == 0 else None)
+        tfx.comm_init(d.world, d.rank, uid)
+
+    nx, ny, nz, ndata = a.nx, a.ny, a.nz, a.ndata
+    N = nx * ny * nz
+    ncl = tfx.calculate_nelements_at_cpu(N, d.rank, d.world)          # column slab of this rank
+    cell0 = tfx.get_nsmaller(N, d.rank, d.world)
+    ncolumns = 2 * ncl                                                # joint_inverse_problem.F90:213-214
+    grid = regular_grid(nx, ny, nz)
+    data_xyz = station_lattice(ndata, 100.0 * nx, 100.0 * ny, z=-0.1)
+    cw = depth_weight_type1(grid, 2.0, 0.0, 4.0e3)
+    dw = np.ones((ndata, 1))
+    problem_weight, alpha_damp = 1.0, 1.0e-11                         # parameters_init.f90:339-345,329
+
+    par = tfx.SensitParams()
+    par.problem_type = 1
+    par.nx, par.ny, par.nz = nx, ny, nz
+    par.ndata, par.ndata_components, par.nmodel_components, par.data_type = ndata, 1, 1, 1
+    par.compression_type, par.compression_rate = 0, 1.0
+    par.problem_weight = problem_weight
+    par.cell0, par.ncells_local, par.param_shift, par.ncolumns = cell0, ncl, 0, ncolumns
+
+    free_b, total_b = tfx.device_mem_info()
+    need = ((ndata + 3) // 4 * 4) * ncl * 4 + 6 * ncolumns * 8 + 7 * N * 8 + (1 << 30)
+    if need > free_b:
+        raise SystemExit("bench: the %s block needs %.1f GB of HBM, only %.1f GB free" %
+                         (workload_name(a), need / 1e9, free_b / 1e9))
+
+    t0 = time.perf_counter()
+    S, _, _, nnz_loc = tfx.calculate_sensit(par, grid, data_xyz, cw, dw)
+    tfx.synchronize()
+    t_assemble = time.perf_counter() - t0
+    assert S.storage_kind() == 1
+
+    # model damping block alpha*I (damping.F90:158-179): N rows, this rank stores its own ncl rows
+    sa = np.full(ncl, alpha_damp * problem_weight, dtype=np.float32)
+    C = tfx.SparseMatrix.from_arrays(N, ncolumns, sa, np.arange(1, ncl + 1, dtype=np.int32),
+                                     np.arange(1, ncl + 2, dtype=np.int64),
+                                     np.arange(cell0 + 1, cell0 + ncl + 1, dtype=np.int32))
+
+    # observed data = S * (m_true / cw) summed over the column slabs (model.F90:243-293); start model 0
+    m = np.zeros((nz, ny, nx))
+    sl = lambda n: slice(max(0, n // 2 - max(1, n // 8)), n // 2 + max(1, n // 8))
+    m[sl(nz), sl(ny), sl(nx)] = 250.0
+    xs = np.zeros(ncolumns)
+    xs[:ncl] = (m.ravel() / cw)[cell0:cell0 + ncl]
+    d_obs = S.mult_vector(xs)
+    if d.world > 1:
+        tfx.comm_allreduce_sum(d_obs, ndata)
+    nlines = ndata + N
+    b = np.zeros(nlines)
+    b[:ndata] = problem_weight * d_obs                                # calculate_b_RHS; damping RHS is 0 (m = m_prior)
+    del grid, xs, m
+
+    def solve(u, x, niter):
+        tfx.lsqr_solve_sensit(nlines, ncolumns, niter, 1.0e-13, 0.0, 0.0, S, C, u, x, [1, 0], ncl, nx, ny, nz, 1,
+                              0, True, myrank=d.rank, nbproc=d.world)
+
+    # ---- device-resident measurement ("value")
+    u_dev, x_dev = tfx.Buffer(nlines), tfx.Buffer(ncolumns)
+    tfx.set_option("profile_sweeps", 1)
+    tfx.copy(u_dev, b, nlines)
+    solve(u_dev, x_dev, a.warmup)                                     # W untimed warm-up iterations
+    tfx.copy(u_dev, b, nlines)
+    tfx.synchronize()
+    d.barrier()
+    sampler = ClockSampler(d.local_rank)
+    if d.rank == 0:
+        sampler.start()
+    l0 = tfx.launch_count()
+    solve(u_dev, x_dev, a.steps)
+    tfx.synchronize()
+    launches = tfx.launch_count() - l0
+    loop_ms, sweep_ms, nsweeps = tfx.last_timing()
+    hist, iters, fused = tfx.last_history()
+    d.barrier()
+    clocks = sampler.stop() if d.rank == 0 else None
+    loop_ms_max = d.max(loop_ms)
+    assert iters == a.steps and fused, (iters, fused)
+    # the fused sweep is launched once before the loop and once per iteration
+    sweep_avg_ms = d.max(sweep_ms / max(nsweeps, 1))
+
+    # ---- end to end through the C ABI with pinned HOST buffers ("e2e")
+    tfx.set_option("profile_sweeps", 0)
+    u_pin, x_pin = tfx.Buffer(nlines, "pinned"), tfx.Buffer(ncolumns, "pinned")
+    u_pin.numpy()[:] = b
+    d.barrier()
+    t0 = time.perf_counter()
+    solve(u_pin, x_pin, a.steps)
+    e2e_s = d.max(time.perf_counter() - t0)
+    x_host = x_pin.numpy().copy()
+    d.barrier()
+
+    if d.rank == 0:
+        peak, peak_src = hbm_peak()
+        # algorithmic bytes of one fused sweep launch: every matrix entry once (4 B) + v, g, vhat (8 B each per
+        # column) + u (8 B per row) + the per-CTA partial q vectors
+        nnz_loc_f = float(((ndata + 3) // 4 * 4)) * ncl
+        alg_bytes = 4.0 * nnz_loc_f + 24.0 * ncl + 8.0 * ndata + 8.0 * ndata * 148
+        achieved = alg_bytes / (sweep_avg_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp) and d.world == 1:
+            try:
+                tj = json.load(open(tp))
+                if tj.get("workload") == workload_name(a):
+                    traffic = tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        value = a.steps / (loop_ms_max * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": d.world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": loop_ms_max / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64 (f32 matrix values, f64 vectors/accumulation)", "data": "synthetic",
+            "config": {"workload": workload_name(a), "parallelism": "column slabs x%d" % d.world,
+                       "matrix_bytes_per_gpu": int(nnz_loc_f * 4), "l2_policy": "inputs larger than L2 (matrix "
+                       "%.1f GB per GPU streamed every step)" % (nnz_loc_f * 4 / 1e9),
+                       "lsqr": "fused single-sweep path, damping block alpha=1e-11, rmin=1e-13",
+                       "assemble_s": round(t_assemble, 2), "residual_last": float(hist[-1]) if len(hist) else None},
+            "e2e": {"value": a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(nlines * 8 / a.steps),
+                    "d2h_bytes_per_step": int((nlines + ncolumns) * 8 / a.steps)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "dense_sweep_kernel<K,FUSED>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": sweep_avg_ms,
+                         "note": "one launch = S^T u AND S vhat on one read of S; by the reference's 16 B/nnz-per-"
+                                 "iteration CSR accounting the same launch is worth %.0f GB/s" %
+                                 (16.0 * nnz_loc_f / (sweep_avg_ms * 1e-3) / 1e9)},
+        }
+        if d.world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference(a, steps=2, warmup=1, seconds_hint=20.0)
+        print(json.dumps(line), flush=True)
+    d.finish()
+    return x_host
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ----------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One 'MPI rank' of the reference's column split: LSQR iterations on its own column slab."""
+    seed, nrows, ncols, iters = args
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as orc
+    rng = np.random.default_rng(seed)
+    m = orc.SparseMatrix(nrows, ncols, nrows * ncols)
+    cols = np.arange(1, ncols + 1, dtype=np.int32)
+    for _ in range(nrows):
+        m.add_row(rng.standard_normal(ncols, dtype=np.float32), cols)
+        m.new_row()
+    m.finalize()
+    b = rng.standard_normal(nrows)
+    orc.lsqr_solve(1, 1e-300, 0.0, m, b)                               # warm the caches / page in
+    t0 = time.perf_counter()
+    x, hist, it = orc.lsqr_solve(iters, 1e-300, 0.0, m, b)
+    dt = time.perf_counter() - t0
+    # lsqr_solve does the initial S^T u (half an iteration's matrix traffic) plus `it` iterations
+    return dt, it + 0.5, float(nrows) * ncols
+
+
+def cpu_reference(a, steps, warmup, seconds_hint=20.0):
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    nrows = a.ndata
+    # bounded sample: each worker owns a slab of columns sized for ~seconds_hint of work in total
+    # (~2.5 ns per matrix entry and product on one core), capped by host memory (8 B per entry)
+    per_iter_entries = seconds_hint / max(steps + warmup + 1.5, 1.0) / 2.5e-9 / 2.0
+    ncols = int(max(256, min(per_iter_entries / nrows, 3.0e9 / (8.0 * nrows))))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(1000 + i, nrows, ncols, steps + warmup) for i in range(cores)])
+    # ranks run concurrently; an iteration of the whole slab set ends when the slowest rank ends
+    t_iter = max(dt / its for dt, its, _ in res)
+    sample_entries = sum(e for _, _, e in res)
+    full_entries = float(a.ndata) * a.nx * a.ny * a.nz
+    its_per_s_sample = 1.0 / t_iter
+    value = its_per_s_sample * sample_entries / full_entries          # SpMV cost is linear in nnz
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle lsqr_solve (C port of lsqr_solver2.F90:321-473 + sparse_matrix.f90:313-405), "
+                      "%d column-slab processes x (%d rows x %d dense columns, CSR f32+i32), %d iterations each; "
+                      "scaled linearly in nnz from %.3g to %.3g entries; damping block omitted (O(N))" %
+                      (cores, nrows, ncols, steps + warmup, sample_entries, full_entries)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference(a, steps=a.steps, warmup=a.warmup, seconds_hint=60.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 (f32 matrix values, f64 vectors/accumulation)",
+            "data": "synthetic", "config": {"workload": workload_name(a), "parallelism": "%d host processes "
+                                            "(column split, lsqr_solver2.F90:16)" % cb["cores"]},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference = Fortran 2008 + MPI, not buildable in this image (no Fortran compiler, no MPI): "
+                    "timed arm is the line-faithful C port (oracle/)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=256)
+    ap.add_argument("--ny", type=int, default=256)
+    ap.add_argument("--nz", type=int, default=64)
+    ap.add_argument("--ndata", type=int, default=10000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,8 +39,19 @@ int         tfx_finalize(void);
 int         tfx_device_synchronize(void);
 /* Number of GPU kernels launched by the library so far (bench.py's gpu_launches). */
 uint64_t    tfx_launch_count(void);
-/* Options: "dense_detect" (1: finalize() turns an uncompressed CSR into the dense block). */
+/* Options: "dense_detect" (1: finalize() turns an uncompressed CSR into the dense block);
+ * "strict_order" (1: LSQR sums in the reference's sequential order -- slow parity mode);
+ * "profile_sweeps" (1: CUDA events around every fused sweep launch). */
 int         tfx_set_option(const char *name, int value);
+
+/* Memory helpers for callers that keep their vectors on the device (or in pinned host memory)
+ * between calls; thin wrappers of cudaMalloc / cudaMallocHost / cudaMemcpy(Default) / cudaMemGetInfo. */
+int tfx_device_alloc(void **p, int64_t bytes);
+int tfx_device_free(void *p);
+int tfx_host_alloc(void **p, int64_t bytes);
+int tfx_host_free(void *p);
+int tfx_memcpy(void *dst, const void *src, int64_t bytes);
+int tfx_device_mem_info(int64_t *free_bytes, int64_t *total_bytes);
 
 /* ---- communicator: stands in for MPI_COMM_WORLD on the solver's reductions ---------------------
  * lsqr_solver2.F90:214 (MPI_Allreduce of u) and :514 (scalar Allreduce) become ncclAllReduce.
@@ -111,6 +122,10 @@ int tfx_lsqr_solve_sensit(int32_t nlines, int32_t ncolumns, int32_t niter, doubl
  * prints the final one, :302-306), number of executed iterations, 1 if the fused single-sweep path
  * ran. r_hist may be NULL. */
 int tfx_lsqr_last_history(double *r_hist, int32_t capacity, int32_t *iters, int32_t *fused);
+/* Device time of the last solve measured with CUDA events on the library's stream: the iteration loop
+ * (excluding the initialisation before the reference's `do while`, lsqr_solver2.F90:120-157) and, with
+ * option "profile_sweeps" = 1, the summed duration / count of the fused sweep kernel launches. */
+int tfx_lsqr_last_timing(double *loop_ms, double *sweep_ms, int32_t *nsweeps);
 
 /* ---- module sensitivity_gravmag (src/forward/gravmag/sensitivity_gravmag.F90) ------------------ */
 typedef struct tfx_sensit_params {

@@ -91,6 +91,7 @@ def lib():
     L.tfx_lsqr_solve_sensit.argtypes = [i32, i32, i32, dbl, dbl, dbl, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                         i32, i32, C.POINTER(dbl), i32, i32]
     L.tfx_lsqr_last_history.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.tfx_lsqr_last_timing.argtypes = [C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i32)]
     L.tfx_calculate_sensit.argtypes = [C.POINTER(vp), C.POINTER(SensitParams)] + [vp] * 11 + [vp, C.POINTER(dbl),
                                                                                               C.POINTER(i64)]
     L.tfx_sensit_lines.argtypes = [C.POINTER(SensitParams)] + [vp] * 6 + [i32] + [vp] * 4
@@ -117,6 +118,58 @@ def set_option(name, value):
 
 def synchronize():
     _check(lib().tfx_device_synchronize())
+
+
+class Buffer:
+    """A float64 vector in device memory (kind='device') or pinned host memory (kind='pinned')."""
+
+    def __init__(self, n, kind="device"):
+        self.n, self.kind = int(n), kind
+        self.ptr = C.c_void_p()
+        L = lib()
+        fn = L.tfx_device_alloc if kind == "device" else L.tfx_host_alloc
+        fn.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
+        _check(fn(C.byref(self.ptr), self.n * 8))
+
+    def data_ptr(self):
+        return self.ptr.value
+
+    def numpy(self):
+        """View of a pinned buffer / copy of a device buffer."""
+        if self.kind == "pinned":
+            return np.ctypeslib.as_array((C.c_double * self.n).from_address(self.ptr.value))
+        out = np.empty(self.n)
+        copy(out, self, self.n)
+        return out
+
+    def free(self):
+        if self.ptr:
+            L = lib()
+            fn = L.tfx_device_free if self.kind == "device" else L.tfx_host_free
+            fn.argtypes = [C.c_void_p]
+            fn(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def copy(dst, src, n):
+    """cudaMemcpyDefault of n float64 between numpy arrays / Buffers / device tensors."""
+    L = lib()
+    L.tfx_memcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    _check(L.tfx_memcpy(_ptr(dst), _ptr(src), int(n) * 8))
+
+
+def device_mem_info():
+    L = lib()
+    f, t = C.c_int64(0), C.c_int64(0)
+    L.tfx_device_mem_info.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    _check(L.tfx_device_mem_info(C.byref(f), C.byref(t)))
+    return f.value, t.value
 
 
 def _ptr(a):
@@ -295,6 +348,13 @@ def last_history():
     h = np.zeros(max(it.value, 1))
     _check(lib().tfx_lsqr_last_history(h.ctypes.data, it.value, C.byref(it), C.byref(fused)))
     return h[:it.value], it.value, bool(fused.value)
+
+
+def last_timing():
+    """(loop_ms, sweep_ms, nsweeps) of the last solve, CUDA-event timed on the library stream."""
+    a, b, n = C.c_double(0), C.c_double(0), C.c_int32(0)
+    _check(lib().tfx_lsqr_last_timing(C.byref(a), C.byref(b), C.byref(n)))
+    return a.value, b.value, n.value
 
 
 def lsqr_solve(nlines, nelements, niter, rmin, gamma, matrix, u, x, myrank=0):

@@ -20,6 +20,7 @@ namespace tfx {
 // ---------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int g_opt_dense_detect = 1;
+int g_opt_profile_sweeps = 0; // 1: CUDA events around every fused sweep launch (bench roofline)
 int g_opt_strict_order = 0;   // 1: LSQR uses the reference's sequential summation order (parity mode)
 
 void set_error(const std::string &msg) { g_err = msg; }
@@ -208,6 +209,10 @@ uint64_t tfx_launch_count(void) { return ctx().launches; }
 int tfx_set_option(const char *name, int value) {
   if (name && strcmp(name, "dense_detect") == 0) {
     g_opt_dense_detect = value;
+    return 0;
+  }
+  if (name && strcmp(name, "profile_sweeps") == 0) {
+    g_opt_profile_sweeps = value;
     return 0;
   }
   if (name && strcmp(name, "strict_order") == 0) {
@@ -574,6 +579,47 @@ int tfx_lsqr_solve_sensit(int32_t nlines, int32_t ncolumns, int32_t niter, doubl
     *memory = (double)(tot - fr) / (1024.0 * 1024.0 * 1024.0);   // device memory in use [GB] (reference: host PSS)
   }
   return rc;
+}
+
+// ---- device / pinned-host memory helpers ---------------------------------------------------------
+int tfx_device_alloc(void **p, int64_t bytes) {
+  TFX_TRY(ensure_init());
+  TFX_CUDA(cudaMalloc(p, (size_t)bytes));
+  return 0;
+}
+int tfx_device_free(void *p) {
+  if (p) TFX_CUDA(cudaFree(p));
+  return 0;
+}
+int tfx_host_alloc(void **p, int64_t bytes) {
+  TFX_TRY(ensure_init());
+  TFX_CUDA(cudaMallocHost(p, (size_t)bytes));
+  return 0;
+}
+int tfx_host_free(void *p) {
+  if (p) TFX_CUDA(cudaFreeHost(p));
+  return 0;
+}
+int tfx_memcpy(void *dst, const void *src, int64_t bytes) {
+  TFX_TRY(ensure_init());
+  TFX_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, ctx().stream));
+  TFX_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+int tfx_device_mem_info(int64_t *free_bytes, int64_t *total_bytes) {
+  TFX_TRY(ensure_init());
+  size_t f = 0, t = 0;
+  TFX_CUDA(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+  return 0;
+}
+
+int tfx_lsqr_last_timing(double *loop_ms, double *sweep_ms, int32_t *nsweeps) {
+  if (loop_ms) *loop_ms = g_last.loop_ms;
+  if (sweep_ms) *sweep_ms = g_last.sweep_ms;
+  if (nsweeps) *nsweeps = g_last.nsweeps;
+  return 0;
 }
 
 int tfx_lsqr_last_history(double *r_hist, int32_t capacity, int32_t *iters, int32_t *fused) {

@@ -16,6 +16,12 @@
 // By linearity S*(vhat/alpha) = (S*vhat)/alpha, so the normalisation of v by alpha = |vhat| (only
 // known after the sweep) is applied afterwards to the short vector q. One LSQR iteration therefore
 // reads S exactly once: 4 B/nnz of HBM traffic instead of the reference's 16 B/nnz.
+//
+// Instruction budget (ncu, round 1): at the HBM rate an SM has ~1800 cycles per 10^4-row column. The
+// f32->f64 conversion (F2F on the XU pipe, 16 lanes/clk/SM) costs 640 cycles per use, so the first use
+// converts with F2F and the second rebuilds the double from the f32 bits with integer ops (ALU pipe);
+// two columns share one block barrier and one transposed shuffle reduction; the ring slots are laid
+// out so that every thread can read its K rows without bounds predicates.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -24,6 +30,7 @@
 namespace tfx {
 
 static const int kThreads = 1024;
+static const int kMaxSlots = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -62,7 +69,16 @@ __device__ __forceinline__ void cp_async_8(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// f32 -> f64 without the XU pipe: rebias the exponent and spread the mantissa with integer ops.
+// Exact for every normal float; zeros / subnormals (|x| < 1.2e-38) are NOT handled -- the host only
+// selects this path for blocks that contain neither (DenseCM::fastcvt_ok).
+__device__ __forceinline__ double f32bits_to_f64(uint32_t b) {
+  const uint32_t hi = ((uint32_t)((int32_t)b >> 3) & 0x8FFFFFFFu) + 0x38000000u;
+  const uint32_t lo = b << 29;
+  return __hiloint2double((int)hi, (int)lo);
+}
 
 struct DenseArgs {
   const float *S;
@@ -73,19 +89,32 @@ struct DenseArgs {
   const double *nbeta;
   double *partial_q, *partial_n2;
   int ns;
-  unsigned col_bytes;
+  unsigned col_bytes;    // bytes of one column in global memory and in a ring slot (ld * 4)
+  unsigned ring_bytes;   // ns * col_bytes + zeroed guard so that row index K*1024-1 is always readable
   const int *done;
 };
 
-template <int K, int MODE>
+// Sum of `a` over the warp for column 0 and of `b` for column 1 with ONE transposed butterfly:
+// on return even lanes hold sum(a), odd lanes hold sum(b).
+__device__ __forceinline__ double warp_sum2(double a, double b, int lane) {
+  const bool odd = lane & 1;
+  double keep = odd ? b : a;
+  const double send = odd ? a : b;
+  keep += __shfl_xor_sync(0xffffffffu, send, 1);
+#pragma unroll
+  for (int o = 2; o <= 16; o <<= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+  return keep;
+}
+
+template <int K, int MODE, bool FASTCVT>
 __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
   if (a.done && *a.done) return;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *ring = smem;
-  uint64_t *full = (uint64_t *)(smem + (size_t)a.ns * a.col_bytes);
-  double *red = (double *)(full + 8);   // [2][32]
-  double *vq = red + 64;                // [8]
-  double *gq = vq + 8;                  // [8]
+  uint64_t *full = (uint64_t *)(smem + a.ring_bytes);
+  double *red = (double *)(full + kMaxSlots);   // [2 buffers][2 columns][32 warps]
+  double *vq = red + 128;                       // [kMaxSlots]
+  double *gq = vq + kMaxSlots;                  // [kMaxSlots]
 
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int c_lo = (int)((long long)a.ncols * blockIdx.x / gridDim.x);
@@ -93,6 +122,10 @@ __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
   const int ncl = c_hi - c_lo;
   const int ns = a.ns;
   const bool has_g = (MODE == DENSE_FUSED) && (a.g != nullptr);
+
+  // Every word of the ring (+ guard) must always hold a finite float: rows beyond nrows are read
+  // unpredicated (their u is 0 and their accumulators are never stored).
+  for (unsigned i = t * 16u; i < a.ring_bytes; i += kThreads * 16u) *(uint4 *)(ring + i) = make_uint4(0, 0, 0, 0);
 
   double ur[K], acc[K];
 #pragma unroll
@@ -104,6 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
   const double nbeta = (MODE == DENSE_FUSED) ? *a.nbeta : 0.0;
   double n2 = 0.0;
   uint64_t policy = 0;
+  __syncthreads();
 
   if (t == 0) {
     for (int s = 0; s < ns; ++s) mbar_init(&full[s], 1);
@@ -118,70 +152,95 @@ __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
         cp_async_8(&vq[s], a.v + a.col0 + c_lo + s);
         if (has_g) cp_async_8(&gq[s], a.g + a.col0 + c_lo + s);
       }
-      cp_async_commit();
     }
+    cp_async_commit();
   }
   __syncthreads();
 
-  for (int j = 0; j < ncl; ++j) {
-    const int s = j % ns;
-    const uint32_t parity = (uint32_t)((j / ns) & 1);
-    const float *col = (const float *)(ring + (size_t)s * a.col_bytes);
-    mbar_wait(&full[s], parity);
+  // Two columns per step: one block barrier and one pair of transposed reductions per step.
+  for (int j0 = 0; j0 < ncl; j0 += 2) {
+    const bool two = (j0 + 1 < ncl);
+    const int s0 = j0 % ns, s1 = (j0 + 1) % ns;
+    const float *col0p = (const float *)(ring + (size_t)s0 * a.col_bytes) + t;
+    const float *col1p = (const float *)(ring + (size_t)s1 * a.col_bytes) + t;
+    mbar_wait(&full[s0], (uint32_t)((j0 / ns) & 1));
+    if (two) mbar_wait(&full[s1], (uint32_t)(((j0 + 1) / ns) & 1));
+    const int buf = (j0 >> 1) & 1;
 
-    double tj = 0.0;
     if (MODE != DENSE_F_ONLY) {
-      // ---- transposed product: partial dot of this thread's rows, then fixed-order tree reduction
-      double p = 0.0;
+      // ---- transposed product: partial dots of this thread's rows (F2F conversions, XU pipe)
+      double p0 = 0.0, p1 = 0.0;
 #pragma unroll
-      for (int m = 0; m < K; ++m) {
-        const int row = t + kThreads * m;
-        const float f = (row < a.nrows) ? col[row] : 0.0f;
-        p = fma((double)f, ur[m], p);
+      for (int m = 0; m < K; ++m) p0 = fma((double)col0p[kThreads * m], ur[m], p0);
+      if (two) {
+#pragma unroll
+        for (int m = 0; m < K; ++m) p1 = fma((double)col1p[kThreads * m], ur[m], p1);
       }
-      p = warp_sum(p);
-      if (lane == 0) red[(j & 1) * 32 + wid] = p;
+      const double r = warp_sum2(p0, p1, lane);
+      if (lane < 2) red[(buf * 2 + lane) * 32 + wid] = r;
     }
-    if (t == 0 && MODE != DENSE_T_ONLY) cp_async_wait_1();   // v_j / g_j prefetched >= 1 iteration ago
+    if (t == 0 && MODE != DENSE_T_ONLY) cp_async_wait_all();   // v_j / g_j were requested >= 1 step ago
     __syncthreads();
 
-    // Every thread has finished with the slot of column j-1: refill it.
-    if (t == 0 && j >= 1) {
-      const int jn = j - 1 + ns;
-      if (jn < ncl) {
-        const int sn = (j - 1) % ns;
-        mbar_expect_tx(&full[sn], a.col_bytes);
-        tma_load_1d(ring + (size_t)sn * a.col_bytes, a.S + (long long)(c_lo + jn) * a.ld, a.col_bytes, &full[sn], policy);
-        if (MODE != DENSE_T_ONLY) {
-          cp_async_8(&vq[sn], a.v + a.col0 + c_lo + jn);
-          if (has_g) cp_async_8(&gq[sn], a.g + a.col0 + c_lo + jn);
+    // Every thread has finished with the slots of the previous step: refill them.
+    if (t == 0 && j0 >= 2) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int jp = j0 - 2 + c, jn = jp + ns;
+        if (jn < ncl) {
+          const int sn = jp % ns;
+          mbar_expect_tx(&full[sn], a.col_bytes);
+          tma_load_1d(ring + (size_t)sn * a.col_bytes, a.S + (long long)(c_lo + jn) * a.ld, a.col_bytes, &full[sn], policy);
+          if (MODE != DENSE_T_ONLY) {
+            cp_async_8(&vq[sn], a.v + a.col0 + c_lo + jn);
+            if (has_g) cp_async_8(&gq[sn], a.g + a.col0 + c_lo + jn);
+          }
         }
       }
-      cp_async_commit();   // (possibly empty) group keeps the wait_group accounting uniform
+      cp_async_commit();
     }
 
-    double xj;
+    double x0, x1 = 0.0;
     if (MODE == DENSE_F_ONLY) {
-      xj = vq[s];
+      x0 = vq[s0];
+      if (two) x1 = vq[s1];
     } else {
-      tj = warp_sum(red[(j & 1) * 32 + lane]);
+      const double r = warp_sum2(red[(buf * 2 + 0) * 32 + lane], red[(buf * 2 + 1) * 32 + lane], lane);
+      const double t0 = __shfl_sync(0xffffffffu, r, 0), t1 = __shfl_sync(0xffffffffu, r, 1);
       if (MODE == DENSE_FUSED) {
-        xj = fma(nbeta, vq[s], tj);            // v = -beta v ; v = v + S^T u   (lsqr_solver2.F90:225,236)
-        if (has_g) xj += gq[s];                //                + C^T u_cons  (:238)
-        n2 = fma(xj, xj, n2);
+        x0 = fma(nbeta, vq[s0], t0);             // v = -beta v ; v = v + S^T u   (lsqr_solver2.F90:225,236)
+        if (has_g) x0 += gq[s0];                 //                + C^T u_cons  (:238)
+        n2 = fma(x0, x0, n2);
+        if (two) {
+          x1 = fma(nbeta, vq[s1], t1);
+          if (has_g) x1 += gq[s1];
+          n2 = fma(x1, x1, n2);
+        }
       } else {
-        xj = tj;
+        x0 = t0;
+        x1 = t1;
       }
-      if (t == 0) a.out[a.col0 + c_lo + j] = xj;
+      if (t == 0) {
+        a.out[a.col0 + c_lo + j0] = x0;
+        if (two) a.out[a.col0 + c_lo + j0 + 1] = x1;
+      }
     }
 
     if (MODE != DENSE_T_ONLY) {
-      // ---- forward product with the column that is still in shared memory
+      // ---- forward product with the columns that are still in shared memory
 #pragma unroll
       for (int m = 0; m < K; ++m) {
-        const int row = t + kThreads * m;
-        const float f = (row < a.nrows) ? col[row] : 0.0f;
-        acc[m] = fma((double)f, xj, acc[m]);
+        const float f = col0p[kThreads * m];
+        const double d = FASTCVT ? f32bits_to_f64(__float_as_uint(f)) : (double)f;
+        acc[m] = fma(d, x0, acc[m]);
+      }
+      if (two) {
+#pragma unroll
+        for (int m = 0; m < K; ++m) {
+          const float f = col1p[kThreads * m];
+          const double d = FASTCVT ? f32bits_to_f64(__float_as_uint(f)) : (double)f;
+          acc[m] = fma(d, x1, acc[m]);
+        }
       }
     }
   }
@@ -214,23 +273,49 @@ __global__ void __launch_bounds__(256) dense_reduce_kernel(const double *partial
   }
 }
 
-template <int K>
+// Flags a block that contains zeros or subnormal floats (the integer f32->f64 path cannot convert them).
+__global__ void __launch_bounds__(256) dense_scan_kernel(const float *__restrict__ S, long long ld, int nrows,
+                                                         long long ncols, int *flag) {
+  const long long total = ld * ncols;
+  int bad = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if ((int)(i % ld) >= nrows) continue;
+    const uint32_t b = __float_as_uint(S[i]);
+    if ((b & 0x7F800000u) == 0u) bad = 1;
+  }
+  if (bad) atomicExch(flag, 1);
+}
+
+int dense_scan_fastcvt(DenseCM &S, cudaStream_t st) {
+  DevBuf<int> flag;
+  TFX_TRY(flag.alloc(1));
+  TFX_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+  dense_scan_kernel<<<ctx().num_sms * 8, 256, 0, st>>>(S.val.p, S.ld, S.nrows, S.ncols, flag.p);
+  ctx().launches++;
+  int h = 0;
+  TFX_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  S.fastcvt_ok = (h == 0) ? 1 : 0;
+  return 0;
+}
+
+template <int K, bool FASTCVT>
 static int launch_k(DenseMode mode, const DenseArgs &a, int grid, size_t smem, cudaStream_t st) {
   switch (mode) {
     case DENSE_FUSED: {
-      auto k = dense_sweep_kernel<K, DENSE_FUSED>;
+      auto k = dense_sweep_kernel<K, DENSE_FUSED, FASTCVT>;
       TFX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       k<<<grid, kThreads, smem, st>>>(a);
       break;
     }
     case DENSE_T_ONLY: {
-      auto k = dense_sweep_kernel<K, DENSE_T_ONLY>;
+      auto k = dense_sweep_kernel<K, DENSE_T_ONLY, false>;
       TFX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       k<<<grid, kThreads, smem, st>>>(a);
       break;
     }
     default: {
-      auto k = dense_sweep_kernel<K, DENSE_F_ONLY>;
+      auto k = dense_sweep_kernel<K, DENSE_F_ONLY, FASTCVT>;
       TFX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       k<<<grid, kThreads, smem, st>>>(a);
       break;
@@ -239,18 +324,28 @@ static int launch_k(DenseMode mode, const DenseArgs &a, int grid, size_t smem, c
   return 0;
 }
 
+template <int K>
+static int launch_kf(DenseMode mode, const DenseArgs &a, int grid, size_t smem, bool fast, cudaStream_t st) {
+  return fast ? launch_k<K, true>(mode, a, grid, smem, st) : launch_k<K, false>(mode, a, grid, smem, st);
+}
+
 int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v, const double *d_g, double *d_out,
                 const double *d_nbeta, double *d_q, double *d_n2, const int *d_done, cudaStream_t st) {
   Context &c = ctx();
   if (S.empty()) return 0;
   if (S.nrows > kDenseMaxRows)
     return fail(-30, "dense sweep: more than " + std::to_string(kDenseMaxRows) + " data rows per block is not supported yet");
+  if (S.fastcvt_ok < 0) TFX_TRY(dense_scan_fastcvt(S, st));
+  const int K = (S.nrows + kThreads - 1) / kThreads;
   const unsigned col_bytes = (unsigned)(S.ld * sizeof(float));
-  const size_t tail = 8 * sizeof(uint64_t) + (64 + 16) * sizeof(double);
-  const size_t budget = 227 * 1024 - 1024;
-  int ns = (int)std::min<size_t>(8, (budget - tail) / col_bytes);
-  if (ns < 3) return fail(-31, "dense sweep: column does not fit the shared-memory ring");
-  const size_t smem = (size_t)ns * col_bytes + tail;
+  const size_t span = (size_t)K * kThreads * sizeof(float);                 // bytes a thread block may read per slot
+  const size_t guard = (span > col_bytes) ? ((span - col_bytes + 15) / 16 * 16) : 0;
+  const size_t tail = kMaxSlots * sizeof(uint64_t) + (128 + 2 * kMaxSlots) * sizeof(double);
+  const size_t budget = 227 * 1024 - 256;
+  if (budget < tail + guard + 3 * (size_t)col_bytes) return fail(-31, "dense sweep: column does not fit the shared-memory ring");
+  int ns = (int)std::min<size_t>(kMaxSlots, (budget - tail - guard) / col_bytes);
+  const size_t ring_bytes = (size_t)ns * col_bytes + guard;
+  const size_t smem = ring_bytes + tail;
   if (S.grid <= 0) {
     S.grid = std::min(c.num_sms, S.ncols);
     TFX_TRY(S.partial_q.alloc((size_t)S.grid * S.ld));
@@ -260,20 +355,20 @@ int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v
   a.S = S.val.p; a.ld = S.ld; a.nrows = S.nrows; a.ncols = S.ncols; a.col0 = S.col0;
   a.u = d_u; a.v = d_v; a.g = d_g; a.out = d_out; a.nbeta = d_nbeta;
   a.partial_q = S.partial_q.p; a.partial_n2 = S.partial_n2.p;
-  a.ns = ns; a.col_bytes = col_bytes; a.done = d_done;
-  const int K = (S.nrows + kThreads - 1) / kThreads;
+  a.ns = ns; a.col_bytes = col_bytes; a.ring_bytes = (unsigned)ring_bytes; a.done = d_done;
+  const bool fast = S.fastcvt_ok == 1;
   int rc;
   switch (K) {
-    case 1: rc = launch_k<1>(mode, a, S.grid, smem, st); break;
-    case 2: rc = launch_k<2>(mode, a, S.grid, smem, st); break;
-    case 3: rc = launch_k<3>(mode, a, S.grid, smem, st); break;
-    case 4: rc = launch_k<4>(mode, a, S.grid, smem, st); break;
-    case 5: rc = launch_k<5>(mode, a, S.grid, smem, st); break;
-    case 6: rc = launch_k<6>(mode, a, S.grid, smem, st); break;
-    case 7: rc = launch_k<7>(mode, a, S.grid, smem, st); break;
-    case 8: rc = launch_k<8>(mode, a, S.grid, smem, st); break;
-    case 9: rc = launch_k<9>(mode, a, S.grid, smem, st); break;
-    default: rc = launch_k<10>(mode, a, S.grid, smem, st); break;
+    case 1: rc = launch_kf<1>(mode, a, S.grid, smem, fast, st); break;
+    case 2: rc = launch_kf<2>(mode, a, S.grid, smem, fast, st); break;
+    case 3: rc = launch_kf<3>(mode, a, S.grid, smem, fast, st); break;
+    case 4: rc = launch_kf<4>(mode, a, S.grid, smem, fast, st); break;
+    case 5: rc = launch_kf<5>(mode, a, S.grid, smem, fast, st); break;
+    case 6: rc = launch_kf<6>(mode, a, S.grid, smem, fast, st); break;
+    case 7: rc = launch_kf<7>(mode, a, S.grid, smem, fast, st); break;
+    case 8: rc = launch_kf<8>(mode, a, S.grid, smem, fast, st); break;
+    case 9: rc = launch_kf<9>(mode, a, S.grid, smem, fast, st); break;
+    default: rc = launch_kf<10>(mode, a, S.grid, smem, fast, st); break;
   }
   TFX_TRY(rc);
   c.launches++;

@@ -62,6 +62,7 @@ struct DenseCM {
   int32_t ncols = 0;       // local columns held by this rank
   int32_t col0 = 0;        // 0-based position of column 0 inside the solver's column space
   int32_t grid = 0;        // CTAs of the sweep kernel (== partial buffers)
+  int32_t fastcvt_ok = -1; // 1: no zero / subnormal entries (integer f32->f64 path allowed); -1: not scanned yet
   DevBuf<double> partial_q;    // [grid][ld]
   DevBuf<double> partial_n2;   // [grid]
   bool empty() const { return nrows == 0 || ncols == 0; }

@@ -242,6 +242,29 @@ __global__ void k_scal_misfit(const double *sumsq, LsqrScalars *sc, double targe
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+struct Timing {
+  cudaEvent_t loop0 = nullptr, loop1 = nullptr;
+  std::vector<cudaEvent_t> sw;   // pairs around the dominant sweep kernel (option "profile_sweeps")
+  size_t used = 0;
+  int ensure() {
+    if (!loop0) { TFX_CUDA(cudaEventCreate(&loop0)); TFX_CUDA(cudaEventCreate(&loop1)); }
+    return 0;
+  }
+  int next(cudaEvent_t *e) {
+    if (used == sw.size()) {
+      cudaEvent_t n;
+      TFX_CUDA(cudaEventCreate(&n));
+      sw.push_back(n);
+    }
+    *e = sw[used++];
+    return 0;
+  }
+};
+Timing &timing() {
+  static Timing t;
+  return t;
+}
+
 struct Work {
   DevBuf<double> v, w, v2, g, q, b0, sx, partial, red;
   DevBuf<LsqrScalars> sc;
@@ -307,6 +330,9 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
   res.iters = 0;
   res.status = 0;
 
+  Timing &T = timing();
+  TFX_TRY(T.ensure());
+  T.used = 0;
   const int GV = vec_grid(std::max<int64_t>(ncol, nlines));
   TFX_TRY(W.v.alloc(ncol)); TFX_TRY(W.w.alloc(ncol)); TFX_TRY(W.v2.alloc(ncol)); TFX_TRY(W.g.alloc(ncol));
   TFX_TRY(W.q.alloc(nlines + 1));
@@ -353,7 +379,13 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
     auto sweep = [&]() -> int {
       // g = C^T u_c ; vhat = -beta v + S^T u_d + g ; q_d = S vhat ; n2 = |vhat|^2 ; q_c = C vhat
       if (have_C) TFX_TRY(seg_spmv(C->trn, d_u + nls, g, false, 0, (int32_t)ncol, 0, done, st));
+      cudaEvent_t ea = nullptr, eb = nullptr;
+      if (g_opt_profile_sweeps && T.used < 4096) {
+        TFX_TRY(T.next(&ea)); TFX_TRY(T.next(&eb));
+        TFX_CUDA(cudaEventRecord(ea, st));
+      }
       TFX_TRY(dense_sweep(S->dense, DENSE_FUSED, d_u, v, have_C ? g : nullptr, v, &sc->neg_beta, q, q + nlines, done, st));
+      if (eb) TFX_CUDA(cudaEventRecord(eb, st));
       if (outside && have_C) {
         k_outside_update<<<GV, kVecThreads, 0, st>>>(v, g, ncol, S->dense.col0, (int64_t)S->dense.col0 + S->dense.ncols,
                                                      sc, partial); LAUNCHED();
@@ -374,6 +406,7 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
     k_xw_update<<<GV, kVecThreads, 0, st>>>(v, d_x, w, ncol, sc, 1, p.gamma); LAUNCHED();
     const int chk = (S->device_nnz() > (int64_t)2e8) ? 1 : 16;
     int host_done = 0;
+    TFX_CUDA(cudaEventRecord(T.loop0, st));
     for (int it = 1; it <= p.niter && !host_done; ++it) {
       // u = -alpha u + (S vhat, C vhat)/alpha ; beta = |u| ; u /= beta
       k_u_update<<<GV, kVecThreads, 0, st>>>(d_u, q, nlines, sc, 1, partial); LAUNCHED();
@@ -402,6 +435,7 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
     k_xw_update<<<GV, kVecThreads, 0, st>>>(v, d_x, w, ncol, sc, 1, p.gamma); LAUNCHED();
     const int chk = (S->device_nnz() > (int64_t)2e8) ? 1 : 16;
     int host_done = 0;
+    TFX_CUDA(cudaEventRecord(T.loop0, st));
     for (int it = 1; it <= p.niter && !host_done; ++it) {
       if (misfit) {   // :168-189
         TFX_CUDA(cudaMemcpyAsync(v2, d_x, ncol * 8, cudaMemcpyDeviceToDevice, st));
@@ -446,6 +480,7 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
     }
   }
 #undef LAUNCHED
+  TFX_CUDA(cudaEventRecord(T.loop1, st));
   TFX_CUDA(cudaGetLastError());
   LsqrScalars h;
   TFX_CUDA(cudaMemcpyAsync(&h, sc, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -454,6 +489,19 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
   res.status = h.status;
   res.r = h.r;
   if (h.status == -3) return fail(-56, "Could not normalize initial v, zero denominator!");
+  {
+    float ms = 0.f;
+    TFX_CUDA(cudaEventElapsedTime(&ms, T.loop0, T.loop1));
+    res.loop_ms = ms;
+    res.sweep_ms = 0.0;
+    res.nsweeps = 0;
+    for (size_t i = 0; i + 1 < T.used; i += 2) {
+      float t = 0.f;
+      TFX_CUDA(cudaEventElapsedTime(&t, T.sw[i], T.sw[i + 1]));
+      res.sweep_ms += t;
+      res.nsweeps += 1;
+    }
+  }
   res.history.resize((size_t)std::max(0, h.executed));
   if (h.executed > 0)
     TFX_CUDA(cudaMemcpy(res.history.data(), W.hist.p, (size_t)h.executed * 8, cudaMemcpyDeviceToHost));

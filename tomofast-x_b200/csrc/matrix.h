@@ -54,11 +54,15 @@ struct LsqrResult {
   int32_t status = 0;     // 0 ok, 1: |b| = 0
   double r = 1.0;
   bool fused = false;
+  double loop_ms = 0.0;   // device time of the iteration loop (CUDA events on the library stream)
+  double sweep_ms = 0.0;  // summed device time of the fused sweep kernel launches (option profile_sweeps)
+  int32_t nsweeps = 0;
   std::vector<double> history;
 };
 
 // Option "strict_order": reproduce the reference's sequential summation order (slow parity mode).
 extern int g_opt_strict_order;
+extern int g_opt_profile_sweeps;
 
 int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x, LsqrResult &res);
 int lsqr_run_strict(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x, LsqrResult &res);
