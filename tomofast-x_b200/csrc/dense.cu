@@ -106,7 +106,8 @@ __device__ __forceinline__ double warp_sum2(double a, double b, int lane) {
   return keep;
 }
 
-template <int K, int MODE, bool FASTCVT>
+// K2 = float2 row-pairs per thread: thread t owns rows 2*(t + 1024*m) + {0,1}, m < K2.
+template <int K2, int MODE, bool FASTCVT>
 __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
   if (a.done && *a.done) return;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -127,12 +128,15 @@ __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
   // unpredicated (their u is 0 and their accumulators are never stored).
   for (unsigned i = t * 16u; i < a.ring_bytes; i += kThreads * 16u) *(uint4 *)(ring + i) = make_uint4(0, 0, 0, 0);
 
-  double ur[K], acc[K];
+  double ur[2 * K2], acc[2 * K2];
 #pragma unroll
-  for (int m = 0; m < K; ++m) {
-    const int row = t + kThreads * m;
-    ur[m] = (MODE != DENSE_F_ONLY && row < a.nrows) ? a.u[row] : 0.0;
-    acc[m] = 0.0;
+  for (int m = 0; m < K2; ++m) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = 2 * (t + kThreads * m) + h;
+      ur[2 * m + h] = (MODE != DENSE_F_ONLY && row < a.nrows) ? a.u[row] : 0.0;
+      acc[2 * m + h] = 0.0;
+    }
   }
   const double nbeta = (MODE == DENSE_FUSED) ? *a.nbeta : 0.0;
   double n2 = 0.0;
@@ -158,23 +162,37 @@ __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
   __syncthreads();
 
   // Two columns per step: one block barrier and one pair of transposed reductions per step.
+  // (s0, ph0) = ring slot and mbarrier parity of column j0, advanced incrementally (no divisions).
+  int s0 = 0;
+  uint32_t ph0 = 0;
+  int sp0 = 0, sp1 = 0;   // slots of the previous step (refilled after this step's barrier)
   for (int j0 = 0; j0 < ncl; j0 += 2) {
     const bool two = (j0 + 1 < ncl);
-    const int s0 = j0 % ns, s1 = (j0 + 1) % ns;
-    const float *col0p = (const float *)(ring + (size_t)s0 * a.col_bytes) + t;
-    const float *col1p = (const float *)(ring + (size_t)s1 * a.col_bytes) + t;
-    mbar_wait(&full[s0], (uint32_t)((j0 / ns) & 1));
-    if (two) mbar_wait(&full[s1], (uint32_t)(((j0 + 1) / ns) & 1));
+    int s1 = s0 + 1;
+    uint32_t ph1 = ph0;
+    if (s1 == ns) { s1 = 0; ph1 ^= 1u; }
+    const float2 *col0p = (const float2 *)(ring + (size_t)s0 * a.col_bytes) + t;
+    const float2 *col1p = (const float2 *)(ring + (size_t)s1 * a.col_bytes) + t;
+    mbar_wait(&full[s0], ph0);
+    if (two) mbar_wait(&full[s1], ph1);
     const int buf = (j0 >> 1) & 1;
 
     if (MODE != DENSE_F_ONLY) {
       // ---- transposed product: partial dots of this thread's rows (F2F conversions, XU pipe)
       double p0 = 0.0, p1 = 0.0;
 #pragma unroll
-      for (int m = 0; m < K; ++m) p0 = fma((double)col0p[kThreads * m], ur[m], p0);
+      for (int m = 0; m < K2; ++m) {
+        const float2 f = col0p[kThreads * m];
+        p0 = fma((double)f.x, ur[2 * m], p0);
+        p0 = fma((double)f.y, ur[2 * m + 1], p0);
+      }
       if (two) {
 #pragma unroll
-        for (int m = 0; m < K; ++m) p1 = fma((double)col1p[kThreads * m], ur[m], p1);
+        for (int m = 0; m < K2; ++m) {
+          const float2 f = col1p[kThreads * m];
+          p1 = fma((double)f.x, ur[2 * m], p1);
+          p1 = fma((double)f.y, ur[2 * m + 1], p1);
+        }
       }
       const double r = warp_sum2(p0, p1, lane);
       if (lane < 2) red[(buf * 2 + lane) * 32 + wid] = r;
@@ -186,9 +204,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
     if (t == 0 && j0 >= 2) {
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const int jp = j0 - 2 + c, jn = jp + ns;
+        const int jn = j0 - 2 + c + ns;
+        const int sn = c ? sp1 : sp0;
         if (jn < ncl) {
-          const int sn = jp % ns;
           mbar_expect_tx(&full[sn], a.col_bytes);
           tma_load_1d(ring + (size_t)sn * a.col_bytes, a.S + (long long)(c_lo + jn) * a.ld, a.col_bytes, &full[sn], policy);
           if (MODE != DENSE_T_ONLY) {
@@ -229,27 +247,38 @@ __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
     if (MODE != DENSE_T_ONLY) {
       // ---- forward product with the columns that are still in shared memory
 #pragma unroll
-      for (int m = 0; m < K; ++m) {
-        const float f = col0p[kThreads * m];
-        const double d = FASTCVT ? f32bits_to_f64(__float_as_uint(f)) : (double)f;
-        acc[m] = fma(d, x0, acc[m]);
+      for (int m = 0; m < K2; ++m) {
+        const float2 f = col0p[kThreads * m];
+        const double dx = FASTCVT ? f32bits_to_f64(__float_as_uint(f.x)) : (double)f.x;
+        const double dy = FASTCVT ? f32bits_to_f64(__float_as_uint(f.y)) : (double)f.y;
+        acc[2 * m] = fma(dx, x0, acc[2 * m]);
+        acc[2 * m + 1] = fma(dy, x0, acc[2 * m + 1]);
       }
       if (two) {
 #pragma unroll
-        for (int m = 0; m < K; ++m) {
-          const float f = col1p[kThreads * m];
-          const double d = FASTCVT ? f32bits_to_f64(__float_as_uint(f)) : (double)f;
-          acc[m] = fma(d, x1, acc[m]);
+        for (int m = 0; m < K2; ++m) {
+          const float2 f = col1p[kThreads * m];
+          const double dx = FASTCVT ? f32bits_to_f64(__float_as_uint(f.x)) : (double)f.x;
+          const double dy = FASTCVT ? f32bits_to_f64(__float_as_uint(f.y)) : (double)f.y;
+          acc[2 * m] = fma(dx, x1, acc[2 * m]);
+          acc[2 * m + 1] = fma(dy, x1, acc[2 * m + 1]);
         }
       }
     }
+    // advance to the next pair of columns
+    sp0 = s0; sp1 = s1;
+    s0 = s1 + 1; ph0 = ph1;
+    if (s0 == ns) { s0 = 0; ph0 ^= 1u; }
   }
 
   if (MODE != DENSE_T_ONLY) {
 #pragma unroll
-    for (int m = 0; m < K; ++m) {
-      const int row = t + kThreads * m;
-      if (row < a.nrows) a.partial_q[(long long)blockIdx.x * a.ld + row] = acc[m];
+    for (int m = 0; m < K2; ++m) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = 2 * (t + kThreads * m) + h;
+        if (row < a.nrows) a.partial_q[(long long)blockIdx.x * a.ld + row] = acc[2 * m + h];
+      }
     }
   }
   if (MODE == DENSE_FUSED && t == 0) a.partial_n2[blockIdx.x] = n2;
@@ -336,7 +365,8 @@ int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v
   if (S.nrows > kDenseMaxRows)
     return fail(-30, "dense sweep: more than " + std::to_string(kDenseMaxRows) + " data rows per block is not supported yet");
   if (S.fastcvt_ok < 0) TFX_TRY(dense_scan_fastcvt(S, st));
-  const int K = (S.nrows + kThreads - 1) / kThreads;
+  const int K2 = (S.nrows + 2 * kThreads - 1) / (2 * kThreads);   // float2 row-pairs per thread
+  const int K = 2 * K2;
   const unsigned col_bytes = (unsigned)(S.ld * sizeof(float));
   const size_t span = (size_t)K * kThreads * sizeof(float);                 // bytes a thread block may read per slot
   const size_t guard = (span > col_bytes) ? ((span - col_bytes + 15) / 16 * 16) : 0;
@@ -358,17 +388,12 @@ int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v
   a.ns = ns; a.col_bytes = col_bytes; a.ring_bytes = (unsigned)ring_bytes; a.done = d_done;
   const bool fast = S.fastcvt_ok == 1;
   int rc;
-  switch (K) {
+  switch (K2) {
     case 1: rc = launch_kf<1>(mode, a, S.grid, smem, fast, st); break;
     case 2: rc = launch_kf<2>(mode, a, S.grid, smem, fast, st); break;
     case 3: rc = launch_kf<3>(mode, a, S.grid, smem, fast, st); break;
     case 4: rc = launch_kf<4>(mode, a, S.grid, smem, fast, st); break;
-    case 5: rc = launch_kf<5>(mode, a, S.grid, smem, fast, st); break;
-    case 6: rc = launch_kf<6>(mode, a, S.grid, smem, fast, st); break;
-    case 7: rc = launch_kf<7>(mode, a, S.grid, smem, fast, st); break;
-    case 8: rc = launch_kf<8>(mode, a, S.grid, smem, fast, st); break;
-    case 9: rc = launch_kf<9>(mode, a, S.grid, smem, fast, st); break;
-    default: rc = launch_kf<10>(mode, a, S.grid, smem, fast, st); break;
+    default: rc = launch_kf<5>(mode, a, S.grid, smem, fast, st); break;
   }
   TFX_TRY(rc);
   c.launches++;
