@@ -80,6 +80,7 @@ int tfx_sparse_matrix_part_mult_vector(tfx_matrix *m, int32_t nelements, const d
                                        int32_t myrank);                        /* :335-367 */
 int tfx_sparse_matrix_trans_mult_vector(tfx_matrix *m, const double *x, double *b);          /* :373-382 */
 int tfx_sparse_matrix_add_trans_mult_vector(tfx_matrix *m, const double *x, double *b);      /* :388-405 */
+int tfx_sparse_matrix_normalize_columns(tfx_matrix *m, double *column_norm);    /* :414-443 (host builder) */
 int32_t tfx_sparse_matrix_get_total_row_number(const tfx_matrix *m);           /* :448-453 */
 int32_t tfx_sparse_matrix_get_current_row_number(const tfx_matrix *m);         /* :458-463 */
 int32_t tfx_sparse_matrix_get_ncolumns(const tfx_matrix *m);                   /* :468-473 */

@@ -1,0 +1,181 @@
+"""One rank of a column-split LSQR solve (launched by torchrun from tests/test_gpu_multi.py and
+tests/test_dist_model.py).
+
+    python -m torch.distributed.run --nproc-per-node P tests/multi_rank_case.py --backend nccl|model
+
+The decomposition is the reference's (lsqr_solver2.F90:16 "parallelized by model parameters"): rank r owns
+the column slab [nsmaller, nsmaller + nelements) (parallel_tools.f90:46-86), every rank holds all data rows,
+the products S_loc * v_loc are summed over ranks (MPI_Allreduce at lsqr_solver2.F90:214) and |v|^2 is a
+scalar all-reduce (:514).
+
+ --backend nccl  : the product path -- libtfx on one GPU per rank, NCCL inside the library.
+ --backend model : host model of the same decomposition on CPU (numpy products, torch.distributed gloo
+                   all-reduce) -- exercises the partition helpers, the slab builders and the summation
+                   structure without a GPU.
+Rank 0 gathers the slabs and compares with the single-rank oracle solve of the full problem.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def full_problem(kind, seed=7):
+    rng = np.random.default_rng(seed)
+    nx, ny, nz, ndata = 7, 6, 5, 40
+    N = nx * ny * nz
+    if kind == "dense":
+        nel = N
+        cols = [np.arange(N, dtype=np.int32) for _ in range(ndata)]
+    else:
+        nel = N // 3
+        cols = [np.sort(rng.choice(N, size=nel, replace=False)).astype(np.int32) for _ in range(ndata)]
+    vals = [rng.standard_normal(nel).astype(np.float32) for _ in range(ndata)]
+    alpha = (0.3 + 0.1 * (np.arange(N) % 4)).astype(np.float32)        # damping block alpha_p * I (damping.F90:158-179)
+    b = np.concatenate([rng.standard_normal(ndata), 0.01 * rng.standard_normal(N)])
+    return dict(nx=nx, ny=ny, nz=nz, ndata=ndata, N=N, cols=cols, vals=vals, alpha=alpha, b=b)
+
+
+def slab_arrays(pb, cell0, ncl):
+    """CSR arrays (reference storage, 1-based) of S restricted to the column slab, local column indices."""
+    sa, ija, ijl, rowptr = [], [], [1], []
+    for i in range(pb["ndata"]):
+        c, v = pb["cols"][i], pb["vals"][i]
+        sel = (c >= cell0) & (c < cell0 + ncl)
+        if sel.any():
+            sa.append(v[sel]); ija.append(c[sel] - cell0 + 1)
+            ijl.append(ijl[-1] + int(sel.sum())); rowptr.append(i + 1)
+    return (np.concatenate(sa), np.concatenate(ija).astype(np.int32), np.array(ijl, dtype=np.int64),
+            np.array(rowptr, dtype=np.int32))
+
+
+def oracle_reference(pb, niter):
+    from oracle import oracle as orc
+    N, ndata = pb["N"], pb["ndata"]
+    S = orc.SparseMatrix(ndata, 2 * N, sum(len(c) for c in pb["cols"]))
+    for c, v in zip(pb["cols"], pb["vals"]):
+        S.add_row(v, c + 1); S.new_row()
+    S.finalize()
+    Cm = orc.SparseMatrix(N, 2 * N, N)
+    for p in range(N):
+        Cm.add(float(pb["alpha"][p]), p + 1); Cm.new_row()
+    Cm.finalize()
+    x, h, it = orc.lsqr_solve_sensit(niter, 1e-13, 0.0, 0.0, S, Cm, pb["b"], N, pb["nx"], pb["ny"], pb["nz"], 1, 0, True)
+    return x[:N], h, it
+
+
+def solve_nccl(pb, kind, rank, world, td, niter):
+    import tomofastx_b200 as tfx
+    tfx.init(int(os.environ.get("LOCAL_RANK", "0")))
+    box = [tfx.comm_unique_id() if rank == 0 else None]
+    td.broadcast_object_list(box, src=0)
+    tfx.comm_init(world, rank, box[0])
+    N, ndata = pb["N"], pb["ndata"]
+    ncl = tfx.calculate_nelements_at_cpu(N, rank, world)
+    cell0 = tfx.get_nsmaller(N, rank, world)
+    ncol = 2 * ncl
+    sa, ija, ijl, rowptr = slab_arrays(pb, cell0, ncl)
+    tfx.set_option("dense_detect", 1 if kind == "dense" else 0)
+    S = tfx.SparseMatrix.from_arrays(ndata, ncol, sa, ija, ijl, rowptr)
+    tfx.set_option("dense_detect", 1)
+    assert S.storage_kind() == (1 if kind == "dense" else 0)
+    Cm = tfx.SparseMatrix.from_arrays(N, ncol, pb["alpha"][cell0:cell0 + ncl].copy(), np.arange(1, ncl + 1, dtype=np.int32),
+                                      np.arange(1, ncl + 2, dtype=np.int64),
+                                      np.arange(cell0 + 1, cell0 + ncl + 1, dtype=np.int32))
+    u = pb["b"].copy(); x = np.zeros(ncol)
+    tfx.lsqr_solve_sensit(len(u), ncol, niter, 1e-13, 0.0, 0.0, S, Cm, u, x, [1, 0], ncl, pb["nx"], pb["ny"], pb["nz"],
+                          1, 0, True, myrank=rank, nbproc=world)
+    h, it, fused = tfx.last_history()
+    assert fused == (kind == "dense")
+    # a collective through the C ABI on a host buffer, too
+    chk = np.array([rank + 1.0, 1.0]); tfx.comm_allreduce_sum(chk, 2)
+    assert chk[0] == world * (world + 1) / 2 and chk[1] == world
+    tfx.comm_finalize()
+    return x[:ncl], h, it, cell0, ncl
+
+
+def solve_model(pb, kind, rank, world, td, niter):
+    """Host model of lsqr.cu's SPLIT path for one rank (numpy products; gloo all-reduces)."""
+    import torch
+    import tomofastx_b200 as tfx                                      # partition helpers only (no GPU call)
+    N, ndata = pb["N"], pb["ndata"]
+    ncl = tfx.calculate_nelements_at_cpu(N, rank, world)
+    cell0 = tfx.get_nsmaller(N, rank, world)
+    sa, ija, ijl, rowptr = slab_arrays(pb, cell0, ncl)
+    A = np.zeros((ndata, ncl))
+    for s, row in enumerate(rowptr):
+        k0, k1 = ijl[s] - 1, ijl[s + 1] - 1
+        A[row - 1, ija[k0:k1] - 1] = sa[k0:k1].astype(np.float64)
+    al = pb["alpha"][cell0:cell0 + ncl].astype(np.float64)
+
+    def allreduce(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)); td.all_reduce(t); return t.numpy()
+
+    nlines = ndata + N
+    u = pb["b"].copy(); x = np.zeros(ncl); hist = []
+    beta = np.linalg.norm(u); u /= beta; b1 = beta
+    v = A.T @ u[:ndata] + al * u[ndata + cell0:ndata + cell0 + ncl]
+    alpha = np.sqrt(allreduce(np.array([v @ v]))[0]); v /= alpha
+    w = v.copy(); rhobar, phibar = alpha, beta
+    it = 0
+    for it in range(1, niter + 1):
+        q = np.zeros(nlines)
+        q[:ndata] = A @ v
+        q[ndata + cell0:ndata + cell0 + ncl] = al * v
+        u = -alpha * u + allreduce(q)                                 # MPI_Allreduce(u), lsqr_solver2.F90:214
+        beta = np.linalg.norm(u); u /= beta
+        v = -beta * v + A.T @ u[:ndata] + al * u[ndata + cell0:ndata + cell0 + ncl]
+        alpha = np.sqrt(allreduce(np.array([v @ v]))[0]); v /= alpha  # normalize(), :514
+        rho = np.hypot(rhobar, beta); c, s = rhobar / rho, beta / rho
+        theta = s * alpha; rhobar = -c * alpha; phi = c * phibar; phibar = s * phibar
+        x += (phi / rho) * w; w = -(theta / rho) * w + v
+        hist.append(phibar / b1)
+        if hist[-1] <= 1e-13:
+            break
+    return x, np.array(hist), it, cell0, ncl
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "model"])
+    ap.add_argument("--niter", type=int, default=30)
+    a = ap.parse_args()
+    import torch
+    import torch.distributed as td
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    td.init_process_group(backend="gloo", rank=rank, world_size=world)
+    ok = True
+    for kind in ("dense", "sparse"):
+        pb = full_problem(kind)
+        fn = solve_nccl if a.backend == "nccl" else solve_model
+        x_loc, h, it, cell0, ncl = fn(pb, kind, rank, world, td, a.niter)
+        parts = [None] * world
+        td.all_gather_object(parts, (cell0, ncl, x_loc))
+        if rank == 0:
+            x = np.zeros(pb["N"])
+            covered = np.zeros(pb["N"], dtype=int)
+            for c0, n, xl in parts:
+                x[c0:c0 + n] = xl; covered[c0:c0 + n] += 1
+            assert np.all(covered == 1), "column slabs must tile the model exactly once"
+            x_ref, h_ref, it_ref = oracle_reference(pb, a.niter)
+            assert it == it_ref, (it, it_ref)
+            n = min(10, len(h_ref))
+            assert np.allclose(h[:n], h_ref[:n], rtol=1e-6), (kind, h[:n], h_ref[:n])
+            assert abs(h[-1] - h_ref[-1]) <= 1e-6 * h_ref[-1], (kind, h[-1], h_ref[-1])
+            assert np.allclose(x, x_ref, rtol=1e-6, atol=1e-8 * np.abs(x_ref).max()), kind
+            print("multi_rank_case ok: backend=%s kind=%s world=%d iters=%d r_last=%.6e" % (a.backend, kind, world, it, h[-1]),
+                  flush=True)
+    td.barrier()
+    td.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import tomofastx_b200 as tfx
+from tests.conftest import TOL, comparable
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -81,3 +82,26 @@ def test_partition_helpers_match_reference():
     # parallel_tools.f90:46-63 -- remainder goes to the first ranks
     assert [tfx.calculate_nelements_at_cpu(10, r, 3) for r in range(3)] == [4, 3, 3]
     assert [tfx.get_nsmaller(10, r, 3) for r in range(3)] == [0, 4, 7]
+
+
+def test_normalize_columns_reference_unit_test(libtfx, oracle):
+    # tests_sparse_matrix.f90:39-113 on the host-side builder (no device needed before finalize()):
+    # half of the columns are zero; the returned norms equal the dense column norms, the scaled columns
+    # have unit (or zero) length; bit-identical to the oracle's restatement.
+    ncolumns, nrows = 10, 30
+    A = np.zeros((nrows, ncolumns))
+    m = tfx.SparseMatrix(nrows, ncolumns, ncolumns * nrows)
+    mo = oracle.SparseMatrix(nrows, ncolumns, ncolumns * nrows)
+    counter = 0
+    for j in range(nrows):
+        for i in range(ncolumns):
+            counter += 1
+            A[j, i] = float(counter) if (i + 1) <= ncolumns // 2 else 0.0
+            m.add(A[j, i], i + 1); mo.add(A[j, i], i + 1)
+        m.new_row(); mo.new_row()
+    mo.finalize()
+    cn = m.normalize_columns()
+    cn_o = mo.normalize_columns()
+    assert np.array_equal(cn, cn_o)
+    for i in range(ncolumns):
+        assert comparable(cn[i], np.linalg.norm(A[:, i]), TOL)

@@ -79,6 +79,7 @@ def lib():
     for n in ("get_number_elements", "get_nnz"):
         getattr(L, "tfx_sparse_matrix_" + n).argtypes = [vp]
         getattr(L, "tfx_sparse_matrix_" + n).restype = i64
+    L.tfx_sparse_matrix_normalize_columns.argtypes = [vp, vp]
     L.tfx_sparse_matrix_from_arrays.argtypes = [C.POINTER(vp), i32, i32, i32, i64, vp, vp, vp, vp]
     L.tfx_sparse_matrix_storage_kind.argtypes = [vp]
     L.tfx_sparse_matrix_export.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), vp, vp, vp, vp]
@@ -241,6 +242,12 @@ class SparseMatrix:
 
     def add_empty_rows(self, nrows, myrank=0):
         _check(lib().tfx_sparse_matrix_add_empty_rows(self._h, int(nrows), myrank))
+
+    def normalize_columns(self):
+        """normalize_columns (sparse_matrix.f90:414-443): scales the stored values, returns the column norms."""
+        cn = np.zeros(self.get_ncolumns())
+        _check(lib().tfx_sparse_matrix_normalize_columns(self._h, cn.ctypes.data))
+        return cn
 
     def get_total_row_number(self):
         return lib().tfx_sparse_matrix_get_total_row_number(self._h)

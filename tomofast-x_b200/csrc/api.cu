@@ -361,6 +361,31 @@ int tfx_sparse_matrix_from_arrays(tfx_matrix **out, int32_t nl, int32_t ncolumns
   return rc;
 }
 
+// normalize_columns (sparse_matrix.f90:414-443): column norms from the stored real(4) values squared in
+// real(4) (`this%sa(k)**2`), accumulated in real(8); values divided in real(8) and rounded back to real(4).
+// Host-side builder operation (the reference only calls it from its unit test); a finalized matrix is
+// re-mirrored to the device afterwards.
+int tfx_sparse_matrix_normalize_columns(tfx_matrix *h, double *column_norm) {
+  Matrix &m = h->m;
+  TFX_TRY(builder_guard(m));
+  if (!column_norm) return fail(-22, "normalize_columns: null column_norm");
+  for (int32_t j = 0; j < m.ncolumns; ++j) column_norm[j] = 0.0;
+  const int32_t ns = m.finalized ? m.nl_nonempty : m.nl_current;
+  const int64_t nel = m.finalized ? m.nel : m.nel_last;
+  (void)ns;
+  for (int64_t k = 0; k < nel; ++k) {
+    const float sq = m.sa[k] * m.sa[k];
+    column_norm[m.ija[k] - 1] += (double)sq;
+  }
+  for (int32_t j = 0; j < m.ncolumns; ++j) column_norm[j] = sqrt(column_norm[j]);
+  for (int64_t k = 0; k < nel; ++k) {
+    const double cn = column_norm[m.ija[k] - 1];
+    if (cn != 0.0) m.sa[k] = (float)((double)m.sa[k] / cn);
+  }
+  if (m.finalized) TFX_TRY(matrix_upload(m, true));
+  return 0;
+}
+
 int32_t tfx_sparse_matrix_get_total_row_number(const tfx_matrix *h) { return h->m.nl; }
 int32_t tfx_sparse_matrix_get_current_row_number(const tfx_matrix *h) { return h->m.nl_current_all; }
 int32_t tfx_sparse_matrix_get_ncolumns(const tfx_matrix *h) { return h->m.ncolumns; }
