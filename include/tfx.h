@@ -41,7 +41,9 @@ int         tfx_device_synchronize(void);
 uint64_t    tfx_launch_count(void);
 /* Options: "dense_detect" (1: finalize() turns an uncompressed CSR into the dense block);
  * "strict_order" (1: LSQR sums in the reference's sequential order -- slow parity mode);
- * "profile_sweeps" (1: CUDA events around every fused sweep launch). */
+ * "profile_sweeps" (1: CUDA events around every fused sweep launch);
+ * "t16_min_nnz" (matrices with at least this many entries get the T16 layouts; default 4194304);
+ * "t16_tile" (0: automatic tile size, else a power of two <= 16384 -- tests). */
 int         tfx_set_option(const char *name, int value);
 
 /* Memory helpers for callers that keep their vectors on the device (or in pinned host memory)
@@ -90,7 +92,8 @@ int64_t tfx_sparse_matrix_get_nnz(const tfx_matrix *m);                        /
 int tfx_sparse_matrix_from_arrays(tfx_matrix **m, int32_t nl, int32_t ncolumns, int32_t nl_nonempty,
                                   int64_t nel, const float *sa, const int32_t *ija, const int64_t *ijl,
                                   const int32_t *rowptr);
-/* 0: compressed-segment (CSR + CSR of the transpose); 1: dense column-major block. */
+/* 0: compressed-segment (CSR + CSR of the transpose); 1: dense column-major block;
+ * 2: T16 tiled layouts with 16-bit in-tile indices (big compressed matrices, option "t16_min_nnz"). */
 int tfx_sparse_matrix_storage_kind(const tfx_matrix *m);
 /* Copies the device-resident matrix back in the reference's CSR storage (for tests / file writers).
  * Pass NULL arrays to query sizes only. */

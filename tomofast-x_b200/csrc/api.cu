@@ -176,6 +176,22 @@ int matrix_upload(Matrix &m, bool allow_dense) {
     }
   }
   TFX_CUDA(cudaStreamSynchronize(ctx().stream));
+  if (!m.has_dense) TFX_TRY(matrix_build_t16(m));
+  return 0;
+}
+
+int matrix_build_t16(Matrix &m) {
+  m.has_t16 = false;
+  m.t16f.release(); m.t16t.release();
+  if (!m.has_seg || m.fwd.nnz < (int64_t)g_opt_t16_min_nnz) return 0;
+  cudaStream_t st = ctx().stream;
+  TFX_TRY(t16_build(m.fwd, m.t16f, st));
+  if (!m.t16f.valid) return 0;
+  TFX_TRY(t16_build(m.trn, m.t16t, st));
+  if (!m.t16t.valid) { m.t16f.release(); return 0; }
+  m.t16f.nout_total = m.nl;
+  m.t16t.nout_total = m.ncolumns;
+  m.has_t16 = true;
   return 0;
 }
 
@@ -217,6 +233,16 @@ int tfx_set_option(const char *name, int value) {
   }
   if (name && strcmp(name, "strict_order") == 0) {
     g_opt_strict_order = value;
+    return 0;
+  }
+  if (name && strcmp(name, "t16_min_nnz") == 0) {
+    g_opt_t16_min_nnz = value;
+    return 0;
+  }
+  if (name && strcmp(name, "t16_tile") == 0) {
+    if (value != 0 && (value < 2 || value > 16384 || (value & (value - 1)) != 0))
+      return fail(-4, "t16_tile must be 0 (automatic) or a power of two in [2, 16384]");
+    g_opt_t16_tile = value;
     return 0;
   }
   return fail(-4, std::string("unknown option: ") + (name ? name : "(null)"));
@@ -266,7 +292,8 @@ int tfx_sparse_matrix_reset(tfx_matrix *h) {
   m.sa.clear(); m.ija.clear();
   std::fill(m.ijl.begin(), m.ijl.end(), 0);
   std::fill(m.rowptr.begin(), m.rowptr.end(), 0);
-  m.finalized = false; m.has_seg = false; m.has_dense = false;
+  m.finalized = false; m.has_seg = false; m.has_dense = false; m.has_t16 = false;
+  m.t16f.release(); m.t16t.release();
   return 0;
 }
 
@@ -391,7 +418,7 @@ int32_t tfx_sparse_matrix_get_current_row_number(const tfx_matrix *h) { return h
 int32_t tfx_sparse_matrix_get_ncolumns(const tfx_matrix *h) { return h->m.ncolumns; }
 int64_t tfx_sparse_matrix_get_number_elements(const tfx_matrix *h) { return h->m.nel; }
 int64_t tfx_sparse_matrix_get_nnz(const tfx_matrix *h) { return h->m.nnz; }
-int tfx_sparse_matrix_storage_kind(const tfx_matrix *h) { return h->m.has_dense ? 1 : 0; }
+int tfx_sparse_matrix_storage_kind(const tfx_matrix *h) { return h->m.has_dense ? 1 : (h->m.has_t16 ? 2 : 0); }
 
 // Products. kind: 0 forward, 1 transposed.
 static int product(Matrix &m, const double *x, double *b, bool accumulate, bool transposed) {
@@ -402,7 +429,9 @@ static int product(Matrix &m, const double *x, double *b, bool accumulate, bool 
   VecIO vx, vb;
   TFX_TRY(vx.bind(const_cast<double *>(x), nin, true));
   TFX_TRY(vb.bind(b, nout, accumulate));
-  if (m.has_seg) {
+  if (m.has_t16) {
+    TFX_TRY(t16_spmv(transposed ? m.t16t : m.t16f, vx.dev, vb.dev, accumulate, 0, nullptr, st));
+  } else if (m.has_seg) {
     SegMatrix &s = transposed ? m.trn : m.fwd;
     TFX_TRY(seg_spmv(s, vx.dev, vb.dev, accumulate, 0, (int32_t)nout, 0, nullptr, st));
   } else if (m.has_dense) {
@@ -450,7 +479,14 @@ int tfx_sparse_matrix_part_mult_vector(tfx_matrix *h, int32_t nelements, const d
   VecIO vx, vb;
   TFX_TRY(vx.bind(const_cast<double *>(x), (size_t)nelements, true));
   TFX_TRY(vb.bind(b, (size_t)ndata, false));
-  if (m.has_seg) {
+  if (m.has_t16 && m.t16f.in0 >= param_shift && m.t16f.in0 - param_shift + m.t16f.nin <= nelements) {
+    // all rows through the F layout (x read at column - param_shift), then the requested window
+    DevBuf<double> full;
+    TFX_TRY(full.alloc((size_t)m.nl));
+    TFX_TRY(t16_spmv(m.t16f, vx.dev, full.p, false, param_shift, nullptr, st));
+    TFX_CUDA(cudaMemcpyAsync(vb.dev, full.p + (line_start - 1), (size_t)ndata * 8, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaStreamSynchronize(st));
+  } else if (m.has_seg) {
     TFX_TRY(seg_spmv(m.fwd, vx.dev, vb.dev, false, line_start - 1, line_end, param_shift, nullptr, st));
   } else if (m.has_dense) {
     // dense block covers rows [dense_row0, dense_row0 + nrows) and columns [col0, col0 + ncols):

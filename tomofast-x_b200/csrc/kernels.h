@@ -52,6 +52,40 @@ int seg_spmv(SegMatrix &m, const double *d_x, double *d_y, bool accumulate, int3
 // y += x (device vectors).
 int vec_add_inplace(double *y, const double *x, size_t n, cudaStream_t st);
 
+// ---- t16.cu -----------------------------------------------------------------------------------
+// Tiled layout with 16-bit in-tile indices (see t16.cu). One instance serves one product direction.
+enum T16Mode { T16_DIRECT = 0, T16_TILES = 1 };
+struct T16Matrix {
+  bool valid = false;
+  int64_t nnz = 0, nnz_padded = 0;
+  int32_t nout_total = 0;  // length of the output vector
+  int32_t out0 = 0, nseg = 0;      // outputs covered: [out0, out0 + nseg)
+  int32_t in0 = 0, nin = 0;        // gathered elements covered: [in0, in0 + nin)
+  int32_t tile = 0, ntiles = 0;
+  int32_t grid = 0;                // TILES: CTAs (== partial vectors)
+  T16Mode mode = T16_DIRECT;
+  DevBuf<float> val;               // [nnz_padded]
+  DevBuf<uint16_t> key;            // [nnz_padded]
+  DevBuf<int64_t> ptr;             // [ntiles * nseg + 1], tile-major
+  DevBuf<int32_t> cta_tile;        // TILES: [grid + 1]
+  DevBuf<double> partial;          // TILES: [grid][nseg]
+  void release() {
+    valid = false;
+    val.release(); key.release(); ptr.release(); cta_tile.release(); partial.release();
+    nnz = nnz_padded = 0; nseg = ntiles = 0;
+  }
+  int64_t bytes() const { return nnz_padded * 6 + ((int64_t)ntiles * nseg + 1) * 8; }
+};
+extern int g_opt_t16_min_nnz;
+extern int g_opt_t16_tile;
+// Builds the layout from a compressed-segment matrix (segments = outputs, idx = gathered index). Leaves
+// T.valid == false (and returns 0) when the source does not qualify (indices not strictly ascending).
+int t16_build(const SegMatrix &src, T16Matrix &T, cudaStream_t st);
+// y[out0 .. out0+nseg) (+)= A x ; when !accumulate the rest of y[0 .. nout_total) is zeroed.
+// Element g of the layout's gathered range is read from d_x[g - xshift].
+int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int32_t xshift, const int *d_done,
+             cudaStream_t st);
+
 // ---- dense.cu ---------------------------------------------------------------------------------
 // Uncompressed sensitivity block: column-major f32, column j at base + j*ld (ld % 4 == 0), rows
 // [0, nrows). No column indices are stored (columns are 1..N, sensitivity_gravmag.F90:288-295).

@@ -365,11 +365,13 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
       TFX_CUDA(cudaMemsetAsync(out, 0, ncol * 8, st));
       return dense_sweep(S->dense, DENSE_T_ONLY, u_d, nullptr, nullptr, out, nullptr, nullptr, nullptr, done, st);
     }
+    if (S->has_t16) return t16_spmv(S->t16t, u_d, out, false, 0, done, st);
     return seg_spmv(S->trn, u_d, out, false, 0, (int32_t)ncol, 0, done, st);
   };
   auto S_fwd = [&](const double *xin, double *out) -> int {     // out(nls) = S xin
     if (dense_ok)
       return dense_sweep(S->dense, DENSE_F_ONLY, nullptr, xin, nullptr, nullptr, nullptr, out, nullptr, done, st);
+    if (S->has_t16) return t16_spmv(S->t16f, xin, out, false, 0, done, st);
     return seg_spmv(S->fwd, xin, out, false, 0, nls, 0, done, st);
   };
 

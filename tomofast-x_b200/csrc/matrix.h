@@ -29,6 +29,8 @@ struct Matrix {
 
   SegMatrix fwd, trn;
   bool has_seg = false;
+  T16Matrix t16f, t16t;       // tiled 16-bit layouts of A (forward) and A^T (transposed), big matrices only
+  bool has_t16 = false;
   DenseCM dense;
   bool has_dense = false;
   int32_t dense_row0 = 0;     // 0-based global row of dense row 0
@@ -37,6 +39,8 @@ struct Matrix {
 };
 
 int matrix_upload(Matrix &m, bool allow_dense);
+// Builds the T16 layouts from fwd/trn when the matrix is big enough (option "t16_min_nnz").
+int matrix_build_t16(Matrix &m);
 
 // ---- lsqr.cu ----------------------------------------------------------------------------------
 struct LsqrParams {

@@ -348,6 +348,7 @@ extern "C" int tfx_calculate_sensit(tfx_matrix **out, const tfx_sensit_params *p
   TFX_TRY(seg_build_items(T, tptr.data()));
 
   M.has_seg = true;
+  TFX_TRY(matrix_build_t16(M));
   M.nnz = M.nel = nnz;
   M.nl_nonempty = F.nseg;
   M.finalized = true;
