@@ -39,6 +39,10 @@ int         tfx_finalize(void);
 int         tfx_device_synchronize(void);
 /* Number of GPU kernels launched by the library so far (bench.py's gpu_launches). */
 uint64_t    tfx_launch_count(void);
+/* CUDA-event stopwatch on the library stream: start records an event, stop records a second one, waits
+ * for it and returns the elapsed device time in milliseconds. */
+int         tfx_timer_start(void);
+int         tfx_timer_stop(double *ms);
 /* Options: "dense_detect" (1: finalize() turns an uncompressed CSR into the dense block);
  * "strict_order" (1: LSQR sums in the reference's sequential order -- slow parity mode);
  * "profile_sweeps" (1: CUDA events around every fused sweep launch);
@@ -95,6 +99,13 @@ int tfx_sparse_matrix_from_arrays(tfx_matrix **m, int32_t nl, int32_t ncolumns, 
 /* 0: compressed-segment (CSR + CSR of the transpose); 1: dense column-major block;
  * 2: T16 tiled layouts with 16-bit in-tile indices (big compressed matrices, option "t16_min_nnz"). */
 int tfx_sparse_matrix_storage_kind(const tfx_matrix *m);
+/* Mean device time (ms, CUDA events on the library stream) of `reps` back-to-back products b = A x
+ * (transposed = 0) or b = A^T x (1) on DEVICE-resident vectors: the SpMV GB/s figures of bench.py. */
+int tfx_sparse_matrix_time_product(tfx_matrix *m, int transposed, const double *x, double *b, int reps, double *ms);
+/* Device memory held by the matrix (all representations), bytes. */
+int64_t tfx_sparse_matrix_device_bytes(const tfx_matrix *m);
+/* Frees the generic CSR copies of a matrix that has the T16 layouts (export / strict_order unavailable after). */
+int tfx_sparse_matrix_drop_csr(tfx_matrix *m);
 /* Copies the device-resident matrix back in the reference's CSR storage (for tests / file writers).
  * Pass NULL arrays to query sizes only. */
 int tfx_sparse_matrix_export(tfx_matrix *m, int64_t *nel, int32_t *nl_nonempty, float *sa, int32_t *ija,

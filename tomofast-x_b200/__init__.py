@@ -80,6 +80,11 @@ def lib():
         getattr(L, "tfx_sparse_matrix_" + n).argtypes = [vp]
         getattr(L, "tfx_sparse_matrix_" + n).restype = i64
     L.tfx_sparse_matrix_normalize_columns.argtypes = [vp, vp]
+    L.tfx_sparse_matrix_time_product.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.POINTER(dbl)]
+    L.tfx_sparse_matrix_device_bytes.argtypes = [vp]
+    L.tfx_sparse_matrix_device_bytes.restype = i64
+    L.tfx_sparse_matrix_drop_csr.argtypes = [vp]
+    L.tfx_timer_stop.argtypes = [C.POINTER(dbl)]
     L.tfx_sparse_matrix_from_arrays.argtypes = [C.POINTER(vp), i32, i32, i32, i64, vp, vp, vp, vp]
     L.tfx_sparse_matrix_storage_kind.argtypes = [vp]
     L.tfx_sparse_matrix_export.argtypes = [vp, C.POINTER(i64), C.POINTER(i32), vp, vp, vp, vp]
@@ -115,6 +120,17 @@ def launch_count():
 
 def set_option(name, value):
     _check(lib().tfx_set_option(name.encode(), int(value)))
+
+
+def timer_start():
+    _check(lib().tfx_timer_start())
+
+
+def timer_stop():
+    """Elapsed device time (ms) on the library stream since timer_start()."""
+    ms = C.c_double(0.0)
+    _check(lib().tfx_timer_stop(C.byref(ms)))
+    return ms.value
 
 
 def synchronize():
@@ -263,6 +279,18 @@ class SparseMatrix:
 
     def get_nnz(self):
         return lib().tfx_sparse_matrix_get_nnz(self._h)
+
+    def time_product(self, transposed, x, b, reps=10):
+        """Mean device milliseconds of one product on device-resident vectors (CUDA events)."""
+        ms = C.c_double(0.0)
+        _check(lib().tfx_sparse_matrix_time_product(self._h, int(transposed), _ptr(x), _ptr(b), int(reps), C.byref(ms)))
+        return ms.value
+
+    def device_bytes(self):
+        return int(lib().tfx_sparse_matrix_device_bytes(self._h))
+
+    def drop_csr(self):
+        _check(lib().tfx_sparse_matrix_drop_csr(self._h))
 
     def storage_kind(self):
         return lib().tfx_sparse_matrix_storage_kind(self._h)

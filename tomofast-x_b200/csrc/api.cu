@@ -222,6 +222,42 @@ int tfx_device_synchronize(void) {
   return 0;
 }
 uint64_t tfx_launch_count(void) { return ctx().launches; }
+
+// CUDA-event stopwatch on the library stream (bench.py times kernels with it).
+static cudaEvent_t g_timer0 = nullptr, g_timer1 = nullptr;
+int tfx_timer_start(void) {
+  TFX_TRY(ensure_init());
+  if (!g_timer0) { TFX_CUDA(cudaEventCreate(&g_timer0)); TFX_CUDA(cudaEventCreate(&g_timer1)); }
+  TFX_CUDA(cudaEventRecord(g_timer0, ctx().stream));
+  return 0;
+}
+int tfx_timer_stop(double *ms) {
+  if (!g_timer0) return fail(-5, "tfx_timer_stop without tfx_timer_start");
+  TFX_CUDA(cudaEventRecord(g_timer1, ctx().stream));
+  TFX_CUDA(cudaEventSynchronize(g_timer1));
+  float t = 0.f;
+  TFX_CUDA(cudaEventElapsedTime(&t, g_timer0, g_timer1));
+  if (ms) *ms = t;
+  return 0;
+}
+// Bytes of device memory held by the matrix representations (values, indices, pointer tables).
+int64_t tfx_sparse_matrix_device_bytes(const tfx_matrix *h) {
+  const Matrix &m = h->m;
+  int64_t b = 0;
+  if (m.has_seg) b += (m.fwd.nnz + m.trn.nnz) * 8 + ((int64_t)m.fwd.nseg + m.trn.nseg) * 12;
+  if (m.has_t16) b += m.t16f.bytes() + m.t16t.bytes();
+  if (m.has_dense) b += (int64_t)m.dense.ld * m.dense.ncols * 4;
+  return b;
+}
+// Drops the generic CSR copies of a matrix that has the T16 layouts (frees 16 B/nnz); export() and the
+// strict_order mode are no longer available for it.
+int tfx_sparse_matrix_drop_csr(tfx_matrix *h) {
+  Matrix &m = h->m;
+  if (!m.has_t16) return fail(-24, "drop_csr: the matrix has no T16 layouts");
+  m.fwd.release(); m.trn.release();
+  m.has_seg = false;
+  return 0;
+}
 int tfx_set_option(const char *name, int value) {
   if (name && strcmp(name, "dense_detect") == 0) {
     g_opt_dense_detect = value;
@@ -458,6 +494,35 @@ static int product(Matrix &m, const double *x, double *b, bool accumulate, bool 
   }
   TFX_TRY(vb.copy_back());
   TFX_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// Times `reps` back-to-back products (device-resident vectors required) with CUDA events on the library
+// stream, without host synchronisation between launches; returns the mean milliseconds per product.
+int tfx_sparse_matrix_time_product(tfx_matrix *h, int transposed, const double *x, double *b, int reps, double *ms) {
+  Matrix &m = h->m;
+  TFX_TRY(ensure_init());
+  if (!m.finalized) return fail(-20, "sparse_matrix: product called before finalize()");
+  if (!is_device_ptr(x) || !is_device_ptr(b)) return fail(-25, "time_product: vectors must be device pointers");
+  if (reps < 1) reps = 1;
+  cudaStream_t st = ctx().stream;
+  cudaEvent_t e0, e1;
+  TFX_CUDA(cudaEventCreate(&e0)); TFX_CUDA(cudaEventCreate(&e1));
+  const int32_t nout = transposed ? m.ncolumns : m.nl;
+  auto once = [&]() -> int {
+    if (m.has_t16) return t16_spmv(transposed ? m.t16t : m.t16f, x, b, false, 0, nullptr, st);
+    if (m.has_seg) return seg_spmv(transposed ? m.trn : m.fwd, x, b, false, 0, nout, 0, nullptr, st);
+    return fail(-21, "time_product: needs a compressed representation");
+  };
+  TFX_TRY(once());
+  TFX_CUDA(cudaEventRecord(e0, st));
+  for (int r = 0; r < reps; ++r) TFX_TRY(once());
+  TFX_CUDA(cudaEventRecord(e1, st));
+  TFX_CUDA(cudaEventSynchronize(e1));
+  float t = 0.f;
+  TFX_CUDA(cudaEventElapsedTime(&t, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (ms) *ms = (double)t / reps;
   return 0;
 }
 

@@ -36,6 +36,11 @@ struct SegMatrix {
   DevBuf<int32_t> seg_item0;   // [nseg+1] first item of each segment
   DevBuf<double> partial;      // [nitems]
   bool empty() const { return nnz == 0 || nseg == 0; }
+  void release() {
+    ptr.release(); idx.release(); val.release(); segmap.release(); item_seg.release(); item_beg.release();
+    item_end.release(); seg_item0.release(); partial.release();
+    nnz = 0; nseg = 0; nitems = 0;
+  }
 };
 
 static const int kItemLen = 8192;
@@ -62,19 +67,19 @@ struct T16Matrix {
   int32_t out0 = 0, nseg = 0;      // outputs covered: [out0, out0 + nseg)
   int32_t in0 = 0, nin = 0;        // gathered elements covered: [in0, in0 + nin)
   int32_t tile = 0, ntiles = 0;
-  int32_t grid = 0;                // TILES: CTAs (== partial vectors)
+  int32_t nsplit = 1;              // TILES: work items per tile
   T16Mode mode = T16_DIRECT;
   DevBuf<float> val;               // [nnz_padded]
   DevBuf<uint16_t> key;            // [nnz_padded]
   DevBuf<int64_t> ptr;             // [ntiles * nseg + 1], tile-major
-  DevBuf<int32_t> cta_tile;        // TILES: [grid + 1]
-  DevBuf<double> partial;          // TILES: [grid][nseg]
+  DevBuf<double> partial;          // TILES: [ntiles][nseg], written once per product
+  DevBuf<int> counter;             // dynamic work distribution
   void release() {
     valid = false;
-    val.release(); key.release(); ptr.release(); cta_tile.release(); partial.release();
+    val.release(); key.release(); ptr.release(); partial.release();
     nnz = nnz_padded = 0; nseg = ntiles = 0;
   }
-  int64_t bytes() const { return nnz_padded * 6 + ((int64_t)ntiles * nseg + 1) * 8; }
+  int64_t bytes() const { return nnz_padded * 6 + ((int64_t)ntiles * nseg + 1) * 8 + (int64_t)partial.n * 8; }
 };
 extern int g_opt_t16_min_nnz;
 extern int g_opt_t16_tile;

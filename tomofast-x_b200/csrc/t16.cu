@@ -35,9 +35,11 @@ namespace tfx {
 int g_opt_t16_min_nnz = 1 << 22;   // matrices with fewer entries stay on the generic CSR kernels
 int g_opt_t16_tile = 0;            // 0: automatic; otherwise forced tile size (power of two <= 16384), tests
 
-static const int kT16Threads = 1024;
+static const int kT16Threads = 768;
 static const int kT16MaxTile = 16384;
-static const int kShortSeg = 24;   // all 32 segments of a block <= this many entries -> one segment per lane
+static const int kLongSeg = 256;    // longer segments are summed by the whole warp, one at a time
+static const int kFlatMax = 1024;   // entries per flat run (512 packet products = 4 KB of shared memory per warp)
+static const int kDirectChunk = 1;  // DIRECT: blocks of 32 outputs a warp draws at a time
 
 struct T16Args {
   const float *val;
@@ -45,70 +47,120 @@ struct T16Args {
   const int64_t *ptr;      // [ntiles * nseg + 1]
   const double *x;         // gathered vector, already shifted: element g of the layout is x[g]
   double *y;               // DIRECT: output vector (offset applied: y[o] is output o of the layout)
-  double *partial;         // TILES: [grid][nseg]
-  const int32_t *cta_tile; // TILES: [grid + 1]
+  double *partial;         // TILES: [ntiles][nseg], every element written exactly once per product
+  int *counter;            // dynamic work distribution (results do not depend on it: write-once outputs)
   int32_t nseg, tile, ntiles, nin;   // nin: number of valid gathered elements (in0-relative)
+  int32_t nsplit;          // TILES: work items per tile
   int32_t t0;              // DIRECT: the tile to process
   int accumulate;          // DIRECT: y += instead of y =
   const int *done;
 };
 
-// Sum over one segment [beg, end) (even bounds) with the whole warp; all lanes return the total.
-__device__ __forceinline__ double t16_warp_segment(const float *__restrict__ val, const uint16_t *__restrict__ key,
-                                                   const double *xs, int64_t beg, int64_t end, int lane) {
+// Lane-partial sum over the rest of a long segment: entries [k0 + 2*lane + 64*i, end), 8 packets in flight.
+__device__ __forceinline__ double t16_long_partial(const float *__restrict__ val, const uint16_t *__restrict__ key,
+                                                   const double *xs, int k, int end) {
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
-  int64_t k = beg + 2 * lane;
-  for (; k + 192 < end; k += 256) {
-    const float2 v0 = __ldg((const float2 *)(val + k));
-    const float2 v1 = __ldg((const float2 *)(val + k + 64));
-    const float2 v2 = __ldg((const float2 *)(val + k + 128));
-    const float2 v3 = __ldg((const float2 *)(val + k + 192));
-    const uint32_t k0 = __ldg((const uint32_t *)(key + k));
-    const uint32_t k1 = __ldg((const uint32_t *)(key + k + 64));
-    const uint32_t k2 = __ldg((const uint32_t *)(key + k + 128));
-    const uint32_t k3 = __ldg((const uint32_t *)(key + k + 192));
-    a0 = fma((double)v0.x, xs[k0 & 0xffffu], a0);
-    a1 = fma((double)v0.y, xs[k0 >> 16], a1);
-    a2 = fma((double)v1.x, xs[k1 & 0xffffu], a2);
-    a3 = fma((double)v1.y, xs[k1 >> 16], a3);
-    a4 = fma((double)v2.x, xs[k2 & 0xffffu], a4);
-    a5 = fma((double)v2.y, xs[k2 >> 16], a5);
-    a6 = fma((double)v3.x, xs[k3 & 0xffffu], a6);
-    a7 = fma((double)v3.y, xs[k3 >> 16], a7);
+  for (; k + 448 < end; k += 512) {
+    float2 v[8];
+    uint32_t kk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = __ldg((const float2 *)(val + k + 64 * i));
+      kk[i] = __ldg((const uint32_t *)(key + k + 64 * i));
+    }
+    a0 = fma((double)v[0].x, xs[kk[0] & 0xffffu], a0); a0 = fma((double)v[0].y, xs[kk[0] >> 16], a0);
+    a1 = fma((double)v[1].x, xs[kk[1] & 0xffffu], a1); a1 = fma((double)v[1].y, xs[kk[1] >> 16], a1);
+    a2 = fma((double)v[2].x, xs[kk[2] & 0xffffu], a2); a2 = fma((double)v[2].y, xs[kk[2] >> 16], a2);
+    a3 = fma((double)v[3].x, xs[kk[3] & 0xffffu], a3); a3 = fma((double)v[3].y, xs[kk[3] >> 16], a3);
+    a4 = fma((double)v[4].x, xs[kk[4] & 0xffffu], a4); a4 = fma((double)v[4].y, xs[kk[4] >> 16], a4);
+    a5 = fma((double)v[5].x, xs[kk[5] & 0xffffu], a5); a5 = fma((double)v[5].y, xs[kk[5] >> 16], a5);
+    a6 = fma((double)v[6].x, xs[kk[6] & 0xffffu], a6); a6 = fma((double)v[6].y, xs[kk[6] >> 16], a6);
+    a7 = fma((double)v[7].x, xs[kk[7] & 0xffffu], a7); a7 = fma((double)v[7].y, xs[kk[7] >> 16], a7);
   }
-  for (; k < end; k += 64) {
-    const float2 v0 = __ldg((const float2 *)(val + k));
-    const uint32_t k0 = __ldg((const uint32_t *)(key + k));
-    a0 = fma((double)v0.x, xs[k0 & 0xffffu], a0);
-    a1 = fma((double)v0.y, xs[k0 >> 16], a1);
+  if (k < end) {   // tail: up to 8 predicated packets, all in flight together
+    float2 v[8];
+    uint32_t kk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool in = k + 64 * i < end;
+      v[i] = in ? __ldg((const float2 *)(val + k + 64 * i)) : make_float2(0.f, 0.f);
+      kk[i] = in ? __ldg((const uint32_t *)(key + k + 64 * i)) : 0u;
+    }
+    a0 = fma((double)v[0].x, xs[kk[0] & 0xffffu], a0); a0 = fma((double)v[0].y, xs[kk[0] >> 16], a0);
+    a1 = fma((double)v[1].x, xs[kk[1] & 0xffffu], a1); a1 = fma((double)v[1].y, xs[kk[1] >> 16], a1);
+    a2 = fma((double)v[2].x, xs[kk[2] & 0xffffu], a2); a2 = fma((double)v[2].y, xs[kk[2] >> 16], a2);
+    a3 = fma((double)v[3].x, xs[kk[3] & 0xffffu], a3); a3 = fma((double)v[3].y, xs[kk[3] >> 16], a3);
+    a4 = fma((double)v[4].x, xs[kk[4] & 0xffffu], a4); a4 = fma((double)v[4].y, xs[kk[4] >> 16], a4);
+    a5 = fma((double)v[5].x, xs[kk[5] & 0xffffu], a5); a5 = fma((double)v[5].y, xs[kk[5] >> 16], a5);
+    a6 = fma((double)v[6].x, xs[kk[6] & 0xffffu], a6); a6 = fma((double)v[6].y, xs[kk[6] >> 16], a6);
+    a7 = fma((double)v[7].x, xs[kk[7] & 0xffffu], a7); a7 = fma((double)v[7].y, xs[kk[7] >> 16], a7);
   }
-  return warp_sum(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
+  return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
 // 32 consecutive outputs [o0, o0 + 32) of tile t: lane j returns the sum of segment o0 + j.
-__device__ __forceinline__ double t16_block32(const T16Args &a, const double *xs, int64_t tbase, int o0, int lane) {
+//  * segments longer than kLongSeg entries: one at a time with the whole warp (t16_long_partial);
+//  * all others: FLAT -- maximal runs of consecutive segments spanning <= kFlatMax entries are streamed as
+//    one contiguous range (every lane loads packets, all loads independent and coalesced), the packet
+//    products are parked in the warp's shared-memory strip and every lane then adds up its own segment.
+__device__ __forceinline__ double t16_block32(const T16Args &a, const double *xs, double *wbuf, int64_t tbase, int o0,
+                                              int lane) {
   const int o = o0 + lane;
-  const int64_t pb = (o <= a.nseg) ? __ldg(a.ptr + tbase + o) : 0;
+  // lanes past the last output read the end pointer: empty segments, offsets stay monotone
+  const int64_t pb = __ldg(a.ptr + tbase + min(o, a.nseg));
   int64_t pe = __shfl_down_sync(0xffffffffu, pb, 1);
-  if (lane == 31) pe = (o + 1 <= a.nseg) ? __ldg(a.ptr + tbase + o + 1) : 0;
-  const int64_t len = (o < a.nseg) ? (pe - pb) : 0;
-  int maxlen = (int)min(len, (int64_t)0x7fffffff);
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, s));
+  if (lane == 31) pe = __ldg(a.ptr + tbase + min(o + 1, a.nseg));
+  const int64_t pb0 = __shfl_sync(0xffffffffu, pb, 0);
+  const int len = (int)(pe - pb);                              // a segment never exceeds the tile size
+  const int rel = (int)(pb - pb0);                             // 32 segments span < 2^31 entries
   double result = 0.0;
-  if (maxlen == 0) return result;
-  if (maxlen <= kShortSeg) {
-    // one segment per lane, sequential (the 32 segments are adjacent in memory: L1-friendly)
-    for (int64_t k = pb; k < pb + len; ++k)
-      result = fma((double)__ldg(a.val + k), xs[__ldg(a.key + k)], result);
-    return result;
-  }
-  for (int j = 0; j < 32; ++j) {
-    const int64_t b = __shfl_sync(0xffffffffu, pb, j);
-    const int64_t l = __shfl_sync(0xffffffffu, len, j);
-    if (l == 0) continue;
-    const double s = t16_warp_segment(a.val, a.key, xs, b, b + l, lane);
+  if (__ballot_sync(0xffffffffu, len > 0) == 0u) return result;
+  const float *__restrict__ val = a.val + pb0;                 // pb0 is even: 8-byte aligned packets
+  const uint16_t *__restrict__ key = a.key + pb0;
+  const bool is_long = len > kLongSeg;
+  unsigned longmask = __ballot_sync(0xffffffffu, is_long);
+  const unsigned flatmask = ~longmask;
+  while (longmask) {
+    const int j = __ffs(longmask) - 1;
+    longmask &= longmask - 1;
+    const int r = __shfl_sync(0xffffffffu, rel, j);
+    const int l = __shfl_sync(0xffffffffu, len, j);
+    const double s = warp_sum(t16_long_partial(val, key, xs, r + 2 * lane, r + l));
     if (lane == j) result = s;
+  }
+  int j0 = 0;
+  while (j0 < 32) {
+    if (!((flatmask >> j0) & 1u)) { ++j0; continue; }
+    const int start = __shfl_sync(0xffffffffu, rel, j0);
+    const bool fits = !is_long && lane >= j0 && (rel + len - start) <= kFlatMax;
+    const unsigned fm = __ballot_sync(0xffffffffu, fits) >> j0;      // bit 0 is set: a flat segment always fits
+    const int cnt = (fm == 0xffffffffu) ? 32 : (__ffs(~fm) - 1);       // consecutive segments in this run
+    const int j1 = j0 + cnt;
+    const int endrel = __shfl_sync(0xffffffffu, rel + len, j1 - 1);
+    const int npk = (endrel - start) >> 1;
+    for (int p = lane; p < npk; p += 256) {
+      float2 v[8];
+      uint32_t kk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool in = p + 32 * i < npk;
+        v[i] = in ? __ldg((const float2 *)(val + start + 2 * (p + 32 * i))) : make_float2(0.f, 0.f);
+        kk[i] = in ? __ldg((const uint32_t *)(key + start + 2 * (p + 32 * i))) : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (p + 32 * i < npk)
+          wbuf[p + 32 * i] = fma((double)v[i].y, xs[kk[i] >> 16], (double)v[i].x * xs[kk[i] & 0xffffu]);
+    }
+    __syncwarp();
+    if (lane >= j0 && lane < j1) {
+      double s = 0.0;
+      const int q0 = (rel - start) >> 1, q1 = (rel + len - start) >> 1;
+      for (int q = q0; q < q1; ++q) s += wbuf[q];
+      result = s;
+    }
+    __syncwarp();
+    j0 = j1;
   }
   return result;
 }
@@ -121,53 +173,89 @@ __device__ __forceinline__ void t16_load_tile(const T16Args &a, double *xs, int 
   }
 }
 
+// DIRECT: one tile; every warp draws kDirectChunk blocks of 32 outputs at a time from a global counter
+// (the nonzeros are concentrated in the shallow cells, i.e. in a few column ranges: static splits starve).
 __global__ void __launch_bounds__(kT16Threads, 1) t16_direct_kernel(T16Args a) {
   if (a.done && *a.done) return;
   extern __shared__ __align__(16) double xs[];
   t16_load_tile(a, xs, a.t0);
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int nwarps = gridDim.x * (kT16Threads / 32);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double *wbuf = xs + a.tile + wid * (kFlatMax / 2);
   const int64_t tbase = (int64_t)a.t0 * a.nseg;
   const int nblk = (a.nseg + 31) / 32;
-  for (int blk = blockIdx.x * (kT16Threads / 32) + (threadIdx.x >> 5); blk < nblk; blk += nwarps) {
-    const double r = t16_block32(a, xs, tbase, blk * 32, lane);
-    const int o = blk * 32 + lane;
-    if (o < a.nseg) a.y[o] = a.accumulate ? (a.y[o] + r) : r;
+  __syncthreads();
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(a.counter, kDirectChunk);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= nblk) break;
+    const int b_hi = min(nblk, base + kDirectChunk);
+    for (int blk = base; blk < b_hi; ++blk) {
+      const double r = t16_block32(a, xs, wbuf, tbase, blk * 32, lane);
+      const int o = blk * 32 + lane;
+      if (o < a.nseg) a.y[o] = a.accumulate ? (a.y[o] + r) : r;
+    }
   }
 }
 
+// TILES: a CTA parks on a tile (gathered slice in shared memory) and its warps draw blocks of 32 outputs from
+// that tile's counter; CTAs start on evenly spread tiles and walk forward, skipping exhausted tiles, so heavy
+// (dense, shallow-depth) tiles are finished by several CTAs together. partial[tile][output] is written exactly
+// once per product, hence the result does not depend on who computed what.
 __global__ void __launch_bounds__(kT16Threads, 1) t16_tiles_kernel(T16Args a) {
   if (a.done && *a.done) return;
   extern __shared__ __align__(16) double xs[];
+  __shared__ int s_next;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double *wbuf = xs + a.tile + wid * (kFlatMax / 2);
   const int nblk = (a.nseg + 31) / 32;
-  double *mine = a.partial + (int64_t)blockIdx.x * a.nseg;
-  const int t_lo = a.cta_tile[blockIdx.x], t_hi = a.cta_tile[blockIdx.x + 1];
-  if (t_lo >= t_hi) {   // idle CTA: its partial vector must still read as zero
-    for (int o = threadIdx.x; o < a.nseg; o += blockDim.x) mine[o] = 0.0;
-    return;
-  }
-  for (int t = t_lo; t < t_hi; ++t) {
+  const int start = (int)((int64_t)blockIdx.x * a.ntiles / gridDim.x);
+  int i = 0;   // tiles visited so far (relative to start)
+  for (;;) {
+    __syncthreads();   // everybody is done with xs and s_next
+    if (wid == 0) {    // find the next tile that still has undrawn blocks, 32 candidates at a time
+      int found = a.ntiles;
+      for (int base = i; base < a.ntiles && found == a.ntiles; base += 32) {
+        const int c = base + lane;
+        bool open = false;
+        if (c < a.ntiles) {
+          int t = start + c;
+          if (t >= a.ntiles) t -= a.ntiles;
+          open = *((volatile int *)(a.counter + t)) < nblk;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, open);
+        if (m) found = base + __ffs(m) - 1;
+      }
+      if (lane == 0) s_next = found;
+    }
+    __syncthreads();
+    i = s_next;
+    if (i >= a.ntiles) break;
+    int t = start + i;
+    if (t >= a.ntiles) t -= a.ntiles;
     t16_load_tile(a, xs, t);
     __syncthreads();
     const int64_t tbase = (int64_t)t * a.nseg;
-    for (int blk = wid; blk < nblk; blk += kT16Threads / 32) {
-      const double r = t16_block32(a, xs, tbase, blk * 32, lane);
+    for (;;) {
+      int blk = 0;
+      if (lane == 0) blk = atomicAdd(a.counter + t, 1);
+      blk = __shfl_sync(0xffffffffu, blk, 0);
+      if (blk >= nblk) break;
+      const double r = t16_block32(a, xs, wbuf, tbase, blk * 32, lane);
       const int o = blk * 32 + lane;
-      if (o < a.nseg) mine[o] = (t == t_lo) ? r : (mine[o] + r);
+      if (o < a.nseg) a.partial[tbase + o] = r;
     }
-    __syncthreads();
+    ++i;
   }
 }
 
-// y[o] (+)= sum_b partial[b][o], b ascending.
-__global__ void __launch_bounds__(256) t16_reduce_kernel(const double *__restrict__ partial, int nblocks, int nseg,
+// y[o] (+)= sum_t partial[t][o], t ascending.
+__global__ void __launch_bounds__(256) t16_reduce_kernel(const double *__restrict__ partial, int ntiles, int nseg,
                                                          double *__restrict__ y, int accumulate, const int *done) {
   if (done && *done) return;
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < nseg; o += gridDim.x * blockDim.x) {
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * nseg + o];
+    for (int t = 0; t < ntiles; ++t) s += partial[(int64_t)t * nseg + o];
     y[o] = accumulate ? (y[o] + s) : s;
   }
 }
@@ -200,34 +288,38 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
   a.val = m.val.p; a.key = m.key.p; a.ptr = m.ptr.p;
   a.x = d_x + m.in0 - xshift;
   a.y = d_y + m.out0;
-  a.partial = m.partial.p; a.cta_tile = m.cta_tile.p;
-  a.nseg = m.nseg; a.tile = m.tile; a.ntiles = m.ntiles; a.nin = m.nin;
+  a.partial = m.partial.p; a.counter = m.counter.p;
+  a.nseg = m.nseg; a.tile = m.tile; a.ntiles = m.ntiles; a.nin = m.nin; a.nsplit = m.nsplit;
   a.t0 = 0; a.accumulate = accumulate ? 1 : 0; a.done = d_done;
-  const size_t smem = (size_t)m.tile * sizeof(double);
+  const size_t smem = ((size_t)m.tile + (size_t)(kT16Threads / 32) * (kFlatMax / 2)) * sizeof(double);
+  const int nblk = (m.nseg + 31) / 32;
   if (m.mode == T16_DIRECT) {
     static bool attr = false;
     if (!attr) {
-      TFX_CUDA(cudaFuncSetAttribute(t16_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT16MaxTile * 8));
+      TFX_CUDA(cudaFuncSetAttribute(t16_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kT16MaxTile + (kT16Threads / 32) * (kFlatMax / 2)) * 8));
       attr = true;
     }
-    const int nblk = (m.nseg + 31) / 32;
-    const int grid = std::max(1, std::min(c.num_sms, (nblk + 31) / 32));
+    const int nitems = (nblk + kDirectChunk - 1) / kDirectChunk;
+    const int grid = std::max(1, std::min(c.num_sms, (nitems + kT16Threads / 32 - 1) / (kT16Threads / 32)));
     for (int t = 0; t < m.ntiles; ++t) {
       a.t0 = t;
       a.accumulate = (accumulate || t > 0) ? 1 : 0;
+      TFX_CUDA(cudaMemsetAsync(m.counter.p, 0, sizeof(int), st));
       t16_direct_kernel<<<grid, kT16Threads, smem, st>>>(a);
       c.launches++;
     }
   } else {
     static bool attr = false;
     if (!attr) {
-      TFX_CUDA(cudaFuncSetAttribute(t16_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT16MaxTile * 8));
+      TFX_CUDA(cudaFuncSetAttribute(t16_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kT16MaxTile + (kT16Threads / 32) * (kFlatMax / 2)) * 8));
       attr = true;
     }
-    t16_tiles_kernel<<<m.grid, kT16Threads, smem, st>>>(a);
+    const int grid = std::max(1, std::min(c.num_sms, m.ntiles));
+    TFX_CUDA(cudaMemsetAsync(m.counter.p, 0, sizeof(int) * (size_t)m.ntiles, st));
+    t16_tiles_kernel<<<grid, kT16Threads, smem, st>>>(a);
     c.launches++;
     const int blocks = std::max(1, std::min((m.nseg + 255) / 256, c.num_sms * 8));
-    t16_reduce_kernel<<<blocks, 256, 0, st>>>(m.partial.p, m.grid, m.nseg, a.y, accumulate ? 1 : 0, d_done);
+    t16_reduce_kernel<<<blocks, 256, 0, st>>>(m.partial.p, m.ntiles, m.nseg, a.y, accumulate ? 1 : 0, d_done);
     c.launches++;
   }
   TFX_CUDA(cudaGetLastError());
@@ -321,17 +413,6 @@ __global__ void __launch_bounds__(256) t16_fill_kernel(const int64_t *__restrict
   }
 }
 
-__global__ void t16_tilebase_kernel(const int64_t *__restrict__ tptr, int nseg, int ntiles, int64_t *__restrict__ out) {
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= ntiles; t += gridDim.x * blockDim.x)
-    out[t] = tptr[(int64_t)t * nseg];
-}
-
-int pow2_floor(int64_t v) {
-  int p = 1;
-  while ((int64_t)p * 2 <= v) p *= 2;
-  return p;
-}
-
 }  // namespace
 
 int t16_build(const SegMatrix &src, T16Matrix &T, cudaStream_t st) {
@@ -360,22 +441,23 @@ int t16_build(const SegMatrix &src, T16Matrix &T, cudaStream_t st) {
   T.in0 = h_mm[0];
   T.nin = h_mm[1] - h_mm[0] + 1;
   T.nnz = src.nnz;
-  // ---- tile size and mode
+  // ---- tile size and mode: the largest tile that fits shared memory gives the longest segments
   int tile;
   if (g_opt_t16_tile > 0) {
     tile = g_opt_t16_tile;
   } else if (T.nin <= kT16MaxTile) {
-    tile = T.nin;                                  // one tile: DIRECT
+    tile = T.nin;
   } else {
-    // many tiles: enough of them to balance the CTAs, segments as long as possible otherwise
-    tile = std::max(1024, std::min(kT16MaxTile, pow2_floor(T.nin / (16 * (int64_t)c.num_sms))));
+    // many tiles: the largest tile (longest segments) that still leaves a few tiles per SM
+    tile = kT16MaxTile;
+    while (tile > 2048 && (T.nin + tile - 1) / tile < 2 * c.num_sms) tile >>= 1;
   }
   tile = std::max(2, std::min(tile, kT16MaxTile));
   T.tile = tile;
   T.ntiles = (T.nin + tile - 1) / tile;
   const int64_t table = (int64_t)T.nseg * T.ntiles;
-  // TILES needs a CTA-private partial vector per CTA; DIRECT (tile after tile) is used when the output
-  // side is the long one.
+  // TILES keeps one partial per (tile, output); DIRECT (tile after tile) is used when the output side is
+  // the long one.
   T.mode = (T.ntiles == 1 || (int64_t)T.nseg > (int64_t)1 << 18) ? T16_DIRECT : T16_TILES;
   if (table > ((int64_t)1 << 31)) return 0;        // pointer table would exceed 16 GiB: keep the generic kernels
 
@@ -408,33 +490,10 @@ int t16_build(const SegMatrix &src, T16Matrix &T, cudaStream_t st) {
   t16_fill_kernel<<<fgrid, 256, 0, st>>>(src.ptr.p, src.idx.p, src.val.p, segof.p, T.nseg, T.ntiles, tile, T.in0, T.ptr.p,
                                          T.val.p, T.key.p);
   c.launches++;
-  // ---- TILES schedule: contiguous tile ranges per CTA, balanced by entries (+ a per-tile overhead)
-  if (T.mode == T16_TILES) {
-    DevBuf<int64_t> tb;
-    TFX_TRY(tb.alloc((size_t)T.ntiles + 1));
-    t16_tilebase_kernel<<<std::max(1, std::min(64, (T.ntiles + 256) / 256)), 256, 0, st>>>(T.ptr.p, T.nseg, T.ntiles, tb.p);
-    c.launches++;
-    std::vector<int64_t> h_tb((size_t)T.ntiles + 1);
-    TFX_CUDA(cudaMemcpyAsync(h_tb.data(), tb.p, h_tb.size() * 8, cudaMemcpyDeviceToHost, st));
-    TFX_CUDA(cudaStreamSynchronize(st));
-    T.grid = std::min(c.num_sms, T.ntiles);
-    const double overhead = 4.0 * T.nseg + 2.0 * tile;     // pointer reads + tile load, in entry units
-    std::vector<double> cost((size_t)T.ntiles + 1, 0.0);
-    for (int t = 0; t < T.ntiles; ++t) cost[t + 1] = cost[t] + (double)(h_tb[t + 1] - h_tb[t]) + overhead;
-    std::vector<int32_t> ct((size_t)T.grid + 1, 0);
-    int t = 0;
-    for (int b = 1; b < T.grid; ++b) {
-      const double target = cost[T.ntiles] * b / T.grid;
-      while (t < T.ntiles && cost[t + 1] <= target) ++t;
-      // leave at least one tile for every remaining CTA only when there are enough tiles
-      ct[b] = std::max(ct[b - 1], std::min(t, T.ntiles));
-    }
-    ct[T.grid] = T.ntiles;
-    TFX_TRY(T.cta_tile.alloc(ct.size()));
-    TFX_CUDA(cudaMemcpyAsync(T.cta_tile.p, ct.data(), ct.size() * 4, cudaMemcpyHostToDevice, st));
-    TFX_TRY(T.partial.alloc((size_t)T.grid * T.nseg));
-    TFX_CUDA(cudaStreamSynchronize(st));
-  }
+  // ---- work distribution: one counter per tile (TILES) / one counter (DIRECT)
+  TFX_TRY(T.counter.alloc((size_t)T.ntiles + 1));
+  T.nsplit = 1;
+  if (T.mode == T16_TILES) TFX_TRY(T.partial.alloc((size_t)table));
   TFX_CUDA(cudaStreamSynchronize(st));
   TFX_CUDA(cudaGetLastError());
   T.valid = true;
