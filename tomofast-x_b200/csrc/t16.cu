@@ -35,11 +35,19 @@ namespace tfx {
 int g_opt_t16_min_nnz = 1 << 22;   // matrices with fewer entries stay on the generic CSR kernels
 int g_opt_t16_tile = 0;            // 0: automatic; otherwise forced tile size (power of two <= 16384), tests
 
-static const int kT16Threads = 768;
+static const int kT16Threads = 768;      // DIRECT: one CTA per SM
+static const int kT16TilesThreads = 384; // TILES: two CTAs per SM (barrier / tile-load waits of one overlap the other)
+static const int kT16TilesMaxTile = 8192;
 static const int kT16MaxTile = 16384;
 static const int kLongSeg = 256;    // longer segments are summed by the whole warp, one at a time
 static const int kFlatMax = 1024;   // entries per flat run (512 packet products = 4 KB of shared memory per warp)
 static const int kDirectChunk = 1;  // DIRECT: blocks of 32 outputs a warp draws at a time
+
+// Shared-memory placement of gathered element i of a tile. Wavelet coefficients of level l sit at indices
+// = 2^(l-1) mod 2^l (interleaved lifting layout), so the gathers of one segment hit power-of-two strides:
+// folding the higher index nibbles into the low one spreads them over the 16 eight-byte bank pairs.
+// The keys stored in the matrix are already swizzled (builder), only the tile load pays for it.
+__host__ __device__ __forceinline__ uint32_t t16_swz(uint32_t i) { return i ^ (((i >> 4) ^ (i >> 8) ^ (i >> 12)) & 15u); }
 
 struct T16Args {
   const float *val;
@@ -167,9 +175,10 @@ __device__ __forceinline__ double t16_block32(const T16Args &a, const double *xs
 
 __device__ __forceinline__ void t16_load_tile(const T16Args &a, double *xs, int t) {
   const int base = t * a.tile;
-  for (int i = threadIdx.x; i < a.tile; i += blockDim.x) {
+  const int padded = (a.tile + 15) & ~15;
+  for (int i = threadIdx.x; i < padded; i += blockDim.x) {
     const int g = base + i;
-    xs[i] = (g < a.nin) ? a.x[g] : 0.0;
+    xs[t16_swz((uint32_t)i)] = (i < a.tile && g < a.nin) ? a.x[g] : 0.0;
   }
 }
 
@@ -180,7 +189,7 @@ __global__ void __launch_bounds__(kT16Threads, 1) t16_direct_kernel(T16Args a) {
   extern __shared__ __align__(16) double xs[];
   t16_load_tile(a, xs, a.t0);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double *wbuf = xs + a.tile + wid * (kFlatMax / 2);
+  double *wbuf = xs + ((a.tile + 15) & ~15) + wid * (kFlatMax / 2);
   const int64_t tbase = (int64_t)a.t0 * a.nseg;
   const int nblk = (a.nseg + 31) / 32;
   __syncthreads();
@@ -202,12 +211,12 @@ __global__ void __launch_bounds__(kT16Threads, 1) t16_direct_kernel(T16Args a) {
 // that tile's counter; CTAs start on evenly spread tiles and walk forward, skipping exhausted tiles, so heavy
 // (dense, shallow-depth) tiles are finished by several CTAs together. partial[tile][output] is written exactly
 // once per product, hence the result does not depend on who computed what.
-__global__ void __launch_bounds__(kT16Threads, 1) t16_tiles_kernel(T16Args a) {
+__global__ void __launch_bounds__(kT16TilesThreads, 2) t16_tiles_kernel(T16Args a) {
   if (a.done && *a.done) return;
   extern __shared__ __align__(16) double xs[];
   __shared__ int s_next;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double *wbuf = xs + a.tile + wid * (kFlatMax / 2);
+  double *wbuf = xs + ((a.tile + 15) & ~15) + wid * (kFlatMax / 2);
   const int nblk = (a.nseg + 31) / 32;
   const int start = (int)((int64_t)blockIdx.x * a.ntiles / gridDim.x);
   int i = 0;   // tiles visited so far (relative to start)
@@ -291,12 +300,13 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
   a.partial = m.partial.p; a.counter = m.counter.p;
   a.nseg = m.nseg; a.tile = m.tile; a.ntiles = m.ntiles; a.nin = m.nin; a.nsplit = m.nsplit;
   a.t0 = 0; a.accumulate = accumulate ? 1 : 0; a.done = d_done;
-  const size_t smem = ((size_t)m.tile + (size_t)(kT16Threads / 32) * (kFlatMax / 2)) * sizeof(double);
   const int nblk = (m.nseg + 31) / 32;
   if (m.mode == T16_DIRECT) {
+    const size_t smem = ((size_t)((m.tile + 15) & ~15) + (size_t)(kT16Threads / 32) * (kFlatMax / 2)) * sizeof(double);
     static bool attr = false;
     if (!attr) {
-      TFX_CUDA(cudaFuncSetAttribute(t16_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kT16MaxTile + (kT16Threads / 32) * (kFlatMax / 2)) * 8));
+      TFX_CUDA(cudaFuncSetAttribute(t16_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (kT16MaxTile + (kT16Threads / 32) * (kFlatMax / 2)) * 8));
       attr = true;
     }
     const int nitems = (nblk + kDirectChunk - 1) / kDirectChunk;
@@ -309,14 +319,16 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
       c.launches++;
     }
   } else {
+    const size_t smem = ((size_t)((m.tile + 15) & ~15) + (size_t)(kT16TilesThreads / 32) * (kFlatMax / 2)) * sizeof(double);
     static bool attr = false;
     if (!attr) {
-      TFX_CUDA(cudaFuncSetAttribute(t16_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kT16MaxTile + (kT16Threads / 32) * (kFlatMax / 2)) * 8));
+      TFX_CUDA(cudaFuncSetAttribute(t16_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (kT16TilesMaxTile + (kT16TilesThreads / 32) * (kFlatMax / 2)) * 8));
       attr = true;
     }
-    const int grid = std::max(1, std::min(c.num_sms, m.ntiles));
+    const int grid = std::max(1, std::min(2 * c.num_sms, m.ntiles));
     TFX_CUDA(cudaMemsetAsync(m.counter.p, 0, sizeof(int) * (size_t)m.ntiles, st));
-    t16_tiles_kernel<<<grid, kT16Threads, smem, st>>>(a);
+    t16_tiles_kernel<<<grid, kT16TilesThreads, smem, st>>>(a);
     c.launches++;
     const int blocks = std::max(1, std::min((m.nseg + 255) / 256, c.num_sms * 8));
     t16_reduce_kernel<<<blocks, 256, 0, st>>>(m.partial.p, m.ntiles, m.nseg, a.y, accumulate ? 1 : 0, d_done);
@@ -407,7 +419,7 @@ __global__ void __launch_bounds__(256) t16_fill_kernel(const int64_t *__restrict
     const int base = in0 + t * tile;
     for (int64_t k = lo + lane; k < hi; k += 32) {
       val[dst + (k - lo)] = sval[k];
-      key[dst + (k - lo)] = (uint16_t)(idx[k] - base);
+      key[dst + (k - lo)] = (uint16_t)t16_swz((uint32_t)(idx[k] - base));
     }
     // padding slot (odd run): value 0 contributes exactly 0; key 0 is always a valid tile element
   }
@@ -441,24 +453,22 @@ int t16_build(const SegMatrix &src, T16Matrix &T, cudaStream_t st) {
   T.in0 = h_mm[0];
   T.nin = h_mm[1] - h_mm[0] + 1;
   T.nnz = src.nnz;
-  // ---- tile size and mode: the largest tile that fits shared memory gives the longest segments
+  // ---- mode and tile size. DIRECT: one tile (or tile after tile when the output side is the long one);
+  // TILES: one partial per (tile, output), the largest tile (longest segments) that leaves a few per CTA.
+  const bool long_out = (int64_t)T.nseg > (int64_t)1 << 18;
   int tile;
-  if (g_opt_t16_tile > 0) {
-    tile = g_opt_t16_tile;
-  } else if (T.nin <= kT16MaxTile) {
-    tile = T.nin;
-  } else {
-    // many tiles: the largest tile (longest segments) that still leaves a few tiles per SM
-    tile = kT16MaxTile;
+  if (g_opt_t16_tile > 0) tile = g_opt_t16_tile;
+  else if (T.nin <= kT16MaxTile || long_out) tile = std::min(T.nin, kT16MaxTile);
+  else {
+    tile = kT16TilesMaxTile;
     while (tile > 2048 && (T.nin + tile - 1) / tile < 2 * c.num_sms) tile >>= 1;
   }
   tile = std::max(2, std::min(tile, kT16MaxTile));
+  T.mode = ((T.nin + tile - 1) / tile == 1 || long_out) ? T16_DIRECT : T16_TILES;
+  if (T.mode == T16_TILES) tile = std::min(tile, kT16TilesMaxTile);
   T.tile = tile;
   T.ntiles = (T.nin + tile - 1) / tile;
   const int64_t table = (int64_t)T.nseg * T.ntiles;
-  // TILES keeps one partial per (tile, output); DIRECT (tile after tile) is used when the output side is
-  // the long one.
-  T.mode = (T.ntiles == 1 || (int64_t)T.nseg > (int64_t)1 << 18) ? T16_DIRECT : T16_TILES;
   if (table > ((int64_t)1 << 31)) return 0;        // pointer table would exceed 16 GiB: keep the generic kernels
 
   // ---- output -> stored segment
