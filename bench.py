@@ -299,9 +299,105 @@ def run_ours(a):
         }
         if d.world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(a, steps=2, warmup=1, seconds_hint=20.0)
+    if d.world == 1 and not a.no_compressed:
+        # free the 168 GB dense block before the compressed matrix is assembled
+        del S, C, u_dev, x_dev, u_pin, x_pin
+        import gc
+        gc.collect()
+        comp = compressed_spmv(a, tfx)
+        if d.rank == 0:
+            line["spmv"] = comp
+    if d.rank == 0:
         print(json.dumps(line), flush=True)
     d.finish()
     return x_host
+
+
+def compressed_spmv(a, tfx):
+    """SpMV / SpMV^T GB/s on a wavelet-compressed sensitivity matrix (the second half of BASELINE.json's
+    metric): synthetic gravity, same grid and stations as the headline workload, Haar compression at 5 %
+    (BASELINE config C's rate), assembled on the device by the reference's row pipeline, kept in the T16
+    layouts (6 B/nnz per product). Times come from CUDA events on the library stream around back-to-back
+    products (tfx_sparse_matrix_time_product); the matrix (2 x 12.6 GB) is far larger than L2."""
+    from tests.synth import depth_weight_type1, regular_grid, station_lattice
+    nx, ny, nz, nd, rate = a.nx, a.ny, a.nz, a.comp_ndata, a.comp_rate
+    N = nx * ny * nz
+    grid = regular_grid(nx, ny, nz)
+    xyz = station_lattice(nd, 100.0 * nx, 100.0 * ny, z=-0.1)
+    cw = depth_weight_type1(grid, 2.0, 0.0, 4.0e3)
+    par = tfx.SensitParams()
+    par.problem_type = 1
+    par.nx, par.ny, par.nz = nx, ny, nz
+    par.ndata, par.ndata_components, par.nmodel_components, par.data_type = nd, 1, 1, 1
+    par.compression_type, par.compression_rate = 1, rate
+    par.problem_weight = 1.0
+    par.cell0, par.ncells_local, par.param_shift, par.ncolumns = 0, N, 0, 2 * N
+    t0 = time.perf_counter()
+    S, _, cerr, nnz = tfx.calculate_sensit(par, grid, xyz, cw, np.ones((nd, 1)))
+    tfx.synchronize()
+    t_asm = time.perf_counter() - t0
+    assert S.storage_kind() == 2, "compressed matrix must be in the T16 layouts"
+    peak, peak_src = hbm_peak()
+    rng = np.random.default_rng(1235)
+    x = tfx.Buffer(2 * N); u = tfx.Buffer(nd); q = tfx.Buffer(nd); t = tfx.Buffer(2 * N)
+    tfx.copy(x, rng.uniform(-1.0, 1.0, 2 * N), 2 * N)
+    tfx.copy(u, rng.uniform(-1.0, 1.0, nd), nd)
+    out = {"workload": "synthetic gravity %dx%dx%d cells, %d data, Haar wavelet compression %g" % (nx, ny, nz, nd, rate),
+           "nnz": int(nnz), "compression_error": cerr, "assemble_s": round(t_asm, 2),
+           "layout": "T16 (f32 value + u16 in-tile key = 6 B/nnz per product, one copy per direction)",
+           "peak": peak, "peak_source": peak_src, "unit": "GB/s", "reps": a.comp_reps}
+    l0 = tfx.launch_count()
+    for name, tr, xi, yo in (("forward", 0, x, q), ("transposed", 1, u, t)):
+        ms = S.time_product(tr, xi, yo, a.comp_reps)
+        # algorithmic bytes of SURVEY 8(d): 8 B/nnz (f32 value + int32 column) + the vectors; bytes moved: 6 B/nnz
+        vec = 8.0 * (N + 2 * nd) if tr == 0 else 8.0 * (nd + 2 * N)
+        alg = 8.0 * nnz + vec
+        moved = 6.0 * nnz + vec
+        out[name] = {"ms": ms, "achieved": alg / ms / 1e6, "frac": alg / ms / 1e6 / peak,
+                     "moved_gbs": moved / ms / 1e6, "moved_frac": moved / ms / 1e6 / peak}
+    out["gpu_launches"] = int(tfx.launch_count() - l0)
+    # size-independent parity property at full size: <S x, u> == <x, S^T u> (the two products use two
+    # different copies of the matrix, so this also checks the layouts against each other)
+    xh, uh = x.numpy(), u.numpy()
+    lhs, rhs = float(np.dot(q.numpy(), uh)), float(np.dot(xh, t.numpy()))
+    out["adjoint_rel_err"] = abs(lhs - rhs) / max(abs(lhs), abs(rhs), 1e-300)
+    assert out["adjoint_rel_err"] < 1e-10, out["adjoint_rel_err"]
+    # 3-D wavelet transform on a device-resident volume (SURVEY 8d metric iii: 16 B per element and transform)
+    vol = tfx.Buffer(N)
+    tfx.copy(vol, rng.uniform(-1.0, 1.0, N), N)
+    out["wavelet"] = {}
+    for wname, wtype in (("haar", 1), ("daubechies_d4", 2)):
+        for _ in range(2):
+            tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)
+        tfx.timer_start()
+        for _ in range(10):
+            tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)
+        ms = tfx.timer_stop() / 20.0
+        out["wavelet"][wname] = {"ms_per_transform": ms, "achieved": 16.0 * N / ms / 1e6, "frac": 16.0 * N / ms / 1e6 / peak,
+                                 "note": "algorithmic 16 B/element; the kernel makes 3 axis passes (48 B/element moved)"}
+    out["assembly"] = {"rows_per_s": nd / t_asm, "cell_evaluations_per_s": float(nd) * N / t_asm,
+                       "note": "kernel line + column weight + Haar transform + exact k-th threshold + compaction per row"}
+    # LSQR on the compressed matrix (wavelet-domain solve, split path: one product per direction per iteration)
+    m = np.zeros((nz, ny, nx))
+    sl = lambda n: slice(max(0, n // 2 - max(1, n // 8)), n // 2 + max(1, n // 8))
+    m[sl(nz), sl(ny), sl(nx)] = 250.0
+    xs = np.zeros(2 * N)
+    xs[:N] = tfx.forward_wavelet((m.ravel() / cw).copy(), nx, ny, nz, 1)
+    d_obs = S.mult_vector(xs)
+    Cm = tfx.SparseMatrix.from_arrays(N, 2 * N, np.full(N, 1.0e-11, dtype=np.float32), np.arange(1, N + 1, dtype=np.int32),
+                                      np.arange(1, N + 2, dtype=np.int64), np.arange(1, N + 1, dtype=np.int32))
+    nlines = nd + N
+    b = np.zeros(nlines); b[:nd] = d_obs
+    ub, xb = tfx.Buffer(nlines), tfx.Buffer(2 * N)
+    for niter in (3, a.steps):
+        tfx.copy(ub, b, nlines)
+        tfx.lsqr_solve_sensit(nlines, 2 * N, niter, 1.0e-13, 0.0, 0.0, S, Cm, ub, xb, [1, 0], N, nx, ny, nz, 1, 1, True)
+    loop_ms, _, _ = tfx.last_timing()
+    hist, iters, fused = tfx.last_history()
+    out["lsqr"] = {"it_per_s": iters / (loop_ms * 1e-3), "ms_per_it": loop_ms / max(iters, 1), "iters": int(iters),
+                   "residual_last": float(hist[-1]) if len(hist) else None,
+                   "ref_accounting_gbs": 16.0 * nnz * iters / loop_ms / 1e6}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -381,6 +477,10 @@ def main():
     ap.add_argument("--nz", type=int, default=64)
     ap.add_argument("--ndata", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-compressed", action="store_true", help="skip the compressed SpMV section")
+    ap.add_argument("--comp-ndata", type=int, default=10000)
+    ap.add_argument("--comp-rate", type=float, default=0.05)
+    ap.add_argument("--comp-reps", type=int, default=20)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

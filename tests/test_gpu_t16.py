@@ -114,3 +114,26 @@ def test_direct_mode_tile_after_tile(oracle, force_t16):
     mo, mg, rows = random_matrix(oracle, rng, nl, ncol, lambda i: 5000, 0.0)
     assert mg.storage_kind() == 2
     check_products(mo, mg, rng, nl, ncol)
+
+
+def test_adjoint_identity_real_compressed_matrix(force_t16):
+    # size-independent property on a real Haar-compressed gravity matrix: <S x, u> == <x, S^T u>; the two
+    # products run on two different device copies (F and T layouts), so this ties them together.
+    from tests.synth import make_problem
+    tfx.set_option("t16_tile", 0)
+    pb = make_problem(nx=64, ny=48, nz=16, ndata=300, compression_type=1, rate=0.05)
+    S, nnz_col, cerr, tot = tfx.calculate_sensit(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+    assert S.storage_kind() == 2 and tot <= 300 * int(0.05 * pb.N)
+    rng = np.random.default_rng(8)
+    x = rng.uniform(-1, 1, pb.ncolumns); u = rng.uniform(-1, 1, pb.ndata)
+    lhs = float(np.dot(S.mult_vector(x), u)); rhs = float(np.dot(x, S.trans_mult_vector(u)))
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs))
+    # linearity: S(a x1 + b x2) == a S x1 + b S x2
+    x2 = rng.uniform(-1, 1, pb.ncolumns)
+    y = S.mult_vector(2.0 * x - 3.0 * x2)
+    y_lin = 2.0 * S.mult_vector(x) - 3.0 * S.mult_vector(x2)
+    assert np.allclose(y, y_lin, rtol=1e-10, atol=1e-12 * np.abs(y_lin).max())
+    # the CSR copies can be dropped; products keep working, export does not
+    b0 = S.device_bytes(); S.drop_csr()
+    assert S.device_bytes() < b0
+    assert np.allclose(S.mult_vector(x), (y_lin + 3.0 * S.mult_vector(x2)) / 2.0, rtol=1e-9, atol=1e-12 * np.abs(y_lin).max())

@@ -324,6 +324,7 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
 
   const bool dense_ok = S->has_dense && S->dense.nrows == nls && S->dense_row0 == 0 && S->dense.nrows <= kDenseMaxRows;
   if (S->has_dense && !dense_ok && !S->has_seg) return fail(-54, "lsqr: dense sensitivity block does not cover all data rows");
+  if (!dense_ok && !S->has_t16 && !S->has_seg) return fail(-55, "lsqr: the sensitivity matrix has no device representation");
   const bool fused = dense_ok && !wav && !misfit;
   res.fused = fused;
   res.history.clear();

@@ -9,6 +9,7 @@
 // concatenated at column shift param_shift + (k-1)*nelements (:759-856).
 #include "../../include/tfx.h"
 
+#include <cub/device/device_select.cuh>
 #include <thrust/copy.h>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
@@ -78,6 +79,140 @@ __global__ void __launch_bounds__(256) k_dense_segment(const double *__restrict_
     rowid_out[p] = row;
     if (nnz_count) atomicAdd(&nnz_count[p], 1);
   }
+}
+
+// ---- device-resident row state: the whole row pipeline runs without a host round trip ---------------
+struct RowState {
+  unsigned long long prefix;   // radix select: bits of the k-th smallest |x| found so far
+  long long rank;              // 0-based rank still to locate inside the current prefix bucket
+  int shift;                   // bit position of the digit examined by the current pass
+  int nsel;                    // entries kept in the current segment (cub::DeviceSelect output)
+  double thr;                  // threshold (sensitivity_gravmag.F90:240-256)
+  double cost_full, cost_disc; // sum x^2 before compression / over the discarded entries (:234, :283)
+  double err_sum;              // sum over segments of sqrt(cost_disc / cost_full) (:285)
+  long long nnz;               // entries written so far == offset of the next segment
+  int bad;                     // 1: a segment kept more than nel_compressed entries (:273-275)
+};
+
+static const int kRedBlocks = 592;   // fixed grid of the two-stage sums -> fixed summation order
+
+// partial[b] = sum over this block's elements of f(x): mode 0: x^2 ; mode 1: x^2 where |x| <= thr.
+__global__ void __launch_bounds__(256) k_row_sumsq(const double *__restrict__ line, int n, int mode, const RowState *st,
+                                                    double *__restrict__ partial) {
+  __shared__ double red[32];
+  const double thr = mode ? st->thr : 0.0;
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double x = line[i];
+    if (!mode || !(fabs(x) > thr)) s = fma(x, x, s);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) k_row_sum_final(const double *__restrict__ partial, int nb, RowState *st, int mode) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partial[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    if (mode) st->cost_disc = s;
+    else st->cost_full = s;
+  }
+}
+
+// Exact k-th order statistic of |x| by MSD radix select on the IEEE bit patterns (monotone for x >= 0):
+// 8 passes of 8 bits, 256-bin histogram per pass (warp-aggregated shared-memory atomics).
+__global__ void k_select_begin(RowState *st, long long rank, unsigned *hist) {
+  if (threadIdx.x == 0) {
+    st->prefix = 0ull;
+    st->rank = rank;
+    st->shift = 56;
+  }
+  hist[threadIdx.x] = 0u;
+}
+__global__ void __launch_bounds__(256) k_select_hist(const double *__restrict__ line, int n, const RowState *st,
+                                                      unsigned *__restrict__ hist) {
+  __shared__ unsigned sh[256];
+  sh[threadIdx.x] = 0u;
+  __syncthreads();
+  const int shift = st->shift;
+  const unsigned long long prefix = st->prefix;
+  const unsigned long long himask = (shift >= 56) ? 0ull : (~0ull << (shift + 8));
+  const int nround = (n + 255) / 256 * 256;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+    bool act = false;
+    unsigned bin = 0;
+    if (i < n) {
+      const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(line[i]));
+      act = ((b & himask) == prefix);
+      bin = (unsigned)(b >> shift) & 255u;
+    }
+    const unsigned amask = __ballot_sync(0xffffffffu, act);
+    if (act) {
+      const unsigned peers = __match_any_sync(amask, bin);
+      if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bin], __popc(peers));
+    }
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void k_select_pick(RowState *st, unsigned *hist) {   // <<<1, 256>>>
+  __shared__ unsigned sh[256];
+  sh[threadIdx.x] = hist[threadIdx.x];
+  hist[threadIdx.x] = 0u;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long r = st->rank;
+    int d = 0;
+    for (; d < 255; ++d) {
+      if (r < (long long)sh[d]) break;
+      r -= sh[d];
+    }
+    st->prefix |= (unsigned long long)d << st->shift;
+    st->rank = r;
+    st->shift -= 8;
+  }
+}
+// threshold = |k-th value|, floored at 1e-30 (:252-256); no_select: every entry above the floor is kept.
+__global__ void k_select_end(RowState *st, int no_select) {
+  double t = no_select ? -1.0 : __longlong_as_double((long long)st->prefix);
+  if (t < 1.e-30) t = 1.e-30;
+  st->thr = t;
+}
+
+struct KeepPredDev {
+  const double *line;
+  const RowState *st;
+  __device__ bool operator()(int p) const { return fabs(line[p]) > st->thr; }
+};
+
+// Writes the kept entries of one segment at the running offset: value = real(line(col), 4) * wgt in real(4)
+// (:265 / :837-843), column = p + shift, and counts the entry for sensit_nnz (:267).
+__global__ void __launch_bounds__(256) k_finish_segment_dev(const int32_t *__restrict__ cols, const double *__restrict__ line,
+                                                             float wgt, int32_t shift, int32_t row, const RowState *st,
+                                                             int64_t cap, int32_t *__restrict__ idx_out,
+                                                             float *__restrict__ val_out, int32_t *__restrict__ rowid_out,
+                                                             int32_t *__restrict__ nnz_count) {
+  const int nel = st->nsel;
+  const long long off = st->nnz;
+  if (off + nel > cap) return;   // flagged by k_advance
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nel; i += gridDim.x * blockDim.x) {
+    const int p = cols[i];
+    idx_out[off + i] = p + shift;
+    val_out[off + i] = __fmul_rn((float)line[p], wgt);
+    rowid_out[off + i] = row;
+    if (nnz_count) atomicAdd(&nnz_count[p], 1);
+  }
+}
+__global__ void k_advance(RowState *st, int nel_compressed, int64_t cap, long long *seg_end, int64_t iseg) {
+  if (st->nsel > nel_compressed || st->nnz + st->nsel > cap) st->bad = 1;
+  else st->nnz += st->nsel;
+  st->err_sum += sqrt(st->cost_disc / st->cost_full);   // :283-285
+  seg_end[iseg] = st->nnz;
+}
+__global__ void k_advance_dense(RowState *st, int n, long long *seg_end, int64_t iseg) {
+  st->nnz += n;
+  seg_end[iseg] = st->nnz;
 }
 
 template <typename T>
@@ -218,8 +353,7 @@ extern "C" int tfx_calculate_sensit(tfx_matrix **out, const tfx_sensit_params *p
   DevBuf<int32_t> rowid;
   if (F.idx.alloc((size_t)cap) || F.val.alloc((size_t)cap) || rowid.alloc((size_t)cap)) { delete h; return -101; }
   DevBuf<int32_t> dnnz, dcols;
-  DevBuf<double> dsorted;
-  if (dnnz.alloc(N) || dcols.alloc(N) || dsorted.alloc(N)) { delete h; return -101; }
+  if (dnnz.alloc(N) || dcols.alloc(N)) { delete h; return -101; }
   TFX_CUDA(cudaMemsetAsync(dnnz.p, 0, (size_t)N * 4, st));
 
   // batch of stations whose lines are resident at once (<= ~1 GiB)
@@ -228,16 +362,30 @@ extern "C" int tfx_calculate_sensit(tfx_matrix **out, const tfx_sensit_params *p
   DevBuf<double> dl;
   if (dl.alloc(per_station * B)) { delete h; return -101; }
 
-  std::vector<int64_t> ptr;       // stored rows only (0-based offsets)
-  std::vector<int32_t> segmap;    // 0-based global row of each stored row
   std::vector<double> h_dw((size_t)P.ndata * ndc);
   memcpy(h_dw.data(), data_weight, h_dw.size() * sizeof(double));
-  ptr.push_back(0);
-  int64_t nnz = 0;
-  double err_sum = 0.0;
-  auto pol = thrust::cuda::par.on(st);
   const int vgrid = c.num_sms * 8;
+  auto pol = thrust::cuda::par.on(st);
 
+  // device-resident state of the row pipeline (no host synchronisation per row)
+  DevBuf<RowState> dst;
+  DevBuf<unsigned> dhist;
+  DevBuf<double> dpartial;
+  DevBuf<long long> dsegend;
+  DevBuf<unsigned char> dtemp;
+  if (dst.alloc(1) || dhist.alloc(256) || dpartial.alloc(kRedBlocks) || dsegend.alloc((size_t)nseg_lines)) { delete h; return -101; }
+  TFX_CUDA(cudaMemsetAsync(dst.p, 0, sizeof(RowState), st));
+  size_t temp_bytes = 0;
+  {
+    KeepPredDev pred{dl.p, dst.p};
+    cub::DeviceSelect::If(nullptr, temp_bytes, thrust::counting_iterator<int>(0), dcols.p, &dst.p->nsel, N, pred, st);
+  }
+  if (dtemp.alloc(temp_bytes + 16)) { delete h; return -101; }
+  const long long rank = (long long)N - nel_compressed - 1;   // 0-based rank of sorted(N - nel_compressed), :240-251
+  const bool no_select = nel_compressed >= N;
+  const int rgrid = std::min(kRedBlocks, (N + 255) / 256);
+
+  int64_t iseg = 0;
   for (int32_t b0 = 0; b0 < P.ndata; b0 += B) {
     const int nb = std::min<int>(B, P.ndata - b0);
     int rc = compute_lines(P, g, nb, dx.p + b0, dy.p + b0, dz.p + b0, dl.p, derr.p, st);
@@ -248,54 +396,42 @@ extern "C" int tfx_calculate_sensit(tfx_matrix **out, const tfx_sensit_params *p
       const int32_t idata = b0 + b;   // 0-based
       for (int d = 0; d < ndc; ++d) {
         const int32_t row = idata * ndc + d;
-        const int64_t row_start = nnz;
         // combined_weight = real(problem_weight * data_weight(d, idata), 4)
         const float wgt = (float)(P.problem_weight * h_dw[(size_t)idata * ndc + d]);
-        for (int k = 0; k < nmc; ++k) {
+        for (int k = 0; k < nmc; ++k, ++iseg) {
           double *line = dl.p + ((size_t)b * ndc * nmc + (size_t)d * nmc + k) * N;
           const int32_t shift = P.param_shift + k * N;   // 0-based column = p + shift
           if (P.compression_type > 0) {
-            thrust::device_ptr<double> L(line), Sd(dsorted.p);
-            const double cost_full = thrust::transform_reduce(pol, L, L + N, SqOp(), 0.0, thrust::plus<double>());
-            rc = wavelet3d_device(line, P.nx, P.ny, P.nz, P.compression_type, true, st);
+            k_row_sumsq<<<rgrid, 256, 0, st>>>(line, N, 0, dst.p, dpartial.p);                     // cost_full, :234
+            k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, dst.p, 0);
+            rc = wavelet3d_device(line, P.nx, P.ny, P.nz, P.compression_type, true, st);           // :237
             if (rc) { delete h; return rc; }
-            double threshold;
-            if (nel_compressed >= N) {
-              threshold = -1.0;
-            } else {
-              thrust::transform(pol, L, L + N, Sd, AbsOp());
-              thrust::sort(pol, Sd, Sd + N);
-              TFX_CUDA(cudaMemcpyAsync(&threshold, dsorted.p + (N - nel_compressed - 1), sizeof(double),
-                                       cudaMemcpyDeviceToHost, st));
-              TFX_CUDA(cudaStreamSynchronize(st));
-              threshold = fabs(threshold);
+            if (!no_select) {
+              k_select_begin<<<1, 256, 0, st>>>(dst.p, rank, dhist.p);
+              for (int pass = 0; pass < 8; ++pass) {
+                k_select_hist<<<vgrid, 256, 0, st>>>(line, N, dst.p, dhist.p);
+                k_select_pick<<<1, 256, 0, st>>>(dst.p, dhist.p);
+              }
+              c.launches += 17;
             }
-            if (threshold < 1.e-30) threshold = 1.e-30;
-            thrust::device_ptr<int32_t> Cd(dcols.p);
-            KeepPred pred{line, threshold};
-            auto endp = thrust::copy_if(pol, thrust::counting_iterator<int>(0), thrust::counting_iterator<int>(N), Cd, pred);
-            const int nel = (int)(endp - Cd);
-            if (nel > nel_compressed) { delete h; return fail(-79, "Wrong number of elements in calculate_and_write_sensit!"); }
-            const double cost_disc =
-                thrust::transform_reduce(pol, L, L + N, DiscardedSq{threshold}, 0.0, thrust::plus<double>());
-            err_sum += sqrt(cost_disc / cost_full);   // :283-285
-            if (nel > 0) {
-              k_finish_segment<<<std::min(vgrid, (nel + 255) / 256), 256, 0, st>>>(
-                  dcols.p, nel, line, wgt, shift, row, F.idx.p + nnz, F.val.p + nnz, rowid.p + nnz, dnnz.p);
-              c.launches++;
-            }
-            c.launches += 6;
-            nnz += nel;
+            k_select_end<<<1, 1, 0, st>>>(dst.p, no_select ? 1 : 0);
+            KeepPredDev pred{line, dst.p};
+            size_t tb = temp_bytes;
+            TFX_CUDA(cub::DeviceSelect::If(dtemp.p, tb, thrust::counting_iterator<int>(0), dcols.p, &dst.p->nsel, N, pred, st));
+            k_row_sumsq<<<rgrid, 256, 0, st>>>(line, N, 1, dst.p, dpartial.p);                     // discarded cost, :283
+            k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, dst.p, 1);
+            k_finish_segment_dev<<<std::min(vgrid, (nel_compressed + 255) / 256), 256, 0, st>>>(
+                dcols.p, line, wgt, shift, row, dst.p, cap, F.idx.p, F.val.p, rowid.p, dnnz.p);
+            k_advance<<<1, 1, 0, st>>>(dst.p, nel_compressed, cap, dsegend.p, iseg);
+            c.launches += 9;
           } else {
-            k_dense_segment<<<std::min(vgrid, (N + 255) / 256), 256, 0, st>>>(line, N, wgt, shift, row, F.idx.p + nnz,
-                                                                             F.val.p + nnz, rowid.p + nnz, dnnz.p);
-            c.launches++;
-            nnz += N;
+            // uncompressed general path: the offset is known on the host
+            k_dense_segment<<<std::min(vgrid, (N + 255) / 256), 256, 0, st>>>(line, N, wgt, shift, row,
+                                                                             F.idx.p + iseg * (int64_t)N, F.val.p + iseg * (int64_t)N,
+                                                                             rowid.p + iseg * (int64_t)N, dnnz.p);
+            k_advance_dense<<<1, 1, 0, st>>>(dst.p, N, dsegend.p, iseg);
+            c.launches += 2;
           }
-        }
-        if (nnz > row_start) {   // new_row(): only non-empty rows are stored (sparse_matrix.f90:266-274)
-          ptr.push_back(nnz);
-          segmap.push_back(row);
         }
       }
     }
@@ -303,6 +439,26 @@ extern "C" int tfx_calculate_sensit(tfx_matrix **out, const tfx_sensit_params *p
     TFX_CUDA(cudaMemcpyAsync(&e, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     TFX_CUDA(cudaStreamSynchronize(st));
     if (e) { delete h; return kernel_error(e); }
+  }
+  RowState hst;
+  std::vector<long long> seg_end((size_t)nseg_lines);
+  TFX_CUDA(cudaMemcpyAsync(&hst, dst.p, sizeof(RowState), cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaMemcpyAsync(seg_end.data(), dsegend.p, (size_t)nseg_lines * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  if (hst.bad) { delete h; return fail(-79, "Wrong number of elements in calculate_and_write_sensit!"); }
+  const int64_t nnz = hst.nnz;
+  const double err_sum = hst.err_sum;
+  // matrix rows: one per (idata, d), the nmc segments concatenated; only non-empty rows are stored
+  // (new_row(), sparse_matrix.f90:266-274)
+  std::vector<int64_t> ptr;       // stored rows only (0-based offsets)
+  std::vector<int32_t> segmap;    // 0-based global row of each stored row
+  ptr.push_back(0);
+  for (int32_t row = 0; row < nl; ++row) {
+    const int64_t row_end = seg_end[(size_t)(row + 1) * nmc - 1];
+    if (row_end > ptr.back()) {
+      ptr.push_back(row_end);
+      segmap.push_back(row);
+    }
   }
 
   // ---- forward representation
