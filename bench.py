@@ -252,11 +252,14 @@ def run_ours(a):
     # ---- end to end through the C ABI with pinned HOST buffers ("e2e")
     tfx.set_option("profile_sweeps", 0)
     u_pin, x_pin = tfx.Buffer(nlines, "pinned"), tfx.Buffer(ncolumns, "pinned")
-    u_pin.numpy()[:] = b
-    d.barrier()
-    t0 = time.perf_counter()
-    solve(u_pin, x_pin, a.steps)
-    e2e_s = d.max(time.perf_counter() - t0)
+    e2e_runs = []
+    for _ in range(2):          # first call also pays the one-time staging-buffer allocation; the second is reported
+        u_pin.numpy()[:] = b
+        d.barrier()
+        t0 = time.perf_counter()
+        solve(u_pin, x_pin, a.steps)
+        e2e_runs.append(d.max(time.perf_counter() - t0))
+    e2e_s = e2e_runs[-1]
     x_host = x_pin.numpy().copy()
     d.barrier()
 
@@ -287,7 +290,10 @@ def run_ours(a):
                        "lsqr": "fused single-sweep path, damping block alpha=1e-11, rmin=1e-13",
                        "assemble_s": round(t_assemble, 2), "residual_last": float(hist[-1]) if len(hist) else None},
             "e2e": {"value": a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(nlines * 8 / a.steps),
-                    "d2h_bytes_per_step": int((nlines + ncolumns) * 8 / a.steps)},
+                    "d2h_bytes_per_step": int((nlines + ncolumns) * 8 / a.steps),
+                    "first_call_value": a.steps / e2e_runs[0],
+                    "note": "tfx_lsqr_solve_sensit with pinned HOST u/x: H2D of the right-hand side, the "
+                            "initialisation before the loop, K iterations, D2H of x and u; wall clock around the call"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

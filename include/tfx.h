@@ -173,6 +173,42 @@ int tfx_calculate_sensit(tfx_matrix **matrix_sensit, const tfx_sensit_params *pa
                          const double *column_weight_full, const double *data_weight,
                          int32_t *sensit_nnz, double *comp_error, int64_t *nnz_total);
 
+/* ---- multi-GPU assembly: rows sharded by data, re-partitioned to nnz-balanced column slabs ---------
+ * The reference's three stages with the per-rank files kept in HBM and the per-row MPI_Scatterv
+ * replaced by one all-to-all over NVLink (csrc/sensit_dist.cu):
+ *   calculate_and_write_sensit  (sensitivity_gravmag.F90:82-410)  -> tfx_sensit_assemble_rows
+ *   get_load_balancing_nelements / calculate_new_partitioning (:470-524, :573-642)
+ *                                                                  -> tfx_get_load_balancing_nelements
+ *   read_sensitivity_kernel     (:648-883)                         -> tfx_sensit_repartition            */
+typedef struct tfx_sensit_rows tfx_sensit_rows;   /* stands in for the file sensit_<type>_<nbproc>_<rank> */
+
+/* Row pipeline for the stations of rank `myrank` (even split of par->ndata, parallel_tools.f90:46-86).
+ * par->cell0 / ncells_local / param_shift / ncolumns are ignored (full grid, columns k*N + p).
+ * Outputs are reduced over the communicator when nbproc > 1 (requires tfx_comm_init with nbproc ranks):
+ * sensit_nnz(nx*ny*nz) (:322), nnz_total (:327), comp_error (:346-353). data_weight and problem_weight
+ * are applied in real(4) exactly like read_sensitivity_kernel does (:837-843). */
+int tfx_sensit_assemble_rows(tfx_sensit_rows **rows, const tfx_sensit_params *par,
+                             const double *X1, const double *X2, const double *Y1, const double *Y2,
+                             const double *Z1, const double *Z2,
+                             const double *data_X, const double *data_Y, const double *data_Z,
+                             const double *column_weight_full, const double *data_weight,
+                             int32_t myrank, int32_t nbproc,
+                             int32_t *sensit_nnz, double *comp_error, int64_t *nnz_total);
+int tfx_sensit_rows_info(const tfx_sensit_rows *rows, int32_t *data0, int32_t *ndata_loc, int64_t *nnz_local);
+int tfx_sensit_rows_destroy(tfx_sensit_rows *rows);
+/* get_load_balancing_nelements (:470-524): host integer work, no GPU needed. Joint inversions pass the
+ * sum of both problems' sensit_nnz (:610-625). */
+int tfx_get_load_balancing_nelements(int32_t nelements_total, const int32_t *sensit_nnz, int32_t nbproc,
+                                     int64_t *nnz_at_cpu_new, int32_t *nelements_at_cpu_new);
+/* Builds this rank's column slab (cells nsmaller+1 .. nsmaller+nelements_at_cpu(myrank+1), all data rows,
+ * LOCAL columns (p - nsmaller) + (k-1)*nelements + param_shift(problem_slot), :685-686,:834; ncolumns =
+ * 2*nmodel_components*nelements, joint_inverse_problem.F90:213-214) and consumes the row set.
+ * Without a communicator (single process) the row set must hold all data rows (assembled with
+ * nbproc = 1) and the slab of any (myrank, nbproc) can be built -- used by tests and by hosts that drive
+ * the slabs one after the other. */
+int tfx_sensit_repartition(tfx_matrix **matrix_sensit, tfx_sensit_rows *rows, int32_t problem_slot,
+                           const int32_t *nelements_at_cpu, int32_t myrank, int32_t nbproc);
+
 /* One raw sensitivity line per station (no weighting), for kernel parity tests:
  * lines(ncells, nmodel_components, ndata_components, ndata_batch) Fortran order. */
 int tfx_sensit_lines(const tfx_sensit_params *par, const double *X1, const double *X2, const double *Y1,

@@ -140,6 +140,112 @@ def solve_model(pb, kind, rank, world, td, niter):
     return x, np.array(hist), it, cell0, ncl
 
 
+def dist_sensit_case(rank, world, td, niter):
+    """Multi-GPU assembly (csrc/sensit_dist.cu): rows sharded by data, all-to-all to nnz-balanced column slabs,
+    then a column-split wavelet-domain LSQR solve on the result -- against the single-rank oracle."""
+    import tomofastx_b200 as tfx
+    from oracle import oracle as orc
+    from oracle import partition as orp
+    from tests.synth import make_problem
+    pb = make_problem(nx=12, ny=10, nz=6, ndata=13, compression_type=1, rate=0.2)
+    N, ndata = pb.N, pb.ndata
+    tfx.init(int(os.environ.get("LOCAL_RANK", "0")))
+    box = [tfx.comm_unique_id() if rank == 0 else None]
+    td.broadcast_object_list(box, src=0)
+    tfx.comm_init(world, rank, box[0])
+    rows, nnz_col, cerr, tot = tfx.sensit_assemble_rows(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw, rank, world)
+    d0, nloc, nnz_loc = rows.info()
+    assert nloc == orp.calculate_nelements_at_cpu(ndata, rank, world)
+    nnz_at, nel_at = tfx.get_load_balancing_nelements(nnz_col, world)
+    S = tfx.sensit_repartition(rows, 1, nel_at, rank, world)
+    ncl = int(nel_at[rank]); cell0 = int(nel_at[:rank].sum()); ncol = 2 * ncl
+    assert S.get_number_elements() == nnz_at[rank] and S.get_ncolumns() == ncol
+
+    # oracle: full matrix, slab by the reference's rule
+    So = pb.oracle_matrix(orc)
+    sa, ija, ijl, rowptr = So.arrays()
+    full = {int(rowptr[i]): (ija[ijl[i] - 1:ijl[i + 1] - 1], sa[ijl[i] - 1:ijl[i + 1] - 1]) for i in range(len(rowptr))}
+    want = orp.column_slab(full, N, 1, nel_at, rank, 1)
+    gsa, gija, gijl, growptr = S.export()
+    got = {int(growptr[i]): (gija[gijl[i] - 1:gijl[i + 1] - 1], gsa[gijl[i] - 1:gijl[i + 1] - 1]) for i in range(len(growptr))}
+    bad = sum(len(set(got.get(k, ([], []))[0]) ^ set(want.get(k, ([], []))[0])) for k in set(got) | set(want))
+    assert bad <= 2 * ndata, bad
+    assert abs(tot - So.nel) <= 2 * ndata and abs(cerr) < 1.0
+    for k in set(got) & set(want):
+        if np.array_equal(got[k][0], want[k][0]):
+            assert np.allclose(got[k][1], want[k][1], rtol=3e-6, atol=1e-6 * np.abs(want[k][1]).max())
+
+    # column-split solve on the distributed matrix (damping block alpha*I, wavelet domain)
+    alpha = np.float32(1e-3)
+    Cm = tfx.SparseMatrix.from_arrays(N, ncol, np.full(ncl, alpha, dtype=np.float32), np.arange(1, ncl + 1, dtype=np.int32),
+                                      np.arange(1, ncl + 2, dtype=np.int64),
+                                      np.arange(cell0 + 1, cell0 + ncl + 1, dtype=np.int32))
+    b = np.concatenate([pb.rhs(So, orc), np.zeros(N)])
+    u = b.copy(); x = np.zeros(ncol)
+    tfx.lsqr_solve_sensit(len(u), ncol, niter, 1e-13, 0.0, 0.0, S, Cm, u, x, [1, 0], ncl, pb.nx, pb.ny, pb.nz, 1, 1, True,
+                          myrank=rank, nbproc=world)
+    h, it, fused = tfx.last_history()
+    tfx.comm_finalize()
+    parts = [None] * world
+    td.all_gather_object(parts, (cell0, ncl, x[:ncl]))
+    if rank == 0:
+        xg = np.zeros(N)
+        for c0, n, xl in parts:
+            xg[c0:c0 + n] = xl
+        Co = orc.SparseMatrix(N, 2 * N, N)
+        for p in range(N):
+            Co.add(float(alpha), p + 1); Co.new_row()
+        Co.finalize()
+        x_ref, h_ref, it_ref = orc.lsqr_solve_sensit(niter, 1e-13, 0.0, 0.0, So, Co, b, N, pb.nx, pb.ny, pb.nz, 1, 1, True)
+        assert it == it_ref
+        n = min(8, len(h_ref))
+        # threshold flips (<= a couple of entries per row) perturb the matrix at the 1e-4 level of a row's norm
+        assert np.allclose(h[:n], h_ref[:n], rtol=5e-3), (h[:n], h_ref[:n])
+        print("multi_rank_case ok: backend=nccl kind=dist_sensit world=%d nnz=%d slabs=%s iters=%d r_last=%.6e" %
+              (world, tot, list(map(int, nel_at)), it, h[-1]), flush=True)
+
+
+def dist_sensit_model(rank, world, td):
+    """Host model of csrc/sensit_dist.cu on CPU (gloo): every rank owns the oracle's rows of its stations
+    (even data split), cuts each row at the slab boundaries, sends the pieces to the column owners and
+    concatenates what it receives in source-rank order; the result must equal the reference rule applied to
+    the full matrix, already sorted by (row, column)."""
+    import tomofastx_b200 as tfx                                      # host-only helpers (no GPU call)
+    from oracle import oracle as orc
+    from oracle import partition as orp
+    from tests.synth import make_problem
+    pb = make_problem(nx=8, ny=6, nz=4, ndata=7, compression_type=1, rate=0.25, problem_type=2, nmodel_components=3)
+    N, nmc = pb.N, 3
+    pb.par.param_shift = 0
+    So = pb.oracle_matrix(orc)
+    sa, ija, ijl, rowptr = So.arrays()
+    full = {int(rowptr[i]): (ija[ijl[i] - 1:ijl[i + 1] - 1], sa[ijl[i] - 1:ijl[i + 1] - 1]) for i in range(len(rowptr))}
+    nnz_col = np.zeros(N, dtype=np.int32)
+    for c, _ in full.values():
+        np.add.at(nnz_col, (c - 1) % N, 1)
+    _, nel_at = tfx.get_load_balancing_nelements(nnz_col, world)
+    assert np.array_equal(nel_at, orp.get_load_balancing_nelements(nnz_col, world)[1])
+    d0 = tfx.get_nsmaller(pb.ndata, rank, world)
+    nloc = tfx.calculate_nelements_at_cpu(pb.ndata, rank, world)
+    mine = {r: full[r] for r in range(d0 + 1, d0 + nloc + 1) if r in full}
+    # pack: destination-major, row order inside a destination (k_pack_pieces)
+    send = []
+    for dst in range(world):
+        piece = orp.column_slab(mine, N, nmc, nel_at, dst, 2)
+        send.append([(r, piece[r][0], piece[r][1]) for r in sorted(piece)])
+    allsend = [None] * world
+    td.all_gather_object(allsend, send)
+    recv = [t for src in range(world) for t in allsend[src][rank]]     # source-rank order
+    rows_seq = [t[0] for t in recv]
+    assert rows_seq == sorted(rows_seq), "pieces must arrive in global row order"
+    want = orp.column_slab(full, N, nmc, nel_at, rank, 2)
+    assert [t[0] for t in recv] == sorted(want)
+    for r, c, v in recv:
+        assert np.array_equal(c, want[r][0]) and np.array_equal(v, want[r][1]) and np.all(np.diff(c) > 0)
+        assert c.min() >= 3 * nel_at[rank] + 1 and c.max() <= 6 * nel_at[rank]       # problem 2 of a 3-component model
+    print("multi_rank_case ok: backend=model kind=dist_sensit world=%d slabs=%s" % (world, list(map(int, nel_at))), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--backend", default="nccl", choices=["nccl", "model"])
@@ -171,6 +277,10 @@ def main():
             assert np.allclose(x, x_ref, rtol=1e-6, atol=1e-8 * np.abs(x_ref).max()), kind
             print("multi_rank_case ok: backend=%s kind=%s world=%d iters=%d r_last=%.6e" % (a.backend, kind, world, it, h[-1]),
                   flush=True)
+    if a.backend == "nccl":
+        dist_sensit_case(rank, world, td, a.niter)
+    else:
+        dist_sensit_model(rank, world, td)
     td.barrier()
     td.destroy_process_group()
     if not ok:

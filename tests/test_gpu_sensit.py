@@ -106,3 +106,89 @@ def test_magnetic_compressed_assembly_three_components(oracle):
     assert int(min(want[1][0])) > 3 * pb.N          # param_shift(2) = nelements * ncomponents
     x = pb.model_scaled_w(oracle)
     assert np.allclose(S.mult_vector(x), So.mult_vector(x), rtol=1e-6, atol=1e-9)
+
+
+# ---- rows sharded by data -> nnz-balanced column slabs (csrc/sensit_dist.cu) ---------------------------------
+def _full_rows_no_shift(pb, oracle):
+    """The content of the reference's stream files: rows with columns (k-1)*N + p, weights applied."""
+    shift = pb.par.param_shift
+    pb.par.param_shift = 0
+    try:
+        So = pb.oracle_matrix(oracle)
+    finally:
+        pb.par.param_shift = shift
+    return _rows(*So.arrays())
+
+
+@pytest.mark.parametrize("case", ["grav_haar", "mag3_d4"])
+@pytest.mark.parametrize("nbproc", [1, 2, 3])
+def test_repartition_single_process_vs_oracle(oracle, case, nbproc):
+    from oracle import partition as orp
+    if case == "grav_haar":
+        pb = make_problem(nx=12, ny=10, nz=6, ndata=11, compression_type=1, rate=0.2)
+        slot = 1
+    else:
+        pb = make_problem(nx=8, ny=7, nz=4, ndata=6, compression_type=2, rate=0.3, problem_type=2, nmodel_components=3)
+        slot = 2
+    nmc = pb.par.nmodel_components
+    want_full = _full_rows_no_shift(pb, oracle)
+    rows, nnz_col, cerr, tot = tfx.sensit_assemble_rows(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+    assert rows.info() == (0, pb.ndata, tot)
+    # same counts as the one-call assembly
+    S1, nnz_col1, cerr1, tot1 = tfx.calculate_sensit(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+    assert tot == tot1 and np.array_equal(nnz_col, nnz_col1) and cerr == cerr1
+    nnz_at, nel_at = tfx.get_load_balancing_nelements(nnz_col, nbproc)
+    assert np.array_equal(nel_at, orp.get_load_balancing_nelements(nnz_col, nbproc)[1])
+    full_got = _rows(*S1.export())
+    total = 0
+    for r in range(nbproc):
+        if r > 0:
+            rows, _, _, _ = tfx.sensit_assemble_rows(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+        M = tfx.sensit_repartition(rows, slot, nel_at, r, nbproc)
+        assert M.get_ncolumns() == 2 * nmc * nel_at[r] and M.get_total_row_number() == pb.ndata
+        got = _rows(*M.export())
+        # exact against the device's own full matrix (same kernels, same values), restricted by the oracle's rule
+        shift = pb.par.param_shift
+        dev_rows = {k: (c - shift, v) for k, (c, v) in full_got.items()}
+        want_dev = orp.column_slab(dev_rows, pb.N, nmc, nel_at, r, slot)
+        assert set(got) == set(want_dev)
+        for k in got:
+            assert np.array_equal(got[k][0], want_dev[k][0]) and np.array_equal(got[k][1], want_dev[k][1])
+        # and against the oracle's matrix up to threshold flips (as in test_compressed_assembly_vs_oracle)
+        want = orp.column_slab(want_full, pb.N, nmc, nel_at, r, slot)
+        bad = sum(len(set(got.get(k, ([], []))[0]) ^ set(want.get(k, ([], []))[0])) for k in set(got) | set(want))
+        assert bad <= 2 * pb.ndata * nmc
+        total += M.get_number_elements()
+        assert abs(M.get_number_elements() - nnz_at[r]) == 0
+    assert total == tot
+
+
+def test_repartition_even_split_and_lsqr_slab(oracle):
+    """Even column split (parallel_tools.f90:46-63) and a product on the slab against the oracle's."""
+    from oracle import partition as orp
+    pb = make_problem(nx=12, ny=10, nz=6, ndata=11, compression_type=1, rate=0.25)
+    nbproc = 4
+    nel_at = np.array([orp.calculate_nelements_at_cpu(pb.N, r, nbproc) for r in range(nbproc)], dtype=np.int32)
+    So = pb.oracle_matrix(oracle)
+    x = pb.model_scaled_w(oracle)
+    d_want = So.mult_vector(x)
+    d_got = np.zeros(pb.ndata)
+    cum = np.concatenate([[0], np.cumsum(nel_at)])
+    for r in range(nbproc):
+        rows, _, _, _ = tfx.sensit_assemble_rows(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+        M = tfx.sensit_repartition(rows, 1, nel_at, r, nbproc)
+        xl = np.zeros(2 * nel_at[r])
+        xl[:nel_at[r]] = x[cum[r]:cum[r + 1]]
+        d_got += M.mult_vector(xl)                 # the MPI_Allreduce of model.F90:293, summed here
+    assert np.allclose(d_got, d_want, rtol=1e-6, atol=1e-8 * np.abs(d_want).max())
+
+
+def test_repartition_argument_checks():
+    pb = make_problem(nx=6, ny=5, nz=4, ndata=5, compression_type=1, rate=0.3)
+    rows, _, _, _ = tfx.sensit_assemble_rows(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+    with pytest.raises(tfx.TfxError, match="does not sum"):
+        tfx.sensit_repartition(rows, 1, np.array([10, 10], dtype=np.int32), 0, 2)
+    with pytest.raises(tfx.TfxError, match="problem_slot"):
+        tfx.sensit_repartition(rows, 3, np.array([pb.N], dtype=np.int32), 0, 1)
+    with pytest.raises(tfx.TfxError, match="communicator"):
+        tfx.sensit_assemble_rows(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw, myrank=0, nbproc=2)

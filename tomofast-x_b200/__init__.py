@@ -100,6 +100,12 @@ def lib():
     L.tfx_lsqr_last_timing.argtypes = [C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i32)]
     L.tfx_calculate_sensit.argtypes = [C.POINTER(vp), C.POINTER(SensitParams)] + [vp] * 11 + [vp, C.POINTER(dbl),
                                                                                               C.POINTER(i64)]
+    L.tfx_sensit_assemble_rows.argtypes = [C.POINTER(vp), C.POINTER(SensitParams)] + [vp] * 11 + [i32, i32, vp,
+                                                                                                   C.POINTER(dbl), C.POINTER(i64)]
+    L.tfx_sensit_rows_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
+    L.tfx_sensit_rows_destroy.argtypes = [vp]
+    L.tfx_get_load_balancing_nelements.argtypes = [i32, vp, i32, vp, vp]
+    L.tfx_sensit_repartition.argtypes = [C.POINTER(vp), vp, i32, vp, i32, i32]
     L.tfx_sensit_lines.argtypes = [C.POINTER(SensitParams)] + [vp] * 6 + [i32] + [vp] * 4
     _lib = L
     return L
@@ -432,6 +438,64 @@ def calculate_sensit(par, grid, data_xyz, column_weight_full, data_weight):
                                       cw.ctypes.data, dw.ctypes.data, nnz_col.ctypes.data, C.byref(cerr),
                                       C.byref(tot)))
     return SparseMatrix(_handle=h), nnz_col, cerr.value, tot.value
+
+
+class SensitRows:
+    """Row-sharded kernel of one problem resident on the device: stands in for the per-rank stream file
+    sensit_<type>_<nbproc>_<rank> of calculate_and_write_sensit (sensitivity_gravmag.F90:143-318)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def info(self):
+        """(data0, ndata_loc, nnz_local): 0-based first station, number of stations, entries held."""
+        a, b, n = C.c_int32(0), C.c_int32(0), C.c_int64(0)
+        _check(lib().tfx_sensit_rows_info(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().tfx_sensit_rows_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+def sensit_assemble_rows(par, grid, data_xyz, column_weight_full, data_weight, myrank=0, nbproc=1):
+    """Stage 1 of the multi-GPU assembly. Returns (SensitRows, sensit_nnz, comp_error, nnz_total), the last
+    three reduced over the ranks."""
+    arrs, gp = _grid_ptrs(grid)
+    dx, dy, dz = (np.ascontiguousarray(a, dtype=np.float64) for a in data_xyz)
+    cw = np.ascontiguousarray(column_weight_full, dtype=np.float64)
+    dw = np.ascontiguousarray(data_weight, dtype=np.float64)
+    n = par.nx * par.ny * par.nz
+    assert cw.size == n and dw.size == par.ndata * par.ndata_components and dx.size == par.ndata
+    nnz_col = np.zeros(n, dtype=np.int32)
+    cerr, tot = C.c_double(0.0), C.c_int64(0)
+    h = C.c_void_p()
+    _check(lib().tfx_sensit_assemble_rows(C.byref(h), C.byref(par), *gp, dx.ctypes.data, dy.ctypes.data,
+                                          dz.ctypes.data, cw.ctypes.data, dw.ctypes.data, myrank, nbproc,
+                                          nnz_col.ctypes.data, C.byref(cerr), C.byref(tot)))
+    return SensitRows(h), nnz_col, cerr.value, tot.value
+
+
+def get_load_balancing_nelements(sensit_nnz, nbproc):
+    """get_load_balancing_nelements (sensitivity_gravmag.F90:470-524): (nnz_at_cpu, nelements_at_cpu)."""
+    nnz = np.ascontiguousarray(sensit_nnz, dtype=np.int32)
+    a = np.zeros(nbproc, dtype=np.int64)
+    b = np.zeros(nbproc, dtype=np.int32)
+    _check(lib().tfx_get_load_balancing_nelements(nnz.size, nnz.ctypes.data, nbproc, a.ctypes.data, b.ctypes.data))
+    return a, b
+
+
+def sensit_repartition(rows, problem_slot, nelements_at_cpu, myrank=0, nbproc=1):
+    """Stage 3: this rank's column-slab SparseMatrix (local column indices); consumes `rows`."""
+    nel = np.ascontiguousarray(nelements_at_cpu, dtype=np.int32)
+    assert nel.size == nbproc
+    h = C.c_void_p()
+    _check(lib().tfx_sensit_repartition(C.byref(h), rows._h, problem_slot, nel.ctypes.data, myrank, nbproc))
+    return SparseMatrix(_handle=h)
 
 
 def sensit_lines(par, grid, data_xyz):

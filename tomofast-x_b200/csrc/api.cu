@@ -64,6 +64,20 @@ int ensure_init() {
   return init_device(-1);
 }
 
+// Pool of staging buffers (at most kPoolMax kept, largest first out).
+namespace {
+struct StageBuf { double *p; size_t cap; };
+std::vector<StageBuf> g_stage_pool;
+const size_t kPoolMax = 6;
+}  // namespace
+
+VecIO::~VecIO() {
+  if (!stage) return;
+  if (g_stage_pool.size() < kPoolMax) g_stage_pool.push_back({stage, stage_cap});
+  else cudaFree(stage);
+  stage = nullptr;
+}
+
 int VecIO::bind(double *ptr, size_t count, bool copy_in) {
   n = count;
   if (is_device_ptr(ptr)) {
@@ -72,8 +86,29 @@ int VecIO::bind(double *ptr, size_t count, bool copy_in) {
     return 0;
   }
   host = ptr;
-  TFX_TRY(own.alloc(count));
-  dev = own.p;
+  // smallest pooled buffer that fits
+  int best = -1;
+  for (size_t i = 0; i < g_stage_pool.size(); ++i)
+    if (g_stage_pool[i].cap >= count && (best < 0 || g_stage_pool[i].cap < g_stage_pool[best].cap)) best = (int)i;
+  if (best >= 0) {
+    stage = g_stage_pool[best].p; stage_cap = g_stage_pool[best].cap;
+    g_stage_pool.erase(g_stage_pool.begin() + best);
+  } else {
+    if (g_stage_pool.size() >= kPoolMax) {   // make room: drop the smallest
+      size_t k = 0;
+      for (size_t i = 1; i < g_stage_pool.size(); ++i) if (g_stage_pool[i].cap < g_stage_pool[k].cap) k = i;
+      cudaFree(g_stage_pool[k].p);
+      g_stage_pool.erase(g_stage_pool.begin() + k);
+    }
+    const size_t cap = std::max<size_t>(count, 1);
+    cudaError_t e = cudaMalloc((void **)&stage, cap * sizeof(double));
+    if (e != cudaSuccess) {
+      stage = nullptr;
+      return fail(-101, std::string("cudaMalloc failed (staging): ") + cudaGetErrorString(e));
+    }
+    stage_cap = cap;
+  }
+  dev = stage;
   if (copy_in && count) TFX_CUDA(cudaMemcpyAsync(dev, host, count * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
   return 0;
 }

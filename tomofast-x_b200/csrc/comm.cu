@@ -23,6 +23,11 @@ struct Nccl {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
 };
@@ -45,7 +50,14 @@ int load_nccl() {
   n.CommDestroy = (decltype(n.CommDestroy))dlsym(n.h, "ncclCommDestroy");
   n.AllReduce = (decltype(n.AllReduce))dlsym(n.h, "ncclAllReduce");
   n.GetErrorString = (decltype(n.GetErrorString))dlsym(n.h, "ncclGetErrorString");
-  if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.AllReduce) return fail(-61, "NCCL symbols missing");
+  n.AllGather = (decltype(n.AllGather))dlsym(n.h, "ncclAllGather");
+  n.Send = (decltype(n.Send))dlsym(n.h, "ncclSend");
+  n.Recv = (decltype(n.Recv))dlsym(n.h, "ncclRecv");
+  n.GroupStart = (decltype(n.GroupStart))dlsym(n.h, "ncclGroupStart");
+  n.GroupEnd = (decltype(n.GroupEnd))dlsym(n.h, "ncclGroupEnd");
+  if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.AllReduce || !n.AllGather || !n.Send || !n.Recv ||
+      !n.GroupStart || !n.GroupEnd)
+    return fail(-61, "NCCL symbols missing");
   return 0;
 }
 }  // namespace
@@ -58,6 +70,66 @@ int comm_allreduce_sum(double *d_buf, size_t count, cudaStream_t st) {
   ncclResult_t r = n.AllReduce(d_buf, d_buf, count, ncclDouble, ncclSum, n.comm, st);
   if (r != ncclSuccess) return fail(-62, std::string("ncclAllReduce failed: ") + (n.GetErrorString ? n.GetErrorString(r) : "?"));
   return 0;
+}
+
+int comm_rank() { return N().comm ? N().rank : 0; }
+
+static int nccl_fail(const char *what, ncclResult_t r) {
+  Nccl &n = N();
+  return fail(-62, std::string(what) + " failed: " + (n.GetErrorString ? n.GetErrorString(r) : "?"));
+}
+
+// MPI_Allreduce(sensit_nnz, MPI_INTEGER) (sensitivity_gravmag.F90:322) and the INTEGER8 sum of nnz (:327).
+int comm_allreduce_sum_i32(int32_t *d_buf, size_t count, cudaStream_t st) {
+  Nccl &n = N();
+  if (!n.comm || n.nranks <= 1) return 0;
+  ncclResult_t r = n.AllReduce(d_buf, d_buf, count, ncclInt32, ncclSum, n.comm, st);
+  return r == ncclSuccess ? 0 : nccl_fail("ncclAllReduce", r);
+}
+int comm_allreduce_sum_i64(int64_t *d_buf, size_t count, cudaStream_t st) {
+  Nccl &n = N();
+  if (!n.comm || n.nranks <= 1) return 0;
+  ncclResult_t r = n.AllReduce(d_buf, d_buf, count, ncclInt64, ncclSum, n.comm, st);
+  return r == ncclSuccess ? 0 : nccl_fail("ncclAllReduce", r);
+}
+// recv[r*count .. (r+1)*count) = rank r's send[0 .. count)
+int comm_allgather_i64(const int64_t *d_send, int64_t *d_recv, size_t count, cudaStream_t st) {
+  Nccl &n = N();
+  if (!n.comm || n.nranks <= 1) {
+    if (d_send != d_recv) TFX_CUDA(cudaMemcpyAsync(d_recv, d_send, count * 8, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  ncclResult_t r = n.AllGather(d_send, d_recv, count, ncclInt64, n.comm, st);
+  return r == ncclSuccess ? 0 : nccl_fail("ncclAllGather", r);
+}
+// All-to-all of 4-byte elements with per-peer counts (element offsets, nranks + 1 entries each): the
+// device-to-device replacement of the per-row MPI_Scatterv of read_sensitivity_kernel
+// (sensitivity_gravmag.F90:818-829). One grouped ncclSend/ncclRecv pair per peer over NVLink.
+int comm_alltoallv_4b(const void *d_send, const int64_t *send_off, void *d_recv, const int64_t *recv_off,
+                      cudaStream_t st) {
+  Nccl &n = N();
+  if (!n.comm || n.nranks <= 1) {
+    const int64_t cnt = send_off[1] - send_off[0];
+    if (cnt > 0)
+      TFX_CUDA(cudaMemcpyAsync((char *)d_recv + recv_off[0] * 4, (const char *)d_send + send_off[0] * 4, (size_t)cnt * 4,
+                               cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  ncclResult_t r = n.GroupStart();
+  if (r != ncclSuccess) return nccl_fail("ncclGroupStart", r);
+  for (int q = 0; q < n.nranks; ++q) {
+    const int64_t ns = send_off[q + 1] - send_off[q], nr = recv_off[q + 1] - recv_off[q];
+    if (ns > 0) {
+      r = n.Send((const char *)d_send + send_off[q] * 4, (size_t)ns, ncclInt32, q, n.comm, st);
+      if (r != ncclSuccess) { n.GroupEnd(); return nccl_fail("ncclSend", r); }
+    }
+    if (nr > 0) {
+      r = n.Recv((char *)d_recv + recv_off[q] * 4, (size_t)nr, ncclInt32, q, n.comm, st);
+      if (r != ncclSuccess) { n.GroupEnd(); return nccl_fail("ncclRecv", r); }
+    }
+  }
+  r = n.GroupEnd();
+  return r == ncclSuccess ? 0 : nccl_fail("ncclGroupEnd", r);
 }
 
 int comm_unique_id(char id[128]) {

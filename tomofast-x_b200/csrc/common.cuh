@@ -87,11 +87,18 @@ struct DevBuf {
 };
 
 // Vector that may live on the host (caller-owned, copied in/out) or already on the device.
+// Host vectors are staged through a small pool of device buffers that survive the call, so a host
+// application that calls the solver once per major iteration does not pay cudaMalloc/cudaFree each time.
 struct VecIO {
   double *dev = nullptr;       // device pointer to use
   double *host = nullptr;      // original host pointer (nullptr when caller passed device memory)
-  DevBuf<double> own;          // staging when host != nullptr
+  double *stage = nullptr;     // pooled staging buffer when host != nullptr
+  size_t stage_cap = 0;
   size_t n = 0;
+  VecIO() {}
+  VecIO(const VecIO &) = delete;
+  VecIO &operator=(const VecIO &) = delete;
+  ~VecIO();
   int bind(double *ptr, size_t count, bool copy_in);
   int copy_back();
 };

@@ -42,6 +42,25 @@ int matrix_upload(Matrix &m, bool allow_dense);
 // Builds the T16 layouts from fwd/trn when the matrix is big enough (option "t16_min_nnz").
 int matrix_build_t16(Matrix &m);
 
+// ---- sensit.cu / sensit_dist.cu -----------------------------------------------------------------
+// Matrix entries sorted by (row, column) on the device: the currency between the row pipeline, the
+// re-partitioner and the matrix builder.
+struct RowTriplets {
+  DevBuf<int32_t> idx;     // 0-based column
+  DevBuf<int32_t> rowid;   // 0-based matrix row
+  DevBuf<float> val;
+  int64_t nnz = 0;
+};
+}  // namespace tfx
+struct tfx_sensit_params;
+namespace tfx {
+int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const double *d_dx, const double *d_dy,
+                         const double *d_dz, const double *d_cw, const double *h_dw, int32_t data0, int32_t ndata_loc,
+                         RowTriplets &R, DevBuf<int32_t> &dnnz, std::vector<long long> &seg_end, double *err_sum);
+int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R);
+int upload_grid(GridDev &g, int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
+                const double *Z1, const double *Z2);
+
 // ---- lsqr.cu ----------------------------------------------------------------------------------
 struct LsqrParams {
   int32_t nlines = 0, ncolumns = 0, niter = 0;
@@ -73,7 +92,13 @@ int lsqr_run_strict(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, doub
 
 // ---- comm.cu ----------------------------------------------------------------------------------
 int comm_nranks();
+int comm_rank();
 int comm_allreduce_sum(double *d_buf, size_t count, cudaStream_t st);
+int comm_allreduce_sum_i32(int32_t *d_buf, size_t count, cudaStream_t st);
+int comm_allreduce_sum_i64(int64_t *d_buf, size_t count, cudaStream_t st);
+int comm_allgather_i64(const int64_t *d_send, int64_t *d_recv, size_t count, cudaStream_t st);
+int comm_alltoallv_4b(const void *d_send, const int64_t *send_off, void *d_recv, const int64_t *recv_off,
+                      cudaStream_t st);
 int comm_unique_id(char id[128]);
 int comm_init(int nranks, int rank, const char id[128]);
 int comm_finalize();

@@ -222,7 +222,7 @@ int up(DevBuf<T> &d, const T *h, size_t n) {
   return 0;
 }
 
-int upload_grid(GridDev &g, int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
+int upload_grid_impl(GridDev &g, int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
                 const double *Z1, const double *Z2) {
   g.n = n;
   TFX_TRY(up(g.X1, X1, n)); TFX_TRY(up(g.X2, X2, n)); TFX_TRY(up(g.Y1, Y1, n));
@@ -253,6 +253,209 @@ int compute_lines(const tfx_sensit_params &P, const GridDev &g, int nb, const do
 }
 
 }  // namespace
+
+int upload_grid(GridDev &g, int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
+                const double *Z1, const double *Z2) {
+  return upload_grid_impl(g, n, X1, X2, Y1, Y2, Z1, Z2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row pipeline for the stations [data0, data0 + ndata_loc) (the reference's data loop,
+// sensitivity_gravmag.F90:189-318, for one rank's share of the data). Entries come out sorted by
+// (matrix row, column): R.idx = 0-based column (param_shift and (k-1)*N applied), R.rowid = 0-based
+// GLOBAL matrix row idata*ndc + d. seg_end[i] = running entry count after segment i (segments in
+// the order idata, d, k). dnnz (N): per-cell entry counts (sensit_nnz, :267/:293).
+// ---------------------------------------------------------------------------------------------
+int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const double *d_dx, const double *d_dy,
+                         const double *d_dz, const double *d_cw, const double *h_dw, int32_t data0, int32_t ndata_loc,
+                         RowTriplets &R, DevBuf<int32_t> &dnnz, std::vector<long long> &seg_end, double *err_sum) {
+  Context &c = ctx();
+  cudaStream_t st = c.stream;
+  const int32_t N = P.nx * P.ny * P.nz;
+  const int32_t ndc = P.ndata_components, nmc = P.nmodel_components;
+  const int32_t nel_compressed = (P.compression_type > 0) ? (int32_t)(P.compression_rate * (double)N) : N;
+  const int64_t nseg_lines = (int64_t)ndata_loc * ndc * nmc;
+  const int64_t cap = (int64_t)nel_compressed * nseg_lines;   // upper bound of nnz
+  TFX_TRY(R.idx.alloc((size_t)cap)); TFX_TRY(R.val.alloc((size_t)cap)); TFX_TRY(R.rowid.alloc((size_t)cap));
+  R.nnz = 0;
+  DevBuf<int32_t> dcols;
+  DevBuf<int> derr;
+  TFX_TRY(dnnz.alloc(N)); TFX_TRY(dcols.alloc(N)); TFX_TRY(derr.alloc(1));
+  TFX_CUDA(cudaMemsetAsync(dnnz.p, 0, (size_t)N * 4, st));
+  TFX_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
+  seg_end.assign((size_t)nseg_lines, 0);
+  if (err_sum) *err_sum = 0.0;
+  if (ndata_loc <= 0) return 0;
+
+  // batch of stations whose lines are resident at once (<= ~1 GiB)
+  const size_t per_station = (size_t)N * nmc * ndc;
+  int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)ndata_loc, ((size_t)1 << 27) / per_station));
+  DevBuf<double> dl;
+  TFX_TRY(dl.alloc(per_station * B));
+  const int vgrid = c.num_sms * 8;
+
+  // device-resident state of the row pipeline (no host synchronisation per row)
+  DevBuf<RowState> dst;
+  DevBuf<unsigned> dhist;
+  DevBuf<double> dpartial;
+  DevBuf<long long> dsegend;
+  DevBuf<unsigned char> dtemp;
+  TFX_TRY(dst.alloc(1)); TFX_TRY(dhist.alloc(256)); TFX_TRY(dpartial.alloc(kRedBlocks));
+  TFX_TRY(dsegend.alloc((size_t)nseg_lines));
+  TFX_CUDA(cudaMemsetAsync(dst.p, 0, sizeof(RowState), st));
+  size_t temp_bytes = 0;
+  {
+    KeepPredDev pred{dl.p, dst.p};
+    cub::DeviceSelect::If(nullptr, temp_bytes, thrust::counting_iterator<int>(0), dcols.p, &dst.p->nsel, N, pred, st);
+  }
+  TFX_TRY(dtemp.alloc(temp_bytes + 16));
+  const long long rank = (long long)N - nel_compressed - 1;   // 0-based rank of sorted(N - nel_compressed), :240-251
+  const bool no_select = nel_compressed >= N;
+  const int rgrid = std::min(kRedBlocks, (N + 255) / 256);
+
+  int64_t iseg = 0;
+  for (int32_t b0 = 0; b0 < ndata_loc; b0 += B) {
+    const int nb = std::min<int>(B, ndata_loc - b0);
+    TFX_TRY(compute_lines(P, g, nb, d_dx + data0 + b0, d_dy + data0 + b0, d_dz + data0 + b0, dl.p, derr.p, st));
+    k_apply_cw<<<vgrid, 256, 0, st>>>(dl.p, d_cw, N, (int64_t)per_station * nb);
+    c.launches++;
+    for (int b = 0; b < nb; ++b) {
+      const int32_t idata = data0 + b0 + b;   // 0-based global station
+      for (int d = 0; d < ndc; ++d) {
+        const int32_t row = idata * ndc + d;
+        // combined_weight = real(problem_weight * data_weight(d, idata), 4)
+        const float wgt = (float)(P.problem_weight * h_dw[(size_t)idata * ndc + d]);
+        for (int k = 0; k < nmc; ++k, ++iseg) {
+          double *line = dl.p + ((size_t)b * ndc * nmc + (size_t)d * nmc + k) * N;
+          const int32_t shift = P.param_shift + k * N;   // 0-based column = p + shift
+          if (P.compression_type > 0) {
+            k_row_sumsq<<<rgrid, 256, 0, st>>>(line, N, 0, dst.p, dpartial.p);                     // cost_full, :234
+            k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, dst.p, 0);
+            TFX_TRY(wavelet3d_device(line, P.nx, P.ny, P.nz, P.compression_type, true, st));       // :237
+            if (!no_select) {
+              k_select_begin<<<1, 256, 0, st>>>(dst.p, rank, dhist.p);
+              for (int pass = 0; pass < 8; ++pass) {
+                k_select_hist<<<vgrid, 256, 0, st>>>(line, N, dst.p, dhist.p);
+                k_select_pick<<<1, 256, 0, st>>>(dst.p, dhist.p);
+              }
+              c.launches += 17;
+            }
+            k_select_end<<<1, 1, 0, st>>>(dst.p, no_select ? 1 : 0);
+            KeepPredDev pred{line, dst.p};
+            size_t tb = temp_bytes;
+            TFX_CUDA(cub::DeviceSelect::If(dtemp.p, tb, thrust::counting_iterator<int>(0), dcols.p, &dst.p->nsel, N, pred, st));
+            k_row_sumsq<<<rgrid, 256, 0, st>>>(line, N, 1, dst.p, dpartial.p);                     // discarded cost, :283
+            k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, dst.p, 1);
+            k_finish_segment_dev<<<std::min(vgrid, (nel_compressed + 255) / 256), 256, 0, st>>>(
+                dcols.p, line, wgt, shift, row, dst.p, cap, R.idx.p, R.val.p, R.rowid.p, dnnz.p);
+            k_advance<<<1, 1, 0, st>>>(dst.p, nel_compressed, cap, dsegend.p, iseg);
+            c.launches += 9;
+          } else {
+            // uncompressed general path: the offset is known on the host
+            k_dense_segment<<<std::min(vgrid, (N + 255) / 256), 256, 0, st>>>(line, N, wgt, shift, row,
+                                                                             R.idx.p + iseg * (int64_t)N, R.val.p + iseg * (int64_t)N,
+                                                                             R.rowid.p + iseg * (int64_t)N, dnnz.p);
+            k_advance_dense<<<1, 1, 0, st>>>(dst.p, N, dsegend.p, iseg);
+            c.launches += 2;
+          }
+        }
+      }
+    }
+    int e = 0;
+    TFX_CUDA(cudaMemcpyAsync(&e, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TFX_CUDA(cudaStreamSynchronize(st));
+    if (e) return kernel_error(e);
+  }
+  RowState hst;
+  TFX_CUDA(cudaMemcpyAsync(&hst, dst.p, sizeof(RowState), cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaMemcpyAsync(seg_end.data(), dsegend.p, (size_t)nseg_lines * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  if (hst.bad) return fail(-79, "Wrong number of elements in calculate_and_write_sensit!");
+  R.nnz = hst.nnz;
+  if (err_sum) *err_sum = hst.err_sum;
+  return 0;
+}
+
+// keys (sorted, n entries) -> unique keys + exclusive offsets on the host.
+static int runs_of_sorted_keys(const int32_t *d_keys, int64_t n, int32_t max_unique, std::vector<int32_t> &uniq,
+                               std::vector<int64_t> &ptr) {
+  cudaStream_t st = ctx().stream;
+  auto pol = thrust::cuda::par.on(st);
+  uniq.clear();
+  ptr.assign(1, 0);
+  if (n <= 0) return 0;
+  DevBuf<int32_t> ucols, ucnt;
+  const size_t cap = (size_t)std::min<int64_t>(n, max_unique);
+  TFX_TRY(ucols.alloc(cap)); TFX_TRY(ucnt.alloc(cap));
+  thrust::device_ptr<const int32_t> K(d_keys);
+  thrust::device_ptr<int32_t> UC(ucols.p), UN(ucnt.p);
+  auto ends = thrust::reduce_by_key(pol, K, K + n, thrust::make_constant_iterator<int32_t>(1), UC, UN);
+  const size_t nu = (size_t)(ends.first - UC);
+  uniq.resize(nu);
+  std::vector<int32_t> cnt(nu);
+  TFX_CUDA(cudaMemcpyAsync(uniq.data(), ucols.p, nu * 4, cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaMemcpyAsync(cnt.data(), ucnt.p, nu * 4, cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  ptr.resize(nu + 1);
+  for (size_t i = 0; i < nu; ++i) ptr[i + 1] = ptr[i] + cnt[i];
+  ctx().launches += 2;
+  return 0;
+}
+
+// Finalized device matrix from entries sorted by (row, column). Takes ownership of R's buffers.
+// Matrix rows without entries are not stored (new_row(), sparse_matrix.f90:266-274).
+int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R) {
+  Context &c = ctx();
+  cudaStream_t st = c.stream;
+  auto pol = thrust::cuda::par.on(st);
+  const int64_t nnz = R.nnz;
+  M.nl = nl; M.nl_current_all = nl; M.ncolumns = ncolumns;
+  M.device_only = true;
+
+  // ---- forward representation: runs of equal row ids
+  SegMatrix &F = M.fwd;
+  std::vector<int64_t> ptr;
+  std::vector<int32_t> segmap;
+  TFX_TRY(runs_of_sorted_keys(R.rowid.p, nnz, nl, segmap, ptr));
+  std::swap(F.idx.p, R.idx.p); std::swap(F.idx.n, R.idx.n);
+  std::swap(F.val.p, R.val.p); std::swap(F.val.n, R.val.n);
+  F.nnz = nnz; F.nseg = (int32_t)segmap.size(); F.nout = nl; F.nin = ncolumns;
+  TFX_TRY(up(F.ptr, ptr.data(), ptr.size()));
+  TFX_TRY(up(F.segmap, segmap.data(), segmap.size()));
+  TFX_TRY(seg_build_items(F, ptr.data()));
+
+  // ---- transpose on the device: stable sort by column keeps the row order inside each column
+  SegMatrix &T = M.trn;
+  T.nnz = nnz; T.nout = ncolumns; T.nin = nl;
+  DevBuf<int32_t> keys;
+  TFX_TRY(keys.alloc((size_t)std::max<int64_t>(nnz, 1)));
+  TFX_TRY(T.val.alloc((size_t)std::max<int64_t>(nnz, 1)));
+  std::swap(T.idx.p, R.rowid.p); std::swap(T.idx.n, R.rowid.n);   // row ids become the gathered index of A^T
+  if (!T.idx.p) TFX_TRY(T.idx.alloc(1));
+  std::vector<int64_t> tptr(1, 0);
+  std::vector<int32_t> tmap;
+  if (nnz > 0) {
+    TFX_CUDA(cudaMemcpyAsync(keys.p, F.idx.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaMemcpyAsync(T.val.p, F.val.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
+    thrust::device_ptr<int32_t> K(keys.p), Rw(T.idx.p);
+    thrust::device_ptr<float> V(T.val.p);
+    thrust::stable_sort_by_key(pol, K, K + nnz, thrust::make_zip_iterator(thrust::make_tuple(Rw, V)));
+    c.launches += 2;
+    TFX_TRY(runs_of_sorted_keys(keys.p, nnz, ncolumns, tmap, tptr));
+  }
+  keys.release();
+  T.nseg = (int32_t)tmap.size();
+  TFX_TRY(up(T.ptr, tptr.data(), tptr.size()));
+  TFX_TRY(up(T.segmap, tmap.data(), tmap.size()));
+  TFX_TRY(seg_build_items(T, tptr.data()));
+
+  M.has_seg = true;
+  TFX_TRY(matrix_build_t16(M));
+  M.nnz = M.nel = nnz;
+  M.nl_nonempty = F.nseg;
+  M.finalized = true;
+  return 0;
+}
 
 }  // namespace tfx
 
@@ -348,166 +551,17 @@ extern "C" int tfx_calculate_sensit(tfx_matrix **out, const tfx_sensit_params *p
     return fail(-78, "calculate_sensit: the compressed / magnetic pipeline needs the full grid on the rank");
   }
   const int64_t nseg_lines = (int64_t)P.ndata * ndc * nmc;
-  const int64_t cap = (int64_t)nel_compressed * nseg_lines;   // upper bound of nnz
-  SegMatrix &F = M.fwd;
-  DevBuf<int32_t> rowid;
-  if (F.idx.alloc((size_t)cap) || F.val.alloc((size_t)cap) || rowid.alloc((size_t)cap)) { delete h; return -101; }
-  DevBuf<int32_t> dnnz, dcols;
-  if (dnnz.alloc(N) || dcols.alloc(N)) { delete h; return -101; }
-  TFX_CUDA(cudaMemsetAsync(dnnz.p, 0, (size_t)N * 4, st));
-
-  // batch of stations whose lines are resident at once (<= ~1 GiB)
-  const size_t per_station = (size_t)N * nmc * ndc;
-  int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)P.ndata, ((size_t)1 << 27) / per_station));
-  DevBuf<double> dl;
-  if (dl.alloc(per_station * B)) { delete h; return -101; }
-
+  RowTriplets R;
+  DevBuf<int32_t> dnnz;
+  std::vector<long long> seg_end;
+  double err_sum = 0.0;
   std::vector<double> h_dw((size_t)P.ndata * ndc);
   memcpy(h_dw.data(), data_weight, h_dw.size() * sizeof(double));
-  const int vgrid = c.num_sms * 8;
-  auto pol = thrust::cuda::par.on(st);
-
-  // device-resident state of the row pipeline (no host synchronisation per row)
-  DevBuf<RowState> dst;
-  DevBuf<unsigned> dhist;
-  DevBuf<double> dpartial;
-  DevBuf<long long> dsegend;
-  DevBuf<unsigned char> dtemp;
-  if (dst.alloc(1) || dhist.alloc(256) || dpartial.alloc(kRedBlocks) || dsegend.alloc((size_t)nseg_lines)) { delete h; return -101; }
-  TFX_CUDA(cudaMemsetAsync(dst.p, 0, sizeof(RowState), st));
-  size_t temp_bytes = 0;
-  {
-    KeepPredDev pred{dl.p, dst.p};
-    cub::DeviceSelect::If(nullptr, temp_bytes, thrust::counting_iterator<int>(0), dcols.p, &dst.p->nsel, N, pred, st);
-  }
-  if (dtemp.alloc(temp_bytes + 16)) { delete h; return -101; }
-  const long long rank = (long long)N - nel_compressed - 1;   // 0-based rank of sorted(N - nel_compressed), :240-251
-  const bool no_select = nel_compressed >= N;
-  const int rgrid = std::min(kRedBlocks, (N + 255) / 256);
-
-  int64_t iseg = 0;
-  for (int32_t b0 = 0; b0 < P.ndata; b0 += B) {
-    const int nb = std::min<int>(B, P.ndata - b0);
-    int rc = compute_lines(P, g, nb, dx.p + b0, dy.p + b0, dz.p + b0, dl.p, derr.p, st);
-    if (rc) { delete h; return rc; }
-    k_apply_cw<<<vgrid, 256, 0, st>>>(dl.p, dcw.p, N, (int64_t)per_station * nb);
-    c.launches++;
-    for (int b = 0; b < nb; ++b) {
-      const int32_t idata = b0 + b;   // 0-based
-      for (int d = 0; d < ndc; ++d) {
-        const int32_t row = idata * ndc + d;
-        // combined_weight = real(problem_weight * data_weight(d, idata), 4)
-        const float wgt = (float)(P.problem_weight * h_dw[(size_t)idata * ndc + d]);
-        for (int k = 0; k < nmc; ++k, ++iseg) {
-          double *line = dl.p + ((size_t)b * ndc * nmc + (size_t)d * nmc + k) * N;
-          const int32_t shift = P.param_shift + k * N;   // 0-based column = p + shift
-          if (P.compression_type > 0) {
-            k_row_sumsq<<<rgrid, 256, 0, st>>>(line, N, 0, dst.p, dpartial.p);                     // cost_full, :234
-            k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, dst.p, 0);
-            rc = wavelet3d_device(line, P.nx, P.ny, P.nz, P.compression_type, true, st);           // :237
-            if (rc) { delete h; return rc; }
-            if (!no_select) {
-              k_select_begin<<<1, 256, 0, st>>>(dst.p, rank, dhist.p);
-              for (int pass = 0; pass < 8; ++pass) {
-                k_select_hist<<<vgrid, 256, 0, st>>>(line, N, dst.p, dhist.p);
-                k_select_pick<<<1, 256, 0, st>>>(dst.p, dhist.p);
-              }
-              c.launches += 17;
-            }
-            k_select_end<<<1, 1, 0, st>>>(dst.p, no_select ? 1 : 0);
-            KeepPredDev pred{line, dst.p};
-            size_t tb = temp_bytes;
-            TFX_CUDA(cub::DeviceSelect::If(dtemp.p, tb, thrust::counting_iterator<int>(0), dcols.p, &dst.p->nsel, N, pred, st));
-            k_row_sumsq<<<rgrid, 256, 0, st>>>(line, N, 1, dst.p, dpartial.p);                     // discarded cost, :283
-            k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, dst.p, 1);
-            k_finish_segment_dev<<<std::min(vgrid, (nel_compressed + 255) / 256), 256, 0, st>>>(
-                dcols.p, line, wgt, shift, row, dst.p, cap, F.idx.p, F.val.p, rowid.p, dnnz.p);
-            k_advance<<<1, 1, 0, st>>>(dst.p, nel_compressed, cap, dsegend.p, iseg);
-            c.launches += 9;
-          } else {
-            // uncompressed general path: the offset is known on the host
-            k_dense_segment<<<std::min(vgrid, (N + 255) / 256), 256, 0, st>>>(line, N, wgt, shift, row,
-                                                                             F.idx.p + iseg * (int64_t)N, F.val.p + iseg * (int64_t)N,
-                                                                             rowid.p + iseg * (int64_t)N, dnnz.p);
-            k_advance_dense<<<1, 1, 0, st>>>(dst.p, N, dsegend.p, iseg);
-            c.launches += 2;
-          }
-        }
-      }
-    }
-    int e = 0;
-    TFX_CUDA(cudaMemcpyAsync(&e, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    TFX_CUDA(cudaStreamSynchronize(st));
-    if (e) { delete h; return kernel_error(e); }
-  }
-  RowState hst;
-  std::vector<long long> seg_end((size_t)nseg_lines);
-  TFX_CUDA(cudaMemcpyAsync(&hst, dst.p, sizeof(RowState), cudaMemcpyDeviceToHost, st));
-  TFX_CUDA(cudaMemcpyAsync(seg_end.data(), dsegend.p, (size_t)nseg_lines * sizeof(long long), cudaMemcpyDeviceToHost, st));
-  TFX_CUDA(cudaStreamSynchronize(st));
-  if (hst.bad) { delete h; return fail(-79, "Wrong number of elements in calculate_and_write_sensit!"); }
-  const int64_t nnz = hst.nnz;
-  const double err_sum = hst.err_sum;
-  // matrix rows: one per (idata, d), the nmc segments concatenated; only non-empty rows are stored
-  // (new_row(), sparse_matrix.f90:266-274)
-  std::vector<int64_t> ptr;       // stored rows only (0-based offsets)
-  std::vector<int32_t> segmap;    // 0-based global row of each stored row
-  ptr.push_back(0);
-  for (int32_t row = 0; row < nl; ++row) {
-    const int64_t row_end = seg_end[(size_t)(row + 1) * nmc - 1];
-    if (row_end > ptr.back()) {
-      ptr.push_back(row_end);
-      segmap.push_back(row);
-    }
-  }
-
-  // ---- forward representation
-  F.nnz = nnz; F.nseg = (int32_t)segmap.size(); F.nout = nl; F.nin = P.ncolumns;
-  TFX_TRY(up(F.ptr, ptr.data(), ptr.size()));
-  TFX_TRY(up(F.segmap, segmap.data(), segmap.size()));
-  TFX_TRY(seg_build_items(F, ptr.data()));
-
-  // ---- transpose on the device: stable sort by column keeps the row order inside each column
-  SegMatrix &T = M.trn;
-  T.nnz = nnz; T.nout = P.ncolumns; T.nin = nl;
-  DevBuf<int32_t> keys;
-  TFX_TRY(keys.alloc((size_t)std::max<int64_t>(nnz, 1)));
-  TFX_TRY(T.idx.alloc((size_t)std::max<int64_t>(nnz, 1)));
-  TFX_TRY(T.val.alloc((size_t)std::max<int64_t>(nnz, 1)));
-  std::vector<int64_t> tptr(1, 0);
-  std::vector<int32_t> tmap;
-  if (nnz > 0) {
-    TFX_CUDA(cudaMemcpyAsync(keys.p, F.idx.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
-    TFX_CUDA(cudaMemcpyAsync(T.idx.p, rowid.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
-    TFX_CUDA(cudaMemcpyAsync(T.val.p, F.val.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
-    thrust::device_ptr<int32_t> K(keys.p), R(T.idx.p);
-    thrust::device_ptr<float> V(T.val.p);
-    thrust::stable_sort_by_key(pol, K, K + nnz, thrust::make_zip_iterator(thrust::make_tuple(R, V)));
-    DevBuf<int32_t> ucols, ucnt;
-    TFX_TRY(ucols.alloc((size_t)std::min<int64_t>(nnz, P.ncolumns)));
-    TFX_TRY(ucnt.alloc((size_t)std::min<int64_t>(nnz, P.ncolumns)));
-    thrust::device_ptr<int32_t> UC(ucols.p), UN(ucnt.p);
-    auto ends = thrust::reduce_by_key(pol, K, K + nnz, thrust::make_constant_iterator<int32_t>(1), UC, UN);
-    const size_t nu = (size_t)(ends.first - UC);
-    tmap.resize(nu);
-    std::vector<int32_t> cnt(nu);
-    TFX_CUDA(cudaMemcpyAsync(tmap.data(), ucols.p, nu * 4, cudaMemcpyDeviceToHost, st));
-    TFX_CUDA(cudaMemcpyAsync(cnt.data(), ucnt.p, nu * 4, cudaMemcpyDeviceToHost, st));
-    TFX_CUDA(cudaStreamSynchronize(st));
-    tptr.resize(nu + 1);
-    for (size_t i = 0; i < nu; ++i) tptr[i + 1] = tptr[i] + cnt[i];
-    c.launches += 4;
-  }
-  T.nseg = (int32_t)tmap.size();
-  TFX_TRY(up(T.ptr, tptr.data(), tptr.size()));
-  TFX_TRY(up(T.segmap, tmap.data(), tmap.size()));
-  TFX_TRY(seg_build_items(T, tptr.data()));
-
-  M.has_seg = true;
-  TFX_TRY(matrix_build_t16(M));
-  M.nnz = M.nel = nnz;
-  M.nl_nonempty = F.nseg;
-  M.finalized = true;
+  int rc = assemble_rows_device(P, g, dx.p, dy.p, dz.p, dcw.p, h_dw.data(), 0, P.ndata, R, dnnz, seg_end, &err_sum);
+  if (rc) { delete h; return rc; }
+  const int64_t nnz = R.nnz;
+  rc = matrix_from_triplets(M, nl, P.ncolumns, R);
+  if (rc) { delete h; return rc; }
   if (sensit_nnz) TFX_CUDA(cudaMemcpyAsync(sensit_nnz, dnnz.p, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
   TFX_CUDA(cudaStreamSynchronize(st));
   if (comp_error) *comp_error = (P.compression_type > 0) ? err_sum / (double)nseg_lines : 0.0;   // :346-353
