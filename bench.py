@@ -305,12 +305,12 @@ def run_ours(a):
         }
         if d.world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(a, steps=2, warmup=1, seconds_hint=20.0)
-    if d.world == 1 and not a.no_compressed:
-        # free the 168 GB dense block before the compressed matrix is assembled
+    if not a.no_compressed:
+        # free the dense block before the compressed matrix is assembled
         del S, C, u_dev, x_dev, u_pin, x_pin
         import gc
         gc.collect()
-        comp = compressed_spmv(a, tfx)
+        comp = compressed_spmv(a, tfx, d)
         if d.rank == 0:
             line["spmv"] = comp
     if d.rank == 0:
@@ -319,12 +319,14 @@ def run_ours(a):
     return x_host
 
 
-def compressed_spmv(a, tfx):
+def compressed_spmv(a, tfx, d):
     """SpMV / SpMV^T GB/s on a wavelet-compressed sensitivity matrix (the second half of BASELINE.json's
     metric): synthetic gravity, same grid and stations as the headline workload, Haar compression at 5 %
     (BASELINE config C's rate), assembled on the device by the reference's row pipeline, kept in the T16
     layouts (6 B/nnz per product). Times come from CUDA events on the library stream around back-to-back
-    products (tfx_sparse_matrix_time_product); the matrix (2 x 12.6 GB) is far larger than L2."""
+    products (tfx_sparse_matrix_time_product); the matrix (2 x 12.6 GB) is far larger than L2.
+    With N > 1 ranks: rows are assembled sharded by data, re-partitioned over NVLink to nnz-balanced column
+    slabs (csrc/sensit_dist.cu) and every figure is the whole-job aggregate (total bytes / max time over ranks)."""
     from tests.synth import depth_weight_type1, regular_grid, station_lattice
     nx, ny, nz, nd, rate = a.nx, a.ny, a.nz, a.comp_ndata, a.comp_rate
     N = nx * ny * nz
@@ -338,67 +340,101 @@ def compressed_spmv(a, tfx):
     par.compression_type, par.compression_rate = 1, rate
     par.problem_weight = 1.0
     par.cell0, par.ncells_local, par.param_shift, par.ncolumns = 0, N, 0, 2 * N
-    t0 = time.perf_counter()
-    S, _, cerr, nnz = tfx.calculate_sensit(par, grid, xyz, cw, np.ones((nd, 1)))
     tfx.synchronize()
-    t_asm = time.perf_counter() - t0
+    d.barrier()
+    t0 = time.perf_counter()
+    t_rows = t_part = None
+    if d.world == 1:
+        S, _, cerr, nnz = tfx.calculate_sensit(par, grid, xyz, cw, np.ones((nd, 1)))
+        ncl, cell0, nnz_loc = N, 0, nnz
+        slabs = [N]
+    else:
+        rows, nnz_col, cerr, nnz = tfx.sensit_assemble_rows(par, grid, xyz, cw, np.ones((nd, 1)), d.rank, d.world)
+        tfx.synchronize()
+        t_rows = d.max(time.perf_counter() - t0)
+        nnz_at, nel_at = tfx.get_load_balancing_nelements(nnz_col, d.world)
+        S = tfx.sensit_repartition(rows, 1, nel_at, d.rank, d.world)
+        ncl, cell0, nnz_loc = int(nel_at[d.rank]), int(nel_at[:d.rank].sum()), int(nnz_at[d.rank])
+        slabs = [int(v) for v in nel_at]
+        del rows
+    tfx.synchronize()
+    t_asm = d.max(time.perf_counter() - t0)
+    if t_rows is not None:
+        t_part = t_asm - t_rows
+    ncol = 2 * ncl
     assert S.storage_kind() == 2, "compressed matrix must be in the T16 layouts"
     peak, peak_src = hbm_peak()
     rng = np.random.default_rng(1235)
-    x = tfx.Buffer(2 * N); u = tfx.Buffer(nd); q = tfx.Buffer(nd); t = tfx.Buffer(2 * N)
-    tfx.copy(x, rng.uniform(-1.0, 1.0, 2 * N), 2 * N)
+    x = tfx.Buffer(ncol); u = tfx.Buffer(nd); q = tfx.Buffer(nd); t = tfx.Buffer(ncol)
+    x_full = rng.uniform(-1.0, 1.0, N)
+    x_loc = np.zeros(ncol); x_loc[:ncl] = x_full[cell0:cell0 + ncl]
+    tfx.copy(x, x_loc, ncol)
     tfx.copy(u, rng.uniform(-1.0, 1.0, nd), nd)
     out = {"workload": "synthetic gravity %dx%dx%d cells, %d data, Haar wavelet compression %g" % (nx, ny, nz, nd, rate),
            "nnz": int(nnz), "compression_error": cerr, "assemble_s": round(t_asm, 2),
            "layout": "T16 (f32 value + u16 in-tile key = 6 B/nnz per product, one copy per direction)",
-           "peak": peak, "peak_source": peak_src, "unit": "GB/s", "reps": a.comp_reps}
+           "peak": peak * d.world, "peak_source": peak_src + (" x %d GPUs" % d.world if d.world > 1 else ""),
+           "unit": "GB/s", "reps": a.comp_reps}
+    if d.world > 1:
+        out["column_slabs"] = slabs
+        out["nnz_per_rank_max_over_mean"] = d.max(float(nnz_loc)) / (float(nnz) / d.world)
+        out["assemble_rows_s"], out["repartition_s"] = round(t_rows, 2), round(t_part, 2)
     l0 = tfx.launch_count()
     for name, tr, xi, yo in (("forward", 0, x, q), ("transposed", 1, u, t)):
-        ms = S.time_product(tr, xi, yo, a.comp_reps)
+        d.barrier()
+        ms = d.max(S.time_product(tr, xi, yo, a.comp_reps))
         # algorithmic bytes of SURVEY 8(d): 8 B/nnz (f32 value + int32 column) + the vectors; bytes moved: 6 B/nnz
-        vec = 8.0 * (N + 2 * nd) if tr == 0 else 8.0 * (nd + 2 * N)
+        vec = 8.0 * (N + 2 * nd * d.world) if tr == 0 else 8.0 * (nd * d.world + 2 * N)
         alg = 8.0 * nnz + vec
         moved = 6.0 * nnz + vec
-        out[name] = {"ms": ms, "achieved": alg / ms / 1e6, "frac": alg / ms / 1e6 / peak,
-                     "moved_gbs": moved / ms / 1e6, "moved_frac": moved / ms / 1e6 / peak}
+        out[name] = {"ms": ms, "achieved": alg / ms / 1e6, "frac": alg / ms / 1e6 / (peak * d.world),
+                     "moved_gbs": moved / ms / 1e6, "moved_frac": moved / ms / 1e6 / (peak * d.world)}
     out["gpu_launches"] = int(tfx.launch_count() - l0)
     # size-independent parity property at full size: <S x, u> == <x, S^T u> (the two products use two
     # different copies of the matrix, so this also checks the layouts against each other)
     xh, uh = x.numpy(), u.numpy()
-    lhs, rhs = float(np.dot(q.numpy(), uh)), float(np.dot(xh, t.numpy()))
+    lhs, rhs = d.sum(float(np.dot(q.numpy(), uh))), d.sum(float(np.dot(xh, t.numpy())))
     out["adjoint_rel_err"] = abs(lhs - rhs) / max(abs(lhs), abs(rhs), 1e-300)
     assert out["adjoint_rel_err"] < 1e-10, out["adjoint_rel_err"]
-    # 3-D wavelet transform on a device-resident volume (SURVEY 8d metric iii: 16 B per element and transform)
-    vol = tfx.Buffer(N)
-    tfx.copy(vol, rng.uniform(-1.0, 1.0, N), N)
-    out["wavelet"] = {}
-    for wname, wtype in (("haar", 1), ("daubechies_d4", 2)):
-        for _ in range(2):
-            tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)
-        tfx.timer_start()
-        for _ in range(10):
-            tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)
-        ms = tfx.timer_stop() / 20.0
-        out["wavelet"][wname] = {"ms_per_transform": ms, "achieved": 16.0 * N / ms / 1e6, "frac": 16.0 * N / ms / 1e6 / peak,
-                                 "note": "algorithmic 16 B/element; the kernel makes 3 axis passes (48 B/element moved)"}
+    if d.world == 1:
+        # 3-D wavelet transform on a device-resident volume (SURVEY 8d metric iii: 16 B per element and transform)
+        vol = tfx.Buffer(N)
+        tfx.copy(vol, rng.uniform(-1.0, 1.0, N), N)
+        out["wavelet"] = {}
+        for wname, wtype in (("haar", 1), ("daubechies_d4", 2)):
+            for _ in range(2):
+                tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)
+            tfx.timer_start()
+            for _ in range(10):
+                tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)
+            ms = tfx.timer_stop() / 20.0
+            out["wavelet"][wname] = {"ms_per_transform": ms, "achieved": 16.0 * N / ms / 1e6, "frac": 16.0 * N / ms / 1e6 / peak,
+                                     "note": "algorithmic 16 B/element; the kernel makes 3 axis passes (48 B/element moved)"}
+        del vol
     out["assembly"] = {"rows_per_s": nd / t_asm, "cell_evaluations_per_s": float(nd) * N / t_asm,
-                       "note": "kernel line + column weight + Haar transform + exact k-th threshold + compaction per row"}
+                       "note": "kernel line + column weight + Haar transform + exact k-th threshold + compaction per row"
+                               + ("; rows sharded over %d GPUs + all-to-all re-partitioning" % d.world if d.world > 1 else "")}
     # LSQR on the compressed matrix (wavelet-domain solve, split path: one product per direction per iteration)
     m = np.zeros((nz, ny, nx))
     sl = lambda n: slice(max(0, n // 2 - max(1, n // 8)), n // 2 + max(1, n // 8))
     m[sl(nz), sl(ny), sl(nx)] = 250.0
-    xs = np.zeros(2 * N)
-    xs[:N] = tfx.forward_wavelet((m.ravel() / cw).copy(), nx, ny, nz, 1)
+    xs = np.zeros(ncol)
+    xs[:ncl] = tfx.forward_wavelet((m.ravel() / cw).copy(), nx, ny, nz, 1)[cell0:cell0 + ncl]
     d_obs = S.mult_vector(xs)
-    Cm = tfx.SparseMatrix.from_arrays(N, 2 * N, np.full(N, 1.0e-11, dtype=np.float32), np.arange(1, N + 1, dtype=np.int32),
-                                      np.arange(1, N + 2, dtype=np.int64), np.arange(1, N + 1, dtype=np.int32))
+    if d.world > 1:
+        tfx.comm_allreduce_sum(d_obs, nd)
+    Cm = tfx.SparseMatrix.from_arrays(N, ncol, np.full(ncl, 1.0e-11, dtype=np.float32), np.arange(1, ncl + 1, dtype=np.int32),
+                                      np.arange(1, ncl + 2, dtype=np.int64), np.arange(cell0 + 1, cell0 + ncl + 1, dtype=np.int32))
     nlines = nd + N
     b = np.zeros(nlines); b[:nd] = d_obs
-    ub, xb = tfx.Buffer(nlines), tfx.Buffer(2 * N)
+    ub, xb = tfx.Buffer(nlines), tfx.Buffer(ncol)
     for niter in (3, a.steps):
         tfx.copy(ub, b, nlines)
-        tfx.lsqr_solve_sensit(nlines, 2 * N, niter, 1.0e-13, 0.0, 0.0, S, Cm, ub, xb, [1, 0], N, nx, ny, nz, 1, 1, True)
+        d.barrier()
+        tfx.lsqr_solve_sensit(nlines, ncol, niter, 1.0e-13, 0.0, 0.0, S, Cm, ub, xb, [1, 0], ncl, nx, ny, nz, 1, 1, True,
+                              myrank=d.rank, nbproc=d.world)
     loop_ms, _, _ = tfx.last_timing()
+    loop_ms = d.max(loop_ms)
     hist, iters, fused = tfx.last_history()
     out["lsqr"] = {"it_per_s": iters / (loop_ms * 1e-3), "ms_per_it": loop_ms / max(iters, 1), "iters": int(iters),
                    "residual_last": float(hist[-1]) if len(hist) else None,
