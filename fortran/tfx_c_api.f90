@@ -16,6 +16,23 @@ module tfx_c_api
 
   public
 
+  ! struct tfx_sensit_params (include/tfx.h)
+  type, bind(C) :: tfx_sensit_params
+    integer(c_int32_t) :: problem_type
+    integer(c_int32_t) :: nx, ny, nz
+    integer(c_int32_t) :: ndata
+    integer(c_int32_t) :: ndata_components
+    integer(c_int32_t) :: nmodel_components
+    integer(c_int32_t) :: data_type
+    integer(c_int32_t) :: compression_type
+    real(c_double) :: compression_rate
+    real(c_double) :: problem_weight
+    real(c_double) :: mi, md, theta, intensity
+    integer(c_int32_t) :: cell0, ncells_local
+    integer(c_int32_t) :: param_shift
+    integer(c_int32_t) :: ncolumns
+  end type tfx_sensit_params
+
   interface
     function tfx_init(device) bind(C, name="tfx_init") result(rc)
       import :: c_int
@@ -239,6 +256,150 @@ module tfx_c_api
       real(c_double), intent(inout) :: u(*), x(*)
       integer(c_int32_t), intent(in) :: solve_problem(2)
       real(c_double), intent(out) :: memory
+      integer(c_int) :: rc
+    end function
+    ! ---- sensitivity_gravmag (csrc/sensit.cu, sensit_dist.cu, sensit_io.cu) ---------------------
+    function tfx_device_mem_info(free_bytes, total_bytes) bind(C, name="tfx_device_mem_info") result(rc)
+      import :: c_int, c_int64_t
+      integer(c_int64_t), intent(out) :: free_bytes, total_bytes
+      integer(c_int) :: rc
+    end function
+
+    function tfx_calculate_sensit(matrix_sensit, par, X1, X2, Y1, Y2, Z1, Z2, data_X, data_Y, data_Z, &
+                                  column_weight_full, data_weight, sensit_nnz, comp_error, nnz_total) &
+        bind(C, name="tfx_calculate_sensit") result(rc)
+      import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr, tfx_sensit_params
+      type(c_ptr), intent(out) :: matrix_sensit
+      type(tfx_sensit_params), intent(in) :: par
+      real(c_double), intent(in) :: X1(*), X2(*), Y1(*), Y2(*), Z1(*), Z2(*), data_X(*), data_Y(*), data_Z(*)
+      real(c_double), intent(in) :: column_weight_full(*), data_weight(*)
+      integer(c_int32_t), intent(out) :: sensit_nnz(*)
+      real(c_double), intent(out) :: comp_error
+      integer(c_int64_t), intent(out) :: nnz_total
+      integer(c_int) :: rc
+    end function
+
+    function tfx_sensit_assemble_rows(rows, par, X1, X2, Y1, Y2, Z1, Z2, data_X, data_Y, data_Z, &
+                                      column_weight_full, data_weight, myrank, nbproc, sensit_nnz, comp_error, nnz_total) &
+        bind(C, name="tfx_sensit_assemble_rows") result(rc)
+      import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr, tfx_sensit_params
+      type(c_ptr), intent(out) :: rows
+      type(tfx_sensit_params), intent(in) :: par
+      real(c_double), intent(in) :: X1(*), X2(*), Y1(*), Y2(*), Z1(*), Z2(*), data_X(*), data_Y(*), data_Z(*)
+      real(c_double), intent(in) :: column_weight_full(*), data_weight(*)
+      integer(c_int32_t), value :: myrank, nbproc
+      integer(c_int32_t), intent(out) :: sensit_nnz(*)
+      real(c_double), intent(out) :: comp_error
+      integer(c_int64_t), intent(out) :: nnz_total
+      integer(c_int) :: rc
+    end function
+
+    function tfx_sensit_rows_apply_weights(rows, problem_weight, data_weight) &
+        bind(C, name="tfx_sensit_rows_apply_weights") result(rc)
+      import :: c_int, c_double, c_ptr
+      type(c_ptr), value :: rows
+      real(c_double), value :: problem_weight
+      real(c_double), intent(in) :: data_weight(*)
+      integer(c_int) :: rc
+    end function
+
+    function tfx_sensit_rows_destroy(rows) bind(C, name="tfx_sensit_rows_destroy") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: rows
+      integer(c_int) :: rc
+    end function
+
+    function tfx_get_load_balancing_nelements(nelements_total, sensit_nnz, nbproc, nnz_at_cpu_new, nelements_at_cpu_new) &
+        bind(C, name="tfx_get_load_balancing_nelements") result(rc)
+      import :: c_int, c_int32_t, c_int64_t
+      integer(c_int32_t), value :: nelements_total, nbproc
+      integer(c_int32_t), intent(in) :: sensit_nnz(*)
+      integer(c_int64_t), intent(out) :: nnz_at_cpu_new(*)
+      integer(c_int32_t), intent(out) :: nelements_at_cpu_new(*)
+      integer(c_int) :: rc
+    end function
+
+    function tfx_sensit_repartition_into(matrix_sensit, rows, problem_slot, nelements_at_cpu, myrank, nbproc) &
+        bind(C, name="tfx_sensit_repartition_into") result(rc)
+      import :: c_int, c_int32_t, c_ptr
+      type(c_ptr), value :: matrix_sensit, rows
+      integer(c_int32_t), value :: problem_slot, myrank, nbproc
+      integer(c_int32_t), intent(in) :: nelements_at_cpu(*)
+      integer(c_int) :: rc
+    end function
+
+    function tfx_create_sensit_directory(dir) bind(C, name="tfx_create_sensit_directory") result(rc)
+      import :: c_int, c_char
+      character(kind=c_char), intent(in) :: dir(*)
+      integer(c_int) :: rc
+    end function
+
+    function tfx_write_sensit_file(rows, dir) bind(C, name="tfx_write_sensit_file") result(rc)
+      import :: c_int, c_char, c_ptr
+      type(c_ptr), value :: rows
+      character(kind=c_char), intent(in) :: dir(*)
+      integer(c_int) :: rc
+    end function
+
+    function tfx_write_sensit_metadata(par, dir, nbproc, depth_weighting_type, comp_error, nnz_total, sensit_nnz) &
+        bind(C, name="tfx_write_sensit_metadata") result(rc)
+      import :: c_int, c_int32_t, c_int64_t, c_double, c_char, tfx_sensit_params
+      type(tfx_sensit_params), intent(in) :: par
+      character(kind=c_char), intent(in) :: dir(*)
+      integer(c_int32_t), value :: nbproc, depth_weighting_type
+      real(c_double), value :: comp_error
+      integer(c_int64_t), value :: nnz_total
+      integer(c_int32_t), intent(in) :: sensit_nnz(*)
+      integer(c_int) :: rc
+    end function
+
+    function tfx_read_sensitivity_metadata(par, dir, depth_weighting_type, nbproc_sensit, comp_error, nnz_total) &
+        bind(C, name="tfx_read_sensitivity_metadata") result(rc)
+      import :: c_int, c_int32_t, c_int64_t, c_double, c_char, tfx_sensit_params
+      type(tfx_sensit_params), intent(in) :: par
+      character(kind=c_char), intent(in) :: dir(*)
+      integer(c_int32_t), value :: depth_weighting_type
+      integer(c_int32_t), intent(out) :: nbproc_sensit
+      real(c_double), intent(out) :: comp_error
+      integer(c_int64_t), intent(out) :: nnz_total
+      integer(c_int) :: rc
+    end function
+
+    function tfx_read_sensit_nnz(par, dir, sensit_nnz) bind(C, name="tfx_read_sensit_nnz") result(rc)
+      import :: c_int, c_int32_t, c_char, tfx_sensit_params
+      type(tfx_sensit_params), intent(in) :: par
+      character(kind=c_char), intent(in) :: dir(*)
+      integer(c_int32_t), intent(out) :: sensit_nnz(*)
+      integer(c_int) :: rc
+    end function
+
+    function tfx_write_depth_weight(par, dir, column_weight_full) bind(C, name="tfx_write_depth_weight") result(rc)
+      import :: c_int, c_double, c_char, tfx_sensit_params
+      type(tfx_sensit_params), intent(in) :: par
+      character(kind=c_char), intent(in) :: dir(*)
+      real(c_double), intent(in) :: column_weight_full(*)
+      integer(c_int) :: rc
+    end function
+
+    function tfx_read_depth_weight(par, dir, column_weight_full) bind(C, name="tfx_read_depth_weight") result(rc)
+      import :: c_int, c_double, c_char, tfx_sensit_params
+      type(tfx_sensit_params), intent(in) :: par
+      character(kind=c_char), intent(in) :: dir(*)
+      real(c_double), intent(out) :: column_weight_full(*)
+      integer(c_int) :: rc
+    end function
+
+    function tfx_read_sensitivity_kernel_into(matrix_sensit, par, dir, data_weight, depth_weighting_type, problem_slot, &
+                                              myrank, nbproc, nelements_at_cpu, nnz_local) &
+        bind(C, name="tfx_read_sensitivity_kernel_into") result(rc)
+      import :: c_int, c_int32_t, c_int64_t, c_double, c_char, c_ptr, tfx_sensit_params
+      type(c_ptr), value :: matrix_sensit
+      type(tfx_sensit_params), intent(in) :: par
+      character(kind=c_char), intent(in) :: dir(*)
+      real(c_double), intent(in) :: data_weight(*)
+      integer(c_int32_t), value :: depth_weighting_type, problem_slot, myrank, nbproc
+      integer(c_int32_t), intent(in) :: nelements_at_cpu(*)
+      integer(c_int64_t), intent(out) :: nnz_local
       integer(c_int) :: rc
     end function
   end interface

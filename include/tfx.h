@@ -194,6 +194,9 @@ int tfx_sensit_assemble_rows(tfx_sensit_rows **rows, const tfx_sensit_params *pa
                              const double *column_weight_full, const double *data_weight,
                              int32_t myrank, int32_t nbproc,
                              int32_t *sensit_nnz, double *comp_error, int64_t *nnz_total);
+/* Multiplies the values of a row set assembled with unit weights by real(problem_weight * data_weight(d, i), 4)
+ * in real(4) (:837-843): what read_sensitivity_kernel does after reading the unweighted file. */
+int tfx_sensit_rows_apply_weights(tfx_sensit_rows *rows, double problem_weight, const double *data_weight);
 int tfx_sensit_rows_info(const tfx_sensit_rows *rows, int32_t *data0, int32_t *ndata_loc, int64_t *nnz_local);
 int tfx_sensit_rows_destroy(tfx_sensit_rows *rows);
 /* get_load_balancing_nelements (:470-524): host integer work, no GPU needed. Joint inversions pass the
@@ -208,6 +211,42 @@ int tfx_get_load_balancing_nelements(int32_t nelements_total, const int32_t *sen
  * the slabs one after the other. */
 int tfx_sensit_repartition(tfx_matrix **matrix_sensit, tfx_sensit_rows *rows, int32_t problem_slot,
                            const int32_t *nelements_at_cpu, int32_t myrank, int32_t nbproc);
+
+/* Same, appending the rows to a matrix under construction (tfx_sparse_matrix_initialize ... finalize): the
+ * reference calls read_sensitivity_kernel once per problem on jinv%matrix_sensit
+ * (problem_joint_gravmag.F90:241-248); finalize() then builds the device representations. */
+int tfx_sensit_repartition_into(tfx_matrix *matrix_sensit, tfx_sensit_rows *rows, int32_t problem_slot,
+                                const int32_t *nelements_at_cpu, int32_t myrank, int32_t nbproc);
+
+/* ---- the reference's on-disk sensitivity formats (csrc/sensit_io.cu) -------------------------------
+ * `dir` is the SENSIT folder (path_output/SENSIT or par%sensit_path). Byte order is big-endian like the
+ * reference build (-fconvert=big-endian, Makefile:51). */
+int tfx_create_sensit_directory(const char *dir);                               /* file_utils.F90:31-40 */
+/* The rank's stream file sensit_<grav|magn>_<nbproc>_<rank> (:143-148,:183,:306-309). The row set must have
+ * been assembled with problem_weight = 1 and unit data weights (the file stores the unweighted kernel). */
+int tfx_write_sensit_file(const tfx_sensit_rows *rows, const char *dir);
+/* sensit_<..>_meta.txt (:359-376) and sensit_<..>_nnz (:381-392; skipped when sensit_nnz is NULL). Rank 0 only. */
+int tfx_write_sensit_metadata(const tfx_sensit_params *par, const char *dir, int32_t nbproc,
+                              int32_t depth_weighting_type, double comp_error, int64_t nnz_total,
+                              const int32_t *sensit_nnz);
+/* read_sensitivity_metadata (:974-1037) incl. its consistency checks; outputs may be NULL. */
+int tfx_read_sensitivity_metadata(const tfx_sensit_params *par, const char *dir, int32_t depth_weighting_type,
+                                  int32_t *nbproc_sensit, double *comp_error, int64_t *nnz_total);
+int tfx_read_sensit_nnz(const tfx_sensit_params *par, const char *dir, int32_t *sensit_nnz);   /* :529-568 */
+int tfx_write_depth_weight(const tfx_sensit_params *par, const char *dir, const double *column_weight_full); /* :415-465 */
+int tfx_read_depth_weight(const tfx_sensit_params *par, const char *dir, double *column_weight_full);        /* :888-969 */
+/* read_sensitivity_kernel (:648-883): scans the files of all writer ranks, keeps the column slab of `myrank`
+ * (nelements_at_cpu from tfx_get_load_balancing_nelements), applies the index shift (:834) and the real(4)
+ * weights (:837-843) and leaves the finalized matrix on the device. */
+int tfx_read_sensitivity_kernel(tfx_matrix **matrix_sensit, const tfx_sensit_params *par, const char *dir,
+                                const double *data_weight, int32_t depth_weighting_type, int32_t problem_slot,
+                                int32_t myrank, int32_t nbproc, const int32_t *nelements_at_cpu,
+                                int64_t *nnz_local);
+
+int tfx_read_sensitivity_kernel_into(tfx_matrix *matrix_sensit, const tfx_sensit_params *par, const char *dir,
+                                     const double *data_weight, int32_t depth_weighting_type, int32_t problem_slot,
+                                     int32_t myrank, int32_t nbproc, const int32_t *nelements_at_cpu,
+                                     int64_t *nnz_local);
 
 /* One raw sensitivity line per station (no weighting), for kernel parity tests:
  * lines(ncells, nmodel_components, ndata_components, ndata_batch) Fortran order. */

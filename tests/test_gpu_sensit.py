@@ -192,3 +192,22 @@ def test_repartition_argument_checks():
         tfx.sensit_repartition(rows, 3, np.array([pb.N], dtype=np.int32), 0, 1)
     with pytest.raises(tfx.TfxError, match="communicator"):
         tfx.sensit_assemble_rows(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw, myrank=0, nbproc=2)
+
+
+def test_rows_apply_weights_equals_weighting_at_assembly():
+    """Unit-weight rows (the file content) + apply_weights == rows assembled with the weights: both are
+    real(line, 4) * real(pw * dw, 4) in real(4) (sensitivity_gravmag.F90:265, :837-843)."""
+    pb = make_problem(nx=9, ny=8, nz=5, ndata=8, compression_type=1, rate=0.3)
+    dw = np.linspace(0.3, 1.7, pb.ndata).reshape(pb.ndata, 1)
+    pb.par.problem_weight = 0.625
+    rows_w, _, _, _ = tfx.sensit_assemble_rows(pb.par, pb.grid, pb.data_xyz, pb.cw, dw)
+    A = tfx.sensit_repartition(rows_w, 1, [pb.N])
+    pb.par.problem_weight = 1.0
+    rows_u, _, _, _ = tfx.sensit_assemble_rows(pb.par, pb.grid, pb.data_xyz, pb.cw, np.ones_like(dw))
+    tfx.sensit_rows_apply_weights(rows_u, 0.625, dw)
+    with pytest.raises(tfx.TfxError, match="already carry weights"):
+        tfx.sensit_rows_apply_weights(rows_u, 0.625, dw)
+    B = tfx.sensit_repartition(rows_u, 1, [pb.N])
+    a, b = A.export(), B.export()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)

@@ -540,3 +540,109 @@ def calculate_nelements_at_cpu(nelements_total, myrank, nbproc):
 def get_nsmaller(nelements_total, myrank, nbproc):
     """Number of elements on ranks below myrank for the even split (parallel_tools.f90:68-86)."""
     return sum(calculate_nelements_at_cpu(nelements_total, r, nbproc) for r in range(myrank))
+
+
+# ---- the reference's on-disk sensitivity formats (csrc/sensit_io.cu) ------------------------------------
+def _sigs_io():
+    L = lib()
+    vp, i32, i64, dbl, cp = C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_char_p
+    L.tfx_create_sensit_directory.argtypes = [cp]
+    L.tfx_write_sensit_file.argtypes = [vp, cp]
+    L.tfx_write_sensit_metadata.argtypes = [C.POINTER(SensitParams), cp, i32, i32, dbl, i64, vp]
+    L.tfx_read_sensitivity_metadata.argtypes = [C.POINTER(SensitParams), cp, i32, C.POINTER(i32), C.POINTER(dbl),
+                                                C.POINTER(i64)]
+    L.tfx_read_sensit_nnz.argtypes = [C.POINTER(SensitParams), cp, vp]
+    L.tfx_write_depth_weight.argtypes = [C.POINTER(SensitParams), cp, vp]
+    L.tfx_read_depth_weight.argtypes = [C.POINTER(SensitParams), cp, vp]
+    L.tfx_read_sensitivity_kernel.argtypes = [C.POINTER(vp), C.POINTER(SensitParams), cp, vp, i32, i32, i32, i32, vp,
+                                              C.POINTER(i64)]
+    return L
+
+
+def write_sensit_file(rows, path):
+    """The rank's stream file sensit_<grav|magn>_<nbproc>_<rank> (sensitivity_gravmag.F90:143-318)."""
+    L = _sigs_io()
+    _check(L.tfx_create_sensit_directory(path.encode()))
+    _check(L.tfx_write_sensit_file(rows._h, path.encode()))
+
+
+def write_sensit_metadata(par, path, nbproc, depth_weighting_type, comp_error, nnz_total, sensit_nnz=None):
+    L = _sigs_io()
+    _check(L.tfx_create_sensit_directory(path.encode()))
+    nnz = None if sensit_nnz is None else np.ascontiguousarray(sensit_nnz, dtype=np.int32)
+    _check(L.tfx_write_sensit_metadata(C.byref(par), path.encode(), nbproc, depth_weighting_type, float(comp_error),
+                                       int(nnz_total), None if nnz is None else nnz.ctypes.data))
+
+
+def read_sensitivity_metadata(par, path, depth_weighting_type):
+    """read_sensitivity_metadata (:974-1037): (nbproc_sensit, comp_error, nnz_total)."""
+    L = _sigs_io()
+    nb, ce, nt = C.c_int32(0), C.c_double(0.0), C.c_int64(0)
+    _check(L.tfx_read_sensitivity_metadata(C.byref(par), path.encode(), depth_weighting_type, C.byref(nb), C.byref(ce),
+                                           C.byref(nt)))
+    return nb.value, ce.value, nt.value
+
+
+def read_sensit_nnz(par, path):
+    L = _sigs_io()
+    out = np.zeros(par.nx * par.ny * par.nz, dtype=np.int32)
+    _check(L.tfx_read_sensit_nnz(C.byref(par), path.encode(), out.ctypes.data))
+    return out
+
+
+def write_depth_weight(par, path, column_weight_full):
+    L = _sigs_io()
+    cw = np.ascontiguousarray(column_weight_full, dtype=np.float64)
+    assert cw.size == par.nx * par.ny * par.nz
+    _check(L.tfx_write_depth_weight(C.byref(par), path.encode(), cw.ctypes.data))
+
+
+def read_depth_weight(par, path):
+    L = _sigs_io()
+    out = np.zeros(par.nx * par.ny * par.nz)
+    _check(L.tfx_read_depth_weight(C.byref(par), path.encode(), out.ctypes.data))
+    return out
+
+
+def read_sensitivity_kernel(par, path, data_weight, depth_weighting_type, problem_slot, nelements_at_cpu, myrank=0,
+                            nbproc=1):
+    """read_sensitivity_kernel (:648-883): this rank's column-slab SparseMatrix from the stream files."""
+    L = _sigs_io()
+    dw = np.ascontiguousarray(data_weight, dtype=np.float64)
+    nel = np.ascontiguousarray(nelements_at_cpu, dtype=np.int32)
+    assert nel.size == nbproc and dw.size == par.ndata * par.ndata_components
+    h, nloc = C.c_void_p(), C.c_int64(0)
+    _check(L.tfx_read_sensitivity_kernel(C.byref(h), C.byref(par), path.encode(), dw.ctypes.data, depth_weighting_type,
+                                         problem_slot, myrank, nbproc, nel.ctypes.data, C.byref(nloc)))
+    return SparseMatrix(_handle=h)
+
+
+def sensit_repartition_into(matrix, rows, problem_slot, nelements_at_cpu, myrank=0, nbproc=1):
+    """Appends this rank's slab of `rows` to a SparseMatrix under construction (the reference's calling convention:
+    read_sensitivity_kernel once per problem, then finalize; problem_joint_gravmag.F90:241-248)."""
+    L = lib()
+    L.tfx_sensit_repartition_into.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]
+    nel = np.ascontiguousarray(nelements_at_cpu, dtype=np.int32)
+    assert nel.size == nbproc
+    _check(L.tfx_sensit_repartition_into(matrix._h, rows._h, problem_slot, nel.ctypes.data, myrank, nbproc))
+
+
+def read_sensitivity_kernel_into(matrix, par, path, data_weight, depth_weighting_type, problem_slot, nelements_at_cpu,
+                                 myrank=0, nbproc=1):
+    L = _sigs_io()
+    L.tfx_read_sensitivity_kernel_into.argtypes = [C.c_void_p, C.POINTER(SensitParams), C.c_char_p, C.c_void_p, C.c_int32,
+                                                   C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]
+    dw = np.ascontiguousarray(data_weight, dtype=np.float64)
+    nel = np.ascontiguousarray(nelements_at_cpu, dtype=np.int32)
+    nloc = C.c_int64(0)
+    _check(L.tfx_read_sensitivity_kernel_into(matrix._h, C.byref(par), path.encode(), dw.ctypes.data, depth_weighting_type,
+                                              problem_slot, myrank, nbproc, nel.ctypes.data, C.byref(nloc)))
+    return nloc.value
+
+
+def sensit_rows_apply_weights(rows, problem_weight, data_weight):
+    """combined_weight = real(problem_weight * data_weight, 4) applied in real(4) (sensitivity_gravmag.F90:837-843)."""
+    L = lib()
+    L.tfx_sensit_rows_apply_weights.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+    dw = np.ascontiguousarray(data_weight, dtype=np.float64)
+    _check(L.tfx_sensit_rows_apply_weights(rows._h, float(problem_weight), dw.ctypes.data))

@@ -420,7 +420,20 @@ int tfx_sparse_matrix_add_empty_rows(tfx_matrix *h, int32_t nrows, int32_t myran
 int tfx_sparse_matrix_finalize(tfx_matrix *h, int32_t myrank) {
   (void)myrank;
   Matrix &m = h->m;
-  if (m.device_only) return 0;
+  if (m.device_only && m.finalized) return 0;
+  if (m.pend.nnz > 0 || m.pend.idx.p) {
+    // rows appended on the device (read_sensitivity_kernel / re-partitioner): same row-count check as the reference
+    if (m.nl_current_all != m.nl)
+      return fail(-16, "Error in total number of rows in sparse_matrix_finalize!\nnl_current=" +
+                           std::to_string(m.nl_current) + "\nnl=" + std::to_string(m.nl));
+    if (m.nel != 0) return fail(-25, "sparse_matrix_finalize: host-built and device-appended rows cannot be mixed");
+    RowTriplets R;
+    std::swap(R.idx.p, m.pend.idx.p); std::swap(R.idx.n, m.pend.idx.n);
+    std::swap(R.val.p, m.pend.val.p); std::swap(R.val.n, m.pend.val.n);
+    std::swap(R.rowid.p, m.pend.rowid.p); std::swap(R.rowid.n, m.pend.rowid.n);
+    R.nnz = m.pend.nnz; m.pend.nnz = 0;
+    return matrix_from_triplets(m, m.nl, m.ncolumns, R);
+  }
   if (m.nl_current_all != m.nl)
     return fail(-16, "Error in total number of rows in sparse_matrix_finalize!\nnl_current=" +
                          std::to_string(m.nl_current) + "\nnl=" + std::to_string(m.nl));

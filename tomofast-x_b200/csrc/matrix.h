@@ -9,6 +9,15 @@
 
 namespace tfx {
 
+// Matrix entries sorted by (row, column) on the device: the currency between the row pipeline, the
+// re-partitioner and the matrix builder.
+struct RowTriplets {
+  DevBuf<int32_t> idx;     // 0-based column
+  DevBuf<int32_t> rowid;   // 0-based matrix row
+  DevBuf<float> val;
+  int64_t nnz = 0;
+};
+
 // Mirrors t_sparse_matrix (src/inversion/sparse_matrix.f90:31-98). The host-side builder keeps the
 // reference's exact storage (sa real(4), ija int32 1-based, ijl int64 1-based, rowptr int32);
 // finalize() validates it like the reference and mirrors it to the device:
@@ -31,6 +40,9 @@ struct Matrix {
   bool has_seg = false;
   T16Matrix t16f, t16t;       // tiled 16-bit layouts of A (forward) and A^T (transposed), big matrices only
   bool has_t16 = false;
+  // Device-resident rows appended by read_sensitivity_kernel / the re-partitioner before finalize()
+  // (the reference appends one problem after the other with add_row / new_row, sensitivity_gravmag.F90:846-853).
+  RowTriplets pend;
   DenseCM dense;
   bool has_dense = false;
   int32_t dense_row0 = 0;     // 0-based global row of dense row 0
@@ -43,21 +55,16 @@ int matrix_upload(Matrix &m, bool allow_dense);
 int matrix_build_t16(Matrix &m);
 
 // ---- sensit.cu / sensit_dist.cu -----------------------------------------------------------------
-// Matrix entries sorted by (row, column) on the device: the currency between the row pipeline, the
-// re-partitioner and the matrix builder.
-struct RowTriplets {
-  DevBuf<int32_t> idx;     // 0-based column
-  DevBuf<int32_t> rowid;   // 0-based matrix row
-  DevBuf<float> val;
-  int64_t nnz = 0;
-};
 }  // namespace tfx
-struct tfx_sensit_params;
+#include "../../include/tfx.h"
 namespace tfx {
 int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const double *d_dx, const double *d_dy,
                          const double *d_dz, const double *d_cw, const double *h_dw, int32_t data0, int32_t ndata_loc,
                          RowTriplets &R, DevBuf<int32_t> &dnnz, std::vector<long long> &seg_end, double *err_sum);
 int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R);
+// Appends nrows matrix rows held as device triplets (row ids relative to the appended block) to a matrix that
+// is still being built; finalize() turns the accumulated rows into the device representations.
+int matrix_append_triplets(Matrix &M, RowTriplets &R, int32_t nrows, int32_t ncolumns);
 int upload_grid(GridDev &g, int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
                 const double *Z1, const double *Z2);
 
@@ -104,6 +111,17 @@ int comm_init(int nranks, int rank, const char id[128]);
 int comm_finalize();
 
 }  // namespace tfx
+
+// Row-sharded kernel of one problem, resident on the device (stands in for the file
+// sensit_<type>_<nbproc>_<rank>; csrc/sensit_dist.cu builds it, csrc/sensit_io.cu writes / reads the file).
+struct tfx_sensit_rows {
+  tfx_sensit_params par;
+  int32_t data0 = 0, ndata_loc = 0;   // stations [data0, data0 + ndata_loc) of par.ndata
+  int32_t myrank = 0, nbproc = 1;
+  bool unit_weights = true;           // problem_weight * data_weight == 1 for every row (file content is unweighted)
+  tfx::RowTriplets R;                 // idx = k*N + p (0-based, no problem shift), rowid = global matrix row
+  std::vector<long long> seg_end;     // running entry count after each (idata, d, k) segment
+};
 
 // The opaque handle of include/tfx.h.
 struct tfx_matrix {

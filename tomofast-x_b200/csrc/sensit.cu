@@ -376,6 +376,56 @@ int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const dou
   return 0;
 }
 
+__global__ void __launch_bounds__(256) k_add_i32(int32_t *__restrict__ a, int64_t n, int32_t delta) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] += delta;
+}
+
+int matrix_append_triplets(Matrix &M, RowTriplets &R, int32_t nrows, int32_t ncolumns) {
+  Context &c = ctx();
+  cudaStream_t st = c.stream;
+  if (M.finalized) return fail(-26, "sparse_matrix: rows cannot be appended to a finalized matrix");
+  if (M.ncolumns != ncolumns)
+    return fail(-27, "sparse_matrix: appended rows have " + std::to_string(ncolumns) + " columns, the matrix " +
+                         std::to_string(M.ncolumns));
+  if (M.nel != 0) return fail(-25, "sparse_matrix: host-built and device-appended rows cannot be mixed");
+  if (M.nl_current_all + nrows > M.nl) return fail(-28, "Error in total number of rows in sparse_matrix (append)!");
+  if (M.pend.nnz + R.nnz > M.nnz)
+    return fail(-15, "Error in nnz or nl in sparse_matrix_add! nnz=" + std::to_string(M.nnz));   // the reference's capacity check (:222)
+  if (R.nnz > 0 && M.nl_current_all != 0) {
+    k_add_i32<<<(int)std::min<int64_t>((R.nnz + 255) / 256, (int64_t)c.num_sms * 16), 256, 0, st>>>(R.rowid.p, R.nnz,
+                                                                                                   M.nl_current_all);
+    c.launches++;
+  }
+  if (M.pend.nnz == 0) {
+    M.pend.idx.release(); M.pend.val.release(); M.pend.rowid.release();
+    std::swap(M.pend.idx.p, R.idx.p); std::swap(M.pend.idx.n, R.idx.n);
+    std::swap(M.pend.val.p, R.val.p); std::swap(M.pend.val.n, R.val.n);
+    std::swap(M.pend.rowid.p, R.rowid.p); std::swap(M.pend.rowid.n, R.rowid.n);
+    M.pend.nnz = R.nnz;
+    if (!M.pend.idx.p) { TFX_TRY(M.pend.idx.alloc(1)); TFX_TRY(M.pend.val.alloc(1)); TFX_TRY(M.pend.rowid.alloc(1)); }
+  } else if (R.nnz > 0) {
+    RowTriplets cat;
+    const int64_t a = M.pend.nnz, b = R.nnz;
+    TFX_TRY(cat.idx.alloc((size_t)(a + b))); TFX_TRY(cat.val.alloc((size_t)(a + b))); TFX_TRY(cat.rowid.alloc((size_t)(a + b)));
+    TFX_CUDA(cudaMemcpyAsync(cat.idx.p, M.pend.idx.p, (size_t)a * 4, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaMemcpyAsync(cat.idx.p + a, R.idx.p, (size_t)b * 4, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaMemcpyAsync(cat.val.p, M.pend.val.p, (size_t)a * 4, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaMemcpyAsync(cat.val.p + a, R.val.p, (size_t)b * 4, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaMemcpyAsync(cat.rowid.p, M.pend.rowid.p, (size_t)a * 4, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaMemcpyAsync(cat.rowid.p + a, R.rowid.p, (size_t)b * 4, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaStreamSynchronize(st));
+    M.pend.idx.release(); M.pend.val.release(); M.pend.rowid.release();
+    std::swap(M.pend.idx.p, cat.idx.p); std::swap(M.pend.idx.n, cat.idx.n);
+    std::swap(M.pend.val.p, cat.val.p); std::swap(M.pend.val.n, cat.val.n);
+    std::swap(M.pend.rowid.p, cat.rowid.p); std::swap(M.pend.rowid.n, cat.rowid.n);
+    M.pend.nnz = a + b;
+  }
+  TFX_CUDA(cudaStreamSynchronize(st));
+  R.idx.release(); R.val.release(); R.rowid.release(); R.nnz = 0;
+  M.nl_current_all += nrows;
+  return 0;
+}
+
 // keys (sorted, n entries) -> unique keys + exclusive offsets on the host.
 static int runs_of_sorted_keys(const int32_t *d_keys, int64_t n, int32_t max_unique, std::vector<int32_t> &uniq,
                                std::vector<int64_t> &ptr) {

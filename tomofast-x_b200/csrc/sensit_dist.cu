@@ -29,15 +29,6 @@
 #include "kernels.h"
 #include "matrix.h"
 
-// Row-sharded kernel of one problem, resident on the device (stands in for the file sensit_<type>_<nbproc>_<rank>).
-struct tfx_sensit_rows {
-  tfx_sensit_params par;
-  int32_t data0 = 0, ndata_loc = 0;   // stations [data0, data0 + ndata_loc) of par.ndata
-  int32_t myrank = 0, nbproc = 1;
-  tfx::RowTriplets R;                 // idx = k*N + p (0-based, no problem shift), rowid = global matrix row
-  std::vector<long long> seg_end;     // running entry count after each (idata, d, k) segment
-};
-
 namespace tfx {
 
 // parallel_tools.f90:46-63 / :68-86
@@ -106,6 +97,13 @@ __global__ void __launch_bounds__(256) k_pack_pieces(const int32_t *__restrict__
   }
 }
 
+// val[i] *= wgt[rowid[i]] in real(4): sensit_compressed(j) * combined_weight (sensitivity_gravmag.F90:837-843)
+__global__ void __launch_bounds__(256) k_apply_row_weight(float *__restrict__ val, const int32_t *__restrict__ rowid,
+                                                           int64_t n, const float *__restrict__ wgt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    val[i] = __fmul_rn(val[i], wgt[rowid[i]]);
+}
+
 template <typename T>
 static int up(DevBuf<T> &d, const T *h, size_t n) {
   TFX_TRY(d.alloc(n));
@@ -157,6 +155,34 @@ extern "C" int tfx_sensit_rows_destroy(tfx_sensit_rows *rows) {
   return 0;
 }
 
+// Applies combined_weight = real(problem_weight * data_weight(d, idata), 4) to a row set assembled with unit
+// weights (the state in which it can be written to the reference's files): the in-HBM shortcut of
+// read_sensitivity_kernel's weighting (:837-843), bit-identical to weighting at assembly time.
+extern "C" int tfx_sensit_rows_apply_weights(tfx_sensit_rows *rows, double problem_weight, const double *data_weight) {
+  TFX_TRY(ensure_init());
+  if (!rows) return fail(-82, "sensit_rows: null handle");
+  if (!rows->unit_weights) return fail(-89, "sensit_rows_apply_weights: the rows already carry weights");
+  const tfx_sensit_params &P = rows->par;
+  const size_t nl = (size_t)P.ndata * P.ndata_components;
+  std::vector<float> w(nl);
+  bool unit = true;
+  for (size_t i = 0; i < nl; ++i) {
+    w[i] = (float)(problem_weight * data_weight[i]);
+    unit = unit && (w[i] == 1.0f);
+  }
+  rows->par.problem_weight = problem_weight;
+  if (unit || rows->R.nnz == 0) return 0;
+  DevBuf<float> dw;
+  TFX_TRY(up(dw, w.data(), nl));
+  Context &c = ctx();
+  k_apply_row_weight<<<(int)std::min<int64_t>((rows->R.nnz + 255) / 256, (int64_t)c.num_sms * 16), 256, 0, c.stream>>>(
+      rows->R.val.p, rows->R.rowid.p, rows->R.nnz, dw.p);
+  c.launches++;
+  TFX_CUDA(cudaStreamSynchronize(c.stream));
+  rows->unit_weights = false;
+  return 0;
+}
+
 extern "C" int tfx_sensit_rows_info(const tfx_sensit_rows *rows, int32_t *data0, int32_t *ndata_loc, int64_t *nnz_local) {
   if (!rows) return fail(-82, "sensit_rows: null handle");
   if (data0) *data0 = rows->data0;
@@ -189,6 +215,9 @@ extern "C" int tfx_sensit_assemble_rows(tfx_sensit_rows **out, const tfx_sensit_
   h->par.param_shift = 0;                 // columns stay k*N + p until the destination is known
   h->par.cell0 = 0; h->par.ncells_local = N;
   h->myrank = myrank; h->nbproc = nbproc;
+  h->unit_weights = true;
+  for (int64_t i = 0; i < (int64_t)par->ndata * ndc; ++i)
+    if ((float)(par->problem_weight * data_weight[i]) != 1.0f) { h->unit_weights = false; break; }
   h->ndata_loc = nelements_at_cpu_even(par->ndata, myrank, nbproc);   // sensitivity_gravmag.F90:179-180
   h->data0 = nsmaller_even(par->ndata, myrank, nbproc);
 
@@ -230,12 +259,13 @@ extern "C" int tfx_sensit_assemble_rows(tfx_sensit_rows **out, const tfx_sensit_
   return 0;
 }
 
-extern "C" int tfx_sensit_repartition(tfx_matrix **out, tfx_sensit_rows *rows, int32_t problem_slot,
-                                      const int32_t *nelements_at_cpu, int32_t myrank, int32_t nbproc) {
+// Core of the re-partitioning: leaves this rank's slab as triplets sorted by (row, local column).
+static int repartition_core(tfx_sensit_rows *rows, int32_t problem_slot, const int32_t *nelements_at_cpu, int32_t myrank,
+                            int32_t nbproc, RowTriplets &Rx, int32_t *nl_out, int32_t *ncolumns_out) {
   TFX_TRY(ensure_init());
   Context &c = ctx();
   cudaStream_t st = c.stream;
-  if (!out || !rows) return fail(-82, "sensit_repartition: null handle");
+  if (!rows) return fail(-82, "sensit_repartition: null handle");
   if (problem_slot != 1 && problem_slot != 2) return fail(-85, "sensit_repartition: problem_slot must be 1 or 2");
   if (nbproc < 1 || myrank < 0 || myrank >= nbproc) return fail(-83, "sensit_repartition: wrong rank");
   const tfx_sensit_params &P = rows->par;
@@ -319,7 +349,6 @@ extern "C" int tfx_sensit_repartition(tfx_matrix **out, tfx_sensit_rows *rows, i
   rows->ndata_loc = 0;
 
   // ---- exchange
-  RowTriplets Rx;
   if (single) {
     std::swap(Rx.idx.p, S.idx.p); std::swap(Rx.idx.n, S.idx.n);
     std::swap(Rx.val.p, S.val.p); std::swap(Rx.val.n, S.val.n);
@@ -340,13 +369,33 @@ extern "C" int tfx_sensit_repartition(tfx_matrix **out, tfx_sensit_rows *rows, i
     Rx.nnz = nrecv;
   }
 
-  // ---- the column-slab matrix of this rank: all data rows, local columns (joint_inverse_problem.F90:213-214)
+  // the column slab of this rank: all data rows, local columns (joint_inverse_problem.F90:213-214)
+  *nl_out = P.ndata * ndc;
+  *ncolumns_out = 2 * nmc * nelements_at_cpu[myrank];
+  return 0;
+}
+
+extern "C" int tfx_sensit_repartition(tfx_matrix **out, tfx_sensit_rows *rows, int32_t problem_slot,
+                                      const int32_t *nelements_at_cpu, int32_t myrank, int32_t nbproc) {
+  if (!out) return fail(-82, "sensit_repartition: null handle");
+  RowTriplets Rx;
+  int32_t nl = 0, ncolumns = 0;
+  TFX_TRY(repartition_core(rows, problem_slot, nelements_at_cpu, myrank, nbproc, Rx, &nl, &ncolumns));
   tfx_matrix *h = new tfx_matrix();
-  const int32_t nel_loc = nelements_at_cpu[myrank];
-  const int32_t ncolumns = 2 * nmc * nel_loc;
-  int rc = matrix_from_triplets(h->m, P.ndata * ndc, ncolumns, Rx);
+  int rc = matrix_from_triplets(h->m, nl, ncolumns, Rx);
   if (rc) { delete h; return rc; }
-  TFX_CUDA(cudaStreamSynchronize(st));
+  TFX_CUDA(cudaStreamSynchronize(ctx().stream));
   *out = h;
   return 0;
+}
+
+// Same, but the rows are APPENDED to a matrix under construction (initialize ... finalize), like the reference's
+// read_sensitivity_kernel which is called once per problem on jinv%matrix_sensit (problem_joint_gravmag.F90:241-248).
+extern "C" int tfx_sensit_repartition_into(tfx_matrix *matrix_sensit, tfx_sensit_rows *rows, int32_t problem_slot,
+                                           const int32_t *nelements_at_cpu, int32_t myrank, int32_t nbproc) {
+  if (!matrix_sensit) return fail(-82, "sensit_repartition_into: null handle");
+  RowTriplets Rx;
+  int32_t nl = 0, ncolumns = 0;
+  TFX_TRY(repartition_core(rows, problem_slot, nelements_at_cpu, myrank, nbproc, Rx, &nl, &ncolumns));
+  return matrix_append_triplets(matrix_sensit->m, Rx, nl, ncolumns);
 }
