@@ -118,11 +118,25 @@ int tfx_Haar3D(double *s, int32_t n1, int32_t n2, int32_t n3);                  
 int tfx_iHaar3D(double *s, int32_t n1, int32_t n2, int32_t n3);                                 /* :158-236 */
 int tfx_DaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3);                                /* :243-367 */
 int tfx_iDaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3);                               /* :374-498 */
-/* module wavelet_utils: apply_wavelet_transform (src/inversion/wavelet_utils.F90:37-72), nbproc = 1:
- * v(nelements, ncomponents, nproblems), model_full is not needed (no gather). */
+/* module wavelet_utils: apply_wavelet_transform (src/inversion/wavelet_utils.F90:37-72):
+ * v(nelements, ncomponents, nproblems) holds this rank's cell slab of every volume. With nbproc > 1 (needs
+ * tfx_comm_init) the slabs are assembled on every GPU by one all-reduce, transformed, and the own slab is kept --
+ * the reference's gather to rank 0 / serial transform / scatter (:57-67) without the serial section; model_full
+ * is not needed. */
 int tfx_apply_wavelet_transform(int32_t nelements, int32_t nx, int32_t ny, int32_t nz, int32_t ncomponents,
                                 double *v, int32_t fwd, int32_t compression_type, int32_t nproblems,
                                 const int32_t *solve_problem, int32_t myrank, int32_t nbproc);
+
+/* ---- t_model%calculate_data (src/inversion/model.F90:220-307) -------------------------------------
+ * data_calc = (S W(model / column_weight)) / problem_weight / data_weight for one problem of the (joint)
+ * matrix: rows [line_start, line_start + ndata*ndata_components), columns shifted by param_shift (part_mult_vector).
+ * model_val(nelements, ncomponents), column_weight(nelements), data_weight and data_calc(ndata_components, ndata)
+ * may be host or device pointers; the MPI_Allreduce of :293 is an NCCL all-reduce when nbproc > 1. */
+int tfx_calculate_data(tfx_matrix *matrix_sensit, int32_t nelements, int32_t ncomponents, const double *model_val,
+                       int32_t ndata, int32_t ndata_components, double problem_weight, const double *column_weight,
+                       const double *data_weight, double *data_calc, int32_t compression_type,
+                       int32_t nx, int32_t ny, int32_t nz, int32_t line_start, int32_t param_shift,
+                       int32_t myrank, int32_t nbproc);
 
 /* ---- module lsqr_solver (src/inversion/lsqr_solver2.F90) --------------------------------------- */
 int tfx_lsqr_solve(int32_t nlines, int32_t nelements, int32_t niter, double rmin, double gamma,

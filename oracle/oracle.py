@@ -302,3 +302,23 @@ def admm_iterate(xmin, xmax, x, z, u):
 def norm2(x):
     x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
     return lib().orc_norm2(x.size, x)
+
+
+def calculate_data(S, model_val, ndata, ndata_components, problem_weight, column_weight, data_weight,
+                   compression_type, nx, ny, nz, line_start=1, param_shift=0):
+    """t_model%calculate_data, serial version (src/inversion/model.F90:220-307). model_val: (ncomponents, nelements);
+    returns data_calc (ndata, ndata_components)."""
+    model_val = np.atleast_2d(np.asarray(model_val, dtype=np.float64))
+    cw = np.asarray(column_weight, dtype=np.float64)
+    scaled = np.zeros_like(model_val)
+    for k in range(model_val.shape[0]):                                  # :243-251
+        nz_ = cw != 0.0
+        scaled[k, nz_] = model_val[k, nz_] / cw[nz_]
+        if compression_type > 0:                                         # :278-283
+            scaled[k] = forward_wavelet(scaled[k].copy(), nx, ny, nz, compression_type)
+    d = S.part_mult_vector(scaled.ravel(), ndata * ndata_components, line_start, param_shift)   # :288
+    if problem_weight == 0.0:
+        raise RuntimeError("Zero problem weight in model_calculate_data!")
+    d = d / problem_weight                                               # :297
+    d = d / np.asarray(data_weight, dtype=np.float64).ravel()            # :304
+    return d.reshape(ndata, ndata_components)

@@ -185,6 +185,28 @@ def dist_sensit_case(rank, world, td, niter):
     tfx.lsqr_solve_sensit(len(u), ncol, niter, 1e-13, 0.0, 0.0, S, Cm, u, x, [1, 0], ncl, pb.nx, pb.ny, pb.nz, 1, 1, True,
                           myrank=rank, nbproc=world)
     h, it, fused = tfx.last_history()
+
+    # ---- distributed wavelet (wavelet_utils.F90:37-72) and calculate_data (model.F90:220-307) on the slabs
+    rng = np.random.default_rng(11)
+    vol = rng.standard_normal(N)
+    mine = vol[cell0:cell0 + ncl].copy()
+    tfx.apply_wavelet_transform(ncl, pb.nx, pb.ny, pb.nz, 1, mine, True, 1, 1, [1], rank, world)
+    want_w = orc.forward_wavelet(vol.copy(), pb.nx, pb.ny, pb.nz, 1)
+    assert np.array_equal(mine, want_w[cell0:cell0 + ncl]), "distributed Haar must be bit-identical to the serial one"
+    tfx.apply_wavelet_transform(ncl, pb.nx, pb.ny, pb.nz, 1, mine, False, 1, 1, [1], rank, world)
+    assert np.array_equal(mine, orc.inverse_wavelet(want_w.copy(), pb.nx, pb.ny, pb.nz, 1)[cell0:cell0 + ncl])
+    dwt = np.linspace(0.5, 1.5, ndata).reshape(ndata, 1)
+    d_got = tfx.calculate_data(S, pb.m_true[:, cell0:cell0 + ncl], ndata, 1, 1.0, pb.cw[cell0:cell0 + ncl], dwt, 1,
+                               pb.nx, pb.ny, pb.nz, 1, 0, rank, world)
+    d_want = orc.calculate_data(So, pb.m_true, ndata, 1, 1.0, pb.cw, dwt, 1, pb.nx, pb.ny, pb.nz, 1, 0)
+    assert np.allclose(d_got, d_want, rtol=1e-5, atol=1e-7 * np.abs(d_want).max())
+
+    # ---- the same system solved in the physical domain: wavelet transforms inside the loop (WAVELET_DOMAIN = F,
+    # lsqr_solver2.F90:200-207,228-235) on the distributed vectors
+    u2 = b.copy(); x2 = np.zeros(ncol)
+    tfx.lsqr_solve_sensit(len(u2), ncol, niter, 1e-13, 0.0, 0.0, S, Cm, u2, x2, [1, 0], ncl, pb.nx, pb.ny, pb.nz, 1, 1, False,
+                          myrank=rank, nbproc=world)
+    h2, it2, _ = tfx.last_history()
     tfx.comm_finalize()
     parts = [None] * world
     td.all_gather_object(parts, (cell0, ncl, x[:ncl]))
@@ -201,6 +223,8 @@ def dist_sensit_case(rank, world, td, niter):
         n = min(8, len(h_ref))
         # threshold flips (<= a couple of entries per row) perturb the matrix at the 1e-4 level of a row's norm
         assert np.allclose(h[:n], h_ref[:n], rtol=5e-3), (h[:n], h_ref[:n])
+        x_ref2, h_ref2, it_ref2 = orc.lsqr_solve_sensit(niter, 1e-13, 0.0, 0.0, So, Co, b, N, pb.nx, pb.ny, pb.nz, 1, 1, False)
+        assert it2 == it_ref2 and np.allclose(h2[:n], h_ref2[:n], rtol=5e-3), (h2[:n], h_ref2[:n])
         print("multi_rank_case ok: backend=nccl kind=dist_sensit world=%d nnz=%d slabs=%s iters=%d r_last=%.6e" %
               (world, tot, list(map(int, nel_at)), it, h[-1]), flush=True)
 

@@ -646,3 +646,23 @@ def sensit_rows_apply_weights(rows, problem_weight, data_weight):
     L.tfx_sensit_rows_apply_weights.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
     dw = np.ascontiguousarray(data_weight, dtype=np.float64)
     _check(L.tfx_sensit_rows_apply_weights(rows._h, float(problem_weight), dw.ctypes.data))
+
+
+def calculate_data(matrix_sensit, model_val, ndata, ndata_components, problem_weight, column_weight, data_weight,
+                   compression_type, nx, ny, nz, line_start=1, param_shift=0, myrank=0, nbproc=1, data_calc=None):
+    """t_model%calculate_data (model.F90:220-307). model_val: (ncomponents, nelements) C-ordered == Fortran
+    val(nelements, ncomponents). Returns data_calc with shape (ndata, ndata_components)."""
+    L = lib()
+    vp, i32, dbl = C.c_void_p, C.c_int32, C.c_double
+    L.tfx_calculate_data.argtypes = [vp, i32, i32, vp, i32, i32, dbl, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32]
+    m = _f64(model_val)
+    cw = _f64(column_weight)
+    dw = _f64(data_weight)
+    nelements = cw.size if isinstance(cw, np.ndarray) else cw.n
+    ncomp = (m.size if isinstance(m, np.ndarray) else m.n) // nelements
+    if data_calc is None:
+        data_calc = np.zeros((ndata, ndata_components))
+    _check(L.tfx_calculate_data(matrix_sensit._h, nelements, ncomp, _ptr(m), ndata, ndata_components, float(problem_weight),
+                                _ptr(cw), _ptr(dw), _ptr(data_calc), compression_type, nx, ny, nz, line_start, param_shift,
+                                myrank, nbproc))
+    return data_calc

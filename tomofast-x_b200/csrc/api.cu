@@ -691,26 +691,6 @@ int tfx_iHaar3D(double *s, int32_t n1, int32_t n2, int32_t n3) { return wavelet_
 int tfx_DaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3) { return wavelet_call(s, n1, n2, n3, 2, true); }
 int tfx_iDaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3) { return wavelet_call(s, n1, n2, n3, 2, false); }
 
-int tfx_apply_wavelet_transform(int32_t nelements, int32_t nx, int32_t ny, int32_t nz, int32_t ncomponents, double *v,
-                                int32_t fwd, int32_t compression_type, int32_t nproblems, const int32_t *solve_problem,
-                                int32_t myrank, int32_t nbproc) {
-  (void)myrank;
-  TFX_TRY(ensure_init());
-  if (nbproc != 1 || (int64_t)nx * ny * nz != nelements)
-    return fail(-24, "apply_wavelet_transform: the device path needs the full model on the rank (nbproc = 1)");
-  VecIO io;
-  TFX_TRY(io.bind(v, (size_t)nelements * ncomponents * nproblems, true));
-  for (int i = 0; i < nproblems; ++i) {
-    if (!solve_problem[i]) continue;
-    for (int k = 0; k < ncomponents; ++k)
-      TFX_TRY(wavelet3d_device(io.dev + ((size_t)i * ncomponents + k) * nelements, nx, ny, nz, compression_type, fwd != 0,
-                               ctx().stream));
-  }
-  TFX_TRY(io.copy_back());
-  TFX_CUDA(cudaStreamSynchronize(ctx().stream));
-  return 0;
-}
-
 // ---- lsqr_solver --------------------------------------------------------------------------------
 static LsqrResult g_last;
 

@@ -10,6 +10,8 @@
 #include <nccl.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "matrix.h"
 
@@ -92,6 +94,12 @@ int comm_allreduce_sum_i64(int64_t *d_buf, size_t count, cudaStream_t st) {
   ncclResult_t r = n.AllReduce(d_buf, d_buf, count, ncclInt64, ncclSum, n.comm, st);
   return r == ncclSuccess ? 0 : nccl_fail("ncclAllReduce", r);
 }
+int comm_allreduce_max(double *d_buf, size_t count, cudaStream_t st) {
+  Nccl &n = N();
+  if (!n.comm || n.nranks <= 1) return 0;
+  ncclResult_t r = n.AllReduce(d_buf, d_buf, count, ncclDouble, ncclMax, n.comm, st);
+  return r == ncclSuccess ? 0 : nccl_fail("ncclAllReduce", r);
+}
 // recv[r*count .. (r+1)*count) = rank r's send[0 .. count)
 int comm_allgather_i64(const int64_t *d_send, int64_t *d_recv, size_t count, cudaStream_t st) {
   Nccl &n = N();
@@ -130,6 +138,27 @@ int comm_alltoallv_4b(const void *d_send, const int64_t *send_off, void *d_recv,
   }
   r = n.GroupEnd();
   return r == ncclSuccess ? 0 : nccl_fail("ncclGroupEnd", r);
+}
+
+int comm_slab_offset(int64_t mine, int64_t *offset, int64_t *total) {
+  Nccl &n = N();
+  *offset = 0; *total = mine;
+  if (!n.comm || n.nranks <= 1) return 0;
+  cudaStream_t st = ctx().stream;
+  DevBuf<int64_t> d_mine, d_all;
+  TFX_TRY(d_mine.alloc(1)); TFX_TRY(d_all.alloc((size_t)n.nranks));
+  TFX_CUDA(cudaMemcpyAsync(d_mine.p, &mine, 8, cudaMemcpyHostToDevice, st));
+  TFX_TRY(comm_allgather_i64(d_mine.p, d_all.p, 1, st));
+  std::vector<int64_t> all((size_t)n.nranks);
+  TFX_CUDA(cudaMemcpyAsync(all.data(), d_all.p, all.size() * 8, cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  int64_t off = 0, tot = 0;
+  for (int r = 0; r < n.nranks; ++r) {
+    if (r < n.rank) off += all[(size_t)r];
+    tot += all[(size_t)r];
+  }
+  *offset = off; *total = tot;
+  return 0;
 }
 
 int comm_unique_id(char id[128]) {

@@ -282,14 +282,15 @@ inline int vec_grid(int64_t n) {
   return (int)std::max<int64_t>(1, std::min(b, cap));
 }
 
-// apply_wavelet_transform for one rank (src/inversion/wavelet_utils.F90:37-72): every active problem
-// and component of v(nelements, ncomponents, 2) is an independent nx*ny*nz volume.
-int apply_wavelet(const LsqrParams &p, double *d_v, bool fwd, cudaStream_t st) {
+// apply_wavelet_transform (src/inversion/wavelet_utils.F90:37-72): every active problem and component of
+// v(nelements, ncomponents, 2) is one nx*ny*nz volume; with several ranks the slabs are assembled into the full
+// volume on every GPU (wavelet_slab_device, data.cu) instead of the reference's gather to rank 0 / scatter.
+int apply_wavelet(const LsqrParams &p, double *d_v, bool fwd, int64_t nsmaller, cudaStream_t st) {
   for (int i = 0; i < 2; ++i) {
     if (!p.solve_problem[i]) continue;
     for (int k = 0; k < p.ncomponents; ++k) {
       double *vol = d_v + ((size_t)i * p.ncomponents + k) * (size_t)p.nelements;
-      TFX_TRY(wavelet3d_device(vol, p.nx, p.ny, p.nz, p.compression_type, fwd, st));
+      TFX_TRY(wavelet_slab_device(vol, p.nelements, nsmaller, p.nx, p.ny, p.nz, p.compression_type, fwd, st));
     }
   }
   return 0;
@@ -315,10 +316,13 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
     return fail(-50, p.single_matrix ? "Wrong matrix size in lsqr_solve! Exiting."
                                      : "Wrong matrix sizes in lsqr_solve_sensit! Exiting.");
   if (!S->finalized || (C && !C->finalized)) return fail(-51, "lsqr: matrix is not finalized");
-  if (wav && p.nbproc > 1)
-    return fail(-52, "lsqr: wavelet transform inside the loop is only supported with nbproc = 1 in this version");
-  if (wav && ((int64_t)p.nx * p.ny * p.nz != p.nelements))
-    return fail(-53, "lsqr: nelements must equal nx*ny*nz when the wavelet transform runs inside the loop");
+  int64_t nsmaller = 0;
+  if (wav) {
+    int64_t total = 0;
+    TFX_TRY(comm_slab_offset(p.nelements, &nsmaller, &total));
+    if (total != (int64_t)p.nx * p.ny * p.nz)
+      return fail(-53, "lsqr: the ranks' nelements must add up to nx*ny*nz when the wavelet transform runs inside the loop");
+  }
 
   if (g_opt_strict_order) return lsqr_run_strict(p, S, C, d_u, d_x, res);
 
@@ -428,7 +432,7 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
     // =========================== SPLIT PATH (reference order) ===========================
     // v = S^T u_d [inverse wavelet] + C^T u_c ; alpha = |v| ; v /= alpha ; w = v   (:137-157)
     TFX_TRY(S_trans(d_u, v2));
-    if (wav) TFX_TRY(apply_wavelet(p, v2, false, st));
+    if (wav) TFX_TRY(apply_wavelet(p, v2, false, nsmaller, st));
     k_v_update<<<GV, kVecThreads, 0, st>>>(v, v2, ncol, sc); LAUNCHED();
     if (have_C) TFX_TRY(seg_spmv(C->trn, d_u + nls, v, true, 0, (int32_t)ncol, 0, done, st));
     k_sumsq_partial<<<GV, kVecThreads, 0, st>>>(v, ncol, partial, done); LAUNCHED();
@@ -442,7 +446,7 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
     for (int it = 1; it <= p.niter && !host_done; ++it) {
       if (misfit) {   // :168-189
         TFX_CUDA(cudaMemcpyAsync(v2, d_x, ncol * 8, cudaMemcpyDeviceToDevice, st));
-        if (wav) TFX_TRY(apply_wavelet(p, v2, true, st));
+        if (wav) TFX_TRY(apply_wavelet(p, v2, true, nsmaller, st));
         TFX_TRY(S_fwd(v2, W.sx.p));
         if (nranks > 1) TFX_TRY(comm_allreduce_sum(W.sx.p, nls, st));
         k_diffsq_partial<<<vec_grid(nls), kVecThreads, 0, st>>>(W.sx.p, W.b0.p, nls, partial, done); LAUNCHED();
@@ -453,7 +457,7 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
       const double *vin = v;
       if (wav) {
         TFX_CUDA(cudaMemcpyAsync(v2, v, ncol * 8, cudaMemcpyDeviceToDevice, st));
-        TFX_TRY(apply_wavelet(p, v2, true, st));
+        TFX_TRY(apply_wavelet(p, v2, true, nsmaller, st));
         vin = v2;
       }
       TFX_TRY(S_fwd(vin, q));
@@ -468,7 +472,7 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
       k_scale<<<GV, kVecThreads, 0, st>>>(d_u, nlines, &sc->inv_beta, done); LAUNCHED();
       // v = -beta v + W^-1(S^T u_d) + C^T u_c ; alpha = |v| (:225-245)
       TFX_TRY(S_trans(d_u, v2));
-      if (wav) TFX_TRY(apply_wavelet(p, v2, false, st));
+      if (wav) TFX_TRY(apply_wavelet(p, v2, false, nsmaller, st));
       k_v_update<<<GV, kVecThreads, 0, st>>>(v, v2, ncol, sc); LAUNCHED();
       if (have_C) TFX_TRY(seg_spmv(C->trn, d_u + nls, v, true, 0, (int32_t)ncol, 0, done, st));
       k_sumsq_partial<<<GV, kVecThreads, 0, st>>>(v, ncol, partial, done); LAUNCHED();

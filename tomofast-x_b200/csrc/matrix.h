@@ -100,6 +100,14 @@ int lsqr_run_strict(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, doub
 // ---- comm.cu ----------------------------------------------------------------------------------
 int comm_nranks();
 int comm_rank();
+// Position of this rank's slab in the concatenation of all ranks' slabs (get_nsmaller with arbitrary slab sizes,
+// parallel_tools.f90:68-86 + :91-110) and the total; one small all-gather.
+int comm_slab_offset(int64_t mine, int64_t *offset, int64_t *total);
+int comm_allreduce_max(double *d_buf, size_t count, cudaStream_t st);
+// In-place wavelet transform of a distributed volume: d_slab holds cells [nsmaller, nsmaller + nelements) of the
+// nx*ny*nz volume (wavelet_utils.F90:57-67 without the rank-0 bottleneck). data.cu
+int wavelet_slab_device(double *d_slab, int64_t nelements, int64_t nsmaller, int nx, int ny, int nz, int wavelet_type,
+                        bool forward, cudaStream_t st);
 int comm_allreduce_sum(double *d_buf, size_t count, cudaStream_t st);
 int comm_allreduce_sum_i32(int32_t *d_buf, size_t count, cudaStream_t st);
 int comm_allreduce_sum_i64(int64_t *d_buf, size_t count, cudaStream_t st);
