@@ -138,6 +138,61 @@ int tfx_calculate_data(tfx_matrix *matrix_sensit, int32_t nelements, int32_t nco
                        int32_t nx, int32_t ny, int32_t nz, int32_t line_start, int32_t param_shift,
                        int32_t myrank, int32_t nbproc);
 
+/* ---- module weights_gravmag: calculate_depth_weight (src/forward/gravmag/weights_gravmag.f90:46-199) ----
+ * column_weight(nelements) for the rank's cells nsmaller+1 .. nsmaller+nelements of the full grid (grid arrays
+ * hold all nelements_total cells): type 1 depth weighting (:71-79, calc_depth_weight_pixel :204-223), type 2
+ * distance weighting (:81-138, O(ncells*ndata) pow evaluations), type 3 minimum distance (:140-161); then the
+ * cell-volume scaling (:170-175), normalisation by the global maximum (:228-250; an NCCL max all-reduce when
+ * nbproc > 1) and inversion (:189-195). Grid, data and output pointers may be host or device memory. Aborts with
+ * the reference's messages ("non-positive depth", "Zero depth weight norm", "Zero damping weight", "Not known
+ * depth weight type"). */
+int tfx_calculate_depth_weight(int32_t depth_weighting_type, double depth_weighting_power,
+                               double depth_weighting_beta, double Z0, int32_t nelements_total,
+                               const double *X1, const double *X2, const double *Y1, const double *Y2,
+                               const double *Z1, const double *Z2, int32_t ndata, const double *data_X,
+                               const double *data_Y, const double *data_Z, int32_t nsmaller, int32_t nelements,
+                               double *column_weight, int32_t myrank, int32_t nbproc);
+
+/* ---- constraint-matrix producers on the device (csrc/cons.cu) --------------------------------------
+ * Each call appends its rows to `matrix` (initialize ... [producers] ... finalize; host-built rows may precede or
+ * follow) in the reference's add() order and writes the matching entries of b_RHS(nrows), the constraint part of
+ * the right-hand side (b_RHS(lc:), joint_inverse_problem.F90:465), indexed by the matrix row number like the
+ * reference does (get_current_row_number). Array arguments may be host or device pointers. With nbproc > 1 the
+ * rank's slab position is taken from the communicator (get_nsmaller, parallel_tools.f90:68-86). */
+/* t_damping%add (src/inversion/damping.F90:97-201, add_RHS :206-232, get_norm_multiplier :249-261): nx*ny*nz rows,
+ * the rank's nelements diagonal entries alpha*problem_weight[*Lp multiplier][*local_weight] at columns
+ * param_shift + i; model, model_ref, column_weight and local_weight (may be NULL) are the rank's slabs. Also the
+ * ADMM term (joint_inverse_problem.F90:497-527: alpha = rho_ADMM, model_ref = x0_ADMM). cost = sum(b_RHS block^2). */
+int tfx_damping_add(tfx_matrix *matrix, int32_t nrows, double *b_RHS, double alpha, double problem_weight,
+                    double norm_power, int32_t compression_type, int32_t nx, int32_t ny, int32_t nz,
+                    int32_t nelements, const double *column_weight, const double *model, const double *model_ref,
+                    int32_t param_shift, int32_t wavelet_domain, const double *local_weight,
+                    int32_t myrank, int32_t nbproc, double *cost);
+/* t_damping_gradient%add (src/inversion/damping_gradient.F90:93-203; forward differences of gradient.F90:88-93,
+ * boundary values of :175-225): nx*ny*nz rows for one direction (1 x, 2 y, 3 z) of one model component.
+ * dX(nx), dY(ny), dZ(nz): t_grad_grid cell sizes (grid.F90:359-403); val_full and local_weight: full grid;
+ * column_weight: the rank's slab. cost = sum of the squared gradient component. */
+int tfx_damping_gradient_add(tfx_matrix *matrix, int32_t nrows, double *b_RHS, double beta, double problem_weight,
+                             int32_t nx, int32_t ny, int32_t nz, const double *dX, const double *dY, const double *dZ,
+                             int32_t nelements, const double *val_full, const double *column_weight,
+                             const double *local_weight, int32_t param_shift, int32_t direction,
+                             int32_t myrank, int32_t nbproc, double *cost);
+/* t_cross_gradient%calculate with add = .true. and vec_field_type = 0 (src/inversion/cross_gradient.F90:220-391;
+ * calculate_tau :455-567, calculate_tau_backward :676-740): 3*nx*ny*nz rows (x, y, z component per cell), columns
+ * ind and ind + nparams_loc. model1/model2: full grid; column_weight1/2: the rank's slab; der_type 1 (forward) or
+ * 2 (central), anything else aborts like the reference (:281-283). Outputs: cost[3] (:298-300) and, when not NULL,
+ * cross_grad(nx*ny*nz) = |tau| per cell (:293-296). */
+int tfx_cross_gradient_calculate(tfx_matrix *matrix, int32_t nrows, double *b_RHS, int32_t nx, int32_t ny, int32_t nz,
+                                 const double *dX, const double *dY, const double *dZ, int32_t nparams_loc,
+                                 const double *model1, const double *model2, const double *column_weight1,
+                                 const double *column_weight2, int32_t der_type, double glob_weight,
+                                 const int32_t keep_model_constant[2], int32_t myrank, int32_t nbproc,
+                                 double cost[3], double *cross_grad);
+/* t_admm_method%iterate_admm_arrays (src/inversion/admm_method.F90:70-134): z = P_C(x + u), u += x - z,
+ * x0 = z - u; xmin/xmax(nlithos, nelements) Fortran order; z and u are updated in place. */
+int tfx_admm_iterate_admm_arrays(int32_t nelements, int32_t nlithos, const double *xmin, const double *xmax,
+                                 const double *x, double *z, double *u, double *x0);
+
 /* ---- module lsqr_solver (src/inversion/lsqr_solver2.F90) --------------------------------------- */
 int tfx_lsqr_solve(int32_t nlines, int32_t nelements, int32_t niter, double rmin, double gamma,
                    tfx_matrix *matrix, double *u, double *x, int32_t myrank);                    /* :321-473 */

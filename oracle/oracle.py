@@ -87,6 +87,15 @@ def lib():
                                    C.c_double, C.c_double, C.c_double, _d]
     L.orc_admm_iterate.argtypes = [C.c_int32, C.c_int32, _d, _d, _d, _d, _d, _d]
     L.orc_admm_iterate.restype = None
+    L.orc_damping_add.argtypes = [P, _d, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_int32, _d, _d, _d, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.POINTER(C.c_double)]
+    L.orc_damping_gradient_add.argtypes = [P, _d, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32, _d, _d, _d,
+                                           C.c_int32, C.c_int32, _d, _d, _d, C.c_int32, C.c_int32,
+                                           C.POINTER(C.c_double)]
+    L.orc_cross_gradient_calculate.argtypes = [P, _d, C.c_int32, C.c_int32, C.c_int32, _d, _d, _d, C.c_int32, C.c_int32,
+                                               _d, _d, _d, _d, C.c_int32, C.c_double, _i, _d, C.c_void_p,
+                                               C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     L.orc_norm2.argtypes = [C.c_int64, _d]
     L.orc_norm2.restype = C.c_double
     _lib = L
@@ -113,6 +122,8 @@ class SparseMatrix:
     ncolumns = property(lambda s: s._p.contents.ncolumns)
     nel = property(lambda s: s._p.contents.nel)
     nl_nonempty = property(lambda s: s._p.contents.nl_nonempty)
+
+    current_row = property(lambda s: s._p.contents.nl_current_all)   # get_current_row_number (:458-463)
 
     def reset(self):
         lib().orc_csr_reset(self._p)
@@ -322,3 +333,50 @@ def calculate_data(S, model_val, ndata, ndata_components, problem_weight, column
     d = d / problem_weight                                               # :297
     d = d / np.asarray(data_weight, dtype=np.float64).ravel()            # :304
     return d.reshape(ndata, ndata_components)
+
+
+def _dd(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def damping_add(matrix, b_RHS, alpha, problem_weight, norm_power, compression_type, nx, ny, nz, nsmaller, nelements,
+                column_weight, model, model_ref, param_shift, wavelet_domain, local_weight=None):
+    """damping_add (damping.F90:97-201) on full-grid arrays, the rank's slab = (nsmaller, nelements). b_RHS (the
+    constraint part of the right-hand side) is filled in place; returns the damping cost."""
+    cost = C.c_double(0.0)
+    lw = None if local_weight is None else _dd(local_weight)
+    rc = lib().orc_damping_add(matrix._p, b_RHS, alpha, problem_weight, norm_power, compression_type, nx, ny, nz,
+                               nsmaller, nelements, _dd(column_weight), _dd(model), _dd(model_ref), param_shift,
+                               int(bool(wavelet_domain)), None if lw is None else lw.ctypes.data, C.byref(cost))
+    if rc != 0:
+        raise RuntimeError("Sanity check failed in damping_add!" if rc == -1 else "sparse matrix overflow in damping_add")
+    return cost.value
+
+
+def damping_gradient_add(matrix, b_RHS, beta, problem_weight, nx, ny, nz, dX, dY, dZ, nsmaller, nelements, val_full,
+                         column_weight, local_weight, param_shift, direction):
+    """damping_gradient_add (damping_gradient.F90:93-203); returns the cost."""
+    cost = C.c_double(0.0)
+    rc = lib().orc_damping_gradient_add(matrix._p, b_RHS, beta, problem_weight, nx, ny, nz, _dd(dX), _dd(dY), _dd(dZ),
+                                        nsmaller, nelements, _dd(val_full), _dd(column_weight), _dd(local_weight),
+                                        param_shift, direction, C.byref(cost))
+    if rc != 0:
+        raise RuntimeError("Wrong direction in damping_gradient_add!" if rc == -1 else "sparse matrix overflow")
+    return cost.value
+
+
+def cross_gradient_calculate(matrix, b_RHS, nx, ny, nz, dX, dY, dZ, nsmaller, nparams_loc, model1, model2,
+                             column_weight1, column_weight2, der_type, glob_weight, keep_model_constant=(0, 0)):
+    """cross_gradient_calculate with add = .true. (cross_gradient.F90:220-391). Returns (cost[3], cross_grad(N), nnz,
+    nl_nonempty)."""
+    cost = np.zeros(3)
+    cg = np.zeros(nx * ny * nz)
+    nnz, nne = C.c_int64(0), C.c_int32(0)
+    keep = np.ascontiguousarray(keep_model_constant, dtype=np.int32)
+    rc = lib().orc_cross_gradient_calculate(matrix._p, b_RHS, nx, ny, nz, _dd(dX), _dd(dY), _dd(dZ), nsmaller,
+                                            nparams_loc, _dd(model1), _dd(model2), _dd(column_weight1),
+                                            _dd(column_weight2), der_type, glob_weight, keep, cost, cg.ctypes.data,
+                                            C.byref(nnz), C.byref(nne))
+    if rc != 0:
+        raise RuntimeError("Unsupported derivative type!" if rc == -1 else "sparse matrix overflow")
+    return cost, cg, nnz.value, nne.value

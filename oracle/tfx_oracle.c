@@ -804,3 +804,269 @@ void orc_admm_iterate(int32_t n, int32_t nlithos, const double *xmin, const doub
   for (int32_t i = 0; i < n; ++i) u[i] = u[i] + x[i] - z[i];
   for (int32_t i = 0; i < n; ++i) x0[i] = z[i] - u[i];
 }
+
+/* ========================================================================== */
+/* Constraint-matrix producers.                             */
+/* Serial restatements with the rank's column slab given explicitly:           */
+/* nsmaller = get_nsmaller(nelements, myrank, nbproc), local cells             */
+/* nsmaller+1 .. nsmaller+nelements.  b_RHS is the constraint part of the      */
+/* right-hand side (b_RHS(lc:) in joint_inverse_problem.F90:465).              */
+/* ========================================================================== */
+
+/* damping_add + damping_add_RHS + get_norm_multiplier, src/inversion/damping.F90:97-261.
+ * model / model_ref / column_weight / local_weight (may be NULL) hold the FULL model here (the serial
+ * union of all ranks' slabs); only entries of the slab go into the matrix, the right-hand side is the
+ * gathered one (get_full_array_in_place, :230). Returns 0, -1 on the sanity check of :176-177. */
+int orc_damping_add(orc_csr *matrix, double *b_RHS, double alpha, double problem_weight, double norm_power,
+                    int32_t compression_type, int32_t nx, int32_t ny, int32_t nz,
+                    int32_t nsmaller, int32_t nelements, const double *column_weight, const double *model,
+                    const double *model_ref, int32_t param_shift, int32_t wavelet_domain,
+                    const double *local_weight, double *cost) {
+  const int32_t ntot = nx * ny * nz;
+  double *model_diff = (double *)malloc(sizeof(double) * (size_t)ntot);
+  for (int32_t i = 0; i < ntot; ++i) {                                         /* :117-126 */
+    double dm = model[i] - model_ref[i];
+    model_diff[i] = (column_weight[i] != 0.0) ? dm / column_weight[i] : 0.0;
+  }
+  if (compression_type > 0 && wavelet_domain)                                  /* :128-142 */
+    orc_forward_wavelet(model_diff, nx, ny, nz, compression_type);
+  const int32_t row_beg = matrix->nl_current_all + 1;                          /* :145 */
+  orc_csr_add_empty_rows(matrix, nsmaller);                                    /* :151 */
+  for (int32_t i = 0; i < nelements; ++i) {                                    /* :154-168 */
+    const int32_t p = nsmaller + i;
+    double value = alpha * problem_weight;
+    if (norm_power != 2.0)
+      value = value * ((model_diff[p] != 0.0) ? pow(fabs(model_diff[p]), norm_power / 2.0 - 1.0) : 1.0);
+    if (local_weight) value = value * local_weight[p];
+    if (orc_csr_add(matrix, value, param_shift + i + 1) != 0) { free(model_diff); return -2; }
+    if (orc_csr_new_row(matrix) != 0) { free(model_diff); return -2; }
+  }
+  orc_csr_add_empty_rows(matrix, ntot - nelements - nsmaller);                 /* :171 */
+  const int32_t row_end = matrix->nl_current_all;
+  if (row_end - row_beg + 1 != ntot) { free(model_diff); return -1; }          /* :176-177 */
+  double c = 0.0;
+  for (int32_t i = 0; i < ntot; ++i) {                                         /* :213-230 (all ranks' slabs) */
+    double b = -alpha * problem_weight * model_diff[i];
+    if (norm_power != 2.0)
+      b = b * ((model_diff[i] != 0.0) ? pow(fabs(model_diff[i]), norm_power / 2.0 - 1.0) : 1.0);
+    if (local_weight) b = b * local_weight[i];
+    b_RHS[row_beg - 1 + i] = b;
+    c += b * b;                                                                /* :190 */
+  }
+  if (cost) *cost = c;
+  free(model_diff);
+  return 0;
+}
+
+/* grad_get_par, src/inversion/gradient.F90:175-225: zero outside the domain. */
+static double orc_grad_par(const double *val, int32_t nx, int32_t ny, int32_t nz, int32_t i, int32_t j, int32_t k) {
+  if (i == nx + 1 || j == ny + 1 || k == nz + 1) return 0.0;
+  if (i == 0 || j == 0 || k == 0) return 0.0;
+  return val[(i - 1) + (size_t)(j - 1) * nx + (size_t)(k - 1) * nx * ny];
+}
+/* grad_grid_get_ind, src/inversion/grid.F90:409-426: 1-based, -1 outside. */
+static int32_t orc_get_ind(int32_t nx, int32_t ny, int32_t nz, int32_t i, int32_t j, int32_t k) {
+  if (i < 1 || i > nx || j < 1 || j > ny || k < 1 || k > nz) return -1;
+  return i + (j - 1) * nx + (k - 1) * nx * ny;
+}
+/* get_grad, src/inversion/gradient.F90:71-170: type 0 backward, 1 forward, 2 central. */
+static void orc_get_grad(const double *val, int32_t nx, int32_t ny, int32_t nz, const double *dX, const double *dY,
+                         const double *dZ, int32_t i, int32_t j, int32_t k, int type, double g[3]) {
+#define PAR(a, b, c) orc_grad_par(val, nx, ny, nz, (a), (b), (c))
+  if (type == 0) {
+    g[0] = (PAR(i, j, k) - PAR(i - 1, j, k)) / dX[i - 1];
+    g[1] = (PAR(i, j, k) - PAR(i, j - 1, k)) / dY[j - 1];
+    g[2] = (PAR(i, j, k) - PAR(i, j, k - 1)) / dZ[k - 1];
+  } else if (type == 1) {
+    g[0] = (PAR(i + 1, j, k) - PAR(i, j, k)) / dX[i - 1];
+    g[1] = (PAR(i, j + 1, k) - PAR(i, j, k)) / dY[j - 1];
+    g[2] = (PAR(i, j, k + 1) - PAR(i, j, k)) / dZ[k - 1];
+  } else {
+    g[0] = (PAR(i + 1, j, k) - PAR(i - 1, j, k)) / 2.0 / dX[i - 1];
+    g[1] = (PAR(i, j + 1, k) - PAR(i, j - 1, k)) / 2.0 / dY[j - 1];
+    g[2] = (PAR(i, j, k + 1) - PAR(i, j, k - 1)) / 2.0 / dZ[k - 1];
+  }
+#undef PAR
+}
+
+/* damping_gradient_add, src/inversion/damping_gradient.F90:93-203. val_full: the full model component;
+ * column_weight: full-grid array, the slab's entries are used (column_weight(ind - nsmaller) there);
+ * local_weight(nx*ny*nz). Returns 0, -1 wrong direction. */
+int orc_damping_gradient_add(orc_csr *matrix, double *b_RHS, double beta, double problem_weight,
+                             int32_t nx, int32_t ny, int32_t nz, const double *dX, const double *dY, const double *dZ,
+                             int32_t nsmaller, int32_t nelements, const double *val_full, const double *column_weight,
+                             const double *local_weight, int32_t param_shift, int32_t direction, double *cost) {
+  if (direction < 1 || direction > 3) return -1;
+  double c = 0.0;
+  int32_t p = 0;
+  for (int32_t k = 1; k <= nz; ++k)
+    for (int32_t j = 1; j <= ny; ++j)
+      for (int32_t i = 1; i <= nx; ++i) {
+        p++;
+        double g[3], delta, gradient_val;
+        int32_t ind[2];
+        orc_get_grad(val_full, nx, ny, nz, dX, dY, dZ, i, j, k, 1, g);
+        if (direction == 1) {
+          delta = dX[i - 1];
+          if (i == nx) { orc_csr_new_row(matrix); continue; }
+          ind[0] = orc_get_ind(nx, ny, nz, i + 1, j, k);
+        } else if (direction == 2) {
+          delta = dY[j - 1];
+          if (j == ny) { orc_csr_new_row(matrix); continue; }
+          ind[0] = orc_get_ind(nx, ny, nz, i, j + 1, k);
+        } else {
+          delta = dZ[k - 1];
+          if (k == nz) { orc_csr_new_row(matrix); continue; }
+          ind[0] = orc_get_ind(nx, ny, nz, i, j, k + 1);
+        }
+        ind[1] = orc_get_ind(nx, ny, nz, i, j, k);
+        gradient_val = g[direction - 1];
+        double val[2];
+        val[0] = 1.0 / delta;
+        val[1] = -val[0];
+        for (int l = 0; l < 2; ++l) {                                          /* :177-184 */
+          if (ind[l] > nsmaller && ind[l] <= nsmaller + nelements) {
+            const int32_t loc = ind[l] - nsmaller;
+            const double v = val[l] * problem_weight * beta * column_weight[ind[l] - 1] * local_weight[p - 1];
+            if (orc_csr_add(matrix, v, param_shift + loc) != 0) return -2;
+          }
+        }
+        if (orc_csr_new_row(matrix) != 0) return -2;
+        b_RHS[matrix->nl_current_all - 1] = -problem_weight * beta * gradient_val * local_weight[p - 1];   /* :189 */
+        c = c + gradient_val * gradient_val;                                   /* :192 */
+      }
+  if (cost) *cost = c;
+  return 0;
+}
+
+/* cross_gradient_calculate with add = .true., vec_field_type = 0 (src/inversion/cross_gradient.F90:220-391),
+ * calculate_tau (:455-567) and calculate_tau_backward (:676-740). der_type 1 (forward) or 2 (central).
+ * model1/model2: full models; column_weight1/2: full-grid arrays (the slab's entries are used);
+ * cost[3]; cross_grad(nx*ny*nz) may be NULL. Returns 0, -1 unsupported derivative type. */
+typedef struct { double val[3]; double dm1[4][3]; double dm2[4][3]; int32_t ind[4][3]; } orc_tau;
+
+static void orc_tau_zero(orc_tau *t) { memset(t, 0, sizeof(*t)); }
+
+static void orc_calc_tau(const double *m1, const double *m2, int32_t nx, int32_t ny, int32_t nz, const double *dX,
+                         const double *dY, const double *dZ, int32_t i, int32_t j, int32_t k, int der_type, orc_tau *t) {
+  double g1[3], g2[3];
+  orc_tau_zero(t);
+  orc_get_grad(m1, nx, ny, nz, dX, dY, dZ, i, j, k, der_type == 1 ? 1 : 2, g1);   /* get_der_type: 1 FWD, 2 CNT */
+  orc_get_grad(m2, nx, ny, nz, dX, dY, dZ, i, j, k, der_type == 1 ? 1 : 2, g2);
+  t->val[0] = g1[1] * g2[2] - g1[2] * g2[1];                                   /* vector.f90 cross_product */
+  t->val[1] = g1[2] * g2[0] - g1[0] * g2[2];
+  t->val[2] = g1[0] * g2[1] - g1[1] * g2[0];
+  double sx = dX[i - 1], sy = dY[j - 1], sz = dZ[k - 1];
+  if (der_type != 1) { sx = 2.0 * sx; sy = 2.0 * sy; sz = 2.0 * sz; }
+#define IND(a, b, c) orc_get_ind(nx, ny, nz, (a), (b), (c))
+  /* x */
+  t->dm1[0][0] = g2[2] / sy;  t->dm2[0][0] = -g1[2] / sy;
+  t->dm1[1][0] = -g2[1] / sz; t->dm2[1][0] = g1[1] / sz;
+  t->ind[0][0] = IND(i, j + 1, k); t->ind[1][0] = IND(i, j, k + 1);
+  if (der_type == 1) {
+    t->dm1[2][0] = -(g2[2] / sy - g2[1] / sz); t->dm2[2][0] = -(g1[1] / sz - g1[2] / sy);
+    t->ind[2][0] = IND(i, j, k);
+  } else {
+    t->dm1[2][0] = -t->dm1[0][0]; t->dm2[2][0] = -t->dm2[0][0];
+    t->dm1[3][0] = -t->dm1[1][0]; t->dm2[3][0] = -t->dm2[1][0];
+    t->ind[2][0] = IND(i, j - 1, k); t->ind[3][0] = IND(i, j, k - 1);
+  }
+  /* y */
+  t->dm1[0][1] = -g2[2] / sx; t->dm2[0][1] = g1[2] / sx;
+  t->dm1[1][1] = g2[0] / sz;  t->dm2[1][1] = -g1[0] / sz;
+  t->ind[0][1] = IND(i + 1, j, k); t->ind[1][1] = IND(i, j, k + 1);
+  if (der_type == 1) {
+    t->dm1[2][1] = -(g2[0] / sz - g2[2] / sx); t->dm2[2][1] = -(g1[2] / sx - g1[0] / sz);
+    t->ind[2][1] = IND(i, j, k);
+  } else {
+    t->dm1[2][1] = -t->dm1[0][1]; t->dm2[2][1] = -t->dm2[0][1];
+    t->dm1[3][1] = -t->dm1[1][1]; t->dm2[3][1] = -t->dm2[1][1];
+    t->ind[2][1] = IND(i - 1, j, k); t->ind[3][1] = IND(i, j, k - 1);
+  }
+  /* z */
+  t->dm1[0][2] = g2[1] / sx;  t->dm2[0][2] = -g1[1] / sx;
+  t->dm1[1][2] = -g2[0] / sy; t->dm2[1][2] = g1[0] / sy;
+  t->ind[0][2] = IND(i + 1, j, k); t->ind[1][2] = IND(i, j + 1, k);
+  if (der_type == 1) {
+    t->dm1[2][2] = -(g2[1] / sx - g2[0] / sy); t->dm2[2][2] = -(g1[0] / sy - g1[1] / sx);
+    t->ind[2][2] = IND(i, j, k);
+  } else {
+    t->dm1[2][2] = -t->dm1[0][2]; t->dm2[2][2] = -t->dm2[0][2];
+    t->dm1[3][2] = -t->dm1[1][2]; t->dm2[3][2] = -t->dm2[1][2];
+    t->ind[2][2] = IND(i - 1, j, k); t->ind[3][2] = IND(i, j - 1, k);
+  }
+}
+
+static void orc_calc_tau_backward(const double *m1, const double *m2, int32_t nx, int32_t ny, int32_t nz,
+                                  const double *dX, const double *dY, const double *dZ, int32_t i, int32_t j, int32_t k,
+                                  orc_tau *t) {
+  double g1[3], g2[3];
+  orc_tau_zero(t);
+  orc_get_grad(m1, nx, ny, nz, dX, dY, dZ, i, j, k, 0, g1);
+  orc_get_grad(m2, nx, ny, nz, dX, dY, dZ, i, j, k, 0, g2);
+  t->val[0] = g1[1] * g2[2] - g1[2] * g2[1];
+  t->val[1] = g1[2] * g2[0] - g1[0] * g2[2];
+  t->val[2] = g1[0] * g2[1] - g1[1] * g2[0];
+  const double sx = dX[i - 1], sy = dY[j - 1], sz = dZ[k - 1];
+  t->dm1[0][0] = -g2[2] / sy; t->dm1[1][0] = g2[1] / sz;  t->dm1[2][0] = g2[2] / sy - g2[1] / sz;
+  t->dm2[0][0] = g1[2] / sy;  t->dm2[1][0] = -g1[1] / sz; t->dm2[2][0] = g1[1] / sz - g1[2] / sy;
+  t->ind[0][0] = IND(i, j - 1, k); t->ind[1][0] = IND(i, j, k - 1); t->ind[2][0] = IND(i, j, k);
+  t->dm1[0][1] = g2[2] / sx;  t->dm1[1][1] = -g2[0] / sz; t->dm1[2][1] = g2[0] / sz - g2[2] / sx;
+  t->dm2[0][1] = -g1[2] / sx; t->dm2[1][1] = g1[0] / sz;  t->dm2[2][1] = g1[2] / sx - g1[0] / sz;
+  t->ind[0][1] = IND(i - 1, j, k); t->ind[1][1] = IND(i, j, k - 1); t->ind[2][1] = IND(i, j, k);
+  t->dm1[0][2] = -g2[1] / sx; t->dm1[1][2] = g2[0] / sy;  t->dm1[2][2] = g2[1] / sx - g2[0] / sy;
+  t->dm2[0][2] = g1[1] / sx;  t->dm2[1][2] = -g1[0] / sy; t->dm2[2][2] = g1[0] / sy - g1[1] / sx;
+  t->ind[0][2] = IND(i - 1, j, k); t->ind[1][2] = IND(i, j - 1, k); t->ind[2][2] = IND(i, j, k);
+#undef IND
+}
+
+int orc_cross_gradient_calculate(orc_csr *matrix, double *b_RHS, int32_t nx, int32_t ny, int32_t nz,
+                                 const double *dX, const double *dY, const double *dZ,
+                                 int32_t nsmaller, int32_t nparams_loc, const double *model1, const double *model2,
+                                 const double *column_weight1, const double *column_weight2,
+                                 int32_t der_type, double glob_weight, const int32_t keep_model_constant[2],
+                                 double cost[3], double *cross_grad, int64_t *nnz_out, int32_t *nl_nonempty_out) {
+  if (der_type != 1 && der_type != 2) return -1;                               /* :281-283 */
+  const int nderiv = (der_type == 1) ? 3 : 4;                                  /* :203-215 */
+  int64_t nnz = 0;
+  int32_t nl_nonempty = 0, p = 0;
+  cost[0] = cost[1] = cost[2] = 0.0;
+  for (int32_t k = 1; k <= nz; ++k)
+    for (int32_t j = 1; j <= ny; ++j)
+      for (int32_t i = 1; i <= nx; ++i) {
+        p++;
+        orc_tau t;
+        const int left = (i == 1 || j == 1 || k == 1), right = (i == nx || j == ny || k == nz);
+        if (left && right) orc_tau_zero(&t);                                   /* :262-266 */
+        else if (der_type == 2 && left) orc_calc_tau(model1, model2, nx, ny, nz, dX, dY, dZ, i, j, k, 1, &t);
+        else if (right) orc_calc_tau_backward(model1, model2, nx, ny, nz, dX, dY, dZ, i, j, k, &t);
+        else orc_calc_tau(model1, model2, nx, ny, nz, dX, dY, dZ, i, j, k, der_type, &t);
+        if (keep_model_constant[0]) memset(t.dm1, 0, sizeof(t.dm1));           /* :286-287 */
+        if (keep_model_constant[1]) memset(t.dm2, 0, sizeof(t.dm2));
+        if (cross_grad) cross_grad[p - 1] = sqrt(t.val[0] * t.val[0] + t.val[1] * t.val[1] + t.val[2] * t.val[2]);
+        for (int c = 0; c < 3; ++c) cost[c] = cost[c] + t.val[c] * t.val[c];   /* :298-300 */
+        for (int c = 0; c < 3; ++c) {                                          /* :305-371 */
+          int included = 0;
+          for (int l = 0; l < nderiv; ++l) {
+            int32_t ind = t.ind[l][c];
+            if (ind > nsmaller && ind <= nsmaller + nparams_loc) {
+              const double val1 = t.dm1[l][c] * column_weight1[ind - 1] * glob_weight;
+              const double val2 = t.dm2[l][c] * column_weight2[ind - 1] * glob_weight;
+              ind = ind - nsmaller;
+              if (orc_csr_add(matrix, val1, ind) != 0) return -2;
+              if (orc_csr_add(matrix, val2, ind + nparams_loc) != 0) return -2;
+              nnz += 2;
+              included = 1;
+            }
+          }
+          if (orc_csr_new_row(matrix) != 0) return -2;
+          b_RHS[matrix->nl_current_all - 1] = -t.val[c] * glob_weight;
+          if (included) nl_nonempty++;
+        }
+      }
+  if (keep_model_constant[0] && keep_model_constant[1]) nnz = 0;               /* :378-383 */
+  else if (keep_model_constant[0] || keep_model_constant[1]) nnz = nnz / 2;
+  if (nnz_out) *nnz_out = nnz;
+  if (nl_nonempty_out) *nl_nonempty_out = nl_nonempty;
+  return 0;
+}

@@ -118,6 +118,26 @@ int orc_depth_weight(int32_t type, int32_t n, const double *X1, const double *X2
 void orc_admm_iterate(int32_t n, int32_t nlithos, const double *xmin, const double *xmax,
                       const double *x, double *z, double *u, double *x0);
 
+/* ---- constraint-matrix producers ("parity unpinned": no reference test covers them) ----
+ * damping.F90:97-261, damping_gradient.F90:93-203 (+ gradient.F90:71-225, grid.F90:409-426),
+ * cross_gradient.F90:220-391,455-567,676-740. Full-grid input arrays; the rank's column slab is
+ * (nsmaller, nelements). b_RHS = the constraint part of the right-hand side. */
+int orc_damping_add(orc_csr *matrix, double *b_RHS, double alpha, double problem_weight, double norm_power,
+                    int32_t compression_type, int32_t nx, int32_t ny, int32_t nz,
+                    int32_t nsmaller, int32_t nelements, const double *column_weight, const double *model,
+                    const double *model_ref, int32_t param_shift, int32_t wavelet_domain,
+                    const double *local_weight, double *cost);
+int orc_damping_gradient_add(orc_csr *matrix, double *b_RHS, double beta, double problem_weight,
+                             int32_t nx, int32_t ny, int32_t nz, const double *dX, const double *dY, const double *dZ,
+                             int32_t nsmaller, int32_t nelements, const double *val_full, const double *column_weight,
+                             const double *local_weight, int32_t param_shift, int32_t direction, double *cost);
+int orc_cross_gradient_calculate(orc_csr *matrix, double *b_RHS, int32_t nx, int32_t ny, int32_t nz,
+                                 const double *dX, const double *dY, const double *dZ,
+                                 int32_t nsmaller, int32_t nparams_loc, const double *model1, const double *model2,
+                                 const double *column_weight1, const double *column_weight2,
+                                 int32_t der_type, double glob_weight, const int32_t keep_model_constant[2],
+                                 double cost[3], double *cross_grad, int64_t *nnz_out, int32_t *nl_nonempty_out);
+
 double orc_norm2(int64_t n, const double *x);
 
 #ifdef __cplusplus

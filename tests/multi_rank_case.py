@@ -201,6 +201,32 @@ def dist_sensit_case(rank, world, td, niter):
     d_want = orc.calculate_data(So, pb.m_true, ndata, 1, 1.0, pb.cw, dwt, 1, pb.nx, pb.ny, pb.nz, 1, 0)
     assert np.allclose(d_got, d_want, rtol=1e-5, atol=1e-7 * np.abs(d_want).max())
 
+    # ---- constraint producers and depth weight on the slabs (csrc/cons.cu, csrc/weights.cu) vs the oracle's slab mode
+    def same(Sg, Sref):
+        a, b_ = Sg.export(), Sref.arrays()
+        return all(np.array_equal(p_, q_) for p_, q_ in zip(a, b_))
+    dX, dY, dZ = np.full(pb.nx, 100.0), np.full(pb.ny, 100.0), np.full(pb.nz, 50.0)
+    m1 = rng.standard_normal(N); m2 = rng.standard_normal(N); lw = rng.uniform(0.5, 1.5, N); cw2 = rng.uniform(0.5, 2.0, N)
+    sl = slice(cell0, cell0 + ncl)
+    nlc = 5 * N
+    Cg, Co = tfx.SparseMatrix(nlc, 2 * ncl, 30 * N), orc.SparseMatrix(nlc, 2 * ncl, 30 * N)
+    bg, bo = np.zeros(nlc), np.zeros(nlc)
+    c1 = tfx.damping_add(Cg, bg, 1e-2, 0.9, 2.0, 1, pb.nx, pb.ny, pb.nz, pb.cw[sl], m1[sl], m2[sl], 0, True, lw[sl], rank, world)
+    c1o = orc.damping_add(Co, bo, 1e-2, 0.9, 2.0, 1, pb.nx, pb.ny, pb.nz, cell0, ncl, pb.cw, m1, m2, 0, True, lw)
+    c2 = tfx.damping_gradient_add(Cg, bg, 3e-2, 0.9, pb.nx, pb.ny, pb.nz, dX, dY, dZ, m1, pb.cw[sl], lw, 0, 2, rank, world)
+    c2o = orc.damping_gradient_add(Co, bo, 3e-2, 0.9, pb.nx, pb.ny, pb.nz, dX, dY, dZ, cell0, ncl, m1, pb.cw, lw, 0, 2)
+    c3, cg_g = tfx.cross_gradient_calculate(Cg, bg, pb.nx, pb.ny, pb.nz, dX, dY, dZ, m1, m2, pb.cw[sl], cw2[sl], 1, 0.5,
+                                            (0, 0), rank, world)
+    c3o, cg_o, _, _ = orc.cross_gradient_calculate(Co, bo, pb.nx, pb.ny, pb.nz, dX, dY, dZ, cell0, ncl, m1, m2, pb.cw, cw2, 1, 0.5)
+    Cg.finalize(); Co.finalize()
+    assert same(Cg, Co), "device-built constraint slab differs from the oracle's"
+    assert np.array_equal(bg, bo) and np.array_equal(cg_g, cg_o)
+    assert np.allclose([c1, c2] + list(c3), [c1o, c2o] + list(c3o), rtol=1e-13)
+    xyz = pb.data_xyz
+    dwg = tfx.calculate_depth_weight(2, pb.grid, xyz, 3.0, 1.5, 0.0, cell0, ncl, rank, world)
+    dwo = orc.depth_weight(2, pb.grid, xyz[0], xyz[1], xyz[2], 3.0, 1.5, 0.0)
+    assert np.allclose(dwg, dwo[sl], rtol=1e-13), "distance weighting: the normalisation maximum must be global"
+
     # ---- the same system solved in the physical domain: wavelet transforms inside the loop (WAVELET_DOMAIN = F,
     # lsqr_solver2.F90:200-207,228-235) on the distributed vectors
     u2 = b.copy(); x2 = np.zeros(ncol)

@@ -666,3 +666,97 @@ def calculate_data(matrix_sensit, model_val, ndata, ndata_components, problem_we
                                 _ptr(cw), _ptr(dw), _ptr(data_calc), compression_type, nx, ny, nz, line_start, param_shift,
                                 myrank, nbproc))
     return data_calc
+
+
+def calculate_depth_weight(depth_weighting_type, grid, data_xyz, power, beta=1.0, Z0=0.0, nsmaller=0, nelements=None,
+                           myrank=0, nbproc=1, column_weight=None):
+    """calculate_depth_weight (weights_gravmag.f90:46-199) for the cells nsmaller+1 .. nsmaller+nelements of the
+    full grid (6 arrays X1, X2, Y1, Y2, Z1, Z2). Returns column_weight(nelements)."""
+    L = lib()
+    vp, i32, dbl = C.c_void_p, C.c_int32, C.c_double
+    L.tfx_calculate_depth_weight.argtypes = [i32, dbl, dbl, dbl, i32] + [vp] * 6 + [i32, vp, vp, vp, i32, i32, vp, i32, i32]
+    g = [_f64(a) for a in grid]
+    xyz = [_f64(a) for a in data_xyz]
+    ntot = g[0].size if isinstance(g[0], np.ndarray) else g[0].n
+    ndata = xyz[0].size if isinstance(xyz[0], np.ndarray) else xyz[0].n
+    if nelements is None:
+        nelements = ntot - nsmaller
+    if column_weight is None:
+        column_weight = np.zeros(nelements)
+    _check(L.tfx_calculate_depth_weight(depth_weighting_type, float(power), float(beta), float(Z0), ntot,
+                                        *[_ptr(a) for a in g], ndata, *[_ptr(a) for a in xyz], nsmaller, nelements,
+                                        _ptr(column_weight), myrank, nbproc))
+    return column_weight
+
+
+# ---- constraint-matrix producers (csrc/cons.cu) ------------------------------------------------------
+def _opt(a):
+    return None if a is None else _f64(a)
+
+
+def damping_add(matrix, b_RHS, alpha, problem_weight, norm_power, compression_type, nx, ny, nz, column_weight, model,
+                model_ref, param_shift, wavelet_domain, local_weight=None, myrank=0, nbproc=1):
+    """t_damping%add (damping.F90:97-201). Slab arrays (nelements); b_RHS (host array or Buffer) is the constraint
+    part of the right-hand side and is updated in place. Returns the damping cost."""
+    L = lib()
+    vp, i32, dbl = C.c_void_p, C.c_int32, C.c_double
+    L.tfx_damping_add.argtypes = [vp, i32, vp, dbl, dbl, dbl, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, i32, i32,
+                                  C.POINTER(dbl)]
+    cw, m, ref, lw = _f64(column_weight), _f64(model), _f64(model_ref), _opt(local_weight)
+    nelements = cw.size if isinstance(cw, np.ndarray) else cw.n
+    nrows = b_RHS.size if isinstance(b_RHS, np.ndarray) else b_RHS.n
+    cost = dbl(0.0)
+    _check(L.tfx_damping_add(matrix._h, nrows, _ptr(b_RHS), float(alpha), float(problem_weight), float(norm_power),
+                             compression_type, nx, ny, nz, nelements, _ptr(cw), _ptr(m), _ptr(ref), param_shift,
+                             int(bool(wavelet_domain)), _ptr(lw), myrank, nbproc, C.byref(cost)))
+    return cost.value
+
+
+def damping_gradient_add(matrix, b_RHS, beta, problem_weight, nx, ny, nz, dX, dY, dZ, val_full, column_weight,
+                         local_weight, param_shift, direction, myrank=0, nbproc=1):
+    """t_damping_gradient%add (damping_gradient.F90:93-203). Returns the cost."""
+    L = lib()
+    vp, i32, dbl = C.c_void_p, C.c_int32, C.c_double
+    L.tfx_damping_gradient_add.argtypes = [vp, i32, vp, dbl, dbl, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, i32, i32,
+                                           i32, i32, C.POINTER(dbl)]
+    dX, dY, dZ, vf, cw, lw = (_f64(a) for a in (dX, dY, dZ, val_full, column_weight, local_weight))
+    nelements = cw.size if isinstance(cw, np.ndarray) else cw.n
+    nrows = b_RHS.size if isinstance(b_RHS, np.ndarray) else b_RHS.n
+    cost = dbl(0.0)
+    _check(L.tfx_damping_gradient_add(matrix._h, nrows, _ptr(b_RHS), float(beta), float(problem_weight), nx, ny, nz,
+                                      _ptr(dX), _ptr(dY), _ptr(dZ), nelements, _ptr(vf), _ptr(cw), _ptr(lw), param_shift,
+                                      direction, myrank, nbproc, C.byref(cost)))
+    return cost.value
+
+
+def cross_gradient_calculate(matrix, b_RHS, nx, ny, nz, dX, dY, dZ, model1, model2, column_weight1, column_weight2,
+                             der_type, glob_weight, keep_model_constant=(0, 0), myrank=0, nbproc=1, want_cross_grad=True):
+    """t_cross_gradient%calculate with add = .true. (cross_gradient.F90:220-391). Returns (cost[3], cross_grad or None)."""
+    L = lib()
+    vp, i32, dbl = C.c_void_p, C.c_int32, C.c_double
+    L.tfx_cross_gradient_calculate.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, dbl, vp,
+                                               i32, i32, vp, vp]
+    dX, dY, dZ, m1, m2, w1, w2 = (_f64(a) for a in (dX, dY, dZ, model1, model2, column_weight1, column_weight2))
+    nloc = w1.size if isinstance(w1, np.ndarray) else w1.n
+    nrows = b_RHS.size if isinstance(b_RHS, np.ndarray) else b_RHS.n
+    keep = np.ascontiguousarray(keep_model_constant, dtype=np.int32)
+    cost = np.zeros(3)
+    cg = np.zeros(nx * ny * nz) if want_cross_grad else None
+    _check(L.tfx_cross_gradient_calculate(matrix._h, nrows, _ptr(b_RHS), nx, ny, nz, _ptr(dX), _ptr(dY), _ptr(dZ), nloc,
+                                          _ptr(m1), _ptr(m2), _ptr(w1), _ptr(w2), der_type, float(glob_weight),
+                                          keep.ctypes.data, myrank, nbproc, cost.ctypes.data, _ptr(cg)))
+    return cost, cg
+
+
+def admm_iterate_admm_arrays(xmin, xmax, x, z, u):
+    """t_admm_method%iterate_admm_arrays (admm_method.F90:70-134); xmin/xmax shape (nelements, nlithos) C-ordered ==
+    Fortran (nlithos, nelements); z and u are updated in place; returns x0."""
+    L = lib()
+    vp, i32 = C.c_void_p, C.c_int32
+    L.tfx_admm_iterate_admm_arrays.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+    xmin, xmax, x = _f64(xmin), _f64(xmax), _f64(x)
+    n = x.size if isinstance(x, np.ndarray) else x.n
+    nlithos = (xmin.size if isinstance(xmin, np.ndarray) else xmin.n) // n
+    x0 = np.zeros(n) if isinstance(x, np.ndarray) else Buffer(n)
+    _check(L.tfx_admm_iterate_admm_arrays(n, nlithos, _ptr(xmin), _ptr(xmax), _ptr(x), _ptr(z), _ptr(u), _ptr(x0)))
+    return x0

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtfx.so")
-SOURCES = ["api.cu", "wavelet.cu", "csr.cu", "t16.cu", "dense.cu", "lsqr.cu", "lsqr_strict.cu", "assembly.cu", "sensit.cu", "sensit_dist.cu", "sensit_io.cu", "data.cu", "comm.cu"]
+SOURCES = ["api.cu", "wavelet.cu", "csr.cu", "t16.cu", "dense.cu", "lsqr.cu", "lsqr_strict.cu", "assembly.cu", "sensit.cu", "sensit_dist.cu", "sensit_io.cu", "data.cu", "weights.cu", "cons.cu", "comm.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
          "--expt-extended-lambda", "-Xcudafe", "--diag_suppress=177"]

@@ -358,7 +358,17 @@ int tfx_sparse_matrix_destroy(tfx_matrix *h) {
 
 int tfx_sparse_matrix_reset(tfx_matrix *h) {
   Matrix &m = h->m;
-  TFX_TRY(builder_guard(m));
+  if (m.device_only) {
+    // matrix_cons is reset and rebuilt before every solve (joint_inverse_problem.F90:364-373), also when its rows
+    // were produced on the device: drop the device representations and go back to an empty builder
+    m.fwd.release(); m.trn.release();
+    m.dense.val.release(); m.dense.partial_q.release(); m.dense.partial_n2.release();
+    m.device_only = false;
+    m.nel = 0;
+    m.ijl.assign((size_t)m.nl_nonempty_allocated + 1, 0);
+    m.rowptr.assign((size_t)std::max(1, m.nl_nonempty_allocated), 0);
+  }
+  m.pend.idx.release(); m.pend.val.release(); m.pend.rowid.release(); m.pend.nnz = 0;
   m.nl_current = 0; m.nl_current_all = 0; m.nel = 0; m.nel_last = 0; m.nl_nonempty = 0;
   m.sa.clear(); m.ija.clear();
   std::fill(m.ijl.begin(), m.ijl.end(), 0);
@@ -426,7 +436,7 @@ int tfx_sparse_matrix_finalize(tfx_matrix *h, int32_t myrank) {
     if (m.nl_current_all != m.nl)
       return fail(-16, "Error in total number of rows in sparse_matrix_finalize!\nnl_current=" +
                            std::to_string(m.nl_current) + "\nnl=" + std::to_string(m.nl));
-    if (m.nel != 0) return fail(-25, "sparse_matrix_finalize: host-built and device-appended rows cannot be mixed");
+    TFX_TRY(matrix_flush_host_rows(m));   // host-built rows that follow the device-appended ones
     RowTriplets R;
     std::swap(R.idx.p, m.pend.idx.p); std::swap(R.idx.n, m.pend.idx.n);
     std::swap(R.val.p, m.pend.val.p); std::swap(R.val.n, m.pend.val.n);

@@ -186,6 +186,20 @@ int comm_init(int nranks, int rank, const char id[128]) {
   if (r != ncclSuccess) return fail(-64, std::string("ncclCommInitRank failed: ") + (n.GetErrorString ? n.GetErrorString(r) : "?"));
   n.nranks = nranks;
   n.rank = rank;
+  // NCCL sets up the ring/tree and the point-to-point channels lazily on first use (seconds with 8 peers): pay for
+  // it here, once, instead of inside the first LSQR iteration / the first re-partitioning.
+  {
+    cudaStream_t st = ctx().stream;
+    DevBuf<double> w;
+    DevBuf<int32_t> a, b;
+    TFX_TRY(w.alloc(8)); TFX_TRY(a.alloc((size_t)nranks)); TFX_TRY(b.alloc((size_t)nranks));
+    TFX_TRY(w.zero()); TFX_TRY(a.zero());
+    TFX_TRY(comm_allreduce_sum(w.p, 8, st));
+    std::vector<int64_t> off((size_t)nranks + 1);
+    for (int q = 0; q <= nranks; ++q) off[(size_t)q] = q;
+    TFX_TRY(comm_alltoallv_4b(a.p, off.data(), b.p, off.data(), st));
+    TFX_CUDA(cudaStreamSynchronize(st));
+  }
   return 0;
 }
 

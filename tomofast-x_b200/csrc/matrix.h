@@ -65,6 +65,8 @@ int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R
 // Appends nrows matrix rows held as device triplets (row ids relative to the appended block) to a matrix that
 // is still being built; finalize() turns the accumulated rows into the device representations.
 int matrix_append_triplets(Matrix &M, RowTriplets &R, int32_t nrows, int32_t ncolumns);
+// Moves the rows built on the host so far into the pending device rows (see sensit.cu).
+int matrix_flush_host_rows(Matrix &M);
 int upload_grid(GridDev &g, int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
                 const double *Z1, const double *Z2);
 

@@ -380,22 +380,9 @@ __global__ void __launch_bounds__(256) k_add_i32(int32_t *__restrict__ a, int64_
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] += delta;
 }
 
-int matrix_append_triplets(Matrix &M, RowTriplets &R, int32_t nrows, int32_t ncolumns) {
-  Context &c = ctx();
-  cudaStream_t st = c.stream;
-  if (M.finalized) return fail(-26, "sparse_matrix: rows cannot be appended to a finalized matrix");
-  if (M.ncolumns != ncolumns)
-    return fail(-27, "sparse_matrix: appended rows have " + std::to_string(ncolumns) + " columns, the matrix " +
-                         std::to_string(M.ncolumns));
-  if (M.nel != 0) return fail(-25, "sparse_matrix: host-built and device-appended rows cannot be mixed");
-  if (M.nl_current_all + nrows > M.nl) return fail(-28, "Error in total number of rows in sparse_matrix (append)!");
-  if (M.pend.nnz + R.nnz > M.nnz)
-    return fail(-15, "Error in nnz or nl in sparse_matrix_add! nnz=" + std::to_string(M.nnz));   // the reference's capacity check (:222)
-  if (R.nnz > 0 && M.nl_current_all != 0) {
-    k_add_i32<<<(int)std::min<int64_t>((R.nnz + 255) / 256, (int64_t)c.num_sms * 16), 256, 0, st>>>(R.rowid.p, R.nnz,
-                                                                                                   M.nl_current_all);
-    c.launches++;
-  }
+// pend <- pend ++ R (row ids already absolute); R is released.
+static int pend_concat(Matrix &M, RowTriplets &R) {
+  cudaStream_t st = ctx().stream;
   if (M.pend.nnz == 0) {
     M.pend.idx.release(); M.pend.val.release(); M.pend.rowid.release();
     std::swap(M.pend.idx.p, R.idx.p); std::swap(M.pend.idx.n, R.idx.n);
@@ -422,6 +409,56 @@ int matrix_append_triplets(Matrix &M, RowTriplets &R, int32_t nrows, int32_t nco
   }
   TFX_CUDA(cudaStreamSynchronize(st));
   R.idx.release(); R.val.release(); R.rowid.release(); R.nnz = 0;
+  return 0;
+}
+
+// Rows built on the host with add() / add_row() / new_row() so far become device-resident pending rows, so that
+// host-built blocks (e.g. the reference's clustering constraints) and device-produced blocks can follow each other
+// in one matrix. Row order is preserved: pending rows always precede the host rows that were added after them.
+int matrix_flush_host_rows(Matrix &M) {
+  if (M.nel == 0) return 0;
+  if (M.nel_last != M.nel)
+    return fail(-17, "Elements were added to the matrix after calling new_row() and before appending device rows!");
+  std::vector<int32_t> rowid((size_t)M.nel), idx((size_t)M.nel);
+  for (int32_t s = 0; s < M.nl_current; ++s) {
+    const int64_t beg = M.ijl[(size_t)s] - 1, end = (s + 1 < M.nl_current) ? M.ijl[(size_t)s + 1] - 1 : M.nel;
+    for (int64_t k = beg; k < end; ++k) {
+      rowid[(size_t)k] = M.rowptr[(size_t)s] - 1;
+      idx[(size_t)k] = M.ija[(size_t)k] - 1;
+      if (idx[(size_t)k] < 0 || idx[(size_t)k] >= M.ncolumns)
+        return fail(-19, "Sparse matrix column-index validation failed!");
+    }
+  }
+  RowTriplets H;
+  TFX_TRY(up(H.rowid, rowid.data(), rowid.size()));
+  TFX_TRY(up(H.idx, idx.data(), idx.size()));
+  TFX_TRY(up(H.val, M.sa.data(), (size_t)M.nel));
+  H.nnz = M.nel;
+  TFX_CUDA(cudaStreamSynchronize(ctx().stream));
+  TFX_TRY(pend_concat(M, H));
+  M.sa.clear(); M.ija.clear();
+  M.nel = M.nel_last = 0;
+  M.nl_current = 0;
+  return 0;
+}
+
+int matrix_append_triplets(Matrix &M, RowTriplets &R, int32_t nrows, int32_t ncolumns) {
+  Context &c = ctx();
+  cudaStream_t st = c.stream;
+  if (M.finalized) return fail(-26, "sparse_matrix: rows cannot be appended to a finalized matrix");
+  if (M.ncolumns != ncolumns)
+    return fail(-27, "sparse_matrix: appended rows have " + std::to_string(ncolumns) + " columns, the matrix " +
+                         std::to_string(M.ncolumns));
+  if (M.nl_current_all + nrows > M.nl) return fail(-28, "Error in total number of rows in sparse_matrix (append)!");
+  if (M.pend.nnz + M.nel + R.nnz > M.nnz)
+    return fail(-15, "Error in nnz or nl in sparse_matrix_add! nnz=" + std::to_string(M.nnz));   // the reference's capacity check (:222)
+  TFX_TRY(matrix_flush_host_rows(M));
+  if (R.nnz > 0 && M.nl_current_all != 0) {
+    k_add_i32<<<(int)std::min<int64_t>((R.nnz + 255) / 256, (int64_t)c.num_sms * 16), 256, 0, st>>>(R.rowid.p, R.nnz,
+                                                                                                   M.nl_current_all);
+    c.launches++;
+  }
+  TFX_TRY(pend_concat(M, R));
   M.nl_current_all += nrows;
   return 0;
 }
@@ -501,7 +538,8 @@ int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R
 
   M.has_seg = true;
   TFX_TRY(matrix_build_t16(M));
-  M.nnz = M.nel = nnz;
+  if (M.nnz < nnz) M.nnz = nnz;   // a matrix created by initialize() keeps its capacity (reset() + rebuild)
+  M.nel = nnz;
   M.nl_nonempty = F.nseg;
   M.finalized = true;
   return 0;
