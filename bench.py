@@ -166,6 +166,8 @@ def run_ours(a):
 
     d = Dist()
     tfx.init(d.local_rank)
+    if a.dense_vec4 is not None:
+        tfx.set_option("dense_vec4", a.dense_vec4)
     if d.world > 1:
         uid = d.bcast_obj(tfx.comm_unique_id() if d.rank == 0 else None)
         tfx.comm_init(d.world, d.rank, uid)
@@ -521,6 +523,7 @@ def main():
     ap.add_argument("--nz", type=int, default=64)
     ap.add_argument("--ndata", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-vec4", type=int, default=None, help="A/B switch of the dense sweep kernel shape (option dense_vec4)")
     ap.add_argument("--no-compressed", action="store_true", help="skip the compressed SpMV section")
     ap.add_argument("--comp-ndata", type=int, default=10000)
     ap.add_argument("--comp-rate", type=float, default=0.05)

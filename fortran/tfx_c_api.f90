@@ -402,6 +402,88 @@ module tfx_c_api
       integer(c_int64_t), intent(out) :: nnz_local
       integer(c_int) :: rc
     end function
+
+    ! ---- t_model%calculate_data (model.F90:220-307), calculate_depth_weight (weights_gravmag.f90:46-199) ----
+    function tfx_calculate_data(matrix_sensit, nelements, ncomponents, model_val, ndata, ndata_components, &
+                                problem_weight, column_weight, data_weight, data_calc, compression_type, &
+                                nx, ny, nz, line_start, param_shift, myrank, nbproc) &
+        bind(C, name="tfx_calculate_data") result(rc)
+      import :: c_int, c_int32_t, c_double, c_ptr
+      type(c_ptr), value :: matrix_sensit
+      integer(c_int32_t), value :: nelements, ncomponents, ndata, ndata_components
+      real(c_double), intent(in) :: model_val(*), column_weight(*), data_weight(*)
+      real(c_double), value :: problem_weight
+      real(c_double), intent(out) :: data_calc(*)
+      integer(c_int32_t), value :: compression_type, nx, ny, nz, line_start, param_shift, myrank, nbproc
+      integer(c_int) :: rc
+    end function
+
+    function tfx_calculate_depth_weight(depth_weighting_type, depth_weighting_power, depth_weighting_beta, Z0, &
+                                        nelements_total, X1, X2, Y1, Y2, Z1, Z2, ndata, data_X, data_Y, data_Z, &
+                                        nsmaller, nelements, column_weight, myrank, nbproc) &
+        bind(C, name="tfx_calculate_depth_weight") result(rc)
+      import :: c_int, c_int32_t, c_double
+      integer(c_int32_t), value :: depth_weighting_type, nelements_total, ndata, nsmaller, nelements, myrank, nbproc
+      real(c_double), value :: depth_weighting_power, depth_weighting_beta, Z0
+      real(c_double), intent(in) :: X1(*), X2(*), Y1(*), Y2(*), Z1(*), Z2(*), data_X(*), data_Y(*), data_Z(*)
+      real(c_double), intent(out) :: column_weight(*)
+      integer(c_int) :: rc
+    end function
+
+    ! ---- constraint-matrix producers (csrc/cons.cu) ----
+    function tfx_damping_add(matrix, nrows, b_RHS, alpha, problem_weight, norm_power, compression_type, nx, ny, nz, &
+                             nelements, column_weight, model, model_ref, param_shift, wavelet_domain, local_weight, &
+                             myrank, nbproc, cost) bind(C, name="tfx_damping_add") result(rc)
+      import :: c_int, c_int32_t, c_double, c_ptr
+      type(c_ptr), value :: matrix
+      integer(c_int32_t), value :: nrows, compression_type, nx, ny, nz, nelements, param_shift, wavelet_domain
+      integer(c_int32_t), value :: myrank, nbproc
+      real(c_double), intent(inout) :: b_RHS(*)
+      real(c_double), value :: alpha, problem_weight, norm_power
+      real(c_double), intent(in) :: column_weight(*), model(*), model_ref(*)
+      type(c_ptr), value :: local_weight          ! c_loc(local_weight) or c_null_ptr when absent
+      real(c_double), intent(out) :: cost
+      integer(c_int) :: rc
+    end function
+
+    function tfx_damping_gradient_add(matrix, nrows, b_RHS, beta, problem_weight, nx, ny, nz, dX, dY, dZ, nelements, &
+                                      val_full, column_weight, local_weight, param_shift, direction, myrank, nbproc, &
+                                      cost) bind(C, name="tfx_damping_gradient_add") result(rc)
+      import :: c_int, c_int32_t, c_double, c_ptr
+      type(c_ptr), value :: matrix
+      integer(c_int32_t), value :: nrows, nx, ny, nz, nelements, param_shift, direction, myrank, nbproc
+      real(c_double), intent(inout) :: b_RHS(*)
+      real(c_double), value :: beta, problem_weight
+      real(c_double), intent(in) :: dX(*), dY(*), dZ(*), val_full(*), column_weight(*), local_weight(*)
+      real(c_double), intent(out) :: cost
+      integer(c_int) :: rc
+    end function
+
+    function tfx_cross_gradient_calculate(matrix, nrows, b_RHS, nx, ny, nz, dX, dY, dZ, nparams_loc, model1, model2, &
+                                          column_weight1, column_weight2, der_type, glob_weight, &
+                                          keep_model_constant, myrank, nbproc, cost, cross_grad) &
+        bind(C, name="tfx_cross_gradient_calculate") result(rc)
+      import :: c_int, c_int32_t, c_double, c_ptr
+      type(c_ptr), value :: matrix
+      integer(c_int32_t), value :: nrows, nx, ny, nz, nparams_loc, der_type, myrank, nbproc
+      real(c_double), intent(inout) :: b_RHS(*)
+      real(c_double), intent(in) :: dX(*), dY(*), dZ(*), model1(*), model2(*), column_weight1(*), column_weight2(*)
+      real(c_double), value :: glob_weight
+      integer(c_int32_t), intent(in) :: keep_model_constant(2)
+      real(c_double), intent(out) :: cost(3)
+      type(c_ptr), value :: cross_grad            ! c_loc(this%cross_grad) on rank 0, c_null_ptr elsewhere
+      integer(c_int) :: rc
+    end function
+
+    function tfx_admm_iterate_admm_arrays(nelements, nlithos, xmin, xmax, x, z, u, x0) &
+        bind(C, name="tfx_admm_iterate_admm_arrays") result(rc)
+      import :: c_int, c_int32_t, c_double
+      integer(c_int32_t), value :: nelements, nlithos
+      real(c_double), intent(in) :: xmin(*), xmax(*), x(*)
+      real(c_double), intent(inout) :: z(*), u(*)
+      real(c_double), intent(out) :: x0(*)
+      integer(c_int) :: rc
+    end function
   end interface
 
 contains

@@ -306,6 +306,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_strict_order = value;
     return 0;
   }
+  if (name && strcmp(name, "dense_vec4") == 0) {
+    g_opt_dense_vec4 = value;
+    return 0;
+  }
   if (name && strcmp(name, "t16_min_nnz") == 0) {
     g_opt_t16_min_nnz = value;
     return 0;

@@ -106,10 +106,29 @@ __device__ __forceinline__ double warp_sum2(double a, double b, int lane) {
   return keep;
 }
 
-// K2 = float2 row-pairs per thread: thread t owns rows 2*(t + 1024*m) + {0,1}, m < K2.
-template <int K2, int MODE, bool FASTCVT>
-__global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
+// Row ownership: thread t owns rows VW*(t + NT*m) + h, h < VW, m < KV (VW consecutive floats = one LDS.64 / LDS.128).
+//   <NT = 1024, VW = 2>: 32 warps, 10 rows per thread at 10^4 rows (64 registers per thread)
+//   <NT =  512, VW = 4>: 16 warps, 20 rows per thread (128 registers): half the shared-memory load instructions and
+//                        half the shuffle reductions per matrix entry -- the kernel is issue/MIO-bound, not HBM-bound,
+//                        once the SM clock drops under the power cap.
+template <int VW>
+struct RowVec;
+template <>
+struct RowVec<2> {
+  typedef float2 type;
+  static __device__ __forceinline__ void get(const float2 &f, float (&o)[2]) { o[0] = f.x; o[1] = f.y; }
+};
+template <>
+struct RowVec<4> {
+  typedef float4 type;
+  static __device__ __forceinline__ void get(const float4 &f, float (&o)[4]) { o[0] = f.x; o[1] = f.y; o[2] = f.z; o[3] = f.w; }
+};
+
+template <int KV, int MODE, bool FASTCVT, int NT, int VW>
+__global__ void __launch_bounds__(NT, 1) dense_sweep_kernel(DenseArgs a) {
   if (a.done && *a.done) return;
+  typedef typename RowVec<VW>::type vec_t;
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *ring = smem;
   uint64_t *full = (uint64_t *)(smem + a.ring_bytes);
@@ -126,16 +145,17 @@ __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
 
   // Every word of the ring (+ guard) must always hold a finite float: rows beyond nrows are read
   // unpredicated (their u is 0 and their accumulators are never stored).
-  for (unsigned i = t * 16u; i < a.ring_bytes; i += kThreads * 16u) *(uint4 *)(ring + i) = make_uint4(0, 0, 0, 0);
+  for (unsigned i = t * 16u; i < a.ring_bytes; i += NT * 16u) *(uint4 *)(ring + i) = make_uint4(0, 0, 0, 0);
+  if (t < 128) red[t] = 0.0;                    // warps that do not exist contribute 0 to the second stage
 
-  double ur[2 * K2], acc[2 * K2];
+  double ur[VW * KV], acc[VW * KV];
 #pragma unroll
-  for (int m = 0; m < K2; ++m) {
+  for (int m = 0; m < KV; ++m) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int row = 2 * (t + kThreads * m) + h;
-      ur[2 * m + h] = (MODE != DENSE_F_ONLY && row < a.nrows) ? a.u[row] : 0.0;
-      acc[2 * m + h] = 0.0;
+    for (int h = 0; h < VW; ++h) {
+      const int row = VW * (t + NT * m) + h;
+      ur[VW * m + h] = (MODE != DENSE_F_ONLY && row < a.nrows) ? a.u[row] : 0.0;
+      acc[VW * m + h] = 0.0;
     }
   }
   const double nbeta = (MODE == DENSE_FUSED) ? *a.nbeta : 0.0;
@@ -171,30 +191,38 @@ __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
     int s1 = s0 + 1;
     uint32_t ph1 = ph0;
     if (s1 == ns) { s1 = 0; ph1 ^= 1u; }
-    const float2 *col0p = (const float2 *)(ring + (size_t)s0 * a.col_bytes) + t;
-    const float2 *col1p = (const float2 *)(ring + (size_t)s1 * a.col_bytes) + t;
+    const vec_t *col0p = (const vec_t *)(ring + (size_t)s0 * a.col_bytes) + t;
+    const vec_t *col1p = (const vec_t *)(ring + (size_t)s1 * a.col_bytes) + t;
     mbar_wait(&full[s0], ph0);
     if (two) mbar_wait(&full[s1], ph1);
     const int buf = (j0 >> 1) & 1;
 
     if (MODE != DENSE_F_ONLY) {
-      // ---- transposed product: partial dots of this thread's rows (F2F conversions, XU pipe)
-      double p0 = 0.0, p1 = 0.0;
+      // ---- transposed product: partial dots of this thread's rows (F2F conversions, XU pipe); two chains per column
+      double p0 = 0.0, p1 = 0.0, p0b = 0.0, p1b = 0.0;
 #pragma unroll
-      for (int m = 0; m < K2; ++m) {
-        const float2 f = col0p[kThreads * m];
-        p0 = fma((double)f.x, ur[2 * m], p0);
-        p0 = fma((double)f.y, ur[2 * m + 1], p0);
+      for (int m = 0; m < KV; ++m) {
+        float f[VW];
+        RowVec<VW>::get(col0p[NT * m], f);
+#pragma unroll
+        for (int h = 0; h < VW; h += 2) {
+          p0 = fma((double)f[h], ur[VW * m + h], p0);
+          p0b = fma((double)f[h + 1], ur[VW * m + h + 1], p0b);
+        }
       }
       if (two) {
 #pragma unroll
-        for (int m = 0; m < K2; ++m) {
-          const float2 f = col1p[kThreads * m];
-          p1 = fma((double)f.x, ur[2 * m], p1);
-          p1 = fma((double)f.y, ur[2 * m + 1], p1);
+        for (int m = 0; m < KV; ++m) {
+          float f[VW];
+          RowVec<VW>::get(col1p[NT * m], f);
+#pragma unroll
+          for (int h = 0; h < VW; h += 2) {
+            p1 = fma((double)f[h], ur[VW * m + h], p1);
+            p1b = fma((double)f[h + 1], ur[VW * m + h + 1], p1b);
+          }
         }
       }
-      const double r = warp_sum2(p0, p1, lane);
+      const double r = warp_sum2(p0 + p0b, p1 + p1b, lane);
       if (lane < 2) red[(buf * 2 + lane) * 32 + wid] = r;
     }
     if (t == 0 && MODE != DENSE_T_ONLY) cp_async_wait_all();   // v_j / g_j were requested >= 1 step ago
@@ -247,21 +275,25 @@ __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
     if (MODE != DENSE_T_ONLY) {
       // ---- forward product with the columns that are still in shared memory
 #pragma unroll
-      for (int m = 0; m < K2; ++m) {
-        const float2 f = col0p[kThreads * m];
-        const double dx = FASTCVT ? f32bits_to_f64(__float_as_uint(f.x)) : (double)f.x;
-        const double dy = FASTCVT ? f32bits_to_f64(__float_as_uint(f.y)) : (double)f.y;
-        acc[2 * m] = fma(dx, x0, acc[2 * m]);
-        acc[2 * m + 1] = fma(dy, x0, acc[2 * m + 1]);
+      for (int m = 0; m < KV; ++m) {
+        float f[VW];
+        RowVec<VW>::get(col0p[NT * m], f);
+#pragma unroll
+        for (int h = 0; h < VW; ++h) {
+          const double d = FASTCVT ? f32bits_to_f64(__float_as_uint(f[h])) : (double)f[h];
+          acc[VW * m + h] = fma(d, x0, acc[VW * m + h]);
+        }
       }
       if (two) {
 #pragma unroll
-        for (int m = 0; m < K2; ++m) {
-          const float2 f = col1p[kThreads * m];
-          const double dx = FASTCVT ? f32bits_to_f64(__float_as_uint(f.x)) : (double)f.x;
-          const double dy = FASTCVT ? f32bits_to_f64(__float_as_uint(f.y)) : (double)f.y;
-          acc[2 * m] = fma(dx, x1, acc[2 * m]);
-          acc[2 * m + 1] = fma(dy, x1, acc[2 * m + 1]);
+        for (int m = 0; m < KV; ++m) {
+          float f[VW];
+          RowVec<VW>::get(col1p[NT * m], f);
+#pragma unroll
+          for (int h = 0; h < VW; ++h) {
+            const double d = FASTCVT ? f32bits_to_f64(__float_as_uint(f[h])) : (double)f[h];
+            acc[VW * m + h] = fma(d, x1, acc[VW * m + h]);
+          }
         }
       }
     }
@@ -273,15 +305,16 @@ __global__ void __launch_bounds__(kThreads, 1) dense_sweep_kernel(DenseArgs a) {
 
   if (MODE != DENSE_T_ONLY) {
 #pragma unroll
-    for (int m = 0; m < K2; ++m) {
+    for (int m = 0; m < KV; ++m) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int row = 2 * (t + kThreads * m) + h;
-        if (row < a.nrows) a.partial_q[(long long)blockIdx.x * a.ld + row] = acc[2 * m + h];
+      for (int h = 0; h < VW; ++h) {
+        const int row = VW * (t + NT * m) + h;
+        if (row < a.nrows) a.partial_q[(long long)blockIdx.x * a.ld + row] = acc[VW * m + h];
       }
     }
   }
   if (MODE == DENSE_FUSED && t == 0) a.partial_n2[blockIdx.x] = n2;
+  (void)NW;
 }
 
 // q[row] = sum_b partial_q[b][row] (b ascending), n2 = sum_b partial_n2[b].
@@ -328,35 +361,38 @@ int dense_scan_fastcvt(DenseCM &S, cudaStream_t st) {
   return 0;
 }
 
-template <int K, bool FASTCVT>
+template <int K, bool FASTCVT, int NT, int VW>
 static int launch_k(DenseMode mode, const DenseArgs &a, int grid, size_t smem, cudaStream_t st) {
   switch (mode) {
     case DENSE_FUSED: {
-      auto k = dense_sweep_kernel<K, DENSE_FUSED, FASTCVT>;
+      auto k = dense_sweep_kernel<K, DENSE_FUSED, FASTCVT, NT, VW>;
       TFX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      k<<<grid, kThreads, smem, st>>>(a);
+      k<<<grid, NT, smem, st>>>(a);
       break;
     }
     case DENSE_T_ONLY: {
-      auto k = dense_sweep_kernel<K, DENSE_T_ONLY, false>;
+      auto k = dense_sweep_kernel<K, DENSE_T_ONLY, false, NT, VW>;
       TFX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      k<<<grid, kThreads, smem, st>>>(a);
+      k<<<grid, NT, smem, st>>>(a);
       break;
     }
     default: {
-      auto k = dense_sweep_kernel<K, DENSE_F_ONLY, FASTCVT>;
+      auto k = dense_sweep_kernel<K, DENSE_F_ONLY, FASTCVT, NT, VW>;
       TFX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      k<<<grid, kThreads, smem, st>>>(a);
+      k<<<grid, NT, smem, st>>>(a);
       break;
     }
   }
   return 0;
 }
 
-template <int K>
+template <int K, int NT, int VW>
 static int launch_kf(DenseMode mode, const DenseArgs &a, int grid, size_t smem, bool fast, cudaStream_t st) {
-  return fast ? launch_k<K, true>(mode, a, grid, smem, st) : launch_k<K, false>(mode, a, grid, smem, st);
+  return fast ? launch_k<K, true, NT, VW>(mode, a, grid, smem, st) : launch_k<K, false, NT, VW>(mode, a, grid, smem, st);
 }
+
+// Option "dense_vec4": 1 = 512 threads x float4 rows (default), 0 = 1024 threads x float2 rows.
+int g_opt_dense_vec4 = 1;
 
 int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v, const double *d_g, double *d_out,
                 const double *d_nbeta, double *d_q, double *d_n2, const int *d_done, cudaStream_t st) {
@@ -365,10 +401,12 @@ int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v
   if (S.nrows > kDenseMaxRows)
     return fail(-30, "dense sweep: more than " + std::to_string(kDenseMaxRows) + " data rows per block is not supported yet");
   if (S.fastcvt_ok < 0) TFX_TRY(dense_scan_fastcvt(S, st));
-  const int K2 = (S.nrows + 2 * kThreads - 1) / (2 * kThreads);   // float2 row-pairs per thread
-  const int K = 2 * K2;
+  const bool vec4 = g_opt_dense_vec4 != 0;
+  const int NT = vec4 ? 512 : kThreads, VW = vec4 ? 4 : 2;
+  const int KV = (S.nrows + VW * NT - 1) / (VW * NT);                       // row vectors per thread
+  const int K = VW * KV;
   const unsigned col_bytes = (unsigned)(S.ld * sizeof(float));
-  const size_t span = (size_t)K * kThreads * sizeof(float);                 // bytes a thread block may read per slot
+  const size_t span = (size_t)K * NT * sizeof(float);                       // bytes a thread block may read per slot
   const size_t guard = (span > col_bytes) ? ((span - col_bytes + 15) / 16 * 16) : 0;
   const size_t tail = kMaxSlots * sizeof(uint64_t) + (128 + 2 * kMaxSlots) * sizeof(double);
   const size_t budget = 227 * 1024 - 256;
@@ -388,12 +426,22 @@ int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v
   a.ns = ns; a.col_bytes = col_bytes; a.ring_bytes = (unsigned)ring_bytes; a.done = d_done;
   const bool fast = S.fastcvt_ok == 1;
   int rc;
-  switch (K2) {
-    case 1: rc = launch_kf<1>(mode, a, S.grid, smem, fast, st); break;
-    case 2: rc = launch_kf<2>(mode, a, S.grid, smem, fast, st); break;
-    case 3: rc = launch_kf<3>(mode, a, S.grid, smem, fast, st); break;
-    case 4: rc = launch_kf<4>(mode, a, S.grid, smem, fast, st); break;
-    default: rc = launch_kf<5>(mode, a, S.grid, smem, fast, st); break;
+  if (vec4) {
+    switch (KV) {
+      case 1: rc = launch_kf<1, 512, 4>(mode, a, S.grid, smem, fast, st); break;
+      case 2: rc = launch_kf<2, 512, 4>(mode, a, S.grid, smem, fast, st); break;
+      case 3: rc = launch_kf<3, 512, 4>(mode, a, S.grid, smem, fast, st); break;
+      case 4: rc = launch_kf<4, 512, 4>(mode, a, S.grid, smem, fast, st); break;
+      default: rc = launch_kf<5, 512, 4>(mode, a, S.grid, smem, fast, st); break;
+    }
+  } else {
+    switch (KV) {
+      case 1: rc = launch_kf<1, 1024, 2>(mode, a, S.grid, smem, fast, st); break;
+      case 2: rc = launch_kf<2, 1024, 2>(mode, a, S.grid, smem, fast, st); break;
+      case 3: rc = launch_kf<3, 1024, 2>(mode, a, S.grid, smem, fast, st); break;
+      case 4: rc = launch_kf<4, 1024, 2>(mode, a, S.grid, smem, fast, st); break;
+      default: rc = launch_kf<5, 1024, 2>(mode, a, S.grid, smem, fast, st); break;
+    }
   }
   TFX_TRY(rc);
   c.launches++;
