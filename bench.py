@@ -168,6 +168,8 @@ def run_ours(a):
     tfx.init(d.local_rank)
     if a.dense_vec4 is not None:
         tfx.set_option("dense_vec4", a.dense_vec4)
+    if a.dense_f2f_rows is not None:
+        tfx.set_option("dense_f2f_rows", a.dense_f2f_rows)
     if d.world > 1:
         uid = d.bcast_obj(tfx.comm_unique_id() if d.rank == 0 else None)
         tfx.comm_init(d.world, d.rank, uid)
@@ -524,6 +526,7 @@ def main():
     ap.add_argument("--ndata", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense-vec4", type=int, default=None, help="A/B switch of the dense sweep kernel shape (option dense_vec4)")
+    ap.add_argument("--dense-f2f-rows", type=int, default=None, help="A/B switch (option dense_f2f_rows)")
     ap.add_argument("--no-compressed", action="store_true", help="skip the compressed SpMV section")
     ap.add_argument("--comp-ndata", type=int, default=10000)
     ap.add_argument("--comp-rate", type=float, default=0.05)

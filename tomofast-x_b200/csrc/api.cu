@@ -310,6 +310,14 @@ int tfx_set_option(const char *name, int value) {
     g_opt_dense_vec4 = value;
     return 0;
   }
+  if (name && strcmp(name, "dense_stream_only") == 0) {
+    g_opt_dense_stream_only = value;
+    return 0;
+  }
+  if (name && strcmp(name, "dense_f2f_rows") == 0) {
+    g_opt_dense_f2f_rows = value;
+    return 0;
+  }
   if (name && strcmp(name, "t16_min_nnz") == 0) {
     g_opt_t16_min_nnz = value;
     return 0;

@@ -124,7 +124,7 @@ struct RowVec<4> {
   static __device__ __forceinline__ void get(const float4 &f, float (&o)[4]) { o[0] = f.x; o[1] = f.y; o[2] = f.z; o[3] = f.w; }
 };
 
-template <int KV, int MODE, bool FASTCVT, int NT, int VW>
+template <int KV, int MODE, int FM, int NT, int VW>
 __global__ void __launch_bounds__(NT, 1) dense_sweep_kernel(DenseArgs a) {
   if (a.done && *a.done) return;
   typedef typename RowVec<VW>::type vec_t;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(NT, 1) dense_sweep_kernel(DenseArgs a) {
     if (two) mbar_wait(&full[s1], ph1);
     const int buf = (j0 >> 1) & 1;
 
-    if (MODE != DENSE_F_ONLY) {
+    if (MODE != DENSE_F_ONLY && MODE != 3) {
       // ---- transposed product: partial dots of this thread's rows (F2F conversions, XU pipe); two chains per column
       double p0 = 0.0, p1 = 0.0, p0b = 0.0, p1b = 0.0;
 #pragma unroll
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NT, 1) dense_sweep_kernel(DenseArgs a) {
     }
 
     double x0, x1 = 0.0;
-    if (MODE == DENSE_F_ONLY) {
+    if (MODE == DENSE_F_ONLY || MODE == 3) {
       x0 = vq[s0];
       if (two) x1 = vq[s1];
     } else {
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NT, 1) dense_sweep_kernel(DenseArgs a) {
       }
     }
 
-    if (MODE != DENSE_T_ONLY) {
+    if (MODE != DENSE_T_ONLY && MODE != 3) {
       // ---- forward product with the columns that are still in shared memory
 #pragma unroll
       for (int m = 0; m < KV; ++m) {
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(NT, 1) dense_sweep_kernel(DenseArgs a) {
         RowVec<VW>::get(col0p[NT * m], f);
 #pragma unroll
         for (int h = 0; h < VW; ++h) {
-          const double d = FASTCVT ? f32bits_to_f64(__float_as_uint(f[h])) : (double)f[h];
+          const double d = (m >= FM) ? f32bits_to_f64(__float_as_uint(f[h])) : (double)f[h];
           acc[VW * m + h] = fma(d, x0, acc[VW * m + h]);
         }
       }
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(NT, 1) dense_sweep_kernel(DenseArgs a) {
           RowVec<VW>::get(col1p[NT * m], f);
 #pragma unroll
           for (int h = 0; h < VW; ++h) {
-            const double d = FASTCVT ? f32bits_to_f64(__float_as_uint(f[h])) : (double)f[h];
+            const double d = (m >= FM) ? f32bits_to_f64(__float_as_uint(f[h])) : (double)f[h];
             acc[VW * m + h] = fma(d, x1, acc[VW * m + h]);
           }
         }
@@ -361,23 +361,36 @@ int dense_scan_fastcvt(DenseCM &S, cudaStream_t st) {
   return 0;
 }
 
-template <int K, bool FASTCVT, int NT, int VW>
+int g_opt_dense_stream_only = 0;
+
+// FM = number of row vectors per thread (of KV) whose SECOND use converts with F2F (XU pipe) instead of the integer
+// path (ALU/FMA pipes, 4 instructions per entry): FM >= KV is the all-F2F kernel that is also correct for blocks
+// with zeros / subnormals.
+template <int K, int FM, int NT, int VW>
 static int launch_k(DenseMode mode, const DenseArgs &a, int grid, size_t smem, cudaStream_t st) {
+  if (g_opt_dense_stream_only && mode == DENSE_FUSED) {
+    // diagnostic: the TMA ring, the barriers and the refills without the two products (results are meaningless):
+    // the streaming ceiling of this access pattern, to tell an HBM-side bound from an SM-side one
+    auto k = dense_sweep_kernel<K, 3, 99, NT, VW>;
+    TFX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    k<<<grid, NT, smem, st>>>(a);
+    return 0;
+  }
   switch (mode) {
     case DENSE_FUSED: {
-      auto k = dense_sweep_kernel<K, DENSE_FUSED, FASTCVT, NT, VW>;
+      auto k = dense_sweep_kernel<K, DENSE_FUSED, FM, NT, VW>;
       TFX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       k<<<grid, NT, smem, st>>>(a);
       break;
     }
     case DENSE_T_ONLY: {
-      auto k = dense_sweep_kernel<K, DENSE_T_ONLY, false, NT, VW>;
+      auto k = dense_sweep_kernel<K, DENSE_T_ONLY, 99, NT, VW>;
       TFX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       k<<<grid, NT, smem, st>>>(a);
       break;
     }
     default: {
-      auto k = dense_sweep_kernel<K, DENSE_F_ONLY, FASTCVT, NT, VW>;
+      auto k = dense_sweep_kernel<K, DENSE_F_ONLY, FM, NT, VW>;
       TFX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       k<<<grid, NT, smem, st>>>(a);
       break;
@@ -386,9 +399,14 @@ static int launch_k(DenseMode mode, const DenseArgs &a, int grid, size_t smem, c
   return 0;
 }
 
+// Option "dense_f2f_rows": row vectors per thread converted with F2F on their second use (0, 2 or 99 = all).
+int g_opt_dense_f2f_rows = 2;
+
 template <int K, int NT, int VW>
 static int launch_kf(DenseMode mode, const DenseArgs &a, int grid, size_t smem, bool fast, cudaStream_t st) {
-  return fast ? launch_k<K, true, NT, VW>(mode, a, grid, smem, st) : launch_k<K, false, NT, VW>(mode, a, grid, smem, st);
+  if (!fast || g_opt_dense_f2f_rows >= K) return launch_k<K, 99, NT, VW>(mode, a, grid, smem, st);
+  if (g_opt_dense_f2f_rows >= 2 && K > 2) return launch_k<K, 2, NT, VW>(mode, a, grid, smem, st);
+  return launch_k<K, 0, NT, VW>(mode, a, grid, smem, st);
 }
 
 // Option "dense_vec4": 1 = 512 threads x float4 rows (default), 0 = 1024 threads x float2 rows.
