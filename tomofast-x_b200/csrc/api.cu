@@ -318,6 +318,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_dense_f2f_rows = value;
     return 0;
   }
+  if (name && strcmp(name, "t16_async") == 0) {
+    g_opt_t16_async = value;
+    return 0;
+  }
   if (name && strcmp(name, "t16_min_nnz") == 0) {
     g_opt_t16_min_nnz = value;
     return 0;

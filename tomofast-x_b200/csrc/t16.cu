@@ -9,7 +9,7 @@
 // tile is staged in shared memory (<= 128 KB of the 227 KB) and every matrix entry addresses it with a
 // 16-bit key, so an entry costs 6 bytes of HBM traffic (f32 value + u16 key) instead of the
 // reference's 8 (f32 + int32), all random accesses hit shared memory, and HBM sees two pure streams.
-// Entries are grouped by (tile, output element) into contiguous segments of even length (2-entry
+// Entries are grouped by (tile, output element) into contiguous segments padded to multiples of 4 entries (2-entry
 // packets: one 8-byte and one 4-byte load per lane), with a dense int64 pointer table per tile.
 //   T layout: x = u (data rows, usually ONE tile), outputs = columns      -> S^T u   (DIRECT mode)
 //   F layout: x = v (column tiles, thousands),     outputs = data rows    -> S v     (TILES mode)
@@ -34,6 +34,9 @@ namespace tfx {
 
 int g_opt_t16_min_nnz = 1 << 22;   // matrices with fewer entries stay on the generic CSR kernels
 int g_opt_t16_tile = 0;            // 0: automatic; otherwise forced tile size (power of two <= 16384), tests
+// Long segments through the cp.async ring when it fits next to the tile: bit 0 = TILES (forward product, measured
+// 3.10 -> 2.72 ms on the bench matrix), bit 1 = DIRECT (transposed product: 2.45 -> 2.56 ms, hence off by default).
+int g_opt_t16_async = 1;
 
 static const int kT16Threads = 768;      // DIRECT: one CTA per SM
 static const int kT16TilesThreads = 384; // TILES: two CTAs per SM (barrier / tile-load waits of one overlap the other)
@@ -61,6 +64,8 @@ struct T16Args {
   int32_t nsplit;          // TILES: work items per tile
   int32_t t0;              // DIRECT: the tile to process
   int accumulate;          // DIRECT: y += instead of y =
+  int async_ring;          // long segments go through the cp.async ring (the warp strip holds kAsyncRingBytes)
+  int wstrip;              // doubles per warp strip (flat-run products / cp.async ring)
   const int *done;
 };
 
@@ -106,6 +111,102 @@ __device__ __forceinline__ double t16_long_partial(const float *__restrict__ val
   return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// ---- asynchronous long path -------------------------------------------------------------------------------------
+// The long segments of a block of 32 outputs are streamed back to back through a per-warp shared-memory ring filled
+// with cp.async (LDGSTS): the bytes in flight sit in shared memory instead of registers, so a lane keeps
+// (kAsyncW - 1) .. kAsyncW rounds = 6 .. 8 sixteen-byte value packets (+ their keys) in flight -- twice what the
+// register-staged path can afford -- and the stream does not drain at segment ends: the producer cursor runs kAsyncW
+// rounds ahead of the consumer cursor, across segments. Every lane reads back only what it copied itself
+// (cp.async.wait_group is per thread), so no warp- or block-level synchronisation is involved.
+// One round = 256 consecutive entries of a segment = kAsyncR packets of 4 entries per lane; segments are padded to
+// multiples of 4 entries by the builder (16-byte aligned value packets, 8-byte aligned key packets).
+static const int kAsyncW = 4;                       // rounds in the ring
+static const int kAsyncR = 2;                       // packets (of 4 entries) per lane and round
+static const int kAsyncRingBytes = kAsyncW * kAsyncR * 32 * 24;   // 6 KB per warp
+
+__device__ __forceinline__ uint32_t t16_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void t16_cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void t16_cp_async8(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void t16_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void t16_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ double t16_long_async(const float *__restrict__ val, const uint16_t *__restrict__ key,
+                                                 const double *xs, unsigned char *ring, unsigned longmask, int rel,
+                                                 int len, int lane, double result) {
+  const uint32_t rv = t16_smem_u32(ring) + lane * 16;                                   // value packets: 512 B per slot
+  const uint32_t rk = t16_smem_u32(ring) + kAsyncW * kAsyncR * 512 + lane * 8;          // key packets:   256 B per slot
+  const float4 *lv = (const float4 *)ring + lane;
+  const uint2 *lk = (const uint2 *)(ring + kAsyncW * kAsyncR * 512) + lane;
+  // producer cursor (copies) and consumer cursor (sums): segment, first entry of the next round, end of the segment
+  unsigned pm = longmask, cm = longmask;
+  int pj = __ffs(pm) - 1;
+  int pk = __shfl_sync(0xffffffffu, rel, pj);
+  int p_end = pk + __shfl_sync(0xffffffffu, len, pj);
+  int cj = pj, ck = pk, c_end = p_end;
+  auto issue = [&](int slot) {
+    if (pm != 0u) {
+#pragma unroll
+      for (int i = 0; i < kAsyncR; ++i) {
+        const int e = pk + 128 * i + 4 * lane;
+        if (e < p_end) {
+          t16_cp_async16(rv + (slot * kAsyncR + i) * 512, val + e);
+          t16_cp_async8(rk + (slot * kAsyncR + i) * 256, key + e);
+        }
+      }
+      pk += 128 * kAsyncR;
+      if (pk >= p_end) {
+        pm &= pm - 1;
+        if (pm != 0u) {
+          pj = __ffs(pm) - 1;
+          pk = __shfl_sync(0xffffffffu, rel, pj);
+          p_end = pk + __shfl_sync(0xffffffffu, len, pj);
+        }
+      }
+    }
+    t16_cp_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kAsyncW; ++s) issue(s);
+  int slot = 0;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  while (cm != 0u) {
+    t16_cp_wait<kAsyncW - 1>();
+#pragma unroll
+    for (int i = 0; i < kAsyncR; ++i) {
+      const int e = ck + 128 * i + 4 * lane;
+      if (e < c_end) {
+        const float4 v = lv[(slot * kAsyncR + i) * 32];
+        const uint2 k = lk[(slot * kAsyncR + i) * 32];
+        a0 = fma((double)v.x, xs[k.x & 0xffffu], a0);
+        a1 = fma((double)v.y, xs[k.x >> 16], a1);
+        a2 = fma((double)v.z, xs[k.y & 0xffffu], a2);
+        a3 = fma((double)v.w, xs[k.y >> 16], a3);
+      }
+    }
+    issue(slot);                                   // refill the slot that was just consumed
+    slot = (slot + 1 == kAsyncW) ? 0 : slot + 1;
+    ck += 128 * kAsyncR;
+    if (ck >= c_end) {                             // end of the consumed segment: reduce, hand the sum to its lane
+      const double t = warp_sum((a0 + a1) + (a2 + a3));
+      if (lane == cj) result = t;
+      a0 = a1 = a2 = a3 = 0.0;
+      cm &= cm - 1;
+      if (cm != 0u) {
+        cj = __ffs(cm) - 1;
+        ck = __shfl_sync(0xffffffffu, rel, cj);
+        c_end = ck + __shfl_sync(0xffffffffu, len, cj);
+      }
+    }
+  }
+  t16_cp_wait<0>();                                // only empty groups are left; the strip is reused by the flat path
+  return result;
+}
+
 // 32 consecutive outputs [o0, o0 + 32) of tile t: lane j returns the sum of segment o0 + j.
 //  * segments longer than kLongSeg entries: one at a time with the whole warp (t16_long_partial);
 //  * all others: FLAT -- maximal runs of consecutive segments spanning <= kFlatMax entries are streamed as
@@ -128,13 +229,17 @@ __device__ __forceinline__ double t16_block32(const T16Args &a, const double *xs
   const bool is_long = len > kLongSeg;
   unsigned longmask = __ballot_sync(0xffffffffu, is_long);
   const unsigned flatmask = ~longmask;
-  while (longmask) {
-    const int j = __ffs(longmask) - 1;
-    longmask &= longmask - 1;
-    const int r = __shfl_sync(0xffffffffu, rel, j);
-    const int l = __shfl_sync(0xffffffffu, len, j);
-    const double s = warp_sum(t16_long_partial(val, key, xs, r + 2 * lane, r + l));
-    if (lane == j) result = s;
+  if (a.async_ring) {
+    if (longmask) result = t16_long_async(val, key, xs, (unsigned char *)wbuf, longmask, rel, len, lane, result);
+  } else {
+    while (longmask) {
+      const int j = __ffs(longmask) - 1;
+      longmask &= longmask - 1;
+      const int r = __shfl_sync(0xffffffffu, rel, j);
+      const int l = __shfl_sync(0xffffffffu, len, j);
+      const double s = warp_sum(t16_long_partial(val, key, xs, r + 2 * lane, r + l));
+      if (lane == j) result = s;
+    }
   }
   int j0 = 0;
   while (j0 < 32) {
@@ -189,7 +294,7 @@ __global__ void __launch_bounds__(kT16Threads, 1) t16_direct_kernel(T16Args a) {
   extern __shared__ __align__(16) double xs[];
   t16_load_tile(a, xs, a.t0);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double *wbuf = xs + ((a.tile + 15) & ~15) + wid * (kFlatMax / 2);
+  double *wbuf = xs + ((a.tile + 15) & ~15) + wid * a.wstrip;
   const int64_t tbase = (int64_t)a.t0 * a.nseg;
   const int nblk = (a.nseg + 31) / 32;
   __syncthreads();
@@ -211,12 +316,13 @@ __global__ void __launch_bounds__(kT16Threads, 1) t16_direct_kernel(T16Args a) {
 // that tile's counter; CTAs start on evenly spread tiles and walk forward, skipping exhausted tiles, so heavy
 // (dense, shallow-depth) tiles are finished by several CTAs together. partial[tile][output] is written exactly
 // once per product, hence the result does not depend on who computed what.
-__global__ void __launch_bounds__(kT16TilesThreads, 2) t16_tiles_kernel(T16Args a) {
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) t16_tiles_kernel(T16Args a) {
   if (a.done && *a.done) return;
   extern __shared__ __align__(16) double xs[];
   __shared__ int s_next;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double *wbuf = xs + ((a.tile + 15) & ~15) + wid * (kFlatMax / 2);
+  double *wbuf = xs + ((a.tile + 15) & ~15) + wid * a.wstrip;
   const int nblk = (a.nseg + 31) / 32;
   const int start = (int)((int64_t)blockIdx.x * a.ntiles / gridDim.x);
   int i = 0;   // tiles visited so far (relative to start)
@@ -301,12 +407,19 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
   a.nseg = m.nseg; a.tile = m.tile; a.ntiles = m.ntiles; a.nin = m.nin; a.nsplit = m.nsplit;
   a.t0 = 0; a.accumulate = accumulate ? 1 : 0; a.done = d_done;
   const int nblk = (m.nseg + 31) / 32;
+  const size_t tile_bytes = (size_t)((m.tile + 15) & ~15) * sizeof(double);
+  const size_t smem_max = 227 * 1024 - 64;
+  const size_t strip_flat = (size_t)(kFlatMax / 2) * sizeof(double), strip_async = (size_t)kAsyncRingBytes;
   if (m.mode == T16_DIRECT) {
-    const size_t smem = ((size_t)((m.tile + 15) & ~15) + (size_t)(kT16Threads / 32) * (kFlatMax / 2)) * sizeof(double);
+    const int warps = kT16Threads / 32;
+    const bool use_async = (g_opt_t16_async & 2) && tile_bytes + warps * strip_async <= smem_max;
+    const size_t strip = use_async ? strip_async : strip_flat;
+    const size_t smem = tile_bytes + warps * strip;
+    a.async_ring = use_async ? 1 : 0;
+    a.wstrip = (int)(strip / sizeof(double));
     static bool attr = false;
     if (!attr) {
-      TFX_CUDA(cudaFuncSetAttribute(t16_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (kT16MaxTile + (kT16Threads / 32) * (kFlatMax / 2)) * 8));
+      TFX_CUDA(cudaFuncSetAttribute(t16_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
       attr = true;
     }
     const int nitems = (nblk + kDirectChunk - 1) / kDirectChunk;
@@ -319,16 +432,34 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
       c.launches++;
     }
   } else {
-    const size_t smem = ((size_t)((m.tile + 15) & ~15) + (size_t)(kT16TilesThreads / 32) * (kFlatMax / 2)) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-      TFX_CUDA(cudaFuncSetAttribute(t16_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (kT16TilesMaxTile + (kT16TilesThreads / 32) * (kFlatMax / 2)) * 8));
-      attr = true;
-    }
-    const int grid = std::max(1, std::min(2 * c.num_sms, m.ntiles));
+    // register-staged long path: two CTAs of 384 threads per SM (barrier / tile-load waits of one overlap the other);
+    // cp.async ring: one CTA of 768 threads (same 24 warps per SM, the ring needs the second CTA's shared memory)
+    const bool use_async = (g_opt_t16_async & 1) && tile_bytes + (kT16Threads / 32) * strip_async <= smem_max;
     TFX_CUDA(cudaMemsetAsync(m.counter.p, 0, sizeof(int) * (size_t)m.ntiles, st));
-    t16_tiles_kernel<<<grid, kT16TilesThreads, smem, st>>>(a);
+    if (use_async) {
+      const size_t smem = tile_bytes + (kT16Threads / 32) * strip_async;
+      a.async_ring = 1;
+      a.wstrip = (int)(strip_async / sizeof(double));
+      static bool attr = false;
+      if (!attr) {
+        TFX_CUDA(cudaFuncSetAttribute(t16_tiles_kernel<kT16Threads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        attr = true;
+      }
+      const int grid = std::max(1, std::min(c.num_sms, m.ntiles));
+      t16_tiles_kernel<kT16Threads, 1><<<grid, kT16Threads, smem, st>>>(a);
+    } else {
+      const size_t smem = tile_bytes + (kT16TilesThreads / 32) * strip_flat;
+      a.async_ring = 0;
+      a.wstrip = (int)(strip_flat / sizeof(double));
+      static bool attr = false;
+      if (!attr) {
+        TFX_CUDA(cudaFuncSetAttribute(t16_tiles_kernel<kT16TilesThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (kT16TilesMaxTile + (kT16TilesThreads / 32) * (kFlatMax / 2)) * 8));
+        attr = true;
+      }
+      const int grid = std::max(1, std::min(2 * c.num_sms, m.ntiles));
+      t16_tiles_kernel<kT16TilesThreads, 2><<<grid, kT16TilesThreads, smem, st>>>(a);
+    }
     c.launches++;
     const int blocks = std::max(1, std::min((m.nseg + 255) / 256, c.num_sms * 8));
     t16_reduce_kernel<<<blocks, 256, 0, st>>>(m.partial.p, m.ntiles, m.nseg, a.y, accumulate ? 1 : 0, d_done);
@@ -380,7 +511,8 @@ __device__ __forceinline__ int64_t t16_lower_bound(const int32_t *__restrict__ i
   return b;
 }
 
-// cnt[t * nseg + o] = even-padded number of entries of output o whose index lies in tile t.
+// cnt[t * nseg + o] = number of entries of output o whose index lies in tile t, padded to a multiple of 4 (16-byte
+// value packets / 8-byte key packets of the cp.async path; the 2-entry packets of the other paths stay aligned too).
 __global__ void __launch_bounds__(256) t16_count_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
                                                         const int32_t *__restrict__ segof, int nseg, int ntiles,
                                                         int tile, int in0, int64_t *__restrict__ cnt) {
@@ -395,7 +527,7 @@ __global__ void __launch_bounds__(256) t16_count_kernel(const int64_t *__restric
       const int64_t hi = (t + 1 == ntiles) ? e : t16_lower_bound(idx, lo, e, in0 + (t + 1) * tile);
       n = hi - lo;
     }
-    cnt[i] = (n + 1) & ~(int64_t)1;
+    cnt[i] = (n + 3) & ~(int64_t)3;
   }
 }
 
@@ -421,7 +553,7 @@ __global__ void __launch_bounds__(256) t16_fill_kernel(const int64_t *__restrict
       val[dst + (k - lo)] = sval[k];
       key[dst + (k - lo)] = (uint16_t)t16_swz((uint32_t)(idx[k] - base));
     }
-    // padding slot (odd run): value 0 contributes exactly 0; key 0 is always a valid tile element
+    // padding slots: value 0 contributes exactly 0; key 0 is always a valid tile element
   }
 }
 
@@ -492,10 +624,10 @@ int t16_build(const SegMatrix &src, T16Matrix &T, cudaStream_t st) {
   TFX_CUDA(cudaMemcpyAsync(&padded, T.ptr.p + table, 8, cudaMemcpyDeviceToHost, st));
   TFX_CUDA(cudaStreamSynchronize(st));
   T.nnz_padded = padded;
-  TFX_TRY(T.val.alloc((size_t)padded + 2));
-  TFX_TRY(T.key.alloc((size_t)padded + 2));
-  TFX_CUDA(cudaMemsetAsync(T.val.p, 0, ((size_t)padded + 2) * 4, st));
-  TFX_CUDA(cudaMemsetAsync(T.key.p, 0, ((size_t)padded + 2) * 2, st));
+  TFX_TRY(T.val.alloc((size_t)padded + 8));
+  TFX_TRY(T.key.alloc((size_t)padded + 8));
+  TFX_CUDA(cudaMemsetAsync(T.val.p, 0, ((size_t)padded + 8) * 4, st));
+  TFX_CUDA(cudaMemsetAsync(T.key.p, 0, ((size_t)padded + 8) * 2, st));
   const int fgrid = (int)std::min<int64_t>((table + 7) / 8, (int64_t)c.num_sms * 32);
   t16_fill_kernel<<<fgrid, 256, 0, st>>>(src.ptr.p, src.idx.p, src.val.p, segof.p, T.nseg, T.ntiles, tile, T.in0, T.ptr.p,
                                          T.val.p, T.key.p);
