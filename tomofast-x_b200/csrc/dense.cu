@@ -338,12 +338,20 @@ __global__ void __launch_bounds__(256) dense_reduce_kernel(const double *partial
 // Flags a block that contains zeros or subnormal floats (the integer f32->f64 path cannot convert them).
 __global__ void __launch_bounds__(256) dense_scan_kernel(const float *__restrict__ S, long long ld, int nrows,
                                                          long long ncols, int *flag) {
-  const long long total = ld * ncols;
+  // one column per CTA step, float4 loads (ld % 4 == 0, columns are 16-byte aligned); rows >= nrows are padding
   int bad = 0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    if ((int)(i % ld) >= nrows) continue;
-    const uint32_t b = __float_as_uint(S[i]);
-    if ((b & 0x7F800000u) == 0u) bad = 1;
+  const int nv = nrows >> 2;
+  for (long long j = blockIdx.x; j < ncols; j += gridDim.x) {
+    const float4 *col = (const float4 *)(S + j * ld);
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      const float4 f = col[i];
+      const uint32_t m = 0x7F800000u;
+      if (!(__float_as_uint(f.x) & m) || !(__float_as_uint(f.y) & m) || !(__float_as_uint(f.z) & m) ||
+          !(__float_as_uint(f.w) & m))
+        bad = 1;
+    }
+    for (int i = 4 * nv + threadIdx.x; i < nrows; i += blockDim.x)
+      if ((__float_as_uint(S[j * ld + i]) & 0x7F800000u) == 0u) bad = 1;
   }
   if (bad) atomicExch(flag, 1);
 }

@@ -602,6 +602,10 @@ int t16_build(const SegMatrix &src, T16Matrix &T, cudaStream_t st) {
   T.ntiles = (T.nin + tile - 1) / tile;
   const int64_t table = (int64_t)T.nseg * T.ntiles;
   if (table > ((int64_t)1 << 31)) return 0;        // pointer table would exceed 16 GiB: keep the generic kernels
+  // The layout pays when segments are long. A matrix with ~1 entry per (tile, output) -- e.g. the diagonal damping
+  // block alpha*I, 4.2e6 entries but a 1e9-entry pointer table -- stays on the generic CSR kernels.
+  // (not applied when the layouts are forced with option t16_min_nnz = 0, as the layout tests do)
+  if (g_opt_t16_min_nnz > 0 && table > std::max<int64_t>(T.nnz / 2, (int64_t)1 << 16)) return 0;
 
   // ---- output -> stored segment
   DevBuf<int32_t> segof;
