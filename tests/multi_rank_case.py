@@ -201,6 +201,26 @@ def dist_sensit_case(rank, world, td, niter):
     d_want = orc.calculate_data(So, pb.m_true, ndata, 1, 1.0, pb.cw, dwt, 1, pb.nx, pb.ny, pb.nz, 1, 0)
     assert np.allclose(d_got, d_want, rtol=1e-5, atol=1e-7 * np.abs(d_want).max())
 
+    # ---- the same slab assembled in two station batches as row blocks (option sensit_row_blocks): same solve
+    import copy
+    tfx.set_option("sensit_row_blocks", 1)
+    Sb = tfx.SparseMatrix(ndata, ncol, int(nnz_at[rank]) + 64)
+    xs_, ys_, zs_ = pb.data_xyz
+    for d0b, nb in ((0, 6), (6, ndata - 6)):
+        parb = copy.copy(pb.par); parb.ndata = nb
+        slb = slice(d0b, d0b + nb)
+        rows_b, _, _, _ = tfx.sensit_assemble_rows(parb, pb.grid, (xs_[slb], ys_[slb], zs_[slb]), pb.cw, pb.dw[slb], rank, world)
+        tfx.sensit_repartition_into(Sb, rows_b, 1, nel_at, rank, world)
+    Sb.finalize()
+    tfx.set_option("sensit_row_blocks", 0)
+    assert Sb.get_number_elements() == S.get_number_elements()
+    ub = b.copy(); xb = np.zeros(ncol)
+    tfx.lsqr_solve_sensit(len(ub), ncol, niter, 1e-13, 0.0, 0.0, Sb, Cm, ub, xb, [1, 0], ncl, pb.nx, pb.ny, pb.nz, 1, 1, True,
+                          myrank=rank, nbproc=world)
+    hb, itb, _ = tfx.last_history()
+    nh = min(10, len(h))
+    assert itb == it and np.allclose(hb[:nh], h[:nh], rtol=1e-9), (hb[:nh], h[:nh])
+
     # ---- constraint producers and depth weight on the slabs (csrc/cons.cu, csrc/weights.cu) vs the oracle's slab mode
     def same(Sg, Sref):
         a, b_ = Sg.export(), Sref.arrays()

@@ -1,0 +1,100 @@
+"""Row-blocked sensitivity matrices (option sensit_row_blocks): the kernel assembled batch of stations after batch of
+stations, each batch an independent row block with its own product layouts -- bounded build memory for the big
+compressed configs. Products, part_mult_vector, calculate_data and the LSQR solve must match the matrix assembled in one
+piece from the same rows."""
+import copy
+
+import numpy as np
+import pytest
+
+import tomofastx_b200 as tfx
+from tests.synth import make_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def blocks_on():
+    tfx.set_option("sensit_row_blocks", 1)
+    yield
+    tfx.set_option("sensit_row_blocks", 0)
+    tfx.set_option("t16_min_nnz", 1 << 22)
+
+
+def _batch_par(pb, n):
+    par = copy.copy(pb.par)
+    par.ndata = n
+    return par
+
+
+def _assemble(pb, batches, blocked, t16):
+    tfx.set_option("sensit_row_blocks", 1 if blocked else 0)
+    tfx.set_option("t16_min_nnz", 0 if t16 else 1 << 22)
+    N, ndc = pb.N, pb.ndc
+    nel_at = np.array([N], dtype=np.int32)
+    S = tfx.SparseMatrix(pb.ndata * ndc, pb.ncolumns, pb.ndata * ndc * N)
+    x, y, z = pb.data_xyz
+    d0 = 0
+    for n in batches:
+        sl = slice(d0, d0 + n)
+        rows, _, _, _ = tfx.sensit_assemble_rows(_batch_par(pb, n), pb.grid, (x[sl], y[sl], z[sl]), pb.cw, pb.dw[sl])
+        tfx.sensit_repartition_into(S, rows, 1, nel_at)
+        d0 += n
+    S.finalize()
+    return S
+
+
+@pytest.mark.parametrize("t16", [False, True])
+@pytest.mark.parametrize("case", ["grav_haar", "mag3_d4"])
+def test_blocked_matrix_matches_single_piece(oracle, blocks_on, case, t16):
+    if case == "grav_haar":
+        pb = make_problem(nx=12, ny=10, nz=6, ndata=23, compression_type=1, rate=0.25)
+    else:
+        pb = make_problem(nx=8, ny=7, nz=4, ndata=11, compression_type=2, rate=0.3, problem_type=2, nmodel_components=3)
+    batches = [pb.ndata // 3, pb.ndata // 3 + 2, pb.ndata - 2 * (pb.ndata // 3) - 2]
+    S1 = _assemble(pb, [pb.ndata], False, t16)
+    Sb = _assemble(pb, batches, True, t16)
+    assert Sb.get_number_elements() == S1.get_number_elements()
+    assert Sb.storage_kind() == (2 if t16 else 0)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(pb.ncolumns); u = rng.standard_normal(pb.ndata * pb.ndc)
+    # forward: every row lives in exactly one block with the same entries in the same order
+    assert np.allclose(Sb.mult_vector(x), S1.mult_vector(x), rtol=1e-13, atol=1e-300)
+    # transposed: the sum over rows is split by block
+    t1 = S1.trans_mult_vector(u)
+    assert np.allclose(Sb.trans_mult_vector(u), t1, rtol=1e-12, atol=1e-13 * np.abs(t1).max())
+    acc = rng.standard_normal(pb.ncolumns)
+    a1, ab = acc.copy(), acc.copy()
+    S1.add_trans_mult_vector(u, a1); Sb.add_trans_mult_vector(u, ab)
+    assert np.allclose(ab, a1, rtol=1e-12, atol=1e-13 * np.abs(a1).max())
+    # a window of rows crossing a block boundary
+    n0, n = batches[0] * pb.ndc - 1, 4
+    xm = rng.standard_normal(pb.N * pb.par.nmodel_components)
+    assert np.allclose(Sb.part_mult_vector(xm, n, n0, 0), S1.part_mult_vector(xm, n, n0, 0), rtol=1e-13, atol=1e-300)
+    d1 = tfx.calculate_data(S1, pb.m_true, pb.ndata, pb.ndc, 1.0, pb.cw, pb.dw, pb.par.compression_type, pb.nx, pb.ny, pb.nz)
+    db = tfx.calculate_data(Sb, pb.m_true, pb.ndata, pb.ndc, 1.0, pb.cw, pb.dw, pb.par.compression_type, pb.nx, pb.ny, pb.nz)
+    assert np.allclose(db, d1, rtol=1e-13, atol=1e-300)
+    # LSQR on both
+    b = S1.mult_vector(rng.standard_normal(pb.ncolumns))
+    hist = []
+    for S in (S1, Sb):
+        uu = b.copy(); xx = np.zeros(pb.ncolumns)
+        tfx.lsqr_solve(len(uu), pb.ncolumns, 25, 1e-13, 0.0, S, uu, xx)
+        h, it, _ = tfx.last_history()
+        hist.append((h, it, xx))
+    assert hist[0][1] == hist[1][1]
+    n = min(10, len(hist[0][0]))
+    assert np.allclose(hist[1][0][:n], hist[0][0][:n], rtol=1e-9)
+    with pytest.raises(tfx.TfxError, match="row-blocked"):
+        Sb.export()
+
+
+def test_blocked_matrix_row_count_is_checked(blocks_on):
+    pb = make_problem(nx=6, ny=5, nz=4, ndata=8, compression_type=1, rate=0.3)
+    tfx.set_option("sensit_row_blocks", 1)
+    S = tfx.SparseMatrix(pb.ndata, pb.ncolumns, pb.ndata * pb.N)
+    x, y, z = pb.data_xyz
+    rows, _, _, _ = tfx.sensit_assemble_rows(_batch_par(pb, 5), pb.grid, (x[:5], y[:5], z[:5]), pb.cw, pb.dw[:5])
+    tfx.sensit_repartition_into(S, rows, 1, np.array([pb.N], dtype=np.int32))
+    with pytest.raises(tfx.TfxError, match="total number of rows"):
+        S.finalize()

@@ -233,6 +233,28 @@ int matrix_build_t16(Matrix &m) {
 // ---------------------------------------------------------------------------------------------
 // Builder (mirrors sparse_matrix.f90 line by line in behaviour, including the error texts)
 // ---------------------------------------------------------------------------------------------
+int matrix_fwd(Matrix &m, const double *d_x, double *d_y, bool accumulate, int32_t xshift, const int *d_done, cudaStream_t st) {
+  if (m.has_blocks) {
+    for (size_t b = 0; b < m.blocks.size(); ++b)
+      TFX_TRY(matrix_fwd(*m.blocks[b], d_x, d_y + m.block_row0[b], accumulate, xshift, d_done, st));
+    return 0;
+  }
+  if (m.has_t16) return t16_spmv(m.t16f, d_x, d_y, accumulate, xshift, d_done, st);
+  if (m.has_seg) return seg_spmv(m.fwd, d_x, d_y, accumulate, 0, m.nl, xshift, d_done, st);
+  return fail(-21, "sparse_matrix: no compressed device representation");
+}
+int matrix_trans(Matrix &m, const double *d_u, double *d_y, bool accumulate, const int *d_done, cudaStream_t st) {
+  if (m.has_blocks) {
+    if (m.blocks.empty() && !accumulate) TFX_CUDA(cudaMemsetAsync(d_y, 0, (size_t)m.ncolumns * 8, st));
+    for (size_t b = 0; b < m.blocks.size(); ++b)
+      TFX_TRY(matrix_trans(*m.blocks[b], d_u + m.block_row0[b], d_y, accumulate || b > 0, d_done, st));
+    return 0;
+  }
+  if (m.has_t16) return t16_spmv(m.t16t, d_u, d_y, accumulate, 0, d_done, st);
+  if (m.has_seg) return seg_spmv(m.trn, d_u, d_y, accumulate, 0, m.ncolumns, 0, d_done, st);
+  return fail(-21, "sparse_matrix: no compressed device representation");
+}
+
 static int builder_guard(const Matrix &m) {
   if (m.device_only) return fail(-10, "sparse_matrix: this matrix was assembled on the device and cannot be modified");
   return 0;
@@ -279,6 +301,13 @@ int tfx_timer_stop(double *ms) {
 int64_t tfx_sparse_matrix_device_bytes(const tfx_matrix *h) {
   const Matrix &m = h->m;
   int64_t b = 0;
+  if (m.has_blocks) {
+    for (const Matrix *blk : m.blocks) {
+      if (blk->has_seg) b += (blk->fwd.nnz + blk->trn.nnz) * 8 + ((int64_t)blk->fwd.nseg + blk->trn.nseg) * 12;
+      if (blk->has_t16) b += blk->t16f.bytes() + blk->t16t.bytes();
+    }
+    return b;
+  }
   if (m.has_seg) b += (m.fwd.nnz + m.trn.nnz) * 8 + ((int64_t)m.fwd.nseg + m.trn.nseg) * 12;
   if (m.has_t16) b += m.t16f.bytes() + m.t16t.bytes();
   if (m.has_dense) b += (int64_t)m.dense.ld * m.dense.ncols * 4;
@@ -316,6 +345,10 @@ int tfx_set_option(const char *name, int value) {
   }
   if (name && strcmp(name, "dense_f2f_rows") == 0) {
     g_opt_dense_f2f_rows = value;
+    return 0;
+  }
+  if (name && strcmp(name, "sensit_row_blocks") == 0) {
+    g_opt_sensit_row_blocks = value;
     return 0;
   }
   if (name && strcmp(name, "t16_async") == 0) {
@@ -385,6 +418,7 @@ int tfx_sparse_matrix_reset(tfx_matrix *h) {
     m.rowptr.assign((size_t)std::max(1, m.nl_nonempty_allocated), 0);
   }
   m.pend.idx.release(); m.pend.val.release(); m.pend.rowid.release(); m.pend.nnz = 0;
+  m.clear_blocks();
   m.nl_current = 0; m.nl_current_all = 0; m.nel = 0; m.nel_last = 0; m.nl_nonempty = 0;
   m.sa.clear(); m.ija.clear();
   std::fill(m.ijl.begin(), m.ijl.end(), 0);
@@ -447,6 +481,18 @@ int tfx_sparse_matrix_finalize(tfx_matrix *h, int32_t myrank) {
   (void)myrank;
   Matrix &m = h->m;
   if (m.device_only && m.finalized) return 0;
+  if (m.has_blocks) {
+    if (m.nl_current_all != m.nl)
+      return fail(-16, "Error in total number of rows in sparse_matrix_finalize!\nnl_current=" +
+                           std::to_string(m.nl_current_all) + "\nnl=" + std::to_string(m.nl));
+    if (m.nel != 0 || m.pend.nnz > 0) return fail(-25, "sparse_matrix_finalize: row blocks cannot be mixed with other rows");
+    int64_t nel = 0;
+    for (const Matrix *b : m.blocks) nel += b->nel;
+    m.nel = nel;
+    m.device_only = true;
+    m.finalized = true;
+    return 0;
+  }
   if (m.pend.nnz > 0 || m.pend.idx.p) {
     // rows appended on the device (read_sensitivity_kernel / re-partitioner): same row-count check as the reference
     if (m.nl_current_all != m.nl)
@@ -528,7 +574,14 @@ int32_t tfx_sparse_matrix_get_current_row_number(const tfx_matrix *h) { return h
 int32_t tfx_sparse_matrix_get_ncolumns(const tfx_matrix *h) { return h->m.ncolumns; }
 int64_t tfx_sparse_matrix_get_number_elements(const tfx_matrix *h) { return h->m.nel; }
 int64_t tfx_sparse_matrix_get_nnz(const tfx_matrix *h) { return h->m.nnz; }
-int tfx_sparse_matrix_storage_kind(const tfx_matrix *h) { return h->m.has_dense ? 1 : (h->m.has_t16 ? 2 : 0); }
+int tfx_sparse_matrix_storage_kind(const tfx_matrix *h) {
+  const Matrix &m = h->m;
+  if (m.has_blocks) {
+    for (const Matrix *b : m.blocks) if (!b->has_t16) return 0;
+    return m.blocks.empty() ? 0 : 2;
+  }
+  return m.has_dense ? 1 : (m.has_t16 ? 2 : 0);
+}
 
 // Products. kind: 0 forward, 1 transposed.
 static int product(Matrix &m, const double *x, double *b, bool accumulate, bool transposed) {
@@ -539,7 +592,10 @@ static int product(Matrix &m, const double *x, double *b, bool accumulate, bool 
   VecIO vx, vb;
   TFX_TRY(vx.bind(const_cast<double *>(x), nin, true));
   TFX_TRY(vb.bind(b, nout, accumulate));
-  if (m.has_t16) {
+  if (m.has_blocks) {
+    if (transposed) TFX_TRY(matrix_trans(m, vx.dev, vb.dev, accumulate, nullptr, st));
+    else TFX_TRY(matrix_fwd(m, vx.dev, vb.dev, accumulate, 0, nullptr, st));
+  } else if (m.has_t16) {
     TFX_TRY(t16_spmv(transposed ? m.t16t : m.t16f, vx.dev, vb.dev, accumulate, 0, nullptr, st));
   } else if (m.has_seg) {
     SegMatrix &s = transposed ? m.trn : m.fwd;
@@ -584,6 +640,7 @@ int tfx_sparse_matrix_time_product(tfx_matrix *h, int transposed, const double *
   TFX_CUDA(cudaEventCreate(&e0)); TFX_CUDA(cudaEventCreate(&e1));
   const int32_t nout = transposed ? m.ncolumns : m.nl;
   auto once = [&]() -> int {
+    if (m.has_blocks) return transposed ? matrix_trans(m, x, b, false, nullptr, st) : matrix_fwd(m, x, b, false, 0, nullptr, st);
     if (m.has_t16) return t16_spmv(transposed ? m.t16t : m.t16f, x, b, false, 0, nullptr, st);
     if (m.has_seg) return seg_spmv(transposed ? m.trn : m.fwd, x, b, false, 0, nout, 0, nullptr, st);
     return fail(-21, "time_product: needs a compressed representation");
@@ -618,7 +675,14 @@ int tfx_sparse_matrix_part_mult_vector(tfx_matrix *h, int32_t nelements, const d
   VecIO vx, vb;
   TFX_TRY(vx.bind(const_cast<double *>(x), (size_t)nelements, true));
   TFX_TRY(vb.bind(b, (size_t)ndata, false));
-  if (m.has_t16 && m.t16f.in0 >= param_shift && m.t16f.in0 - param_shift + m.t16f.nin <= nelements) {
+  if (m.has_blocks) {
+    // all rows of the blocks (x read at column - param_shift), then the requested window
+    DevBuf<double> full;
+    TFX_TRY(full.alloc((size_t)m.nl));
+    TFX_TRY(matrix_fwd(m, vx.dev, full.p, false, param_shift, nullptr, st));
+    TFX_CUDA(cudaMemcpyAsync(vb.dev, full.p + (line_start - 1), (size_t)ndata * 8, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaStreamSynchronize(st));
+  } else if (m.has_t16 && m.t16f.in0 >= param_shift && m.t16f.in0 - param_shift + m.t16f.nin <= nelements) {
     // all rows through the F layout (x read at column - param_shift), then the requested window
     DevBuf<double> full;
     TFX_TRY(full.alloc((size_t)m.nl));
@@ -660,6 +724,7 @@ int tfx_sparse_matrix_export(tfx_matrix *h, int64_t *nel, int32_t *nl_nonempty, 
     return 0;
   }
   TFX_TRY(ensure_init());
+  if (m.has_blocks) return fail(-29, "sparse_matrix_export: a row-blocked matrix keeps only its product layouts");
   if (m.has_seg) {
     const SegMatrix &f = m.fwd;
     if (nel) *nel = f.nnz;

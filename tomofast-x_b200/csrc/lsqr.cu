@@ -324,11 +324,15 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
       return fail(-53, "lsqr: the ranks' nelements must add up to nx*ny*nz when the wavelet transform runs inside the loop");
   }
 
-  if (g_opt_strict_order) return lsqr_run_strict(p, S, C, d_u, d_x, res);
+  if (g_opt_strict_order) {
+    if (S->has_blocks) return fail(-57, "lsqr: strict_order needs the CSR copies, a row-blocked matrix has none");
+    return lsqr_run_strict(p, S, C, d_u, d_x, res);
+  }
 
   const bool dense_ok = S->has_dense && S->dense.nrows == nls && S->dense_row0 == 0 && S->dense.nrows <= kDenseMaxRows;
   if (S->has_dense && !dense_ok && !S->has_seg) return fail(-54, "lsqr: dense sensitivity block does not cover all data rows");
-  if (!dense_ok && !S->has_t16 && !S->has_seg) return fail(-55, "lsqr: the sensitivity matrix has no device representation");
+  if (!dense_ok && !S->has_t16 && !S->has_seg && !S->has_blocks)
+    return fail(-55, "lsqr: the sensitivity matrix has no device representation");
   const bool fused = dense_ok && !wav && !misfit;
   res.fused = fused;
   res.history.clear();
@@ -370,14 +374,12 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
       TFX_CUDA(cudaMemsetAsync(out, 0, ncol * 8, st));
       return dense_sweep(S->dense, DENSE_T_ONLY, u_d, nullptr, nullptr, out, nullptr, nullptr, nullptr, done, st);
     }
-    if (S->has_t16) return t16_spmv(S->t16t, u_d, out, false, 0, done, st);
-    return seg_spmv(S->trn, u_d, out, false, 0, (int32_t)ncol, 0, done, st);
+    return matrix_trans(*S, u_d, out, false, done, st);
   };
   auto S_fwd = [&](const double *xin, double *out) -> int {     // out(nls) = S xin
     if (dense_ok)
       return dense_sweep(S->dense, DENSE_F_ONLY, nullptr, xin, nullptr, nullptr, nullptr, out, nullptr, done, st);
-    if (S->has_t16) return t16_spmv(S->t16f, xin, out, false, 0, done, st);
-    return seg_spmv(S->fwd, xin, out, false, 0, nls, 0, done, st);
+    return matrix_fwd(*S, xin, out, false, 0, done, st);
   };
 
   if (fused) {

@@ -47,8 +47,36 @@ struct Matrix {
   bool has_dense = false;
   int32_t dense_row0 = 0;     // 0-based global row of dense row 0
 
-  int64_t device_nnz() const { return has_dense ? (int64_t)dense.nrows * dense.ncols : fwd.nnz; }
+  // Row-blocked storage: a big compressed kernel assembled batch of stations after batch of stations (option
+  // "sensit_row_blocks"). Block b is an independent finalized device matrix holding the matrix rows
+  // [block_row0[b], block_row0[b] + blocks[b]->nl); S x is the concatenation of the blocks' products, S^T u the sum.
+  // Building a block needs ~3x its own footprint for a moment, never 3x the whole matrix.
+  std::vector<Matrix *> blocks;
+  std::vector<int32_t> block_row0;
+  bool has_blocks = false;
+
+  Matrix() {}
+  Matrix(const Matrix &) = delete;
+  Matrix &operator=(const Matrix &) = delete;
+  ~Matrix() { clear_blocks(); }
+  void clear_blocks() {
+    for (Matrix *b : blocks) delete b;
+    blocks.clear(); block_row0.clear(); has_blocks = false;
+  }
+  int64_t device_nnz() const {
+    if (has_blocks) { int64_t n = 0; for (const Matrix *b : blocks) n += b->device_nnz(); return n; }
+    return has_dense ? (int64_t)dense.nrows * dense.ncols : fwd.nnz;
+  }
 };
+
+// Products with a compressed matrix (T16 / CSR representations, row blocks); the dense block has its own sweep.
+//   matrix_fwd  : y(nl) (+)= S x, x read at (column - xshift)
+//   matrix_trans: y(ncolumns) (+)= S^T u
+int matrix_fwd(Matrix &m, const double *d_x, double *d_y, bool accumulate, int32_t xshift, const int *d_done, cudaStream_t st);
+int matrix_trans(Matrix &m, const double *d_u, double *d_y, bool accumulate, const int *d_done, cudaStream_t st);
+// Appends the rows held as device triplets (row ids relative to the batch) as one more row block.
+int matrix_append_block(Matrix &M, RowTriplets &R, int32_t nrows, int32_t ncolumns);
+extern int g_opt_sensit_row_blocks;
 
 int matrix_upload(Matrix &m, bool allow_dense);
 // Builds the T16 layouts from fwd/trn when the matrix is big enough (option "t16_min_nnz").

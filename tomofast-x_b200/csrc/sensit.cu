@@ -463,6 +463,32 @@ int matrix_append_triplets(Matrix &M, RowTriplets &R, int32_t nrows, int32_t nco
   return 0;
 }
 
+int g_opt_sensit_row_blocks = 0;   // 1: tfx_sensit_repartition_into / read_sensitivity_kernel_into build one row block per call
+
+// One more row block: the batch's rows become an independent finalized device matrix (T16 layouts when it is big
+// enough; its generic CSR copies are then dropped -- 12 B/nnz stay resident).
+int matrix_append_block(Matrix &M, RowTriplets &R, int32_t nrows, int32_t ncolumns) {
+  if (M.finalized) return fail(-26, "sparse_matrix: rows cannot be appended to a finalized matrix");
+  if (M.ncolumns != ncolumns)
+    return fail(-27, "sparse_matrix: appended rows have " + std::to_string(ncolumns) + " columns, the matrix " +
+                         std::to_string(M.ncolumns));
+  if (M.nel != 0 || M.pend.nnz != 0) return fail(-25, "sparse_matrix: row blocks cannot be mixed with other rows");
+  if (M.nl_current_all + nrows > M.nl) return fail(-28, "Error in total number of rows in sparse_matrix (append)!");
+  int64_t have = 0;
+  for (const Matrix *b : M.blocks) have += b->nel;
+  if (have + R.nnz > M.nnz)
+    return fail(-15, "Error in nnz or nl in sparse_matrix_add! nnz=" + std::to_string(M.nnz));   // capacity check (:222)
+  Matrix *blk = new Matrix();
+  int rc = matrix_from_triplets(*blk, nrows, ncolumns, R);
+  if (rc) { delete blk; return rc; }
+  if (blk->has_t16) { blk->fwd.release(); blk->trn.release(); blk->has_seg = false; }
+  M.blocks.push_back(blk);
+  M.block_row0.push_back(M.nl_current_all);
+  M.has_blocks = true;
+  M.nl_current_all += nrows;
+  return 0;
+}
+
 // keys (sorted, n entries) -> unique keys + exclusive offsets on the host.
 static int runs_of_sorted_keys(const int32_t *d_keys, int64_t n, int32_t max_unique, std::vector<int32_t> &uniq,
                                std::vector<int64_t> &ptr) {

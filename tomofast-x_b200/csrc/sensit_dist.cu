@@ -397,5 +397,6 @@ extern "C" int tfx_sensit_repartition_into(tfx_matrix *matrix_sensit, tfx_sensit
   RowTriplets Rx;
   int32_t nl = 0, ncolumns = 0;
   TFX_TRY(repartition_core(rows, problem_slot, nelements_at_cpu, myrank, nbproc, Rx, &nl, &ncolumns));
+  if (g_opt_sensit_row_blocks) return matrix_append_block(matrix_sensit->m, Rx, nl, ncolumns);
   return matrix_append_triplets(matrix_sensit->m, Rx, nl, ncolumns);
 }

@@ -366,5 +366,6 @@ extern "C" int tfx_read_sensitivity_kernel_into(tfx_matrix *matrix_sensit, const
   TFX_TRY(read_kernel_core(par, dir, data_weight, depth_weighting_type, problem_slot, myrank, nbproc, nelements_at_cpu, R,
                            &nl, &ncolumns));
   if (nnz_local) *nnz_local = R.nnz;
+  if (g_opt_sensit_row_blocks) return matrix_append_block(matrix_sensit->m, R, nl, ncolumns);
   return matrix_append_triplets(matrix_sensit->m, R, nl, ncolumns);
 }
