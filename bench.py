@@ -174,6 +174,15 @@ def run_ours(a):
         uid = d.bcast_obj(tfx.comm_unique_id() if d.rank == 0 else None)
         tfx.comm_init(d.world, d.rank, uid)
 
+    if a.no_dense:
+        # the compressed section alone (e.g. BASELINE config C on 8 GPUs: --comp-grid 512 512 128 --comp-ndata 6250
+        # --comp-batch 5000); not the driver's bench line
+        comp = compressed_spmv(a, tfx, d)
+        if d.rank == 0:
+            print(json.dumps({"metric": METRIC, "unit": UNIT, "n_gpus": d.world, "value": comp["lsqr"]["it_per_s"],
+                              "note": "compressed section only (--no-dense)", "spmv": comp}), flush=True)
+        d.finish()
+        return None
     nx, ny, nz, ndata = a.nx, a.ny, a.nz, a.ndata
     N = nx * ny * nz
     ncl = tfx.calculate_nelements_at_cpu(N, d.rank, d.world)          # column slab of this rank
@@ -334,7 +343,8 @@ def compressed_spmv(a, tfx, d):
     from tests.synth import depth_weight_type1, regular_grid, station_lattice
     # weak scaling: the number of stations grows with the number of GPUs, so every GPU keeps a slab of the same nnz
     # (2 x 12.6 GB in the T16 layouts) -- a per-GPU fraction of the HBM peak means something only at that size
-    nx, ny, nz, nd, rate = a.nx, a.ny, a.nz, a.comp_ndata * d.world, a.comp_rate
+    nx, ny, nz = (a.comp_grid if a.comp_grid else (a.nx, a.ny, a.nz))
+    nd, rate = a.comp_ndata * d.world, a.comp_rate
     N = nx * ny * nz
     grid = regular_grid(nx, ny, nz)
     xyz = station_lattice(nd, 100.0 * nx, 100.0 * ny, z=-0.1)
@@ -350,7 +360,42 @@ def compressed_spmv(a, tfx, d):
     d.barrier()
     t0 = time.perf_counter()
     t_rows = t_part = None
-    if d.world == 1:
+    if a.comp_batch > 0:
+        # Row-blocked assembly (bounded build memory, csrc/sensit.cu matrix_append_block): the column partition comes
+        # from a strided sample of the stations (the reference balances on the nnz counts of ALL rows, which it has on
+        # disk before it reads the kernel back; the regular station lattice makes 1/16 of them representative), then
+        # the kernel is assembled batch after batch, every batch re-partitioned over NVLink and built into its own
+        # row block.
+        import copy
+        dw1 = np.ones((nd, 1))
+        stride = max(1, nd // max(256, nd // 16))
+        sx = tuple(np.ascontiguousarray(v[::stride]) for v in xyz)
+        par_s = copy.copy(par); par_s.ndata = sx[0].size
+        rows_s, nnz_col, _, _ = tfx.sensit_assemble_rows(par_s, grid, sx, cw, np.ones((sx[0].size, 1)), d.rank, d.world)
+        del rows_s
+        nnz_at, nel_at = tfx.get_load_balancing_nelements(nnz_col, d.world)
+        tfx.synchronize()
+        t_sample = d.max(time.perf_counter() - t0)
+        ncl, cell0 = int(nel_at[d.rank]), int(nel_at[:d.rank].sum())
+        slabs = [int(v) for v in nel_at]
+        tfx.set_option("sensit_row_blocks", 1)
+        S = tfx.SparseMatrix(nd, 2 * ncl, int(nd) * int(rate * N))
+        nnz = 0
+        cerr_sum = 0.0
+        for b0 in range(0, nd, a.comp_batch):
+            nb = min(a.comp_batch, nd - b0)
+            par_b = copy.copy(par); par_b.ndata = nb
+            xb = tuple(np.ascontiguousarray(v[b0:b0 + nb]) for v in xyz)
+            rows_b, _, cerr_b, tot_b = tfx.sensit_assemble_rows(par_b, grid, xb, cw, dw1[b0:b0 + nb], d.rank, d.world)
+            tfx.sensit_repartition_into(S, rows_b, 1, nel_at, d.rank, d.world)
+            del rows_b
+            nnz += int(tot_b); cerr_sum += cerr_b * nb
+        S.finalize()
+        tfx.set_option("sensit_row_blocks", 0)
+        cerr = cerr_sum / nd
+        nnz_loc = S.get_number_elements()
+        t_rows = None
+    elif d.world == 1:
         S, _, cerr, nnz = tfx.calculate_sensit(par, grid, xyz, cw, np.ones((nd, 1)))
         ncl, cell0, nnz_loc = N, 0, nnz
         slabs = [N]
@@ -381,10 +426,14 @@ def compressed_spmv(a, tfx, d):
            "layout": "T16 (f32 value + u16 in-tile key = 6 B/nnz per product, one copy per direction)",
            "peak": peak * d.world, "peak_source": peak_src + (" x %d GPUs" % d.world if d.world > 1 else ""),
            "unit": "GB/s", "reps": a.comp_reps, "scaling": "weak (%d stations per GPU)" % a.comp_ndata}
+    if a.comp_batch > 0:
+        out["row_blocks"] = {"stations_per_batch": a.comp_batch, "batches": (nd + a.comp_batch - 1) // a.comp_batch,
+                             "partition_sample_s": round(t_sample, 2), "device_bytes_per_rank_max": int(d.max(float(S.device_bytes())))}
     if d.world > 1:
         out["column_slabs"] = slabs
         out["nnz_per_rank_max_over_mean"] = d.max(float(nnz_loc)) / (float(nnz) / d.world)
-        out["assemble_rows_s"], out["repartition_s"] = round(t_rows, 2), round(t_part, 2)
+        if t_rows is not None:
+            out["assemble_rows_s"], out["repartition_s"] = round(t_rows, 2), round(t_part, 2)
     l0 = tfx.launch_count()
     for name, tr, xi, yo in (("forward", 0, x, q), ("transposed", 1, u, t)):
         d.barrier()
@@ -402,7 +451,7 @@ def compressed_spmv(a, tfx, d):
     lhs, rhs = d.sum(float(np.dot(q.numpy(), uh))), d.sum(float(np.dot(xh, t.numpy())))
     out["adjoint_rel_err"] = abs(lhs - rhs) / max(abs(lhs), abs(rhs), 1e-300)
     assert out["adjoint_rel_err"] < 1e-10, out["adjoint_rel_err"]
-    if d.world == 1:
+    if d.world == 1 and a.comp_batch == 0:
         # 3-D wavelet transform on a device-resident volume (SURVEY 8d metric iii: 16 B per element and transform)
         vol = tfx.Buffer(N)
         tfx.copy(vol, rng.uniform(-1.0, 1.0, N), N)
@@ -531,6 +580,11 @@ def main():
     ap.add_argument("--comp-ndata", type=int, default=10000)
     ap.add_argument("--comp-rate", type=float, default=0.05)
     ap.add_argument("--comp-reps", type=int, default=20)
+    ap.add_argument("--comp-grid", type=int, nargs=3, default=None, metavar=("NX", "NY", "NZ"),
+                    help="grid of the compressed section (default: the headline grid); BASELINE config C: 512 512 128")
+    ap.add_argument("--comp-batch", type=int, default=0,
+                    help="assemble the compressed kernel in row blocks of this many stations (all ranks together); 0 = one piece")
+    ap.add_argument("--no-dense", action="store_true", help="run only the compressed section")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

@@ -54,7 +54,14 @@ static int init_device(int device) {
   if (prop.major < 10) return fail(-3, std::string("libtfx is built for sm_100a (B200); found ") + prop.name);
   c.device = device;
   c.num_sms = prop.multiProcessorCount;
-  if (!c.stream) TFX_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  if (!c.stream) {
+    TFX_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      TFX_CUDA(cudaStreamCreateWithFlags(&c.side[i], cudaStreamNonBlocking));
+      TFX_CUDA(cudaEventCreateWithFlags(&c.ev_join[i], cudaEventDisableTiming));
+    }
+    TFX_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+  }
   c.ready = true;
   return 0;
 }
@@ -235,8 +242,21 @@ int matrix_build_t16(Matrix &m) {
 // ---------------------------------------------------------------------------------------------
 int matrix_fwd(Matrix &m, const double *d_x, double *d_y, bool accumulate, int32_t xshift, const int *d_done, cudaStream_t st) {
   if (m.has_blocks) {
+    Context &c = ctx();
+    if (m.blocks.size() < 2 || st != c.stream) {
+      for (size_t b = 0; b < m.blocks.size(); ++b)
+        TFX_TRY(matrix_fwd(*m.blocks[b], d_x, d_y + m.block_row0[b], accumulate, xshift, d_done, st));
+      return 0;
+    }
+    // the blocks write disjoint row ranges: alternate them over the two side streams (fork / join on the main one)
+    TFX_CUDA(cudaEventRecord(c.ev_fork, st));
+    for (int i = 0; i < 2; ++i) TFX_CUDA(cudaStreamWaitEvent(c.side[i], c.ev_fork, 0));
     for (size_t b = 0; b < m.blocks.size(); ++b)
-      TFX_TRY(matrix_fwd(*m.blocks[b], d_x, d_y + m.block_row0[b], accumulate, xshift, d_done, st));
+      TFX_TRY(matrix_fwd(*m.blocks[b], d_x, d_y + m.block_row0[b], accumulate, xshift, d_done, c.side[b & 1]));
+    for (int i = 0; i < 2; ++i) {
+      TFX_CUDA(cudaEventRecord(c.ev_join[i], c.side[i]));
+      TFX_CUDA(cudaStreamWaitEvent(st, c.ev_join[i], 0));
+    }
     return 0;
   }
   if (m.has_t16) return t16_spmv(m.t16f, d_x, d_y, accumulate, xshift, d_done, st);

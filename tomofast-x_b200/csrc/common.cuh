@@ -37,6 +37,10 @@ struct Context {
   int device = -1;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
+  // Two side streams + events: independent row blocks of a forward product are issued alternately on them so that the
+  // tail of one block's kernel (last CTAs still walking their tiles) overlaps the start of the next block's.
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   bool ready = false;
   // Kernel launch counter (bench.py's "gpu_launches" claim).
   unsigned long long launches = 0;
