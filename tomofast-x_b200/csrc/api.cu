@@ -371,6 +371,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_sensit_row_blocks = value;
     return 0;
   }
+  if (name && strcmp(name, "t16_direct_max") == 0) {
+    g_opt_t16_direct_max = value;
+    return 0;
+  }
   if (name && strcmp(name, "t16_async") == 0) {
     g_opt_t16_async = value;
     return 0;

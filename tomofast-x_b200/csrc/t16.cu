@@ -37,6 +37,7 @@ int g_opt_t16_tile = 0;            // 0: automatic; otherwise forced tile size (
 // Long segments through the cp.async ring when it fits next to the tile: bit 0 = TILES (forward product, measured
 // 3.10 -> 2.72 ms on the bench matrix), bit 1 = DIRECT (transposed product: 2.45 -> 2.56 ms, hence off by default).
 int g_opt_t16_async = 1;
+int g_opt_t16_direct_max = 16384;   // gathered ranges up to this many elements use one DIRECT tile; longer ones TILES
 
 static const int kT16Threads = 768;      // DIRECT: one CTA per SM
 static const int kT16TilesThreads = 384; // TILES: two CTAs per SM (barrier / tile-load waits of one overlap the other)
@@ -445,7 +446,7 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
         TFX_CUDA(cudaFuncSetAttribute(t16_tiles_kernel<kT16Threads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         attr = true;
       }
-      const int grid = std::max(1, std::min(c.num_sms, m.ntiles));
+      const int grid = c.num_sms;   // several CTAs may park on the same tile (they share its block counter)
       t16_tiles_kernel<kT16Threads, 1><<<grid, kT16Threads, smem, st>>>(a);
     } else {
       const size_t smem = tile_bytes + (kT16TilesThreads / 32) * strip_flat;
@@ -457,7 +458,7 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
                                       (kT16TilesMaxTile + (kT16TilesThreads / 32) * (kFlatMax / 2)) * 8));
         attr = true;
       }
-      const int grid = std::max(1, std::min(2 * c.num_sms, m.ntiles));
+      const int grid = 2 * c.num_sms;
       t16_tiles_kernel<kT16TilesThreads, 2><<<grid, kT16TilesThreads, smem, st>>>(a);
     }
     c.launches++;
@@ -587,14 +588,16 @@ int t16_build(const SegMatrix &src, T16Matrix &T, cudaStream_t st) {
   T.nnz = src.nnz;
   // ---- mode and tile size. DIRECT: one tile (or tile after tile when the output side is the long one);
   // TILES: one partial per (tile, output), the largest tile (longest segments) that leaves a few per CTA.
-  const bool long_out = (int64_t)T.nseg > (int64_t)1 << 18;
+  // A long output side (S^T u: outputs = columns) with MANY gathered tiles would need a huge partial table: DIRECT,
+  // tile after tile. With a handful of tiles (data rows beyond 16384: 2-8 tiles) one TILES launch over all
+  // (tile, block) items balances far better than one DIRECT launch per tile (measured on 8 GPUs, 80 000 rows x 0.5 M
+  // columns per rank: 5.3 ms as 5 DIRECT launches).
+  const bool few_tiles = (int64_t)(T.nin + kT16TilesMaxTile - 1) / kT16TilesMaxTile <= 16;
+  const bool long_out = (int64_t)T.nseg > (int64_t)1 << 18 && !(T.nin > g_opt_t16_direct_max && few_tiles);
   int tile;
   if (g_opt_t16_tile > 0) tile = g_opt_t16_tile;
-  else if (T.nin <= kT16MaxTile || long_out) tile = std::min(T.nin, kT16MaxTile);
-  else {
-    tile = kT16TilesMaxTile;
-    while (tile > 2048 && (T.nin + tile - 1) / tile < 2 * c.num_sms) tile >>= 1;
-  }
+  else if (T.nin <= g_opt_t16_direct_max || long_out) tile = std::min(T.nin, kT16MaxTile);
+  else tile = kT16TilesMaxTile;   // the grid no longer depends on the tile count: the longest segments win
   tile = std::max(2, std::min(tile, kT16MaxTile));
   T.mode = ((T.nin + tile - 1) / tile == 1 || long_out) ? T16_DIRECT : T16_TILES;
   if (T.mode == T16_TILES) tile = std::min(tile, kT16TilesMaxTile);
