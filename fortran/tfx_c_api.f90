@@ -475,6 +475,22 @@ module tfx_c_api
       integer(c_int) :: rc
     end function
 
+    function tfx_rescale_model(nelements, ncomponents, model, weight) bind(C, name="tfx_rescale_model") result(rc)
+      import :: c_int, c_int32_t, c_double
+      integer(c_int32_t), value :: nelements, ncomponents
+      real(c_double), intent(inout) :: model(*)
+      real(c_double), intent(in) :: weight(*)
+      integer(c_int) :: rc
+    end function
+
+    function tfx_model_update(nelements, ncomponents, val, delta_model) bind(C, name="tfx_model_update") result(rc)
+      import :: c_int, c_int32_t, c_double
+      integer(c_int32_t), value :: nelements, ncomponents
+      real(c_double), intent(inout) :: val(*)
+      real(c_double), intent(in) :: delta_model(*)
+      integer(c_int) :: rc
+    end function
+
     function tfx_admm_iterate_admm_arrays(nelements, nlithos, xmin, xmax, x, z, u, x0) &
         bind(C, name="tfx_admm_iterate_admm_arrays") result(rc)
       import :: c_int, c_int32_t, c_double

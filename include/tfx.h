@@ -138,6 +138,13 @@ int tfx_calculate_data(tfx_matrix *matrix_sensit, int32_t nelements, int32_t nco
                        int32_t nx, int32_t ny, int32_t nz, int32_t line_start, int32_t param_shift,
                        int32_t myrank, int32_t nbproc);
 
+/* rescale_model (src/inversion/model.F90:312-324; called on delta_model at joint_inverse_problem.F90:569-571) and
+ * t_model%update (model.F90:194-200): with tfx_apply_wavelet_transform, tfx_calculate_data, the constraint producers
+ * and tfx_lsqr_solve_sensit they keep the whole major iteration of problem_joint_gravmag.F90:473-547 on device
+ * buffers. Host or device pointers. */
+int tfx_rescale_model(int32_t nelements, int32_t ncomponents, double *model, const double *weight);
+int tfx_model_update(int32_t nelements, int32_t ncomponents, double *val, const double *delta_model);
+
 /* ---- module weights_gravmag: calculate_depth_weight (src/forward/gravmag/weights_gravmag.f90:46-199) ----
  * column_weight(nelements) for the rank's cells nsmaller+1 .. nsmaller+nelements of the full grid (grid arrays
  * hold all nelements_total cells): type 1 depth weighting (:71-79, calc_depth_weight_pixel :204-223), type 2

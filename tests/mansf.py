@@ -183,3 +183,68 @@ class Inversion:
         self.histories.append(hist)
         self.apply(x)
         return b, x, hist
+
+
+class DeviceInversion:
+    """The same major loop with every model-sized vector resident in HBM and every step through the device entry
+    points: tfx_calculate_data, tfx_admm_iterate_admm_arrays, tfx_damping_add (matrix_cons is
+    reset and rebuilt on the device every major iteration, joint_inverse_problem.F90:364-373,497-527),
+    tfx_lsqr_solve_sensit, tfx_apply_wavelet_transform, tfx_rescale_model, tfx_model_update. Only the ndata-sized data
+    vectors visit the host (residuals / costs, data_gravmag.f90:123-150)."""
+
+    def __init__(self, tfx, cfg):
+        self.tfx, self.cfg = tfx, cfg
+        be = TfxBackend(tfx)
+        self.S, self.comp_error = be.assemble(cfg)
+        N, nd = cfg.N, cfg.ndata
+        up = lambda a: self._upload(np.ascontiguousarray(a, dtype=np.float64))
+        self.cw, self.xmin, self.xmax = up(cfg.cw), up(cfg.xmin), up(cfg.xmax)
+        self.m = up(np.zeros(N)); self.z = up(np.zeros(N)); self.u_admm = up(np.zeros(N))
+        self.dw2 = cfg.dw.reshape(nd, 1)
+        self.d_obs = self.calc(up(cfg.m_true))
+        self.d_calc = self.calc(self.m)
+        self.C = tfx.SparseMatrix(N, cfg.ncolumns, N)
+        self.rhs = tfx.Buffer(nd + N)
+        self.x = tfx.Buffer(cfg.ncolumns)
+        self.costs = [self.cost()]
+        self.histories = []
+        self.admm_costs = []
+
+    def _upload(self, a):
+        b = self.tfx.Buffer(a.size)
+        self.tfx.copy(b, a, a.size)
+        return b
+
+    def calc(self, model_buf):
+        cfg = self.cfg
+        return self.tfx.calculate_data(self.S, model_buf, cfg.ndata, 1, cfg.problem_weight, self.cw, self.dw2,
+                                       cfg.compression_type, cfg.nx, cfg.ny, cfg.nz).ravel()
+
+    def cost(self):
+        return float(np.linalg.norm(self.d_calc - self.d_obs) / np.linalg.norm(self.d_obs))
+
+    def step(self):
+        tfx, cfg = self.tfx, self.cfg
+        N, nd = cfg.N, cfg.ndata
+        res = cfg.dw * (self.d_obs - self.d_calc)
+        tfx.copy(self.rhs, np.ascontiguousarray(cfg.problem_weight * res), nd)         # calculate_b_RHS
+        x0 = tfx.admm_iterate_admm_arrays(self.xmin, self.xmax, self.m, self.z, self.u_admm)
+        self.C.reset()
+        cons = tfx.BufferView(self.rhs, nd, N)
+        cost = tfx.damping_add(self.C, cons, cfg.rho_admm, cfg.problem_weight, 2.0, cfg.compression_type, cfg.nx, cfg.ny,
+                               cfg.nz, self.cw, self.m, x0, 0, True)
+        self.C.finalize()
+        self.admm_costs.append(cost)
+        b_host = self.rhs.numpy().copy()
+        tfx.lsqr_solve_sensit(nd + N, cfg.ncolumns, cfg.niter, cfg.rmin, 0.0, 0.0, self.S, self.C, self.rhs, self.x, [1, 0], N,
+                              cfg.nx, cfg.ny, cfg.nz, 1, cfg.compression_type, True)
+        hist, it, fused = tfx.last_history()
+        self.histories.append(hist)
+        x_host = self.x.numpy().copy()
+        delta = tfx.BufferView(self.x, 0, N)
+        tfx.apply_wavelet_transform(N, cfg.nx, cfg.ny, cfg.nz, 1, delta, False, cfg.compression_type, 1, [1], 0, 1)
+        tfx.rescale_model(delta, self.cw)
+        tfx.model_update(self.m, delta)
+        self.d_calc = self.calc(self.m)
+        self.costs.append(self.cost())
+        return b_host, x_host, hist

@@ -85,3 +85,25 @@ def test_free_run_costs(oracle):
         ig.step()
     assert np.allclose(ig.costs, io.costs, rtol=1e-3)
     assert np.abs(ig.m - io.m).max() < 1e-3 * np.abs(io.m).max()
+
+
+def test_device_resident_major_loop(oracle):
+    """The major loop with the model, the ADMM state, matrix_cons and the right-hand side produced and kept on the
+    device (mansf.DeviceInversion) against the oracle's loop: the right-hand side of the first major iteration is
+    bit-identical, the free run tracks the oracle like the host-orchestrated one does."""
+    cfg = mansf.Config()
+    io = mansf.Inversion(mansf.OracleBackend(oracle), cfg, oracle.admm_iterate)
+    idev = mansf.DeviceInversion(tfx, cfg)
+    assert np.allclose(idev.d_obs, io.d_obs, rtol=1e-7, atol=1e-9 * np.abs(io.d_obs).max())
+    for major in range(10):
+        bo, xo, ho = io.step()
+        bd, xd, hd = idev.step()
+        if major == 0:
+            # m = 0, z = u = 0: the constraint part is exactly the oracle's; the data part differs by the matrices
+            assert np.array_equal(bd[cfg.ndata:], bo[cfg.ndata:])
+            assert np.allclose(bd[:cfg.ndata], bo[:cfg.ndata], rtol=1e-7, atol=1e-9 * np.abs(bo[:cfg.ndata]).max())
+            assert np.allclose(hd[:10], ho[:10], rtol=1e-5)
+    assert np.allclose(idev.costs, io.costs, rtol=1e-3)
+    m_dev = idev.m.numpy()
+    assert np.abs(m_dev - io.m).max() < 1e-3 * np.abs(io.m).max()
+    assert len(idev.admm_costs) == 10 and all(np.isfinite(idev.admm_costs))

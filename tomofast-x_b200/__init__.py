@@ -760,3 +760,33 @@ def admm_iterate_admm_arrays(xmin, xmax, x, z, u):
     x0 = np.zeros(n) if isinstance(x, np.ndarray) else Buffer(n)
     _check(L.tfx_admm_iterate_admm_arrays(n, nlithos, _ptr(xmin), _ptr(xmax), _ptr(x), _ptr(z), _ptr(u), _ptr(x0)))
     return x0
+
+
+class BufferView:
+    """n float64 elements of a Buffer starting at element `offset` (device pointer arithmetic only)."""
+
+    def __init__(self, buf, offset, n):
+        assert 0 <= offset and offset + n <= buf.n
+        self.buf, self.offset, self.n = buf, int(offset), int(n)
+
+    def data_ptr(self):
+        return self.buf.data_ptr() + 8 * self.offset
+
+
+def rescale_model(model, weight, ncomponents=1):
+    """rescale_model (model.F90:312-324): model(nelements, ncomponents) *= weight, in place."""
+    L = lib()
+    L.tfx_rescale_model.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    w = _f64(weight)
+    nelements = w.size if isinstance(w, np.ndarray) else w.n
+    _check(L.tfx_rescale_model(nelements, ncomponents, _ptr(model), _ptr(w)))
+    return model
+
+
+def model_update(val, delta_model, ncomponents=1):
+    """t_model%update (model.F90:194-200): val += delta_model, in place."""
+    L = lib()
+    L.tfx_model_update.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    n = val.size if isinstance(val, np.ndarray) else val.n
+    _check(L.tfx_model_update(n // ncomponents, ncomponents, _ptr(val), _ptr(delta_model)))
+    return val

@@ -31,6 +31,16 @@ __global__ void __launch_bounds__(256) k_unweight_data(double *__restrict__ d, c
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     d[i] = __ddiv_rn(__ddiv_rn(d[i], problem_weight), dw[i]);
 }
+// rescale_model (model.F90:312-324): model(i, k) *= weight(i); model_update (:194-200): val += delta
+__global__ void __launch_bounds__(256) k_rescale_model(double *__restrict__ m, const double *__restrict__ w, int64_t nelements,
+                                                       int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    m[i] = __dmul_rn(m[i], w[i % nelements]);
+}
+__global__ void __launch_bounds__(256) k_model_update(double *__restrict__ v, const double *__restrict__ d, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    v[i] = __dadd_rn(v[i], d[i]);
+}
 }  // namespace
 
 int wavelet_slab_device(double *d_slab, int64_t nelements, int64_t nsmaller, int nx, int ny, int nz, int wavelet_type,
@@ -122,6 +132,41 @@ extern "C" int tfx_calculate_data(tfx_matrix *matrix_sensit, int32_t nelements, 
                                                                                                     problem_weight);
   c.launches++;
   TFX_TRY(vd.copy_back());
+  TFX_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// rescale_model (src/inversion/model.F90:312-324), applied to delta_model after the solve
+// (joint_inverse_problem.F90:569-571): model(nelements, ncomponents) *= weight(nelements).
+extern "C" int tfx_rescale_model(int32_t nelements, int32_t ncomponents, double *model, const double *weight) {
+  TFX_TRY(ensure_init());
+  Context &c = ctx();
+  cudaStream_t st = c.stream;
+  const int64_t total = (int64_t)nelements * ncomponents;
+  VecIO vm, vw;
+  TFX_TRY(vm.bind(model, (size_t)total, true));
+  TFX_TRY(vw.bind(const_cast<double *>(weight), (size_t)nelements, true));
+  k_rescale_model<<<(int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)c.num_sms * 8)), 256, 0, st>>>(
+      vm.dev, vw.dev, nelements, total);
+  c.launches++;
+  TFX_TRY(vm.copy_back());
+  TFX_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// t_model%update (src/inversion/model.F90:194-200): val(nelements, ncomponents) += delta_model.
+extern "C" int tfx_model_update(int32_t nelements, int32_t ncomponents, double *val, const double *delta_model) {
+  TFX_TRY(ensure_init());
+  Context &c = ctx();
+  cudaStream_t st = c.stream;
+  const int64_t total = (int64_t)nelements * ncomponents;
+  VecIO vv, vd;
+  TFX_TRY(vv.bind(val, (size_t)total, true));
+  TFX_TRY(vd.bind(const_cast<double *>(delta_model), (size_t)total, true));
+  k_model_update<<<(int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)c.num_sms * 8)), 256, 0, st>>>(
+      vv.dev, vd.dev, total);
+  c.launches++;
+  TFX_TRY(vv.copy_back());
   TFX_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
