@@ -1,0 +1,27 @@
+"""Compressed row pipeline on a few stations (for an ncu launch list): python scratch/assembly_breakdown.py [nz] [ndata]"""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import tomofastx_b200 as tfx
+from tests.synth import depth_weight_type1, regular_grid, station_lattice
+nx, ny = 256, 256
+nz = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+nd = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+N = nx * ny * nz
+tfx.init(0)
+grid = regular_grid(nx, ny, nz)
+xyz = station_lattice(nd, 100.0 * nx, 100.0 * ny, z=-0.1)
+cw = depth_weight_type1(grid, 2.0, 0.0, 4.0e3)
+par = tfx.SensitParams()
+par.problem_type = 1
+par.nx, par.ny, par.nz = nx, ny, nz
+par.ndata, par.ndata_components, par.nmodel_components, par.data_type = nd, 1, 1, 1
+par.compression_type, par.compression_rate = 1, 0.05
+par.problem_weight = 1.0
+par.cell0, par.ncells_local, par.param_shift, par.ncolumns = 0, N, 0, 2 * N
+for rep in range(2):
+    tfx.synchronize(); t0 = time.perf_counter()
+    rows, nnz_col, cerr, tot = tfx.sensit_assemble_rows(par, grid, xyz, cw, np.ones((nd, 1)))
+    tfx.synchronize(); dt = time.perf_counter() - t0
+    print("rows=%d  %.3f ms/row  %.2e cell evaluations/s" % (nd, 1e3 * dt / nd, nd * N / dt), flush=True)
+    del rows

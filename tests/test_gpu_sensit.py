@@ -22,6 +22,36 @@ def test_gravity_lines_vs_oracle(oracle):
         assert err < 1e-12, err
 
 
+def test_gravity_shared_nodes_is_bit_identical_to_per_cell_evaluation(oracle):
+    """Structured grids evaluate every prism corner term once per grid NODE and share it between the (up to 8) cells
+    around it (csrc/assembly.cu grav_lines_nodes_kernel); the per-cell sums keep the reference's order, so the lines are
+    bit-identical to the per-cell kernel. Grid sizes that are not multiples of the 32 x 8 x 8 tile."""
+    pb = make_problem(nx=37, ny=11, nz=9, ndata=5)
+    try:
+        tfx.set_option("grav_shared_nodes", 0)
+        per_cell = tfx.sensit_lines(pb.par, pb.grid, pb.data_xyz)
+    finally:
+        tfx.set_option("grav_shared_nodes", 1)
+    shared = tfx.sensit_lines(pb.par, pb.grid, pb.data_xyz)
+    assert np.array_equal(shared, per_cell)
+    want = oracle.graviprism_z(pb.grid, *(float(a[2]) for a in pb.data_xyz))
+    assert np.abs(shared[2, 0, 0] - want).max() / np.abs(want).max() < 1e-12
+
+
+def test_gravity_lines_on_an_unstructured_set_of_boxes(oracle):
+    """Arbitrary per-cell boxes (the reference stores X1..Z2 per cell, gravity_field.f90:151-156): a grid whose boxes
+    do not share their faces falls back to the per-cell kernel."""
+    pb = make_problem(nx=6, ny=5, nz=4, ndata=4)
+    rng = np.random.default_rng(9)
+    grid = [a.copy() for a in pb.grid]
+    grid[1] -= rng.uniform(0.5, 3.0, grid[1].size)          # X2: gaps between neighbours
+    grid[5] += rng.uniform(0.0, 4.0, grid[5].size)          # Z2: overlapping piles
+    got = tfx.sensit_lines(pb.par, grid, pb.data_xyz)
+    for i in range(pb.ndata):
+        want = oracle.graviprism_z(grid, *(float(a[i]) for a in pb.data_xyz))
+        assert np.abs(got[i, 0, 0] - want).max() / np.abs(want).max() < 1e-12
+
+
 @pytest.mark.parametrize("nmc,ndc", [(1, 1), (3, 1), (1, 3), (3, 3)])
 def test_magnetic_lines_vs_oracle(oracle, nmc, ndc):
     pb = make_problem(nx=9, ny=8, nz=5, ndata=6, problem_type=2, nmodel_components=nmc, ndata_components=ndc)

@@ -367,6 +367,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_dense_f2f_rows = value;
     return 0;
   }
+  if (name && strcmp(name, "grav_shared_nodes") == 0) {
+    g_opt_grav_shared_nodes = value;
+    return 0;
+  }
   if (name && strcmp(name, "sensit_row_blocks") == 0) {
     g_opt_sensit_row_blocks = value;
     return 0;

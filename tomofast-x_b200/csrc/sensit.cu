@@ -584,6 +584,7 @@ extern "C" int tfx_sensit_lines(const tfx_sensit_params *par, const double *X1, 
   const int32_t N = P.nx * P.ny * P.nz;
   GridDev g;
   TFX_TRY(upload_grid(g, N, X1, X2, Y1, Y2, Z1, Z2));
+  TFX_TRY(grid_detect_structured(g, P.nx, P.ny, P.nz, st));
   DevBuf<double> dx, dy, dz, dl;
   DevBuf<int> derr;
   TFX_TRY(up(dx, data_X, nb)); TFX_TRY(up(dy, data_Y, nb)); TFX_TRY(up(dz, data_Z, nb));
@@ -622,6 +623,7 @@ extern "C" int tfx_calculate_sensit(tfx_matrix **out, const tfx_sensit_params *p
 
   GridDev g;
   TFX_TRY(upload_grid(g, N, X1, X2, Y1, Y2, Z1, Z2));
+  TFX_TRY(grid_detect_structured(g, P.nx, P.ny, P.nz, ctx().stream));
   DevBuf<double> dx, dy, dz, dcw, ddw;
   DevBuf<int> derr;
   TFX_TRY(up(dx, data_X, P.ndata)); TFX_TRY(up(dy, data_Y, P.ndata)); TFX_TRY(up(dz, data_Z, P.ndata));

@@ -226,6 +226,7 @@ extern "C" int tfx_sensit_assemble_rows(tfx_sensit_rows **out, const tfx_sensit_
   DevBuf<int32_t> dnnz;
   double err_sum = 0.0;
   int rc = upload_grid(g, N, X1, X2, Y1, Y2, Z1, Z2);
+  if (!rc) rc = grid_detect_structured(g, par->nx, par->ny, par->nz, ctx().stream);
   if (!rc) rc = up(dx, data_X, par->ndata);
   if (!rc) rc = up(dy, data_Y, par->ndata);
   if (!rc) rc = up(dz, data_Z, par->ndata);
