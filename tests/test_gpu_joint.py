@@ -89,3 +89,53 @@ def test_joint_matrix_and_solve(oracle, tmp_path, via_files):
     r_ref = np.linalg.norm(So.mult_vector(x_ref) - b[:g.ndata + m.ndata]) / np.linalg.norm(b)
     assert abs(r_dev - r_ref) <= 5e-3 * max(r_ref, 1e-6) + 1e-6
 
+
+
+def test_joint_solve_with_cross_gradient_constraints(oracle):
+    """BASELINE config E in miniature: joint gravity + magnetic system with model damping on both problems and the
+    cross-gradient coupling (joint_inverse_problem.F90:436-470,529-533,578-608), solved in the physical domain
+    (WAVELET_DOMAIN = F: the cross-gradient rows act on the models, the compressed kernels on their wavelet transforms,
+    lsqr_solver2.F90:200-207,228-235). matrix_cons and its right-hand side are produced on the device
+    (tfx_damping_add x2, tfx_cross_gradient_calculate) and by the oracle's restatements; the same sensitivity matrix is
+    given to both solvers, so the residual histories must agree to the LSQR parity bar."""
+    g, m = _problems()
+    N, nx, ny, nz = g.N, g.nx, g.ny, g.nz
+    So = _oracle_joint(oracle, g, m)
+    S = tfx.SparseMatrix.from_arrays(g.ndata + m.ndata, 2 * N, *So.arrays())
+    rng = np.random.default_rng(21)
+    dX, dY, dZ = np.full(nx, 100.0), np.full(ny, 100.0), np.full(nz, 50.0)
+    m1 = g.m_true.ravel() + 5.0 * rng.standard_normal(N)           # current models of the two problems
+    m2 = m.m_true.ravel()[:N] + 1e-3 * rng.standard_normal(N)
+    prior = np.zeros(N)
+    ncons = 2 * N + 3 * N
+    Co = oracle.SparseMatrix(ncons, 2 * N, 2 * N + 8 * 3 * N)
+    Cg = tfx.SparseMatrix(ncons, 2 * N, 2 * N + 8 * 3 * N)
+    bo, bg = np.zeros(ncons), np.zeros(ncons)
+    alpha = (1e-6, 1e-3)
+    for i, (mod, cw) in enumerate(((m1, g.cw), (m2, m.cw))):
+        oracle.damping_add(Co, bo, alpha[i], 1.0, 2.0, 1, nx, ny, nz, 0, N, cw, mod, prior, i * N, False)
+        tfx.damping_add(Cg, bg, alpha[i], 1.0, 2.0, 1, nx, ny, nz, cw, mod, prior, i * N, False)
+    cost_o, cg_o, nnz_o, _ = oracle.cross_gradient_calculate(Co, bo, nx, ny, nz, dX, dY, dZ, 0, N, m1, m2, g.cw, m.cw, 1, 1e-4)
+    cost_g, cg_g = tfx.cross_gradient_calculate(Cg, bg, nx, ny, nz, dX, dY, dZ, m1, m2, g.cw, m.cw, 1, 1e-4)
+    Co.finalize(); Cg.finalize()
+    assert np.array_equal(bg, bo) and np.array_equal(cg_g, cg_o)
+    assert all(np.array_equal(a, b_) for a, b_ in zip(Cg.export(), Co.arrays()))
+    assert nnz_o > 0 and Cg.get_number_elements() == Co.nel
+
+    data = So.mult_vector(np.concatenate([oracle.forward_wavelet((m1 / g.cw).copy(), nx, ny, nz, 1),
+                                          oracle.forward_wavelet((m2 / m.cw).copy(), nx, ny, nz, 1)]))
+    b = np.concatenate([0.1 * data, bo])
+    niter = 30
+    x_ref, h_ref, it_ref = oracle.lsqr_solve_sensit(niter, 1e-13, 0.0, 0.0, So, Co, b, N, nx, ny, nz, 1, 1, False,
+                                                    solve_problem=(1, 1))
+    u = b.copy(); x = np.zeros(2 * N)
+    tfx.lsqr_solve_sensit(len(u), 2 * N, niter, 1e-13, 0.0, 0.0, S, Cg, u, x, [1, 1], N, nx, ny, nz, 1, 1, False)
+    h, it, fused = tfx.last_history()
+    assert it == it_ref and not fused
+    # the solve converges in ~6 iterations and then creeps along the damping floor (r < 1e-6), where r_k is rounding
+    # noise: the 1e-6 bar applies on the way down
+    descending = h_ref > 1.0e-6
+    assert descending.sum() >= 5
+    assert np.allclose(h[descending], h_ref[descending], rtol=1e-6), (h[:10], h_ref[:10])
+    assert h[-1] < 1.0e-6 and h_ref[-1] < 1.0e-6
+    assert np.allclose(x, x_ref, rtol=1e-4, atol=1e-6 * np.abs(x_ref).max())
