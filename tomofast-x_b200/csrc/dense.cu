@@ -6,7 +6,7 @@
 // 1..N (sensitivity_gravmag.F90:288-295), so the block is stored as bare f32 values (4 B/nnz).
 //
 // B200 design: the number of data rows is small (<= ~10^4) while the number of columns is huge, so
-// u and the accumulators of S*vhat live in REGISTERS (10 rows per thread, 1024 threads per CTA, one
+// u and the accumulators of S*vhat live in REGISTERS (20 rows per thread, 512 threads per CTA, one
 // CTA per SM), and S is stored column-major so that one column is one contiguous 16 B-aligned
 // burst. A column is staged ONCE in shared memory by TMA (cp.async.bulk + mbarrier ring) and used
 // twice while it is there:
@@ -17,11 +17,12 @@
 // known after the sweep) is applied afterwards to the short vector q. One LSQR iteration therefore
 // reads S exactly once: 4 B/nnz of HBM traffic instead of the reference's 16 B/nnz.
 //
-// Instruction budget (ncu, round 1): at the HBM rate an SM has ~1800 cycles per 10^4-row column. The
-// f32->f64 conversion (F2F on the XU pipe, 16 lanes/clk/SM) costs 640 cycles per use, so the first use
-// converts with F2F and the second rebuilds the double from the f32 bits with integer ops (ALU pipe);
-// two columns share one block barrier and one transposed shuffle reduction; the ring slots are laid
-// out so that every thread can read its K rows without bounds predicates.
+// Instruction budget (ncu, round 1, profiles/r1_dense_sweep_v4_*): the TMA ring alone streams at 7.3 TB/s, the
+// kernel is bound by instruction issue and the MIO path (LDS, shuffles, F2F), so every design choice removes
+// instructions per matrix entry (11.4 now): one LDS.128 per 4 rows; two columns per block barrier with one
+// transposed shuffle reduction; the f32->f64 conversion of the second use split between F2F (XU pipe) and an
+// integer rebuild of the double from the f32 bits (ALU/FMA pipes); ring slots laid out so that every thread reads
+// its rows without bounds predicates.
 #include "common.cuh"
 #include "kernels.h"
 

@@ -114,7 +114,7 @@ enum DenseMode { DENSE_FUSED = 0, DENSE_T_ONLY = 1, DENSE_F_ONLY = 2 };
 extern int g_opt_dense_stream_only;      // diagnostic: stream the block through the TMA ring without the products
 extern int g_opt_dense_f2f_rows;         // row vectors per thread converted with F2F on their second use
 extern int g_opt_dense_vec4;             // 1: 512 threads x float4 rows (default), 0: 1024 threads x float2 rows
-static const int kDenseMaxRows = 10240;  // register-resident u / q: 10 rows per thread x 1024 threads
+static const int kDenseMaxRows = 10240;  // register-resident u / q: 20 rows per thread x 512 threads
 
 // One sweep over the block.
 //  FUSED : out[j] = nbeta*v[j] + (S^T u)[j] + g[j];  q += S out;  n2 = |out|^2   (nbeta = *d_nbeta)
