@@ -47,7 +47,15 @@ int         tfx_timer_stop(double *ms);
  * "strict_order" (1: LSQR sums in the reference's sequential order -- slow parity mode);
  * "profile_sweeps" (1: CUDA events around every fused sweep launch);
  * "t16_min_nnz" (matrices with at least this many entries get the T16 layouts; default 4194304);
- * "t16_tile" (0: automatic tile size, else a power of two <= 16384 -- tests). */
+ * "t16_tile" (0: automatic tile size, else a power of two <= 16384 -- tests);
+ * "t16_async" (bit 0 / bit 1: long segments of the TILES / DIRECT kernel through the cp.async ring; default 1);
+ * "t16_direct_max" (gathered ranges up to this many elements use one DIRECT tile; default 16384);
+ * "sensit_row_blocks" (1: tfx_sensit_repartition_into / tfx_read_sensitivity_kernel_into build one independent row
+ *   block per call -- bounded build memory for kernels near the HBM capacity; such matrices cannot be exported);
+ * "grav_shared_nodes" (1, default: gravity lines on structured grids evaluate corner terms once per grid node);
+ * "dense_vec4" (1, default: 512 threads x float4 rows; 0: 1024 threads x float2 rows), "dense_f2f_rows" (row vectors
+ *   per thread whose second use converts with F2F; default 2), "dense_stream_only" (diagnostic: the sweep's TMA ring
+ *   without the products -- results are meaningless, only the time is). */
 int         tfx_set_option(const char *name, int value);
 
 /* Memory helpers for callers that keep their vectors on the device (or in pinned host memory)
