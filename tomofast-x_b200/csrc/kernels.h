@@ -11,6 +11,9 @@ namespace tfx {
 // ---- wavelet.cu -------------------------------------------------------------------------------
 // In-place 3-D transform of a device-resident Fortran-ordered volume s(n1,n2,n3).
 int wavelet3d_device(double *d_s, int n1, int n2, int n3, int wavelet_type, bool forward, cudaStream_t st);
+// The same transform applied to nvol volumes stored back to back (one set of three launches).
+int wavelet3d_device_batch(double *d_s, int n1, int n2, int n3, long long nvol, int wavelet_type, bool forward,
+                           cudaStream_t st);
 
 // ---- csr.cu -----------------------------------------------------------------------------------
 // A compressed-segment matrix view on the device. For the forward product it is the CSR of A

@@ -109,15 +109,12 @@ __global__ void __launch_bounds__(256) k_row_sumsq(const double *__restrict__ li
   s = block_sum(s, red);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
-__global__ void __launch_bounds__(256) k_row_sum_final(const double *__restrict__ partial, int nb, RowState *st, int mode) {
+__global__ void __launch_bounds__(256) k_row_sum_final(const double *__restrict__ partial, int nb, double *target) {
   __shared__ double red[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partial[i];
   s = block_sum(s, red);
-  if (threadIdx.x == 0) {
-    if (mode) st->cost_disc = s;
-    else st->cost_full = s;
-  }
+  if (threadIdx.x == 0) *target = s;
 }
 
 // Exact k-th order statistic of |x| by MSD radix select on the IEEE bit patterns (monotone for x >= 0):
@@ -204,10 +201,11 @@ __global__ void __launch_bounds__(256) k_finish_segment_dev(const int32_t *__res
     if (nnz_count) atomicAdd(&nnz_count[p], 1);
   }
 }
-__global__ void k_advance(RowState *st, int nel_compressed, int64_t cap, long long *seg_end, int64_t iseg) {
+__global__ void k_advance(RowState *st, const double *cost_full, int nel_compressed, int64_t cap, long long *seg_end,
+                          int64_t iseg) {
   if (st->nsel > nel_compressed || st->nnz + st->nsel > cap) st->bad = 1;
   else st->nnz += st->nsel;
-  st->err_sum += sqrt(st->cost_disc / st->cost_full);   // :283-285
+  st->err_sum += sqrt(st->cost_disc / *cost_full);   // :283-285
   seg_end[iseg] = st->nnz;
 }
 __global__ void k_advance_dense(RowState *st, int n, long long *seg_end, int64_t iseg) {
@@ -300,6 +298,7 @@ int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const dou
   DevBuf<double> dpartial;
   DevBuf<long long> dsegend;
   DevBuf<unsigned char> dtemp;
+  DevBuf<double> dcostfull;
   TFX_TRY(dst.alloc(1)); TFX_TRY(dhist.alloc(256)); TFX_TRY(dpartial.alloc(kRedBlocks));
   TFX_TRY(dsegend.alloc((size_t)nseg_lines));
   TFX_CUDA(cudaMemsetAsync(dst.p, 0, sizeof(RowState), st));
@@ -319,6 +318,17 @@ int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const dou
     TFX_TRY(compute_lines(P, g, nb, d_dx + data0 + b0, d_dy + data0 + b0, d_dz + data0 + b0, dl.p, derr.p, st));
     k_apply_cw<<<vgrid, 256, 0, st>>>(dl.p, d_cw, N, (int64_t)per_station * nb);
     c.launches++;
+    const int nseg_b = nb * ndc * nmc;   // segments (lines) of this batch, stored back to back in dl
+    if (P.compression_type > 0) {
+      // cost_full of every line (:234), then ONE batched wavelet transform of all lines of the batch (:237)
+      TFX_TRY(dcostfull.alloc((size_t)nseg_b));
+      for (int sgm = 0; sgm < nseg_b; ++sgm) {
+        k_row_sumsq<<<rgrid, 256, 0, st>>>(dl.p + (size_t)sgm * N, N, 0, dst.p, dpartial.p);
+        k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, dcostfull.p + sgm);
+      }
+      c.launches += 2 * nseg_b;
+      TFX_TRY(wavelet3d_device_batch(dl.p, P.nx, P.ny, P.nz, nseg_b, P.compression_type, true, st));
+    }
     for (int b = 0; b < nb; ++b) {
       const int32_t idata = data0 + b0 + b;   // 0-based global station
       for (int d = 0; d < ndc; ++d) {
@@ -326,12 +336,10 @@ int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const dou
         // combined_weight = real(problem_weight * data_weight(d, idata), 4)
         const float wgt = (float)(P.problem_weight * h_dw[(size_t)idata * ndc + d]);
         for (int k = 0; k < nmc; ++k, ++iseg) {
-          double *line = dl.p + ((size_t)b * ndc * nmc + (size_t)d * nmc + k) * N;
+          const int sgm = (b * ndc + d) * nmc + k;
+          double *line = dl.p + (size_t)sgm * N;
           const int32_t shift = P.param_shift + k * N;   // 0-based column = p + shift
           if (P.compression_type > 0) {
-            k_row_sumsq<<<rgrid, 256, 0, st>>>(line, N, 0, dst.p, dpartial.p);                     // cost_full, :234
-            k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, dst.p, 0);
-            TFX_TRY(wavelet3d_device(line, P.nx, P.ny, P.nz, P.compression_type, true, st));       // :237
             if (!no_select) {
               k_select_begin<<<1, 256, 0, st>>>(dst.p, rank, dhist.p);
               for (int pass = 0; pass < 8; ++pass) {
@@ -345,11 +353,11 @@ int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const dou
             size_t tb = temp_bytes;
             TFX_CUDA(cub::DeviceSelect::If(dtemp.p, tb, thrust::counting_iterator<int>(0), dcols.p, &dst.p->nsel, N, pred, st));
             k_row_sumsq<<<rgrid, 256, 0, st>>>(line, N, 1, dst.p, dpartial.p);                     // discarded cost, :283
-            k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, dst.p, 1);
+            k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, &dst.p->cost_disc);
             k_finish_segment_dev<<<std::min(vgrid, (nel_compressed + 255) / 256), 256, 0, st>>>(
                 dcols.p, line, wgt, shift, row, dst.p, cap, R.idx.p, R.val.p, R.rowid.p, dnnz.p);
-            k_advance<<<1, 1, 0, st>>>(dst.p, nel_compressed, cap, dsegend.p, iseg);
-            c.launches += 9;
+            k_advance<<<1, 1, 0, st>>>(dst.p, dcostfull.p + sgm, nel_compressed, cap, dsegend.p, iseg);
+            c.launches += 7;
           } else {
             // uncompressed general path: the offset is known on the host
             k_dense_segment<<<std::min(vgrid, (N + 255) / 256), 256, 0, st>>>(line, N, wgt, shift, row,
