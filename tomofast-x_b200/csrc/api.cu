@@ -375,6 +375,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_sensit_row_blocks = value;
     return 0;
   }
+  if (name && strcmp(name, "t16_bank_deal") == 0) {
+    g_opt_t16_bank_deal = value;
+    return 0;
+  }
   if (name && strcmp(name, "t16_direct_max") == 0) {
     g_opt_t16_direct_max = value;
     return 0;

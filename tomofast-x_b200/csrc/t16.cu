@@ -34,9 +34,11 @@ namespace tfx {
 
 int g_opt_t16_min_nnz = 1 << 22;   // matrices with fewer entries stay on the generic CSR kernels
 int g_opt_t16_tile = 0;            // 0: automatic; otherwise forced tile size (power of two <= 16384), tests
-// Long segments through the cp.async ring when it fits next to the tile: bit 0 = TILES (forward product, measured
-// 3.10 -> 2.72 ms on the bench matrix), bit 1 = DIRECT (transposed product: 2.45 -> 2.56 ms, hence off by default).
-int g_opt_t16_async = 1;
+// Long segments through the cp.async ring when it fits next to the tile: bit 0 = TILES, bit 1 = DIRECT. Measured on
+// the bench matrix (2.1e9 nnz): forward 3.10 -> 2.72 ms with the ring, -> 2.28 ms with the ring AND the bank-dealt
+// segment order of the builder; transposed 2.45 (registers) -> 2.56 (ring alone) -> 2.28 ms (ring + bank dealing).
+int g_opt_t16_async = 3;
+int g_opt_t16_bank_deal = 1;       // 1: long segments are dealt over the shared-memory banks by the builder
 int g_opt_t16_direct_max = 16384;   // gathered ranges up to this many elements use one DIRECT tile; longer ones TILES
 
 static const int kT16Threads = 768;      // DIRECT: one CTA per SM
@@ -52,6 +54,10 @@ static const int kDirectChunk = 1;  // DIRECT: blocks of 32 outputs a warp draws
 // folding the higher index nibbles into the low one spreads them over the 16 eight-byte bank pairs.
 // The keys stored in the matrix are already swizzled (builder), only the tile load pays for it.
 __host__ __device__ __forceinline__ uint32_t t16_swz(uint32_t i) { return i ^ (((i >> 4) ^ (i >> 8) ^ (i >> 12)) & 15u); }
+
+// Does the kernel of this layout stream its long segments through the cp.async ring? (decided identically by the
+// builder, which lays the segments out for the ring's 4-entry packets, and by the launcher)
+static bool t16_uses_ring(T16Mode mode, int tile);
 
 struct T16Args {
   const float *val;
@@ -381,6 +387,13 @@ __global__ void __launch_bounds__(256) t16_zero_kernel(double *y, int64_t n, con
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = 0.0;
 }
 
+static bool t16_uses_ring(T16Mode mode, int tile) {
+  const size_t tile_bytes = (size_t)((tile + 15) & ~15) * sizeof(double);
+  const size_t smem_max = 227 * 1024 - 64;
+  const int bit = (mode == T16_TILES) ? 1 : 2;
+  return (g_opt_t16_async & bit) && tile_bytes + (size_t)(kT16Threads / 32) * kAsyncRingBytes <= smem_max;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Product
 // ---------------------------------------------------------------------------------------------
@@ -413,7 +426,7 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
   const size_t strip_flat = (size_t)(kFlatMax / 2) * sizeof(double), strip_async = (size_t)kAsyncRingBytes;
   if (m.mode == T16_DIRECT) {
     const int warps = kT16Threads / 32;
-    const bool use_async = (g_opt_t16_async & 2) && tile_bytes + warps * strip_async <= smem_max;
+    const bool use_async = t16_uses_ring(T16_DIRECT, m.tile);
     const size_t strip = use_async ? strip_async : strip_flat;
     const size_t smem = tile_bytes + warps * strip;
     a.async_ring = use_async ? 1 : 0;
@@ -435,7 +448,7 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
   } else {
     // register-staged long path: two CTAs of 384 threads per SM (barrier / tile-load waits of one overlap the other);
     // cp.async ring: one CTA of 768 threads (same 24 warps per SM, the ring needs the second CTA's shared memory)
-    const bool use_async = (g_opt_t16_async & 1) && tile_bytes + (kT16Threads / 32) * strip_async <= smem_max;
+    const bool use_async = t16_uses_ring(T16_TILES, m.tile);
     TFX_CUDA(cudaMemsetAsync(m.counter.p, 0, sizeof(int) * (size_t)m.ntiles, st));
     if (use_async) {
       const size_t smem = tile_bytes + (kT16Threads / 32) * strip_async;
@@ -533,28 +546,71 @@ __global__ void __launch_bounds__(256) t16_count_kernel(const int64_t *__restric
 }
 
 // One warp per (tile, output): copies the run into its padded slot.
+//
+// Long runs (the ones the whole-warp paths stream) are re-ordered so that the shared-memory gathers of a half-warp
+// hit 16 different 8-byte banks: the entries are dealt round-robin over the 16 bank classes of their (swizzled) keys,
+// and the resulting sequence is laid out so that the 16 entries one gather instruction reads for a half-warp are 16
+// consecutive entries of that sequence. `stride` = entries per lane packet of the kernel that will read the layout
+// (2: register-staged path, 4: cp.async ring). The order of summation inside a segment changes with it -- it stays
+// fixed by the layout, i.e. deterministic. ncu before: 6 shared-memory wavefronts per 32-lane gather (ideal 2), the
+// gathers alone filled 60 % of the shared-memory pipe.
 __global__ void __launch_bounds__(256) t16_fill_kernel(const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx,
                                                        const float *__restrict__ sval, const int32_t *__restrict__ segof,
                                                        int nseg, int ntiles, int tile, int in0,
                                                        const int64_t *__restrict__ tptr, float *__restrict__ val,
-                                                       uint16_t *__restrict__ key) {
-  const int lane = threadIdx.x & 31;
+                                                       uint16_t *__restrict__ key, int stride, int reorder) {
+  __shared__ int s_cnt[8][16], s_run[8][16];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const int64_t total = (int64_t)nseg * ntiles;
-  for (int64_t i = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); i < total; i += (int64_t)gridDim.x * wpb) {
+  const int blk = 16 * stride;   // entries one half-warp reads per packet row
+  for (int64_t i = blockIdx.x * (int64_t)wpb + w; i < total; i += (int64_t)gridDim.x * wpb) {
     const int64_t dst = tptr[i];
-    if (tptr[i + 1] == dst) continue;
+    const int64_t npad = tptr[i + 1] - dst;
+    if (npad == 0) continue;
     const int t = (int)(i / nseg), o = (int)(i % nseg);
     const int s = segof[o];
     const int64_t b = ptr[s], e = ptr[s + 1];
     const int64_t lo = (ntiles == 1) ? b : t16_lower_bound(idx, b, e, in0 + t * tile);
     const int64_t hi = (t + 1 == ntiles) ? e : t16_lower_bound(idx, lo, e, in0 + (t + 1) * tile);
     const int base = in0 + t * tile;
-    for (int64_t k = lo + lane; k < hi; k += 32) {
-      val[dst + (k - lo)] = sval[k];
-      key[dst + (k - lo)] = (uint16_t)t16_swz((uint32_t)(idx[k] - base));
+    if (!reorder || npad <= kLongSeg) {
+      for (int64_t k = lo + lane; k < hi; k += 32) {
+        val[dst + (k - lo)] = sval[k];
+        key[dst + (k - lo)] = (uint16_t)t16_swz((uint32_t)(idx[k] - base));
+      }
+      continue;   // padding slots: value 0 contributes exactly 0; key 0 is always a valid tile element
     }
-    // padding slots: value 0 contributes exactly 0; key 0 is always a valid tile element
+    const int n = (int)(hi - lo);
+    const int nfull = n / blk * blk;   // only whole packet rows are permuted, the tail keeps the dealing order
+    if (lane < 16) { s_cnt[w][lane] = 0; s_run[w][lane] = 0; }
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) atomicAdd(&s_cnt[w][t16_swz((uint32_t)(idx[lo + k] - base)) & 15u], 1);
+    __syncwarp();
+    for (int k0 = 0; k0 < n; k0 += 32) {
+      const int k = k0 + lane;
+      const bool act = k < n;
+      const unsigned amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const uint32_t kswz = t16_swz((uint32_t)(idx[lo + k] - base));
+        const int c = (int)(kswz & 15u);
+        const unsigned peers = __match_any_sync(amask, c);
+        const int g = s_run[w][c] + __popc(peers & ((1u << lane) - 1u));   // index of this entry inside its class
+        __syncwarp(amask);
+        if (lane == __ffs(peers) - 1) s_run[w][c] += __popc(peers);
+        // place in the dealing sequence: g full rounds over the classes that still have entries, then the classes below
+        int q = 0;
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {
+          const int m = s_cnt[w][cc];
+          q += min(m, g) + ((cc < c && m > g) ? 1 : 0);
+        }
+        const int pos = (q < nfull) ? (q / blk * blk + stride * (q & 15) + ((q >> 4) % stride)) : q;
+        val[dst + pos] = sval[lo + k];
+        key[dst + pos] = (uint16_t)kswz;
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -636,8 +692,10 @@ int t16_build(const SegMatrix &src, T16Matrix &T, cudaStream_t st) {
   TFX_CUDA(cudaMemsetAsync(T.val.p, 0, ((size_t)padded + 8) * 4, st));
   TFX_CUDA(cudaMemsetAsync(T.key.p, 0, ((size_t)padded + 8) * 2, st));
   const int fgrid = (int)std::min<int64_t>((table + 7) / 8, (int64_t)c.num_sms * 32);
+  // packet width of the kernel that will stream the long segments of this layout (see t16_spmv)
+  const bool ring = t16_uses_ring(T.mode, tile);
   t16_fill_kernel<<<fgrid, 256, 0, st>>>(src.ptr.p, src.idx.p, src.val.p, segof.p, T.nseg, T.ntiles, tile, T.in0, T.ptr.p,
-                                         T.val.p, T.key.p);
+                                         T.val.p, T.key.p, ring ? 4 : 2, g_opt_t16_bank_deal);
   c.launches++;
   // ---- work distribution: one counter per tile (TILES) / one counter (DIRECT)
   TFX_TRY(T.counter.alloc((size_t)T.ntiles + 1));
