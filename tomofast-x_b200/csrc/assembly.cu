@@ -76,6 +76,21 @@ __device__ __forceinline__ double grav_gzz(double x1, double x2, double y1, doub
   return gzz;
 }
 
+// One corner term of graviprism_z (gravity_field.f90:163-188): Z*atan2(X*Y, Z*R) - X*log(R+Y) - Y*log(R+X).
+__device__ __forceinline__ double grav_corner_term(double X, double Y, double Z, int *err) {
+  const double twopi = 2.0 * TFX_PI;
+  const double Rs = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(X, X), __dmul_rn(Y, Y)), __dmul_rn(Z, Z)));
+  double arg3 = atan2(__dmul_rn(X, Y), __dmul_rn(Z, Rs));
+  if (arg3 < 0) arg3 = arg3 + twopi;
+  double arg4 = Rs + X;
+  double arg5 = Rs + Y;
+  if (arg4 <= 0.) *err = 1;   // "Data coordinate coincides with model grid boundary (YZ)"
+  if (arg5 <= 0.) *err = 2;   // "... (XZ)"
+  arg4 = log(arg4);
+  arg5 = log(arg5);
+  return __dsub_rn(__dsub_rn(__dmul_rn(Z, arg3), __dmul_rn(X, arg5)), __dmul_rn(Y, arg4));
+}
+
 // G_grav = 6.674e-11 is a single-precision literal in the reference (gravity_field.f90:26).
 __device__ __forceinline__ double g_grav() { return (double)6.674e-11f; }
 
@@ -98,9 +113,34 @@ __global__ void __launch_bounds__(256) grav_dense_kernel(float *__restrict__ S, 
   const int cbeg = blockIdx.y * cols_per_block;
   const int cend = min(ncols, cbeg + cols_per_block);
   int e = 0;
+  // Consecutive cells of a structured grid share a face: the four corner terms of the x2 face of cell c are, bit for
+  // bit, the four terms of the x1 face of cell c+1 (same station, same corner coordinates), so they are carried over
+  // instead of being recomputed -- half the sqrt/atan2/log work; the sum keeps the reference's order (K outer).
+  double carry[4] = {0.0, 0.0, 0.0, 0.0};
+  double px2 = 0.0, py1 = 0.0, py2 = 0.0, pz1 = 0.0, pz2 = 0.0;
+  bool have = false;
   for (int c = cbeg; c < cend; ++c) {
     const int p = cell0 + c;
-    const double gz = grav_gz(X1[p], X2[p], Y1[p], Y2[p], Z1[p], Z2[p], px, py, pz, &e);
+    const double x1 = X1[p], x2 = X2[p], y1 = Y1[p], y2 = Y2[p], z1 = Z1[p], z2 = Z2[p];
+    const double XX[2] = {px - x1, px - x2}, YY[2] = {py - y1, py - y2}, ZZ[2] = {pz - z1, pz - z2};
+    const bool reuse = have && x1 == px2 && y1 == py1 && y2 == py2 && z1 == pz1 && z2 == pz2;
+    double gz = 0.0;
+#pragma unroll
+    for (int L = 0; L < 2; ++L)
+#pragma unroll
+      for (int M = 0; M < 2; ++M) {
+        const double t = reuse ? carry[2 * L + M] : grav_corner_term(XX[0], YY[L], ZZ[M], &e);
+        gz = __dadd_rn(gz, ((L + M) & 1) ? t : -t);              // dmu = signo(1)*signo(L)*signo(M), K = 1 -> -1
+      }
+#pragma unroll
+    for (int L = 0; L < 2; ++L)
+#pragma unroll
+      for (int M = 0; M < 2; ++M) {
+        const double t = grav_corner_term(XX[1], YY[L], ZZ[M], &e);
+        carry[2 * L + M] = t;
+        gz = __dadd_rn(gz, ((1 + L + M) & 1) ? t : -t);
+      }
+    px2 = x2; py1 = y1; py2 = y2; pz1 = z1; pz2 = z2; have = true;
     const double line = __dmul_rn(__dmul_rn(g_grav(), gz), cw[p]);   // LineZ = G*gz (:192); * column weight (:1051)
     const float v = __fmul_rn((float)line, wgt);                      // real(.,4) (:290) ; * combined_weight (:842)
     S[(long long)c * ld + row] = v;

@@ -129,7 +129,6 @@ template <int KV, int MODE, int FM, int NT, int VW>
 __global__ void __launch_bounds__(NT, 1) dense_sweep_kernel(DenseArgs a) {
   if (a.done && *a.done) return;
   typedef typename RowVec<VW>::type vec_t;
-  constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char *ring = smem;
   uint64_t *full = (uint64_t *)(smem + a.ring_bytes);
@@ -315,7 +314,6 @@ __global__ void __launch_bounds__(NT, 1) dense_sweep_kernel(DenseArgs a) {
     }
   }
   if (MODE == DENSE_FUSED && t == 0) a.partial_n2[blockIdx.x] = n2;
-  (void)NW;
 }
 
 // q[row] = sum_b partial_q[b][row] (b ascending), n2 = sum_b partial_n2[b].
