@@ -48,7 +48,10 @@ int         tfx_timer_stop(double *ms);
  * "profile_sweeps" (1: CUDA events around every fused sweep launch);
  * "t16_min_nnz" (matrices with at least this many entries get the T16 layouts; default 4194304);
  * "t16_tile" (0: automatic tile size, else a power of two <= 16384 -- tests);
- * "t16_async" (bit 0 / bit 1: long segments of the TILES / DIRECT kernel through the cp.async ring; default 1);
+ * "lsqr_graph" (1, default: the iteration body of the split LSQR path is captured once and replayed as a CUDA graph
+ *   when the matrix has fewer than 2e8 entries -- the launch-bound regime);
+ * "t16_bank_deal" (1, default: the T16 builder deals the entries of long segments over the shared-memory banks);
+ * "t16_async" (bit 0 / bit 1: long segments of the TILES / DIRECT kernel through the cp.async ring; default 3);
  * "t16_direct_max" (gathered ranges up to this many elements use one DIRECT tile; default 16384);
  * "sensit_row_blocks" (1: tfx_sensit_repartition_into / tfx_read_sensitivity_kernel_into build one independent row
  *   block per call -- bounded build memory for kernels near the HBM capacity; such matrices cannot be exported);

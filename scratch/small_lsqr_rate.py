@@ -17,13 +17,15 @@ for name, kw, niter in (("A-like 2x128x32, 256 data, Haar 0.15", dict(nx=2, ny=1
                                      np.arange(1, nc + 2, dtype=np.int64), np.arange(1, nc + 1, dtype=np.int32))
     b = np.zeros(nl + nc); b[:nl] = np.random.default_rng(0).standard_normal(nl)
     u, x = tfx.Buffer(nl + nc), tfx.Buffer(ncol)
-    for it in (5, niter):
+    for graph in (0, 1):
+      tfx.set_option("lsqr_graph", graph)
+      for it in (5, niter):
         tfx.copy(u, b, nl + nc)
         l0 = tfx.launch_count()
         t0 = time.perf_counter()
         tfx.lsqr_solve_sensit(nl + nc, ncol, it, 1e-300, 0.0, 0.0, S, C, u, x, [1, 0], N, pb.nx, pb.ny, pb.nz, ncomp, kw["compression_type"], True)
         wall = time.perf_counter() - t0
-    loop_ms, _, _ = tfx.last_timing()
-    h, iters, fused = tfx.last_history()
-    print("%-48s nnz=%d kind=%d iters=%d  %.1f us/it (device loop)  %.1f us/it (wall)  launches/it=%.1f" %
-          (name, nnz, S.storage_kind(), iters, 1e3 * loop_ms / iters, 1e6 * wall / iters, (tfx.launch_count() - l0) / iters), flush=True)
+      loop_ms, _, _ = tfx.last_timing()
+      h, iters, fused = tfx.last_history()
+      print("%-44s graph=%d nnz=%d kind=%d iters=%d  %.1f us/it (device loop)  %.1f us/it (wall)  launches/it=%.1f  r_last=%.15e" %
+            (name, graph, nnz, S.storage_kind(), iters, 1e3 * loop_ms / iters, 1e6 * wall / iters, (tfx.launch_count() - l0) / iters, h[-1]), flush=True)

@@ -21,6 +21,7 @@ namespace tfx {
 static thread_local std::string g_err;
 static int g_opt_dense_detect = 1;
 int g_opt_profile_sweeps = 0; // 1: CUDA events around every fused sweep launch (bench roofline)
+int g_opt_lsqr_graph = 1;     // 1: CUDA-graph replay of the split-path iteration body (launch-bound small matrices)
 int g_opt_strict_order = 0;   // 1: LSQR uses the reference's sequential summation order (parity mode)
 
 void set_error(const std::string &msg) { g_err = msg; }
@@ -349,6 +350,10 @@ int tfx_set_option(const char *name, int value) {
   }
   if (name && strcmp(name, "profile_sweeps") == 0) {
     g_opt_profile_sweeps = value;
+    return 0;
+  }
+  if (name && strcmp(name, "lsqr_graph") == 0) {
+    g_opt_lsqr_graph = value;
     return 0;
   }
   if (name && strcmp(name, "strict_order") == 0) {

@@ -445,7 +445,8 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
     const int chk = (S->device_nnz() > (int64_t)2e8) ? 1 : 16;
     int host_done = 0;
     TFX_CUDA(cudaEventRecord(T.loop0, st));
-    for (int it = 1; it <= p.niter && !host_done; ++it) {
+    // One iteration of the reference's loop body (:160-290) as a stream of launches.
+    auto iter_body = [&]() -> int {
       if (misfit) {   // :168-189
         TFX_CUDA(cudaMemcpyAsync(v2, d_x, ncol * 8, cudaMemcpyDeviceToDevice, st));
         if (wav) TFX_TRY(apply_wavelet(p, v2, true, nsmaller, st));
@@ -482,11 +483,43 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
       if (nranks > 1) TFX_TRY(comm_allreduce_sum(red, 1, st));
       k_scal_alpha<<<1, 1, 0, st>>>(red, sc, 0, p.niter, p.rmin, W.hist.p); LAUNCHED();
       k_xw_update<<<GV, kVecThreads, 0, st>>>(v, d_x, w, ncol, sc, 0, p.gamma); LAUNCHED();
+      return 0;
+    };
+    // Launch-bound regime (small matrices: ~16 launches of a few microseconds each per iteration): the body is
+    // captured once into a CUDA graph -- after a first, directly launched iteration has done every lazy allocation --
+    // and replayed; all kernel arguments are iteration-independent (the scalars live in *sc on the device).
+    cudaGraphExec_t gexec = nullptr;
+    unsigned long long launches_per_iter = 0;
+    const bool want_graph = g_opt_lsqr_graph && nranks == 1 && !S->has_blocks && p.niter >= 4 &&
+                            S->device_nnz() <= (int64_t)2e8;
+    for (int it = 1; it <= p.niter && !host_done; ++it) {
+      if (gexec) {
+        TFX_CUDA(cudaGraphLaunch(gexec, st));
+        c.launches += launches_per_iter;
+      } else {
+        TFX_TRY(iter_body());
+        if (want_graph && it == 1) {
+          cudaGraph_t graph = nullptr;
+          const unsigned long long l0 = c.launches;
+          if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            const int rc = iter_body();
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc == 0 && ce == cudaSuccess && graph && cudaGraphInstantiate(&gexec, graph, 0) == cudaSuccess)
+              launches_per_iter = c.launches - l0;
+            else
+              gexec = nullptr;
+            if (graph) cudaGraphDestroy(graph);
+          }
+          c.launches = l0;                 // nothing ran during the capture
+          (void)cudaGetLastError();        // a failed capture falls back to direct launches
+        }
+      }
       if (it % chk == 0 || it == p.niter) {
         TFX_CUDA(cudaMemcpyAsync(&host_done, &sc->done, sizeof(int), cudaMemcpyDeviceToHost, st));
         TFX_CUDA(cudaStreamSynchronize(st));
       }
     }
+    if (gexec) cudaGraphExecDestroy(gexec);
   }
 #undef LAUNCHED
   TFX_CUDA(cudaEventRecord(T.loop1, st));

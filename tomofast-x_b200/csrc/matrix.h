@@ -123,6 +123,8 @@ struct LsqrResult {
 // Option "strict_order": reproduce the reference's sequential summation order (slow parity mode).
 extern int g_opt_strict_order;
 extern int g_opt_profile_sweeps;
+// Option "lsqr_graph": 1 (default) replays the split-path iteration body as a CUDA graph for small matrices.
+extern int g_opt_lsqr_graph;
 
 int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x, LsqrResult &res);
 int lsqr_run_strict(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x, LsqrResult &res);
