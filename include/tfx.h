@@ -55,7 +55,8 @@ int         tfx_timer_stop(double *ms);
  * "t16_direct_max" (gathered ranges up to this many elements use one DIRECT tile; default 16384);
  * "sensit_row_blocks" (1: tfx_sensit_repartition_into / tfx_read_sensitivity_kernel_into build one independent row
  *   block per call -- bounded build memory for kernels near the HBM capacity; such matrices cannot be exported);
- * "grav_shared_nodes" (1, default: gravity lines on structured grids evaluate corner terms once per grid node);
+ * "grav_shared_nodes" / "mag_shared_nodes" (1, default: forward-kernel lines on structured grids evaluate the prism
+ *   corner terms once per grid node -- and the magnetic edge terms once per grid edge -- instead of once per cell);
  * "dense_vec4" (1, default: 512 threads x float4 rows; 0: 1024 threads x float2 rows), "dense_f2f_rows" (row vectors
  *   per thread whose second use converts with F2F; default 2), "dense_stream_only" (diagnostic: the sweep's TMA ring
  *   without the products -- results are meaningless, only the time is). */

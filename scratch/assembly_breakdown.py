@@ -13,9 +13,13 @@ grid = regular_grid(nx, ny, nz)
 xyz = station_lattice(nd, 100.0 * nx, 100.0 * ny, z=-0.1)
 cw = depth_weight_type1(grid, 2.0, 0.0, 4.0e3)
 par = tfx.SensitParams()
-par.problem_type = 1
+ptype = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+for kv in sys.argv[4:]:
+    k, v = kv.split("="); tfx.set_option(k, int(v))
+par.problem_type = ptype
 par.nx, par.ny, par.nz = nx, ny, nz
 par.ndata, par.ndata_components, par.nmodel_components, par.data_type = nd, 1, 1, 1
+par.mi, par.md, par.theta, par.intensity = 60.0, 10.0, 0.0, 50000.0
 par.compression_type, par.compression_rate = 1, 0.05
 par.problem_weight = 1.0
 par.cell0, par.ncells_local, par.param_shift, par.ncolumns = 0, N, 0, 2 * N

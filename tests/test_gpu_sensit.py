@@ -38,6 +38,26 @@ def test_gravity_shared_nodes_is_bit_identical_to_per_cell_evaluation(oracle):
     assert np.abs(shared[2, 0, 0] - want).max() / np.abs(want).max() < 1e-12
 
 
+@pytest.mark.parametrize("nmc,ndc", [(1, 1), (3, 1), (1, 3), (3, 3)])
+def test_magnetic_shared_terms_are_bit_identical_to_per_cell_evaluation(oracle, nmc, ndc):
+    """Structured grids evaluate sharmbox's corner terms (atan2) once per node and its edge terms (log of a ratio) once
+    per edge (csrc/assembly.cu mag_lines_nodes_kernel); orders and signs of the per-cell sums are the reference's.
+    One station sits inside a cell (six-sub-prism branch, magnetic_field.f90:139-224)."""
+    pb = make_problem(nx=35, ny=10, nz=9, ndata=4, problem_type=2, nmodel_components=nmc, ndata_components=ndc)
+    x, y, z = (a.copy() for a in pb.data_xyz)
+    x[1], y[1], z[1] = 1237.3, 451.9, 161.0                      # inside cell (12, 4, 3)
+    try:
+        tfx.set_option("mag_shared_nodes", 0)
+        per_cell = tfx.sensit_lines(pb.par, pb.grid, (x, y, z))
+    finally:
+        tfx.set_option("mag_shared_nodes", 1)
+    shared = tfx.sensit_lines(pb.par, pb.grid, (x, y, z))
+    assert np.array_equal(shared, per_cell)
+    p = pb.par
+    want = oracle.magprism(pb.grid, float(x[1]), float(y[1]), float(z[1]), nmc, ndc, p.mi, p.md, p.theta, p.intensity)
+    assert np.abs(shared[1] - want).max() / np.abs(want).max() < 1e-11
+
+
 def test_gravity_lines_on_an_unstructured_set_of_boxes(oracle):
     """Arbitrary per-cell boxes (the reference stores X1..Z2 per cell, gravity_field.f90:151-156): a grid whose boxes
     do not share their faces falls back to the per-cell kernel."""

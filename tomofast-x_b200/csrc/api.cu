@@ -372,6 +372,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_dense_f2f_rows = value;
     return 0;
   }
+  if (name && strcmp(name, "mag_shared_nodes") == 0) {
+    g_opt_mag_shared_nodes = value;
+    return 0;
+  }
   if (name && strcmp(name, "grav_shared_nodes") == 0) {
     g_opt_grav_shared_nodes = value;
     return 0;

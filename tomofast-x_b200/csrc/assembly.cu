@@ -475,6 +475,188 @@ __global__ void __launch_bounds__(128) mag_lines_kernel(double *__restrict__ lin
   if (e) atomicExch(err, e);
 }
 
+// ---- structured grids: shared corner / edge terms -------------------------------------------------
+// sharmbox (magnetic_field.f90:321-457) is a signed sum of terms that belong either to ONE corner of the prism
+//   A = atan2(ry*rz, rx*a)  (ts_xx),   B = atan2(rx*rz, ry*a)  (ts_yy),        a = sqrt(rz^2 + (ry^2 + rx^2))
+// or to ONE edge of it (the log of a ratio of the two end corners)
+//   Ez = log((rz2 + a_hi) / (rz1 + a_lo))  (ts_yx, edges along z, the association of a above),
+//   Ex = log((rx1 + a') / (rx2 + a'))      (ts_yz, edges along x, a' = sqrt(rx^2 + (ry^2 + rz^2))),
+//   Ey = log((ry1 + a'') / (ry2 + a''))    (ts_xz, edges along y, a'' = sqrt(ry^2 + (rx^2 + rz^2))).
+// On a structured grid a corner is shared by 8 cells and an edge by 4: a CTA evaluates the terms of a
+// 32 x 8 x 8-cell tile once into shared memory (2 atan2 per node, 1 log per edge instead of 16 atan2 + 12 log per
+// cell) and every cell adds them with the reference's signs in the reference's order -- bit-identical to
+// sharmbox_dev(). The cell that contains the station takes the six-sub-prism branch (:139-224) as before.
+namespace {
+constexpr int kMTX = 32, kMTY = 8, kMTZ = 8;
+constexpr int kMNodes = (kMTX + 1) * (kMTY + 1) * (kMTZ + 1);
+constexpr int kMEz = (kMTX + 1) * (kMTY + 1) * kMTZ, kMEx = kMTX * (kMTY + 1) * (kMTZ + 1), kMEy = (kMTX + 1) * kMTY * (kMTZ + 1);
+constexpr size_t kMagSmem = (size_t)(2 * kMNodes + kMEz + kMEx + kMEy) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(256) mag_lines_nodes_kernel(double *__restrict__ lines, int nx, int ny, int nz, int nb,
+                                                              const double *__restrict__ xn, const double *__restrict__ yn,
+                                                              const double *__restrict__ zn, const double *__restrict__ xd,
+                                                              const double *__restrict__ yd, const double *__restrict__ zd,
+                                                              MagPar mp, int *err) {
+  extern __shared__ double msm[];
+  double *sA = msm, *sB = sA + kMNodes, *sEz = sB + kMNodes, *sEx = sEz + kMEz, *sEy = sEx + kMEx;
+#define NA(a, b, c) sA[((c) * (kMTY + 1) + (b)) * (kMTX + 1) + (a)]
+#define NB(a, b, c) sB[((c) * (kMTY + 1) + (b)) * (kMTX + 1) + (a)]
+#define EZ(a, b, c) sEz[((c) * (kMTY + 1) + (b)) * (kMTX + 1) + (a)]     /* edge (a, b) from node level c to c+1 */
+#define EX(a, b, c) sEx[((c) * (kMTY + 1) + (b)) * kMTX + (a)]           /* edge (b, c) from node a to a+1     */
+#define EY(a, b, c) sEy[((c) * kMTY + (b)) * (kMTX + 1) + (a)]           /* edge (a, c) from node b to b+1     */
+  const int tiles_x = (nx + kMTX - 1) / kMTX, tiles_y = (ny + kMTY - 1) / kMTY;
+  const int tx_ = blockIdx.x % tiles_x, ty_ = (blockIdx.x / tiles_x) % tiles_y, tz_ = blockIdx.x / (tiles_x * tiles_y);
+  const int i0 = tx_ * kMTX, j0 = ty_ * kMTY, k0 = tz_ * kMTZ;
+  const long long n = (long long)nx * ny * nz;
+  int e = 0;
+  for (int b_ = blockIdx.y; b_ < nb; b_ += gridDim.y) {
+    const double Xd = xd[b_], Yd = yd[b_], Zd = zd[b_];
+    // ---- corner terms
+    for (int idx = threadIdx.x; idx < kMNodes; idx += 256) {
+      const int a = idx % (kMTX + 1), b = (idx / (kMTX + 1)) % (kMTY + 1), c = idx / ((kMTX + 1) * (kMTY + 1));
+      const int gi = min(i0 + a, nx), gj = min(j0 + b, ny), gk = min(k0 + c, nz);
+      const double rx = xn[gi] - Xd, ry = yn[gj] - Yd, rz = zn[gk] - Zd;
+      if (i0 + a <= nx && j0 + b <= ny && k0 + c <= nz) {
+        if (rx == 0.) e = 11;
+        if (ry == 0.) e = 12;
+      }
+      const double as1 = sqrt(__dadd_rn(__dmul_rn(rz, rz), __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rx, rx))));
+      sA[idx] = atan2(__dmul_rn(ry, rz), __dmul_rn(rx, as1));
+      sB[idx] = atan2(__dmul_rn(rx, rz), __dmul_rn(ry, as1));
+    }
+    // ---- edge terms
+    for (int idx = threadIdx.x; idx < kMEz; idx += 256) {
+      const int a = idx % (kMTX + 1), b = (idx / (kMTX + 1)) % (kMTY + 1), c = idx / ((kMTX + 1) * (kMTY + 1));
+      const int gi = min(i0 + a, nx), gj = min(j0 + b, ny), g1 = min(k0 + c, nz), g2 = min(k0 + c + 1, nz);
+      const double rx = xn[gi] - Xd, ry = yn[gj] - Yd, rz1 = zn[g1] - Zd, rz2 = zn[g2] - Zd;
+      const double R = __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rx, rx));
+      const double a_lo = sqrt(__dadd_rn(__dmul_rn(rz1, rz1), R)), a_hi = sqrt(__dadd_rn(__dmul_rn(rz2, rz2), R));
+      sEz[idx] = log(__ddiv_rn(rz2 + a_hi, rz1 + a_lo));
+    }
+    for (int idx = threadIdx.x; idx < kMEx; idx += 256) {
+      const int a = idx % kMTX, b = (idx / kMTX) % (kMTY + 1), c = idx / (kMTX * (kMTY + 1));
+      const int g1 = min(i0 + a, nx), g2 = min(i0 + a + 1, nx), gj = min(j0 + b, ny), gk = min(k0 + c, nz);
+      const double rx1 = xn[g1] - Xd, rx2 = xn[g2] - Xd, ry = yn[gj] - Yd, rz = zn[gk] - Zd;
+      const double R = __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rz, rz));
+      const double a1 = sqrt(__dadd_rn(__dmul_rn(rx1, rx1), R)), a2 = sqrt(__dadd_rn(__dmul_rn(rx2, rx2), R));
+      sEx[idx] = log(__ddiv_rn(rx1 + a1, rx2 + a2));
+    }
+    for (int idx = threadIdx.x; idx < kMEy; idx += 256) {
+      const int a = idx % (kMTX + 1), b = (idx / (kMTX + 1)) % kMTY, c = idx / ((kMTX + 1) * kMTY);
+      const int gi = min(i0 + a, nx), g1 = min(j0 + b, ny), g2 = min(j0 + b + 1, ny), gk = min(k0 + c, nz);
+      const double rx = xn[gi] - Xd, ry1 = yn[g1] - Yd, ry2 = yn[g2] - Yd, rz = zn[gk] - Zd;
+      const double R = __dadd_rn(__dmul_rn(rx, rx), __dmul_rn(rz, rz));
+      const double a1 = sqrt(__dadd_rn(__dmul_rn(ry1, ry1), R)), a2 = sqrt(__dadd_rn(__dmul_rn(ry2, ry2), R));
+      sEy[idx] = log(__ddiv_rn(ry1 + a1, ry2 + a2));
+    }
+    __syncthreads();
+    // ---- cells
+    for (int idx = threadIdx.x; idx < kMTX * kMTY * kMTZ; idx += 256) {
+      const int a = idx % kMTX, b = (idx / kMTX) % kMTY, c = idx / (kMTX * kMTY);
+      const int gi = i0 + a, gj = j0 + b, gk = k0 + c;
+      if (gi >= nx || gj >= ny || gk >= nz) continue;
+      const double gx1 = xn[gi], gx2 = xn[gi + 1], gy1 = yn[gj], gy2 = yn[gj + 1], gz1 = zn[gk], gz2 = zn[gk + 1];
+      double tx[3], ty[3], tz[3];
+      if ((gx1 < Xd) && (gx2 > Xd) && (gy1 < Yd) && (gy2 > Yd) && (gz1 < Zd) && (gz2 > Zd)) {
+        double width = (double)0.1f;
+        const double min_clr = fmin(fmin(fmin(fabs(Xd - gx1), fabs(Xd - gx2)), fmin(fabs(Yd - gy1), fabs(Yd - gy2))),
+                                    fmin(fabs(Zd - gz1), fabs(Zd - gz2)));
+        if (width > min_clr) width = 0.5 * min_clr;
+        const double bx1[6] = {gx1, gx1, gx1, Xd + width, Xd - width, Xd - width};
+        const double bx2[6] = {gx2, gx2, Xd - width, gx2, Xd + width, Xd + width};
+        const double by1[6] = {gy1, gy1, gy1, gy1, gy1, Yd + width};
+        const double by2[6] = {gy2, gy2, gy2, gy2, Yd - width, gy2};
+        const double bz1[6] = {gz1, Zd + width, Zd - width, Zd - width, Zd - width, Zd - width};
+        const double bz2[6] = {Zd - width, gz2, Zd + width, Zd + width, Zd + width, Zd + width};
+        for (int q = 0; q < 3; ++q) tx[q] = ty[q] = tz[q] = 0.0;
+        for (int j = 0; j < 6; ++j) {
+          double ax[3], ay[3], az[3];
+          sharmbox_dev(Xd, Yd, Zd, bx1[j], by1[j], bz1[j], bx2[j], by2[j], bz2[j], ax, ay, az, &e);
+          for (int q = 0; q < 3; ++q) {
+            tx[q] = __dadd_rn(tx[q], ax[q]);
+            ty[q] = __dadd_rn(ty[q], ay[q]);
+            tz[q] = __dadd_rn(tz[q], az[q]);
+          }
+        }
+      } else {
+        // corner (x, y, z) in {1, 2}^3  ->  node (a + x - 1, b + y - 1, c + z - 1); orders and signs of :376-442
+        double t = NA(a + 1, b, c + 1);
+        t = __dsub_rn(t, NA(a + 1, b + 1, c + 1));
+        t = __dadd_rn(t, NA(a + 1, b + 1, c));
+        t = __dsub_rn(t, NA(a + 1, b, c));
+        t = __dadd_rn(t, NA(a, b + 1, c + 1));
+        t = __dsub_rn(t, NA(a, b, c + 1));
+        t = __dadd_rn(t, NA(a, b, c));
+        t = __dsub_rn(t, NA(a, b + 1, c));
+        tx[0] = t;
+        t = EZ(a + 1, b + 1, c);
+        t = __dsub_rn(t, EZ(a, b + 1, c));
+        t = __dadd_rn(t, EZ(a, b, c));
+        t = __dsub_rn(t, EZ(a + 1, b, c));
+        ty[0] = t;
+        t = NB(a, b + 1, c + 1);
+        t = __dsub_rn(t, NB(a + 1, b + 1, c + 1));
+        t = __dadd_rn(t, NB(a + 1, b + 1, c));
+        t = __dsub_rn(t, NB(a, b + 1, c));
+        t = __dadd_rn(t, NB(a + 1, b, c + 1));
+        t = __dsub_rn(t, NB(a, b, c + 1));
+        t = __dadd_rn(t, NB(a, b, c));
+        t = __dsub_rn(t, NB(a + 1, b, c));
+        ty[1] = t;
+        t = EX(a, b + 1, c);
+        t = __dsub_rn(t, EX(a, b + 1, c + 1));
+        t = __dadd_rn(t, EX(a, b, c + 1));
+        t = __dsub_rn(t, EX(a, b, c));
+        ty[2] = t;
+        t = EY(a + 1, b, c);
+        t = __dsub_rn(t, EY(a + 1, b, c + 1));
+        t = __dadd_rn(t, EY(a, b, c + 1));
+        t = __dsub_rn(t, EY(a, b, c));
+        tx[2] = t;
+        tz[2] = -1 * (tx[0] + ty[1]);   // Gauss (:446)
+        tz[1] = ty[2];
+        tx[1] = ty[0];
+        tz[0] = tx[2];
+      }
+      const double fourpi = 4.0 * TFX_PI;
+      const long long p = gi + (long long)gj * nx + (long long)gk * nx * ny;
+      double *out = lines + (long long)b_ * mp.ndc * mp.nmc * n;
+#define OUT(k, d) out[((long long)(d)*mp.nmc + (k)) * n + p]
+#define FIN(x) __ddiv_rn(__dmul_rn(mp.mult, (x)), fourpi)
+#define DOT3(v) __dadd_rn(__dadd_rn(__dmul_rn(v[0], mp.magv[0]), __dmul_rn(v[1], mp.magv[1])), __dmul_rn(v[2], mp.magv[2]))
+      if (mp.nmc == 1) {
+        const double mx = DOT3(tx), my = DOT3(ty), mz = DOT3(tz);
+        if (mp.ndc == 1) {
+          OUT(0, 0) = FIN(__dadd_rn(__dadd_rn(__dmul_rn(mx, mp.magv[0]), __dmul_rn(my, mp.magv[1])), __dmul_rn(mz, mp.magv[2])));
+        } else {
+          OUT(0, 0) = FIN(mx); OUT(0, 1) = FIN(my); OUT(0, 2) = FIN(mz);
+        }
+      } else {
+        for (int k = 0; k < 3; ++k) {
+          if (mp.ndc == 1) {
+            OUT(k, 0) = FIN(__dadd_rn(__dadd_rn(__dmul_rn(tx[k], mp.magv[0]), __dmul_rn(ty[k], mp.magv[1])), __dmul_rn(tz[k], mp.magv[2])));
+          } else {
+            OUT(k, 0) = FIN(tx[k]); OUT(k, 1) = FIN(ty[k]); OUT(k, 2) = FIN(tz[k]);
+          }
+        }
+      }
+#undef OUT
+#undef FIN
+#undef DOT3
+    }
+    __syncthreads();
+  }
+#undef NA
+#undef NB
+#undef EZ
+#undef EX
+#undef EY
+  if (e) atomicExch(err, e);
+}
+
+int g_opt_mag_shared_nodes = 1;
+
 int mag_lines(const GridDev &g, int32_t nb, const double *d_xd, const double *d_yd, const double *d_zd, int nmc, int ndc,
               double mi, double md, double theta, double intensity, double *d_lines, int *d_err, cudaStream_t st) {
   if (!((nmc == 1 || nmc == 3) && (ndc == 1 || ndc == 3)))
@@ -491,6 +673,20 @@ int mag_lines(const GridDev &g, int32_t nb, const double *d_xd, const double *d_
   mp.mult = (nmc == 1) ? intensity : (mu0 * T2nT);
   mp.nmc = nmc;
   mp.ndc = ndc;
+  if (g.structured == 1 && g_opt_mag_shared_nodes) {
+    static bool attr = false;
+    if (!attr) {
+      TFX_CUDA(cudaFuncSetAttribute(mag_lines_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMagSmem));
+      attr = true;
+    }
+    const int tiles = ((g.nx + kMTX - 1) / kMTX) * ((g.ny + kMTY - 1) / kMTY) * ((g.nz + kMTZ - 1) / kMTZ);
+    dim3 grid(tiles, std::min(nb, 1024));
+    mag_lines_nodes_kernel<<<grid, 256, kMagSmem, st>>>(d_lines, g.nx, g.ny, g.nz, nb, g.xn.p, g.yn.p, g.zn.p, d_xd, d_yd, d_zd,
+                                                        mp, d_err);
+    ctx().launches++;
+    TFX_CUDA(cudaGetLastError());
+    return 0;
+  }
   dim3 grid((g.n + 127) / 128, std::min(nb, 1024));
   mag_lines_kernel<<<grid, 128, 0, st>>>(d_lines, g.n, nb, g.X1.p, g.X2.p, g.Y1.p, g.Y2.p, g.Z1.p, g.Z2.p, d_xd, d_yd,
                                          d_zd, mp, d_err);

@@ -144,6 +144,7 @@ struct GridDev {
 };
 int grid_detect_structured(GridDev &g, int32_t nx, int32_t ny, int32_t nz, cudaStream_t st);
 extern int g_opt_grav_shared_nodes;
+extern int g_opt_mag_shared_nodes;
 
 // Fills a dense column-major block with the depth-weighted gravity kernel, reproducing
 // graviprism_z (gravity_field.f90:131-195), apply_column_weight (sensitivity_gravmag.F90:228),
