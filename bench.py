@@ -18,6 +18,11 @@ e2e    : iterations/s through the C ABI call tfx_lsqr_solve_sensit with HOST buf
          right-hand side, the initialisation before the loop, K iterations, D2H of x and u.
 roofline: the fused sweep kernel (dense_sweep_kernel): ALGORITHMIC bytes (4 B per matrix entry read
          once + the vectors) / mean launch time from CUDA events, against the measured HBM peak.
+spmv   : (extra object) the compressed half of BASELINE.json's metric: S x / S^T u on a Haar-5 % kernel of the same grid
+         assembled on the device, 10 000 stations per GPU (weak scaling), GB/s by the reference's 8 B/nnz accounting and
+         by the 6 B/nnz the T16 layouts move, wavelet transform times, assembly rate, compressed LSQR it/s.
+         --no-dense --comp-grid 512 512 128 --comp-ndata 6250 --comp-batch 5000 on 8 GPUs is BASELINE config C at full
+         size (row-blocked assembly).
 cpu_baseline / --impl reference: the oracle port of the reference loops (sparse_matrix.f90:313-405,
          lsqr_solver2.F90:321-473) on the host cores, column-split over P processes like the reference's
          MPI ranks, on a bounded column sample of the same matrix shape, scaled linearly in nnz.
