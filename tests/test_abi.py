@@ -47,6 +47,28 @@ def test_library_exports_every_declared_symbol(libtfx):
         assert hasattr(libtfx, s)
 
 
+def test_header_is_plain_c_and_links(libtfx, tmp_path):
+    """include/tfx.h is the drop-in boundary of a Fortran / C host: it must compile as C99 (no C++ in the signatures) and
+    a C translation unit that takes the address of the new entry points must link against libtfx.so."""
+    src = tmp_path / "host.c"
+    src.write_text(
+        '#include "tfx.h"\n#include <stdio.h>\n'
+        "typedef void (*fn)(void);\n"
+        "int main(void) {\n"
+        "  fn p[] = {(fn)tfx_lsqr_solve_sensit, (fn)tfx_calculate_sensit, (fn)tfx_damping_add,\n"
+        "            (fn)tfx_cross_gradient_calculate, (fn)tfx_calculate_depth_weight, (fn)tfx_calculate_data,\n"
+        "            (fn)tfx_sensit_repartition_into, (fn)tfx_model_update};\n"
+        '  printf("%d %d\\n", tfx_version(), (int)(sizeof(p) / sizeof(p[0])));\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(tfx.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-ltfx", "-Wl,-rpath," + libdir,
+                           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lcudart"])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert out == ["100", "8"]
+
+
 def test_library_is_sm100a_only():
     out = subprocess.check_output(["cuobjdump", "-lelf", tfx.LIB_PATH], text=True)
     archs = set(re.findall(r"sm_(\d+a?)", out))
