@@ -536,6 +536,8 @@ def cpu_reference(a, steps, warmup, seconds_hint=20.0):
     ncols = int(max(256, min(per_iter_entries / nrows, 3.0e9 / (8.0 * nrows))))
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
+        # P = 1 (SURVEY 8d asks for both): one process alone on the box, a quarter of a slab
+        dt1, its1, ent1 = pool.map(_cpu_worker, [(999, nrows, max(256, ncols // 4), steps + warmup)])[0]
         res = pool.map(_cpu_worker, [(1000 + i, nrows, ncols, steps + warmup) for i in range(cores)])
     # ranks run concurrently; an iteration of the whole slab set ends when the slowest rank ends
     t_iter = max(dt / its for dt, its, _ in res)
@@ -544,6 +546,7 @@ def cpu_reference(a, steps, warmup, seconds_hint=20.0):
     its_per_s_sample = 1.0 / t_iter
     value = its_per_s_sample * sample_entries / full_entries          # SpMV cost is linear in nnz
     return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "value_1core": (its1 / dt1) * ent1 / full_entries,
             "sample": "oracle lsqr_solve (C port of lsqr_solver2.F90:321-473 + sparse_matrix.f90:313-405), "
                       "%d column-slab processes x (%d rows x %d dense columns, CSR f32+i32), %d iterations each; "
                       "scaled linearly in nnz from %.3g to %.3g entries; damping block omitted (O(N))" %
