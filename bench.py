@@ -373,7 +373,7 @@ def compressed_spmv(a, tfx, d):
         # row block.
         import copy
         dw1 = np.ones((nd, 1))
-        stride = max(1, nd // max(256, nd // 16))
+        stride = max(1, nd // max(256, nd // 16)) | 1      # odd: never a divisor of an even lattice width (no aliasing)
         sx = tuple(np.ascontiguousarray(v[::stride]) for v in xyz)
         par_s = copy.copy(par); par_s.ndata = sx[0].size
         rows_s, nnz_col, _, _ = tfx.sensit_assemble_rows(par_s, grid, sx, cw, np.ones((sx[0].size, 1)), d.rank, d.world)
