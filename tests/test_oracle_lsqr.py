@@ -1,6 +1,7 @@
 """Oracle vs the reference's LSQR / sparse-matrix known answers
 (src/tests/tests_lsqr.f90, src/tests/tests_sparse_matrix.f90)."""
 import numpy as np
+import pytest
 
 from tests.conftest import TOL, comparable
 
@@ -118,3 +119,71 @@ def test_sensit_variant_equals_plain_when_no_constraints(oracle):
     big = h1 > 1e-9
     np.testing.assert_allclose(h1[big], h2[big], rtol=1e-6)
     np.testing.assert_allclose(x1, x2, rtol=1e-9, atol=1e-12)
+
+
+def _random_sensit(oracle, rng, nrows, nx, ny, nz):
+    N = nx * ny * nz
+    A = rng.standard_normal((nrows, N))
+    S = oracle.SparseMatrix(nrows, 2 * N, nrows * N)
+    for i in range(nrows):
+        S.add_row(A[i].astype(np.float32), np.arange(1, N + 1, dtype=np.int32))
+        S.new_row()
+    S.finalize()
+    return S, A.astype(np.float32).astype(np.float64), N
+
+
+@pytest.mark.parametrize("wtype", [1, 2])
+def test_wavelet_in_loop_equals_wavelet_domain_solve(oracle, wtype):
+    """lsqr_solve_sensit with WAVELET_DOMAIN = .false. (transforms inside the loop, lsqr_solver2.F90:200-207,228-235)
+    solves min |S W x - b| for the physical-domain x; with an orthonormal W its iterates are the inverse transforms of
+    the iterates of the wavelet-domain solve min |S y - b| and the residual histories coincide."""
+    rng = np.random.default_rng(40 + wtype)
+    nx, ny, nz, nrows = 6, 5, 4, 14
+    S, A, N = _random_sensit(oracle, rng, nrows, nx, ny, nz)
+    Cm = oracle.SparseMatrix(1, 2 * N, 1, 1)
+    Cm.add_empty_rows(1)
+    Cm.finalize()
+    b = np.concatenate([rng.standard_normal(nrows), [0.0]])
+    y, hy, ity = oracle.lsqr_solve_sensit(12, 1e-13, 0.0, 0.0, S, Cm, b, N, nx, ny, nz, 1, wtype, True)
+    x, hx, itx = oracle.lsqr_solve_sensit(12, 1e-13, 0.0, 0.0, S, Cm, b, N, nx, ny, nz, 1, wtype, False)
+    assert itx == ity
+    np.testing.assert_allclose(hx, hy, rtol=1e-9)
+    np.testing.assert_allclose(x[:N], oracle.inverse_wavelet(y[:N].copy(), nx, ny, nz, wtype), rtol=1e-8, atol=1e-11)
+
+
+def test_target_misfit_exits_early(oracle):
+    """The misfit exit (lsqr_solver2.F90:168-189): RMSE of S x against the incoming right-hand side, checked BEFORE the
+    iteration body -- the run stops at the first iteration whose incoming x is good enough."""
+    rng = np.random.default_rng(50)
+    nx, ny, nz, nrows = 5, 4, 3, 10
+    S, A, N = _random_sensit(oracle, rng, nrows, nx, ny, nz)
+    Cm = oracle.SparseMatrix(1, 2 * N, 1, 1)
+    Cm.add_empty_rows(1)
+    Cm.finalize()
+    b = np.concatenate([rng.standard_normal(nrows), [0.0]])
+    x_full, h_full, it_full = oracle.lsqr_solve_sensit(40, 1e-13, 0.0, 0.0, S, Cm, b, N, nx, ny, nz, 1, 0, True)
+    rmse = lambda x: np.sqrt(np.sum((A @ x[:N] - b[:nrows]) ** 2) / nrows)
+    target = 10.0 * rmse(x_full) + 1e-3
+    x, h, it = oracle.lsqr_solve_sensit(40, 1e-13, 0.0, target, S, Cm, b, N, nx, ny, nz, 1, 0, True)
+    assert 0 < it < it_full
+    assert rmse(x) <= target
+    # the iterations before the exit are those of the run without a target
+    np.testing.assert_allclose(h, h_full[:it], rtol=1e-12)
+
+
+def test_soft_thresholding_shrinks_the_iterate(oracle):
+    """gamma > 0 applies ISTA's proximal step to x after every update (lsqr_solver2.F90:272-275,478-494): entries are
+    pulled towards zero by gamma and small ones vanish; gamma = 0 is the plain solver."""
+    rng = np.random.default_rng(60)
+    nx, ny, nz, nrows = 5, 4, 3, 10
+    S, A, N = _random_sensit(oracle, rng, nrows, nx, ny, nz)
+    Cm = oracle.SparseMatrix(1, 2 * N, 1, 1)
+    Cm.add_empty_rows(1)
+    Cm.finalize()
+    b = np.concatenate([rng.standard_normal(nrows), [0.0]])
+    x0, _, _ = oracle.lsqr_solve_sensit(1, 1e-13, 0.0, 0.0, S, Cm, b, N, nx, ny, nz, 1, 0, True)
+    gamma = 0.5 * np.abs(x0[:N]).max()
+    xg, _, _ = oracle.lsqr_solve_sensit(1, 1e-13, gamma, 0.0, S, Cm, b, N, nx, ny, nz, 1, 0, True)
+    want = np.sign(x0) * np.maximum(np.abs(x0) - gamma, 0.0)             # one iteration: the prox of the plain iterate
+    np.testing.assert_allclose(xg, want, rtol=1e-13, atol=1e-300)
+    assert np.count_nonzero(xg[:N]) < np.count_nonzero(x0[:N])
