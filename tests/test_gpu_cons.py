@@ -113,3 +113,40 @@ def test_reset_and_rebuild_device_built_matrix(oracle):
         So.finalize()
         _same_matrix(S, So)
         assert np.array_equal(b, bo)
+
+
+# ---- the reference's own known answers for the producers (src/tests/tests_inversion.f90) on the device ------------
+def test_ref_golden_add_damping_identity_matrix():
+    """test_add_damping_identity_matrix (tests_inversion.f90:50-127): I * (1..N) = b, assert at :117."""
+    from tests.conftest import TOL, comparable
+    from tests.test_oracle_ref_goldens_cons import damping_identity_case
+    nx, ny, nz, ntot, nel = damping_identity_case(1)
+    M = tfx.SparseMatrix(ntot, nel, nel)
+    b_rhs = np.zeros(ntot)
+    model = np.zeros(ntot)
+    tfx.damping_add(M, b_rhs, 1.0, 1.0, 2.0, 0, nx, ny, nz, np.ones(ntot), model, model, 0, True)
+    M.finalize()
+    b = M.mult_vector(np.arange(1, ntot + 1, dtype=np.float64))
+    for i in range(ntot):
+        assert comparable(b[i], float(i + 1), TOL), i
+
+
+@pytest.mark.parametrize("der_type", [1, 2])
+def test_ref_golden_cross_gradient_457904(oracle, der_type):
+    """test_cross_gradient_calculate (tests_inversion.f90:143-253): 457904 stored elements (:244-246); the device-built
+    CSR is also bit-identical to the oracle's on this case."""
+    from tests.test_oracle_ref_goldens_cons import CG_GOLDEN_NNZ, cross_gradient_case
+    nx, ny, nz, n, m1, m2 = cross_gradient_case()
+    one = np.ones(n)
+    dX, dY, dZ = np.ones(nx), np.ones(ny), np.ones(nz)
+    Sg = tfx.SparseMatrix(3 * n, 2 * n, 8 * 3 * n)
+    bg = np.zeros(3 * n)
+    tfx.cross_gradient_calculate(Sg, bg, nx, ny, nz, dX, dY, dZ, m1, m2, one, one, der_type, 1.0)
+    Sg.finalize()
+    assert Sg.get_number_elements() == CG_GOLDEN_NNZ
+    So = oracle.SparseMatrix(3 * n, 2 * n, 8 * 3 * n)
+    bo = np.zeros(3 * n)
+    oracle.cross_gradient_calculate(So, bo, nx, ny, nz, dX, dY, dZ, 0, n, m1, m2, one, one, der_type, 1.0)
+    So.finalize()
+    _same_matrix(Sg, So)
+    assert np.array_equal(bg, bo)
