@@ -167,7 +167,7 @@ def workload_name(a):
 
 def run_ours(a):
     import tomofastx_b200 as tfx
-    from tests.synth import depth_weight_type1, regular_grid, station_lattice
+    from tomofastx_b200.synth import depth_weight_type1, regular_grid, station_lattice
 
     d = Dist()
     tfx.init(d.local_rank)
@@ -345,7 +345,7 @@ def compressed_spmv(a, tfx, d):
     products (tfx_sparse_matrix_time_product); the matrix (2 x 12.6 GB) is far larger than L2.
     With N > 1 ranks: rows are assembled sharded by data, re-partitioned over NVLink to nnz-balanced column
     slabs (csrc/sensit_dist.cu) and every figure is the whole-job aggregate (total bytes / max time over ranks)."""
-    from tests.synth import depth_weight_type1, regular_grid, station_lattice
+    from tomofastx_b200.synth import depth_weight_type1, regular_grid, station_lattice
     # weak scaling: the number of stations grows with the number of GPUs, so every GPU keeps a slab of the same nnz
     # (2 x 12.6 GB in the T16 layouts) -- a per-GPU fraction of the HBM peak means something only at that size
     nx, ny, nz = (a.comp_grid if a.comp_grid else (a.nx, a.ny, a.nz))

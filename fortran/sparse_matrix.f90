@@ -109,14 +109,14 @@ pure subroutine sparse_matrix_mult_vector(this, x, b)
   class(t_sparse_matrix), intent(in) :: this
   real(kind=CUSTOM_REAL), intent(in) :: x(:)
   real(kind=CUSTOM_REAL), intent(out) :: b(:)
-  call tfx_ignore(tfx_sparse_matrix_mult_vector(this%handle, x, b))
+  call tfx_sparse_matrix_mult_vector_v(this%handle, x, b)
 end subroutine sparse_matrix_mult_vector
 
 pure subroutine sparse_matrix_add_mult_vector(this, x, b)
   class(t_sparse_matrix), intent(in) :: this
   real(kind=CUSTOM_REAL), intent(in) :: x(:)
   real(kind=CUSTOM_REAL), intent(inout) :: b(:)
-  call tfx_ignore(tfx_sparse_matrix_add_mult_vector(this%handle, x, b))
+  call tfx_sparse_matrix_add_mult_vector_v(this%handle, x, b)
 end subroutine sparse_matrix_add_mult_vector
 
 subroutine sparse_matrix_part_mult_vector(this, nelements, x, ndata, b, line_start, param_shift, myrank)
@@ -132,14 +132,14 @@ pure subroutine sparse_matrix_trans_mult_vector(this, x, b)
   class(t_sparse_matrix), intent(in) :: this
   real(kind=CUSTOM_REAL), intent(in) :: x(:)
   real(kind=CUSTOM_REAL), intent(out) :: b(:)
-  call tfx_ignore(tfx_sparse_matrix_trans_mult_vector(this%handle, x, b))
+  call tfx_sparse_matrix_trans_mult_vector_v(this%handle, x, b)
 end subroutine sparse_matrix_trans_mult_vector
 
 pure subroutine sparse_matrix_add_trans_mult_vector(this, x, b)
   class(t_sparse_matrix), intent(in) :: this
   real(kind=CUSTOM_REAL), intent(in) :: x(:)
   real(kind=CUSTOM_REAL), intent(inout) :: b(:)
-  call tfx_ignore(tfx_sparse_matrix_add_trans_mult_vector(this%handle, x, b))
+  call tfx_sparse_matrix_add_trans_mult_vector_v(this%handle, x, b)
 end subroutine sparse_matrix_add_trans_mult_vector
 
 subroutine sparse_matrix_normalize_columns(this, column_norm)

@@ -50,6 +50,11 @@ module tfx_c_api
       type(c_ptr) :: msg
     end function
 
+    function tfx_take_latched_error() bind(C, name="tfx_take_latched_error") result(rc)
+      import :: c_int
+      integer(c_int) :: rc
+    end function
+
     function tfx_comm_unique_id(id) bind(C, name="tfx_comm_unique_id") result(rc)
       import :: c_int, c_char
       character(kind=c_char), intent(out) :: id(128)
@@ -132,23 +137,22 @@ module tfx_c_api
       integer(c_int) :: rc
     end function
 
-    ! The reference declares the products `pure` (sparse_matrix.f90:298,313,373,388); so are these.
-    pure function tfx_sparse_matrix_mult_vector(m, x, b) bind(C, name="tfx_sparse_matrix_mult_vector") result(rc)
-      import :: c_int, c_double, c_ptr
+    ! The reference declares the products `pure` (sparse_matrix.f90:298,313,373,388). A pure FUNCTION may not have an
+    ! intent(inout) dummy (F2008 C1276), a pure SUBROUTINE may: the void C variants (include/tfx.h) latch their return
+    ! code inside the library and tfx_check() collects it at the next non-pure call.
+    pure subroutine tfx_sparse_matrix_mult_vector_v(m, x, b) bind(C, name="tfx_sparse_matrix_mult_vector_v")
+      import :: c_double, c_ptr
       type(c_ptr), value :: m
       real(c_double), intent(in) :: x(*)
       real(c_double), intent(inout) :: b(*)
-      integer(c_int) :: rc
-    end function
+    end subroutine
 
-    pure function tfx_sparse_matrix_add_mult_vector(m, x, b) &
-        bind(C, name="tfx_sparse_matrix_add_mult_vector") result(rc)
-      import :: c_int, c_double, c_ptr
+    pure subroutine tfx_sparse_matrix_add_mult_vector_v(m, x, b) bind(C, name="tfx_sparse_matrix_add_mult_vector_v")
+      import :: c_double, c_ptr
       type(c_ptr), value :: m
       real(c_double), intent(in) :: x(*)
       real(c_double), intent(inout) :: b(*)
-      integer(c_int) :: rc
-    end function
+    end subroutine
 
     function tfx_sparse_matrix_part_mult_vector(m, nelements, x, ndata, b, line_start, param_shift, myrank) &
         bind(C, name="tfx_sparse_matrix_part_mult_vector") result(rc)
@@ -160,23 +164,19 @@ module tfx_c_api
       integer(c_int) :: rc
     end function
 
-    pure function tfx_sparse_matrix_trans_mult_vector(m, x, b) &
-        bind(C, name="tfx_sparse_matrix_trans_mult_vector") result(rc)
-      import :: c_int, c_double, c_ptr
+    pure subroutine tfx_sparse_matrix_trans_mult_vector_v(m, x, b) bind(C, name="tfx_sparse_matrix_trans_mult_vector_v")
+      import :: c_double, c_ptr
       type(c_ptr), value :: m
       real(c_double), intent(in) :: x(*)
       real(c_double), intent(inout) :: b(*)
-      integer(c_int) :: rc
-    end function
+    end subroutine
 
-    pure function tfx_sparse_matrix_add_trans_mult_vector(m, x, b) &
-        bind(C, name="tfx_sparse_matrix_add_trans_mult_vector") result(rc)
-      import :: c_int, c_double, c_ptr
+    pure subroutine tfx_sparse_matrix_add_trans_mult_vector_v(m, x, b) bind(C, name="tfx_sparse_matrix_add_trans_mult_vector_v")
+      import :: c_double, c_ptr
       type(c_ptr), value :: m
       real(c_double), intent(in) :: x(*)
       real(c_double), intent(inout) :: b(*)
-      integer(c_int) :: rc
-    end function
+    end subroutine
 
     function tfx_sparse_matrix_normalize_columns(m, column_norm) &
         bind(C, name="tfx_sparse_matrix_normalize_columns") result(rc)
@@ -513,22 +513,21 @@ contains
     integer, intent(in) :: myrank
     character(kind=c_char), pointer :: cmsg(:)
     character(len=512) :: msg
+    integer(c_int) :: code
     integer :: i
 
-    if (rc == 0) return
+    ! A product called from a `pure` procedure cannot stop the run: its failure is latched in the library and
+    ! reported here, by the next non-pure call (it comes first: it happened first).
+    code = tfx_take_latched_error()
+    if (code == 0) code = rc
+    if (code == 0) return
     msg = ""
     call c_f_pointer(tfx_last_error(), cmsg, [512])
     do i = 1, 512
       if (cmsg(i) == c_null_char) exit
       msg(i:i) = cmsg(i)
     enddo
-    call exit_MPI(trim(msg), myrank, int(rc))
+    call exit_MPI(trim(msg), myrank, int(code))
   end subroutine tfx_check
-
-  ! `pure` callers cannot stop the run; they record the code and the next non-pure call reports it.
-  pure subroutine tfx_ignore(rc)
-    integer(c_int), intent(in) :: rc
-    if (rc /= 0) error stop "libtfx: product failed (see tfx_last_error)"
-  end subroutine tfx_ignore
 
 end module tfx_c_api

@@ -98,6 +98,17 @@ int tfx_sparse_matrix_part_mult_vector(tfx_matrix *m, int32_t nelements, const d
                                        int32_t myrank);                        /* :335-367 */
 int tfx_sparse_matrix_trans_mult_vector(tfx_matrix *m, const double *x, double *b);          /* :373-382 */
 int tfx_sparse_matrix_add_trans_mult_vector(tfx_matrix *m, const double *x, double *b);      /* :388-405 */
+/* The reference declares the four products `pure` (sparse_matrix.f90:298,313,373,388). A Fortran 2008 pure procedure may
+ * only call pure procedures, and a pure FUNCTION may not have intent(out/inout) dummies (C1276), so the shim binds these
+ * void variants as `pure subroutine`s: same products, the return code is LATCHED inside the library (first failure wins,
+ * with its message) and handed to the next non-pure call through tfx_take_latched_error() -- fortran/tfx_c_api.f90
+ * tfx_check() asks for it on every call, so a failed product aborts the run at the next library call. */
+void tfx_sparse_matrix_mult_vector_v(tfx_matrix *m, const double *x, double *b);
+void tfx_sparse_matrix_add_mult_vector_v(tfx_matrix *m, const double *x, double *b);
+void tfx_sparse_matrix_trans_mult_vector_v(tfx_matrix *m, const double *x, double *b);
+void tfx_sparse_matrix_add_trans_mult_vector_v(tfx_matrix *m, const double *x, double *b);
+/* Returns the latched code (0 = none) and clears it; tfx_last_error() then holds the latched message. */
+int tfx_take_latched_error(void);
 int tfx_sparse_matrix_normalize_columns(tfx_matrix *m, double *column_norm);    /* :414-443 (host builder) */
 int32_t tfx_sparse_matrix_get_total_row_number(const tfx_matrix *m);           /* :448-453 */
 int32_t tfx_sparse_matrix_get_current_row_number(const tfx_matrix *m);         /* :458-463 */

@@ -98,3 +98,50 @@ def test_blocked_matrix_row_count_is_checked(blocks_on):
     tfx.sensit_repartition_into(S, rows, 1, np.array([pb.N], dtype=np.int32))
     with pytest.raises(tfx.TfxError, match="total number of rows"):
         S.finalize()
+
+
+@pytest.mark.parametrize("t16", [False, True])
+def test_joint_blocked_matrix_part_products(blocks_on, t16):
+    """Joint matrix_sensit built from row blocks: the blocks of problem 1 hold columns 1..N, those of problem 2 columns
+    N+1..2N (sensitivity_gravmag.F90:685-686). part_mult_vector / calculate_data of one problem (model.F90:288: line_start,
+    param_shift of that problem, x of nelements) must only touch that problem's blocks -- the other problem's columns lie
+    outside x (out-of-bounds read through x[col - param_shift])."""
+    g = make_problem(nx=10, ny=8, nz=5, ndata=9, compression_type=1, rate=0.25, problem_type=1)
+    m = make_problem(nx=10, ny=8, nz=5, ndata=7, compression_type=1, rate=0.25, problem_type=2, nmodel_components=1)
+    N = g.N
+    m.par.param_shift = N
+    m.par.ncolumns = g.par.ncolumns = 2 * N
+    nel_at = np.array([N], dtype=np.int32)
+    mats = []
+    for blocked in (False, True):
+        tfx.set_option("sensit_row_blocks", 1 if blocked else 0)
+        tfx.set_option("t16_min_nnz", 0 if t16 else 1 << 22)
+        S = tfx.SparseMatrix(g.ndata + m.ndata, 2 * N, 2 * int(0.25 * N) * (g.ndata + m.ndata))
+        for slot, pb, batches in ((1, g, [4, 5]), (2, m, [3, 4])):
+            x, y, z = pb.data_xyz
+            d0 = 0
+            for n in (batches if blocked else [pb.ndata]):
+                sl = slice(d0, d0 + n)
+                rows, _, _, _ = tfx.sensit_assemble_rows(_batch_par(pb, n), pb.grid, (x[sl], y[sl], z[sl]), pb.cw, pb.dw[sl])
+                tfx.sensit_repartition_into(S, rows, slot, nel_at)
+                d0 += n
+        S.finalize()
+        mats.append(S)
+    S1, Sb = mats
+    assert Sb.get_number_elements() == S1.get_number_elements()
+    rng = np.random.default_rng(11)
+    for line_start, nd, shift in ((1, g.ndata, 0), (g.ndata + 1, m.ndata, N), (3, 4, 0), (g.ndata + 2, 3, N)):
+        xm = rng.standard_normal(N)
+        want = S1.part_mult_vector(xm, nd, line_start, shift)
+        got = Sb.part_mult_vector(xm, nd, line_start, shift)
+        assert np.all(np.isfinite(got)) and np.abs(want).max() > 0
+        assert np.allclose(got, want, rtol=1e-13, atol=1e-300)
+    for pb, line_start, shift in ((g, 1, 0), (m, g.ndata + 1, N)):
+        ct = pb.par.compression_type
+        d1 = tfx.calculate_data(S1, pb.m_true, pb.ndata, 1, 1.0, pb.cw, pb.dw, ct, pb.nx, pb.ny, pb.nz, line_start, shift)
+        db = tfx.calculate_data(Sb, pb.m_true, pb.ndata, 1, 1.0, pb.cw, pb.dw, ct, pb.nx, pb.ny, pb.nz, line_start, shift)
+        assert np.abs(d1).max() > 0 and np.allclose(db, d1, rtol=1e-13, atol=1e-300)
+    if t16:
+        # a window that spans both problems cannot be served from one nelements-sized x: loud error, no wild read
+        with pytest.raises(tfx.TfxError, match="outside"):
+            Sb.part_mult_vector(rng.standard_normal(N), g.ndata + 2, 1, 0)

@@ -703,6 +703,30 @@ int tfx_sparse_matrix_add_mult_vector(tfx_matrix *h, const double *x, double *b)
 int tfx_sparse_matrix_trans_mult_vector(tfx_matrix *h, const double *x, double *b) { return product(h->m, x, b, false, true); }
 int tfx_sparse_matrix_add_trans_mult_vector(tfx_matrix *h, const double *x, double *b) { return product(h->m, x, b, true, true); }
 
+// `pure` Fortran callers (see include/tfx.h): the code of the first failed product is kept with its message until a
+// non-pure call collects it.
+static int g_latched_rc = 0;
+static std::string g_latched_msg;
+static void latch(int rc) {
+  if (rc != 0 && g_latched_rc == 0) {
+    g_latched_rc = rc;
+    g_latched_msg = g_err;
+  }
+}
+void tfx_sparse_matrix_mult_vector_v(tfx_matrix *h, const double *x, double *b) { latch(product(h->m, x, b, false, false)); }
+void tfx_sparse_matrix_add_mult_vector_v(tfx_matrix *h, const double *x, double *b) { latch(product(h->m, x, b, true, false)); }
+void tfx_sparse_matrix_trans_mult_vector_v(tfx_matrix *h, const double *x, double *b) { latch(product(h->m, x, b, false, true)); }
+void tfx_sparse_matrix_add_trans_mult_vector_v(tfx_matrix *h, const double *x, double *b) { latch(product(h->m, x, b, true, true)); }
+int tfx_take_latched_error(void) {
+  const int rc = g_latched_rc;
+  if (rc != 0) {
+    g_err = g_latched_msg;
+    g_latched_rc = 0;
+    g_latched_msg.clear();
+  }
+  return rc;
+}
+
 int tfx_sparse_matrix_part_mult_vector(tfx_matrix *h, int32_t nelements, const double *x, int32_t ndata, double *b,
                                        int32_t line_start, int32_t param_shift, int32_t myrank) {
   (void)myrank;
@@ -717,11 +741,29 @@ int tfx_sparse_matrix_part_mult_vector(tfx_matrix *h, int32_t nelements, const d
   TFX_TRY(vx.bind(const_cast<double *>(x), (size_t)nelements, true));
   TFX_TRY(vb.bind(b, (size_t)ndata, false));
   if (m.has_blocks) {
-    // all rows of the blocks (x read at column - param_shift), then the requested window
+    // Only the row blocks that intersect the requested window are multiplied: in a joint matrix the blocks of the other
+    // problem hold columns outside [param_shift, param_shift + nelements) and must not be read through x.
     DevBuf<double> full;
-    TFX_TRY(full.alloc((size_t)m.nl));
-    TFX_TRY(matrix_fwd(m, vx.dev, full.p, false, param_shift, nullptr, st));
-    TFX_CUDA(cudaMemcpyAsync(vb.dev, full.p + (line_start - 1), (size_t)ndata * 8, cudaMemcpyDeviceToDevice, st));
+    TFX_CUDA(cudaMemsetAsync(vb.dev, 0, (size_t)ndata * 8, st));
+    for (size_t bi = 0; bi < m.blocks.size(); ++bi) {
+      Matrix &B = *m.blocks[bi];
+      const int32_t r0 = m.block_row0[bi];
+      const int32_t lo = std::max(r0, line_start - 1), hi = std::min(r0 + B.nl, line_end);
+      if (lo >= hi) continue;
+      double *dst = vb.dev + (lo - (line_start - 1));
+      if (B.has_t16) {
+        if (B.t16f.in0 < param_shift || (int64_t)B.t16f.in0 - param_shift + B.t16f.nin > nelements)
+          return fail(-24, "part_mult_vector: a row block inside the requested lines holds columns outside "
+                           "[param_shift, param_shift + nelements)");
+        TFX_TRY(full.alloc((size_t)B.nl));
+        TFX_TRY(t16_spmv(B.t16f, vx.dev, full.p, false, param_shift, nullptr, st));
+        TFX_CUDA(cudaMemcpyAsync(dst, full.p + (lo - r0), (size_t)(hi - lo) * 8, cudaMemcpyDeviceToDevice, st));
+      } else if (B.has_seg) {
+        TFX_TRY(seg_spmv(B.fwd, vx.dev, dst, false, lo - r0, hi - r0, param_shift, nullptr, st));
+      } else {
+        return fail(-21, "sparse_matrix: row block without a device representation");
+      }
+    }
     TFX_CUDA(cudaStreamSynchronize(st));
   } else if (m.has_t16 && m.t16f.in0 >= param_shift && m.t16f.in0 - param_shift + m.t16f.nin <= nelements) {
     // all rows through the F layout (x read at column - param_shift), then the requested window
