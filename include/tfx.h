@@ -226,6 +226,10 @@ int tfx_admm_iterate_admm_arrays(int32_t nelements, int32_t nlithos, const doubl
 /* ---- module lsqr_solver (src/inversion/lsqr_solver2.F90) --------------------------------------- */
 int tfx_lsqr_solve(int32_t nlines, int32_t nelements, int32_t niter, double rmin, double gamma,
                    tfx_matrix *matrix, double *u, double *x, int32_t myrank);                    /* :321-473 */
+/* u (the right-hand side b_RHS on entry) is the solver's work array and is destroyed, like in the reference. With
+ * nbproc > 1 a HOST u is read and written back only on the data rows and on this rank's constraint rows (the rows of
+ * matrix_cons it stores, the rows shared with a neighbouring slab, on rank 0 also the rows stored nowhere); a HOST x only
+ * on the columns of the problems being solved (zero elsewhere). */
 int tfx_lsqr_solve_sensit(int32_t nlines, int32_t ncolumns, int32_t niter, double rmin, double gamma,
                           double target_misfit, tfx_matrix *matrix_sensit, tfx_matrix *matrix_cons,
                           double *u, double *x, const int32_t solve_problem[2], int32_t nelements,
@@ -236,6 +240,10 @@ int tfx_lsqr_solve_sensit(int32_t nlines, int32_t ncolumns, int32_t niter, doubl
  * prints the final one, :302-306), number of executed iterations, 1 if the fused single-sweep path
  * ran. r_hist may be NULL. */
 int tfx_lsqr_last_history(double *r_hist, int32_t capacity, int32_t *iters, int32_t *fused);
+/* Loop bodies executed by the last solve and the iteration count the reference prints (`iter - 1`, :302-306 / :467):
+ * they differ by one only when lsqr_solve leaves through its small-rhobar exit, which sits before `iter = iter + 1`
+ * (:459-465; lsqr_solve_sensit checks after it, :281-289). */
+int tfx_lsqr_last_iterations(int32_t *executed, int32_t *reported);
 /* Device time of the last solve measured with CUDA events on the library's stream: the iteration loop
  * (excluding the initialisation before the reference's `do while`, lsqr_solver2.F90:120-157) and, with
  * option "profile_sweeps" = 1, the summed duration / count of the fused sweep kernel launches. */

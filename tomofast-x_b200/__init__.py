@@ -391,6 +391,13 @@ def last_history():
     return h[:it.value], it.value, bool(fused.value)
 
 
+def last_iterations():
+    """(executed, reported): loop bodies executed and the `iter - 1` the reference prints."""
+    a, b = C.c_int32(0), C.c_int32(0)
+    _check(lib().tfx_lsqr_last_iterations(C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
 def last_timing():
     """(loop_ms, sweep_ms, nsweeps) of the last solve, CUDA-event timed on the library stream."""
     a, b, n = C.c_double(0), C.c_double(0), C.c_int32(0)

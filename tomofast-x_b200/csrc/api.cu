@@ -356,6 +356,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_lsqr_graph = value;
     return 0;
   }
+  if (name && strcmp(name, "lsqr_poll") == 0) {
+    g_opt_lsqr_poll = value;
+    return 0;
+  }
   if (name && strcmp(name, "strict_order") == 0) {
     g_opt_strict_order = value;
     return 0;
@@ -868,14 +872,17 @@ int tfx_iDaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3) { return wavele
 // ---- lsqr_solver --------------------------------------------------------------------------------
 static LsqrResult g_last;
 
-static int lsqr_call(const LsqrParams &p, tfx_matrix *S, tfx_matrix *C, double *u, double *x) {
+static int lsqr_call(const LsqrParams &p0, tfx_matrix *S, tfx_matrix *C, double *u, double *x) {
   TFX_TRY(ensure_init());
+  // Host vectors are staged in pooled device buffers; the solver itself copies what it needs (the data rows and this
+  // rank's constraint rows of u, the active problems' columns of x) in and out -- not the whole vectors.
   VecIO vu, vx;
-  TFX_TRY(vu.bind(u, (size_t)p.nlines, true));
-  TFX_TRY(vx.bind(x, (size_t)p.ncolumns, false));
+  TFX_TRY(vu.bind(u, (size_t)p0.nlines, false));
+  TFX_TRY(vx.bind(x, (size_t)p0.ncolumns, false));
+  LsqrParams p = p0;
+  p.host_u = vu.host;
+  p.host_x = vx.host;
   TFX_TRY(lsqr_run(p, &S->m, C ? &C->m : nullptr, vu.dev, vx.dev, g_last));
-  TFX_TRY(vu.copy_back());   // the reference destroys u (it is the solver's work array)
-  TFX_TRY(vx.copy_back());
   TFX_CUDA(cudaStreamSynchronize(ctx().stream));
   return 0;
 }
@@ -947,6 +954,12 @@ int tfx_lsqr_last_timing(double *loop_ms, double *sweep_ms, int32_t *nsweeps) {
   if (loop_ms) *loop_ms = g_last.loop_ms;
   if (sweep_ms) *sweep_ms = g_last.sweep_ms;
   if (nsweeps) *nsweeps = g_last.nsweeps;
+  return 0;
+}
+
+int tfx_lsqr_last_iterations(int32_t *executed, int32_t *reported) {
+  if (executed) *executed = g_last.iters;
+  if (reported) *reported = g_last.reported_iters;
   return 0;
 }
 

@@ -88,6 +88,13 @@ int comm_allreduce_sum_i32(int32_t *d_buf, size_t count, cudaStream_t st) {
   ncclResult_t r = n.AllReduce(d_buf, d_buf, count, ncclInt32, ncclSum, n.comm, st);
   return r == ncclSuccess ? 0 : nccl_fail("ncclAllReduce", r);
 }
+// Per-row count of ranks holding entries of a constraint row (lsqr.cu build_plan): small integers, one byte each.
+int comm_allreduce_sum_u8(uint8_t *d_buf, size_t count, cudaStream_t st) {
+  Nccl &n = N();
+  if (!n.comm || n.nranks <= 1) return 0;
+  ncclResult_t r = n.AllReduce(d_buf, d_buf, count, ncclUint8, ncclSum, n.comm, st);
+  return r == ncclSuccess ? 0 : nccl_fail("ncclAllReduce", r);
+}
 int comm_allreduce_sum_i64(int64_t *d_buf, size_t count, cudaStream_t st) {
   Nccl &n = N();
   if (!n.comm || n.nranks <= 1) return 0;

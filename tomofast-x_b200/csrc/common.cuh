@@ -125,6 +125,12 @@ struct LsqrScalars {
   int executed;         // loop bodies executed
   int was_active;       // the iteration whose scalars were just computed was live (done was 0 before)
   int do_update;        // x/w update of that iteration must be applied (rho != 0)
+  // Deferred normalisation (split path): the solver keeps uhat = beta*u and vhat = alpha*v and folds the factors into
+  // the next update instead of rescaling the vectors (S(vhat/alpha) = (S vhat)/alpha, S^T(uhat/beta) = (S^T uhat)/beta).
+  double su;            // u = su * uhat  (1/beta, 1 when beta == 0)
+  double sv;            // v = sv * vhat  (1/alpha, 1 when alpha == 0)
+  double cu, cq;        // next u update: uhat = cu*uhat + cq*q
+  double cv;            // next v update: vhat = cv*vhat + su*v2
 };
 
 // ---------------------------------------------------------------------------------------------

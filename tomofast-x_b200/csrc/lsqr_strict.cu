@@ -206,13 +206,19 @@ int lsqr_run_strict(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, doub
     ks_xw<<<vgrid(ncol), 256, 0, st>>>(d_x, w, v, ncol, t1, t2, p.gamma); c.launches++;
     r = phibar / b1;
     res.history.push_back(r);
-    iter += 1;
-    if (fabs(rhobar) < (double)1.e-30f) break;
+    if (p.single_matrix) {   // lsqr_solve: the small-rhobar exit sits before iter = iter + 1 (:459-465)
+      if (fabs(rhobar) < (double)1.e-30f) break;
+      iter += 1;
+    } else {                 // lsqr_solve_sensit: after it (:281-289)
+      iter += 1;
+      if (fabs(rhobar) < (double)1.e-30f) break;
+    }
   }
   (void)mis;
   TFX_CUDA(cudaStreamSynchronize(st));
   TFX_CUDA(cudaGetLastError());
   res.iters = (int32_t)res.history.size();
+  res.reported_iters = iter - 1;
   res.r = r;
   return 0;
 }

@@ -107,10 +107,14 @@ struct LsqrParams {
   bool wavelet_domain = true;
   int32_t myrank = 0, nbproc = 1;
   bool single_matrix = false;   // lsqr_solve (tests): no constraint matrix, no wavelet
+  // Caller's host vectors (null when the caller passed device memory): the solver copies only the rows of u and the
+  // columns of x it works on (data rows + this rank's constraint rows; the active problems' columns).
+  double *host_u = nullptr, *host_x = nullptr;
 };
 
 struct LsqrResult {
-  int32_t iters = 0;      // loop bodies executed (the reference prints iter - 1)
+  int32_t iters = 0;      // loop bodies executed
+  int32_t reported_iters = 0;   // the reference's printed `iter - 1` (one less than iters on lsqr_solve's small-rhobar exit)
   int32_t status = 0;     // 0 ok, 1: |b| = 0
   double r = 1.0;
   bool fused = false;
@@ -125,6 +129,8 @@ extern int g_opt_strict_order;
 extern int g_opt_profile_sweeps;
 // Option "lsqr_graph": 1 (default) replays the split-path iteration body as a CUDA graph for small matrices.
 extern int g_opt_lsqr_graph;
+// Option "lsqr_poll": iterations between two reads of the device-side done flag (default 8).
+extern int g_opt_lsqr_poll;
 
 int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x, LsqrResult &res);
 int lsqr_run_strict(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x, LsqrResult &res);
@@ -142,6 +148,7 @@ int wavelet_slab_device(double *d_slab, int64_t nelements, int64_t nsmaller, int
                         bool forward, cudaStream_t st);
 int comm_allreduce_sum(double *d_buf, size_t count, cudaStream_t st);
 int comm_allreduce_sum_i32(int32_t *d_buf, size_t count, cudaStream_t st);
+int comm_allreduce_sum_u8(uint8_t *d_buf, size_t count, cudaStream_t st);
 int comm_allreduce_sum_i64(int64_t *d_buf, size_t count, cudaStream_t st);
 int comm_allgather_i64(const int64_t *d_send, int64_t *d_recv, size_t count, cudaStream_t st);
 int comm_alltoallv_4b(const void *d_send, const int64_t *send_off, void *d_recv, const int64_t *recv_off,
