@@ -35,6 +35,10 @@ const char *tfx_last_error(void);
 /* Selects the GPU of this rank (device < 0: LOCAL_RANK env or 0) and creates the stream.
  * Replaces nothing in the reference (MPI_Init stays in program_tomofastx.F90:56). */
 int         tfx_init(int device);
+/* Stream ordering: the library works on its own NON-BLOCKING CUDA stream and every entry point returns after that
+ * stream has drained, so a host program (the Fortran reference: single-threaded, blocking) needs nothing. A caller that
+ * hands over DEVICE pointers written by its own streams (another library, torch) must finish that work first
+ * (cudaStreamSynchronize / cudaDeviceSynchronize): the library does not wait for foreign streams. */
 int         tfx_finalize(void);
 int         tfx_device_synchronize(void);
 /* Number of GPU kernels launched by the library so far (bench.py's gpu_launches). */
@@ -48,6 +52,9 @@ int         tfx_timer_stop(double *ms);
  * "profile_sweeps" (1: CUDA events around every fused sweep launch);
  * "t16_min_nnz" (matrices with at least this many entries get the T16 layouts; default 4194304);
  * "t16_tile" (0: automatic tile size, else a power of two <= 16384 -- tests);
+ * "lsqr_poll" (iterations between two reads of the device-side done flag, default 8);
+ * "wavelet_cols" (1, default: column-layout wavelet kernel where the axis fits its tile; 0: generic kernel);
+ * "wavelet_slab_mb" (size of the i3 slabs of the L2-blocked axis-1 / axis-2 passes, 0: whole volume per pass);
  * "lsqr_graph" (1, default: the iteration body of the split LSQR path is captured once and replayed as a CUDA graph
  *   when the matrix has fewer than 2e8 entries -- the launch-bound regime);
  * "t16_bank_deal" (1, default: the T16 builder deals the entries of long segments over the shared-memory banks);

@@ -1,18 +1,25 @@
-"""Timing of the 3-D wavelet transforms on a device-resident volume. Usage: python scratch/wavelet_time.py nx ny nz"""
-import os, sys
+"""Times the 3-D wavelet transforms on device-resident volumes (CUDA events on the library stream)."""
+import sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ".")
 import tomofastx_b200 as tfx
-nx, ny, nz = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (256, 256, 64)
-N = nx * ny * nz
+
 tfx.init(0)
-vol = tfx.Buffer(N)
-tfx.copy(vol, np.random.default_rng(0).uniform(-1, 1, N), N)
-for wname, wtype in (("haar", 1), ("d4", 2)):
-    for _ in range(2):
-        tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)
-    tfx.timer_start()
-    for _ in range(10):
-        tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)
-    ms = tfx.timer_stop() / 20.0
-    print("%dx%dx%d %-5s %.4f ms per transform  %.0f GB/s (16 B/element)" % (nx, ny, nz, wname, ms, 16.0 * N / ms / 1e6))
+rng = np.random.default_rng(0)
+for (nx, ny, nz) in ((256, 256, 64), (512, 512, 128), (1024, 1024, 128)):
+    N = nx * ny * nz
+    vol = tfx.Buffer(N)
+    tfx.copy(vol, rng.uniform(-1, 1, N), N)
+    for slab, tile in ((0, 0), (32, 0), (64, 0), (100, 0)):
+        tfx.set_option("wavelet_slab_mb", slab)
+        tfx.set_option("wavelet_tile_kb", tile)
+        for wname, wtype in (("haar", 1), ("d4", 2)):
+            for _ in range(2):
+                tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)
+            tfx.timer_start()
+            for _ in range(5):
+                tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)
+            ms = tfx.timer_stop() / 10.0
+            print("%dx%dx%d slab=%2d MB tile=%d KB %-4s %.4f ms/transform  %.0f GB/s at 16 B/elem (%.3f of 6456)" %
+                  (nx, ny, nz, slab, tile, wname, ms, 16.0 * N / ms / 1e6, 16.0 * N / ms / 1e6 / 6456), flush=True)
+    del vol

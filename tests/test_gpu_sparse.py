@@ -163,5 +163,6 @@ def test_device_pointer_vectors(oracle):
     x = rng.standard_normal(800)
     xd = torch.from_numpy(x).cuda()
     bd = torch.zeros(50, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()              # libtfx runs on its own non-blocking stream: order torch's work first
     mg.mult_vector(xd, bd)
     assert np.allclose(bd.cpu().numpy(), mo.mult_vector(x), rtol=1e-12, atol=1e-12)

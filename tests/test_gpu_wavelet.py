@@ -10,12 +10,21 @@ from tests.conftest import TOL, comparable
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(3, 4, 5), (10, 11, 12), (2, 128, 32), (67, 67, 30), (1, 1, 7), (5, 1, 1), (1, 9, 1), (64, 64, 16),
-          (33, 17, 65), (256, 3, 2), (2, 2, 2), (1, 1, 1), (130, 70, 9)]
+          (33, 17, 65), (256, 3, 2), (2, 2, 2), (1, 1, 1), (130, 70, 9), (20, 300, 33), (600, 40, 18), (16, 16, 1030)]
+
+
+@pytest.fixture(params=[1, 0], ids=["cols", "generic"])
+def kernel_choice(request):
+    """Both kernels of wavelet.cu: the column-layout kernel (default where the axis fits its tile) and the generic
+    (line, pair) kernel every other shape falls back to."""
+    tfx.set_option("wavelet_cols", request.param)
+    yield request.param
+    tfx.set_option("wavelet_cols", 1)
 
 
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("wtype", [1, 2])
-def test_forward_inverse_bit_exact(oracle, shape, wtype):
+def test_forward_inverse_bit_exact(oracle, shape, wtype, kernel_choice):
     n1, n2, n3 = shape
     rng = np.random.default_rng(1234 + n1 * 7 + n2 * 3 + n3)
     x = rng.standard_normal(n1 * n2 * n3)
@@ -49,9 +58,37 @@ def test_wavelet_diagonal_matrix_46656():
     nnz = 0
     for j in range(n):
         row = eye[j].clone()
+        torch.cuda.synchronize()          # libtfx runs on its own non-blocking stream: order torch's work first
         tfx.forward_wavelet(row, nx, ny, nz, 1)
         nnz += int(torch.count_nonzero(row).item())
     assert nnz == 46656
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 64), (512, 512, 16), (1024, 96, 40)])
+@pytest.mark.parametrize("wtype", [1, 2])
+def test_large_volume_kernels_agree_bit_for_bit(shape, wtype):
+    """At sizes the oracle does not visit in seconds: column-layout kernel (with and without the L2-blocked slabs) ==
+    generic kernel, bit for bit, forward and inverse."""
+    import torch
+    n1, n2, n3 = shape
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(n1 * n2 * n3, dtype=torch.float64, device="cuda", generator=g)
+    outs = []
+    try:
+        for cols, slab in ((0, 0), (1, 0), (1, 4)):
+            tfx.set_option("wavelet_cols", cols); tfx.set_option("wavelet_slab_mb", slab)
+            y = x.clone()
+            torch.cuda.synchronize()      # libtfx runs on its own non-blocking stream: order torch's work first
+            tfx.forward_wavelet(y, n1, n2, n3, wtype)
+            z = y.clone()
+            torch.cuda.synchronize()
+            tfx.inverse_wavelet(z, n1, n2, n3, wtype)
+            outs.append((y, z))
+    finally:
+        tfx.set_option("wavelet_cols", 1); tfx.set_option("wavelet_slab_mb", 0)
+    for y, z in outs[1:]:
+        assert torch.equal(y, outs[0][0]) and torch.equal(z, outs[0][1])
+    assert float((outs[0][1] - x).abs().max()) < 1e-11
 
 
 @pytest.mark.parametrize("wtype", [1, 2])
@@ -62,6 +99,7 @@ def test_norm_preserving_and_roundtrip_full_size(wtype):
     g = torch.Generator(device="cuda").manual_seed(5)
     x = torch.randn(n1 * n2 * n3, dtype=torch.float64, device="cuda", generator=g)
     y = x.clone()
+    torch.cuda.synchronize()              # libtfx runs on its own non-blocking stream: order torch's work first
     tfx.forward_wavelet(y, n1, n2, n3, wtype)
     assert comparable(float(torch.linalg.norm(x)), float(torch.linalg.norm(y)), 1e-12)
     tfx.inverse_wavelet(y, n1, n2, n3, wtype)

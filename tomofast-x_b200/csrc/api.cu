@@ -356,6 +356,18 @@ int tfx_set_option(const char *name, int value) {
     g_opt_lsqr_graph = value;
     return 0;
   }
+  if (name && strcmp(name, "wavelet_tile_kb") == 0) {
+    g_opt_wavelet_tile_kb = value;
+    return 0;
+  }
+  if (name && strcmp(name, "wavelet_cols") == 0) {
+    g_opt_wavelet_cols = value;
+    return 0;
+  }
+  if (name && strcmp(name, "wavelet_slab_mb") == 0) {
+    g_opt_wavelet_slab_mb = value;
+    return 0;
+  }
   if (name && strcmp(name, "lsqr_poll") == 0) {
     g_opt_lsqr_poll = value;
     return 0;

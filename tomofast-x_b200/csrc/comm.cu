@@ -28,6 +28,7 @@ struct Nccl {
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclComm_t comm = nullptr;
@@ -55,10 +56,11 @@ int load_nccl() {
   n.AllGather = (decltype(n.AllGather))dlsym(n.h, "ncclAllGather");
   n.Send = (decltype(n.Send))dlsym(n.h, "ncclSend");
   n.Recv = (decltype(n.Recv))dlsym(n.h, "ncclRecv");
+  n.Broadcast = (decltype(n.Broadcast))dlsym(n.h, "ncclBroadcast");
   n.GroupStart = (decltype(n.GroupStart))dlsym(n.h, "ncclGroupStart");
   n.GroupEnd = (decltype(n.GroupEnd))dlsym(n.h, "ncclGroupEnd");
   if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.AllReduce || !n.AllGather || !n.Send || !n.Recv ||
-      !n.GroupStart || !n.GroupEnd)
+      !n.GroupStart || !n.GroupEnd || !n.Broadcast)
     return fail(-61, "NCCL symbols missing");
   return 0;
 }
@@ -145,6 +147,44 @@ int comm_alltoallv_4b(const void *d_send, const int64_t *send_off, void *d_recv,
   }
   r = n.GroupEnd();
   return r == ncclSuccess ? 0 : nccl_fail("ncclGroupEnd", r);
+}
+
+// In-place all-gather of slabs of different lengths: rank r's slab already sits at d_full + offsets[r]
+// (offsets has nranks + 1 entries); one grouped ncclBroadcast per rank. Replaces get_full_array (MPI_Gatherv to
+// rank 0, parallel_tools.f90:147) + the scatter back: every GPU ends up with the whole vector, moving half the bytes of
+// the all-reduce-into-zeros it replaces.
+int comm_allgatherv_f64(double *d_full, const int64_t *offsets, cudaStream_t st) {
+  Nccl &n = N();
+  if (!n.comm || n.nranks <= 1) return 0;
+  ncclResult_t r = n.GroupStart();
+  if (r != ncclSuccess) return nccl_fail("ncclGroupStart", r);
+  for (int q = 0; q < n.nranks; ++q) {
+    const int64_t cnt = offsets[q + 1] - offsets[q];
+    if (cnt <= 0) continue;
+    r = n.Broadcast(d_full + offsets[q], d_full + offsets[q], (size_t)cnt, ncclDouble, q, n.comm, st);
+    if (r != ncclSuccess) { n.GroupEnd(); return nccl_fail("ncclBroadcast", r); }
+  }
+  r = n.GroupEnd();
+  return r == ncclSuccess ? 0 : nccl_fail("ncclGroupEnd", r);
+}
+
+// Slab lengths of all ranks as prefix offsets (nranks + 1 entries): one small all-gather + host read.
+int comm_slab_offsets(int64_t mine, std::vector<int64_t> &offsets) {
+  Nccl &n = N();
+  offsets.assign(2, 0);
+  offsets[1] = mine;
+  if (!n.comm || n.nranks <= 1) return 0;
+  cudaStream_t st = ctx().stream;
+  DevBuf<int64_t> d_mine, d_all;
+  TFX_TRY(d_mine.alloc(1)); TFX_TRY(d_all.alloc((size_t)n.nranks));
+  TFX_CUDA(cudaMemcpyAsync(d_mine.p, &mine, 8, cudaMemcpyHostToDevice, st));
+  TFX_TRY(comm_allgather_i64(d_mine.p, d_all.p, 1, st));
+  std::vector<int64_t> all((size_t)n.nranks);
+  TFX_CUDA(cudaMemcpyAsync(all.data(), d_all.p, all.size() * 8, cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  offsets.assign((size_t)n.nranks + 1, 0);
+  for (int r = 0; r < n.nranks; ++r) offsets[(size_t)r + 1] = offsets[(size_t)r] + all[(size_t)r];
+  return 0;
 }
 
 int comm_slab_offset(int64_t mine, int64_t *offset, int64_t *total) {

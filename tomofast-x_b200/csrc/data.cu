@@ -43,25 +43,37 @@ __global__ void __launch_bounds__(256) k_model_update(double *__restrict__ v, co
 }
 }  // namespace
 
-int wavelet_slab_device(double *d_slab, int64_t nelements, int64_t nsmaller, int nx, int ny, int nz, int wavelet_type,
-                        bool forward, cudaStream_t st) {
+// Every rank drops its slab at its place in a full volume, the slabs are all-gathered over NVLink (each GPU receives the
+// other ranks' cells once: half the bytes of an all-reduce into a zeroed volume, no additions), every GPU transforms the
+// identical volume and keeps its own cells: get_full_array + scatter_full_array (parallel_tools.f90:147,250) without the
+// rank-0 serial section, bit-identical to the serial transform.
+int wavelet_slab_device_off(double *d_slab, const std::vector<int64_t> &offsets, int nx, int ny, int nz, int wavelet_type,
+                            bool forward, cudaStream_t st) {
   const int64_t N = (int64_t)nx * ny * nz;
-  if (comm_nranks() <= 1) {
-    if (nelements != N) return fail(-24, "apply_wavelet_transform: nelements must equal nx*ny*nz on a single rank");
+  const int nranks = comm_nranks(), rank = comm_rank();
+  if (nranks <= 1) {
+    if (offsets.size() < 2 || offsets[1] - offsets[0] != N)
+      return fail(-24, "apply_wavelet_transform: nelements must equal nx*ny*nz on a single rank");
     return wavelet3d_device(d_slab, nx, ny, nz, wavelet_type, forward, st);
   }
-  if (nsmaller < 0 || nsmaller + nelements > N) return fail(-24, "apply_wavelet_transform: wrong slab position");
-  // Every rank drops its slab into a zeroed full volume; the sum over ranks is the concatenation (x + 0 is exact),
-  // every GPU transforms the identical volume and keeps its own cells: get_full_array + scatter_full_array
-  // (parallel_tools.f90:147,250) as one ncclAllReduce, no rank-0 serial section.
+  if ((int)offsets.size() != nranks + 1 || offsets[(size_t)nranks] != N)
+    return fail(-24, "apply_wavelet_transform: the ranks' nelements must add up to nx*ny*nz");
+  const int64_t nsmaller = offsets[(size_t)rank], nelements = offsets[(size_t)rank + 1] - nsmaller;
   DevBuf<double> &F = full_scratch();
   TFX_TRY(F.alloc((size_t)N));
-  TFX_CUDA(cudaMemsetAsync(F.p, 0, (size_t)N * 8, st));
   TFX_CUDA(cudaMemcpyAsync(F.p + nsmaller, d_slab, (size_t)nelements * 8, cudaMemcpyDeviceToDevice, st));
-  TFX_TRY(comm_allreduce_sum(F.p, (size_t)N, st));
+  TFX_TRY(comm_allgatherv_f64(F.p, offsets.data(), st));
   TFX_TRY(wavelet3d_device(F.p, nx, ny, nz, wavelet_type, forward, st));
   TFX_CUDA(cudaMemcpyAsync(d_slab, F.p + nsmaller, (size_t)nelements * 8, cudaMemcpyDeviceToDevice, st));
   return 0;
+}
+
+int wavelet_slab_device(double *d_slab, int64_t nelements, int64_t nsmaller, int nx, int ny, int nz, int wavelet_type,
+                        bool forward, cudaStream_t st) {
+  (void)nsmaller;
+  std::vector<int64_t> offsets;
+  TFX_TRY(comm_slab_offsets(nelements, offsets));
+  return wavelet_slab_device_off(d_slab, offsets, nx, ny, nz, wavelet_type, forward, st);
 }
 
 }  // namespace tfx

@@ -15,6 +15,10 @@ int wavelet3d_device(double *d_s, int n1, int n2, int n3, int wavelet_type, bool
 int wavelet3d_device_batch(double *d_s, int n1, int n2, int n3, long long nvol, int wavelet_type, bool forward,
                            cudaStream_t st);
 
+extern int g_opt_wavelet_slab_mb;
+extern int g_opt_wavelet_cols;
+extern int g_opt_wavelet_tile_kb;
+
 // ---- csr.cu -----------------------------------------------------------------------------------
 // A compressed-segment matrix view on the device. For the forward product it is the CSR of A
 // (segments = stored rows, idx = column); for the transposed product it is the CSR of A^T

@@ -549,12 +549,12 @@ int col_extent(Matrix &m, int64_t *lo, int64_t *hi) {
 // apply_wavelet_transform (src/inversion/wavelet_utils.F90:37-72): every active problem and component of
 // v(nelements, ncomponents, 2) is one nx*ny*nz volume; with several ranks the slabs are assembled into the full
 // volume on every GPU (wavelet_slab_device, data.cu) instead of the reference's gather to rank 0 / scatter.
-int apply_wavelet(const LsqrParams &p, double *d_v, bool fwd, int64_t nsmaller, cudaStream_t st) {
+int apply_wavelet(const LsqrParams &p, double *d_v, bool fwd, const std::vector<int64_t> &offsets, cudaStream_t st) {
   for (int i = 0; i < 2; ++i) {
     if (!p.solve_problem[i]) continue;
     for (int k = 0; k < p.ncomponents; ++k) {
       double *vol = d_v + ((size_t)i * p.ncomponents + k) * (size_t)p.nelements;
-      TFX_TRY(wavelet_slab_device(vol, p.nelements, nsmaller, p.nx, p.ny, p.nz, p.compression_type, fwd, st));
+      TFX_TRY(wavelet_slab_device_off(vol, offsets, p.nx, p.ny, p.nz, p.compression_type, fwd, st));
     }
   }
   return 0;
@@ -581,11 +581,10 @@ int lsqr_run(const LsqrParams &p, Matrix *S, Matrix *C, double *d_u, double *d_x
     return fail(-50, p.single_matrix ? "Wrong matrix size in lsqr_solve! Exiting."
                                      : "Wrong matrix sizes in lsqr_solve_sensit! Exiting.");
   if (!S->finalized || (C && !C->finalized)) return fail(-51, "lsqr: matrix is not finalized");
-  int64_t nsmaller = 0;
+  std::vector<int64_t> nsmaller;   // slab offsets of all ranks (wavelet inside the loop)
   if (wav) {
-    int64_t total = 0;
-    TFX_TRY(comm_slab_offset(p.nelements, &nsmaller, &total));
-    if (total != (int64_t)p.nx * p.ny * p.nz)
+    TFX_TRY(comm_slab_offsets(p.nelements, nsmaller));
+    if (nsmaller.back() != (int64_t)p.nx * p.ny * p.nz)
       return fail(-53, "lsqr: the ranks' nelements must add up to nx*ny*nz when the wavelet transform runs inside the loop");
   }
 

@@ -146,6 +146,12 @@ int comm_allreduce_max(double *d_buf, size_t count, cudaStream_t st);
 // nx*ny*nz volume (wavelet_utils.F90:57-67 without the rank-0 bottleneck). data.cu
 int wavelet_slab_device(double *d_slab, int64_t nelements, int64_t nsmaller, int nx, int ny, int nz, int wavelet_type,
                         bool forward, cudaStream_t st);
+// The same with the slab layout of all ranks known (offsets: nranks + 1 prefix entries, comm_slab_offsets): no host
+// synchronisation inside, usable in the LSQR loop / under stream capture.
+int wavelet_slab_device_off(double *d_slab, const std::vector<int64_t> &offsets, int nx, int ny, int nz, int wavelet_type,
+                            bool forward, cudaStream_t st);
+int comm_slab_offsets(int64_t mine, std::vector<int64_t> &offsets);
+int comm_allgatherv_f64(double *d_full, const int64_t *offsets, cudaStream_t st);
 int comm_allreduce_sum(double *d_buf, size_t count, cudaStream_t st);
 int comm_allreduce_sum_i32(int32_t *d_buf, size_t count, cudaStream_t st);
 int comm_allreduce_sum_u8(uint8_t *d_buf, size_t count, cudaStream_t st);

@@ -6,6 +6,11 @@
 // axis keeps a tile of complete lines in shared memory and runs ALL scales of that axis on it:
 // 3 passes over the volume in total (16 B/element each), every global access coalesced.
 //
+// HBM traffic: three axis passes = 3 x 16 B per element for volumes beyond L2. (An L2-blocked variant -- axis 1 and axis 2
+// slab of i3 after slab of i3, option "wavelet_slab_mb" -- is bit-identical but measured slower, see g_opt_wavelet_slab_mb.)
+// Tiles are filled with cp.async (LDGSTS, 8 B per element straight into the shared-memory layout): a CTA has its whole
+// tile in flight at once instead of one register-staged load per thread.
+//
 // The volume s(n1,n2,n3) (Fortran order) is viewed per axis as A[outer][L][inner]:
 //   axis 1: inner = 1,     L = n1, outer = n2*n3
 //   axis 2: inner = n1,    L = n2, outer = n3
@@ -27,6 +32,8 @@ namespace tfx {
 
 struct WaveConst {
   double sq2, c0, c1, c2, c3, c4;
+  double isq2;       // RN(1/sqrt(2)), seed of the exact fast division
+  double half_sq2;   // 0.4999 * sqrt(2): acceptance bound of the fast division in units of ulp(q)
 };
 
 __device__ __forceinline__ int ilog2_floor(int n) { return 31 - __clz(n); }
@@ -56,11 +63,15 @@ __global__ void __launch_bounds__(512) wavelet_axis_kernel(double *__restrict__ 
   const int d_ti = nt % TI, d_r = nt / TI, d_l = d_r % L, d_to = d_r / L;
   const int total_i = (int)total;
   {
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
     int ti = (int)threadIdx.x % TI, r0 = (int)threadIdx.x / TI;
     int l = r0 % L, to = r0 / L;
     for (int e = threadIdx.x; e < total_i; e += nt) {
-      if (ti < ti_n && to < to_n)
-        tile[(size_t)l * pitch + to * TI + ti] = s[((o0 + to) * L + l) * inner + (i0 + ti)];
+      if (ti < ti_n && to < to_n) {
+        const double *src = s + ((o0 + to) * L + l) * inner + (i0 + ti);
+        const uint32_t dst = tile_s + (uint32_t)(((size_t)l * pitch + to * TI + ti) * sizeof(double));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+      }
       ti += d_ti;
       int cr = 0;
       if (ti >= TI) { ti -= TI; cr = 1; }
@@ -69,6 +80,8 @@ __global__ void __launch_bounds__(512) wavelet_axis_kernel(double *__restrict__ 
       if (l >= L) { l -= L; cl = 1; }
       to += d_to + cl;
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   // (line, pair) decomposition of the lifting work items: w = p * NL + line, advanced the same way
@@ -198,6 +211,285 @@ __global__ void __launch_bounds__(512) wavelet_axis_kernel(double *__restrict__ 
   }
 }
 
+static WaveConst make_consts();
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Column-layout kernel (round 2). ncu on the kernel above (profiles/r2_wavelet_axis_v1_ncu_summary.csv): 175 thread-
+// instructions per element and pass, ALU pipe 60 %, issue slots 85 % busy, DRAM 28 % -- bound by the integer index
+// arithmetic of the (line, pair) work items, not by memory and not by FP64. Here a thread owns ONE line (tile column c)
+// for the whole kernel: its global base / stride are computed once, shared-memory addresses are row * pitch + c, and
+//   * Haar runs three scales per shared-memory round trip in registers: a thread loads 8 rows of its column (stride B =
+//     8^round), lifts the pairs (0,1)(2,3)(4,5)(6,7), (0,2)(4,6), (0,4) and stores them back -- a chunk of 8 rows is
+//     closed under those three scales, so there is one block barrier per three scales;
+//   * D4 keeps its four phases per scale (neighbour pairs, periodic wrap) with the same cheap addressing.
+// Tile = L rows x NC columns (lines); rows of the tile are contiguous in global memory for the axis-2 / axis-3 passes
+// (lanes read consecutive addresses); for axis 1 (lines contiguous along l) the copy runs with the lanes along l into an
+// odd-pitch tile (conflict-free transposition). Same arithmetic, same order per element: bit-identical.
+// ---------------------------------------------------------------------------------------------------------------------
+// x / sqrt(2), correctly rounded, without the ~20-instruction IEEE division in the common case.
+// q = x*ci corrected once with the exact residual (Markstein) is within one ulp of t = x/c; r = x - q*c is then exactly
+// representable and equals c*(t - q). If |r| <= 0.4999*c*ulp(q) and q is a normal number that is not a power of two
+// (below a power of two the spacing halves), q is the floating-point number nearest to t, i.e. q == RN(x/c). Anything
+// else -- one division in several thousand, zeros excepted -- takes __ddiv_rn. The result is ALWAYS the correctly
+// rounded quotient, so the transform stays bit-identical to the reference's `/ sqrt(2._CUSTOM_REAL)`.
+// Out of line on purpose: inlined, the compiler if-converts the rare branch and runs the whole IEEE division next to the
+// fast path for every element (ncu: one MUFU.RCP64H per division).
+__device__ __noinline__ double div_slow(double x, double c) { return __ddiv_rn(x, c); }
+
+__device__ __forceinline__ double div_sq2(double x, const WaveConst &k) {
+  const double q0 = __dmul_rn(x, k.isq2);
+  if (x == 0.0) return q0;                       // +-0 / c = +-0
+  const double q = __fma_rn(__fma_rn(-q0, k.sq2, x), k.isq2, q0);
+  const double r = __fma_rn(-q, k.sq2, x);
+  const int hi = __double2hiint(q);
+  const int e = (hi >> 20) & 0x7ff;
+  const bool pow2 = ((hi & 0xfffff) | __double2loint(q)) == 0;
+  const double bound = __dmul_rn(__hiloint2double((e - 52) << 20, 0), k.half_sq2);   // 0.4999 * c * ulp(q)
+  if (e > 64 && e < 1980 && !pow2 && fabs(r) <= bound) return q;
+  return div_slow(x, k.sq2);
+}
+
+template <bool FWD>
+__device__ __forceinline__ void haar_pair(double &lo, double &hi, const WaveConst &k) {
+  if (FWD) {   // wavelet_transform.F90:103-149
+    const double h = __dsub_rn(hi, lo);
+    const double l = __dadd_rn(lo, __dmul_rn(h, 0.5));
+    lo = __dmul_rn(l, k.sq2);
+    hi = div_sq2(h, k);
+  } else {     // :186-232
+    double l = div_sq2(lo, k);
+    const double h = __dmul_rn(hi, k.sq2);
+    l = __dsub_rn(l, __dmul_rn(h, 0.5));
+    lo = l;
+    hi = __dadd_rn(h, l);
+  }
+}
+
+template <int TYPE, bool FWD, bool TRANSPOSE>
+__global__ void __launch_bounds__(256) wavelet_cols_kernel(double *__restrict__ s, int L, long long inner, long long nlines,
+                                                           int NC, int pitch, WaveConst k) {
+  extern __shared__ double tile[];
+  const int nt = (int)blockDim.x;
+  const int c = (int)threadIdx.x % NC, rid = (int)threadIdx.x / NC, nrid = nt / NC;
+  const long long q0 = (long long)blockIdx.x * NC;
+  const int ncol = (int)min((long long)NC, nlines - q0);
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+
+  // ---- load
+  long long colbase = 0;
+  if (TRANSPOSE) {   // inner == 1: line q = s[q*L .. q*L + L); lanes along l
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nt >> 5;
+    const int nchunk = (L + 31) >> 5;
+    for (int job = w; job < ncol * nchunk; job += nw) {
+      const int cc = job / nchunk, l = ((job - cc * nchunk) << 5) + lane;
+      if (l < L) {
+        const double *src = s + (q0 + cc) * L + l;
+        const uint32_t dst = tile_s + (uint32_t)((l * pitch + cc) * (int)sizeof(double));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+      }
+    }
+  } else {
+    const long long q = q0 + c;
+    const long long o = q / inner, i = q - o * inner;
+    colbase = o * L * inner + i;
+    if (c < ncol) {
+      const double *src = s + colbase + (long long)rid * inner;
+      uint32_t dst = tile_s + (uint32_t)((rid * pitch + c) * (int)sizeof(double));
+      for (int l = rid; l < L; l += nrid) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+        src += (long long)nrid * inner;
+        dst += (uint32_t)(nrid * pitch * (int)sizeof(double));
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int nscale = (L >= 2) ? ilog2_floor(L) : 0;
+  double *col = tile + c;
+  if (TYPE == 1) {
+    // ---- Haar: rounds of three scales in registers. Round t works on the rows that are multiples of B = 8^t.
+    const int nround = (nscale + 2) / 3;
+    for (int tt = 0; tt < nround; ++tt) {
+      const int t = FWD ? tt : nround - 1 - tt;
+      const int sh = 3 * t;                       // B = 1 << sh
+      const int s1 = sh + 1;                      // scales s1, s1 + 1, s1 + 2 (those <= nscale)
+      const int nchunk = (L + (8 << sh) - 1) >> (sh + 3);
+      const size_t rs = (size_t)pitch << sh;       // distance of two rows of the chunk in the tile
+      const bool sc2 = s1 + 1 <= nscale, sc3 = s1 + 2 <= nscale;
+      for (int g = rid; g < nchunk; g += nrid) {
+        const int r0 = g << (sh + 3);
+        double *base = col + (size_t)r0 * pitch;
+        double a[8];
+        if (r0 + (7 << sh) < L) {
+          // all eight rows inside the line (every chunk but the last of a line whose length is not a multiple of 8B)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = base[j * rs];
+          if (FWD) {
+            haar_pair<true>(a[0], a[1], k); haar_pair<true>(a[2], a[3], k);
+            haar_pair<true>(a[4], a[5], k); haar_pair<true>(a[6], a[7], k);
+            if (sc2) { haar_pair<true>(a[0], a[2], k); haar_pair<true>(a[4], a[6], k); }
+            if (sc3) haar_pair<true>(a[0], a[4], k);
+          } else {
+            if (sc3) haar_pair<false>(a[0], a[4], k);
+            if (sc2) { haar_pair<false>(a[0], a[2], k); haar_pair<false>(a[4], a[6], k); }
+            haar_pair<false>(a[0], a[1], k); haar_pair<false>(a[2], a[3], k);
+            haar_pair<false>(a[4], a[5], k); haar_pair<false>(a[6], a[7], k);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) base[j * rs] = a[j];
+          continue;
+        }
+        // ragged end of the line: a pair (lo, hi) of a scale exists when the row of hi is inside the line (npairs(), :97-101)
+        bool in[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          in[j] = r0 + (j << sh) < L;
+          a[j] = in[j] ? base[j * rs] : 0.0;
+        }
+        if (FWD) {
+          if (in[1]) haar_pair<true>(a[0], a[1], k);
+          if (in[3]) haar_pair<true>(a[2], a[3], k);
+          if (in[5]) haar_pair<true>(a[4], a[5], k);
+          if (in[7]) haar_pair<true>(a[6], a[7], k);
+          if (sc2) {
+            if (in[2]) haar_pair<true>(a[0], a[2], k);
+            if (in[6]) haar_pair<true>(a[4], a[6], k);
+          }
+          if (sc3 && in[4]) haar_pair<true>(a[0], a[4], k);
+        } else {
+          if (sc3 && in[4]) haar_pair<false>(a[0], a[4], k);
+          if (sc2) {
+            if (in[2]) haar_pair<false>(a[0], a[2], k);
+            if (in[6]) haar_pair<false>(a[4], a[6], k);
+          }
+          if (in[1]) haar_pair<false>(a[0], a[1], k);
+          if (in[3]) haar_pair<false>(a[2], a[3], k);
+          if (in[5]) haar_pair<false>(a[4], a[5], k);
+          if (in[7]) haar_pair<false>(a[6], a[7], k);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (in[j]) base[j * rs] = a[j];
+      }
+      __syncthreads();
+    }
+  } else {
+    // ---- D4: four phases per scale (wavelet_transform.F90:280-363 forward, :411-494 inverse); pair p of scale istep =
+    // rows p*step (low) and p*step + half (high); the neighbour pairs wrap periodically among the ng complete pairs.
+    for (int ii = 1; ii <= nscale; ++ii) {
+      const int istep = FWD ? ii : nscale + 1 - ii;
+      const int step = 1 << istep, half = step >> 1, ng = npairs(L, step);
+      const size_t sp = (size_t)step * pitch, hp = (size_t)half * pitch;
+      if (FWD) {
+        for (int p = rid; p < ng; p += nrid) {                      // update 1
+          double *lo = col + p * sp;
+          *lo = __dadd_rn(*lo, __dmul_rn(lo[hp], k.c0));
+        }
+        __syncthreads();
+        for (int p = rid; p < ng; p += nrid) {                      // predict
+          const int pm = (p == 0) ? ng - 1 : p - 1;
+          double *lo = col + p * sp;
+          lo[hp] = __dsub_rn(__dsub_rn(lo[hp], __dmul_rn(*lo, k.c1)), __dmul_rn(col[pm * sp], k.c2));
+        }
+        __syncthreads();
+        for (int p = rid; p < ng; p += nrid) {                      // update 2 + normalise low
+          const int pp = (p == ng - 1) ? 0 : p + 1;
+          double *lo = col + p * sp;
+          *lo = __dmul_rn(__dsub_rn(*lo, col[pp * sp + hp]), k.c3);
+        }
+        __syncthreads();
+        for (int p = rid; p < ng; p += nrid) {                      // normalise high
+          double *hi = col + p * sp + hp;
+          *hi = __dmul_rn(*hi, k.c4);
+        }
+        __syncthreads();
+      } else {
+        for (int p = rid; p < ng; p += nrid) {                      // normalise
+          double *lo = col + p * sp;
+          *lo = __dmul_rn(*lo, k.c4);
+          lo[hp] = __dmul_rn(lo[hp], k.c3);
+        }
+        __syncthreads();
+        for (int p = rid; p < ng; p += nrid) {                      // undo update 2
+          const int pp = (p == ng - 1) ? 0 : p + 1;
+          double *lo = col + p * sp;
+          *lo = __dadd_rn(*lo, col[pp * sp + hp]);
+        }
+        __syncthreads();
+        for (int p = rid; p < ng; p += nrid) {                      // undo predict
+          const int pm = (p == 0) ? ng - 1 : p - 1;
+          double *lo = col + p * sp;
+          lo[hp] = __dadd_rn(__dadd_rn(lo[hp], __dmul_rn(*lo, k.c1)), __dmul_rn(col[pm * sp], k.c2));
+        }
+        __syncthreads();
+        for (int p = rid; p < ng; p += nrid) {                      // undo update 1
+          double *lo = col + p * sp;
+          *lo = __dsub_rn(*lo, __dmul_rn(lo[hp], k.c0));
+        }
+        __syncthreads();
+      }
+    }
+  }
+
+  // ---- store
+  if (TRANSPOSE) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nt >> 5;
+    const int nchunk = (L + 31) >> 5;
+    for (int job = w; job < ncol * nchunk; job += nw) {
+      const int cc = job / nchunk, l = ((job - cc * nchunk) << 5) + lane;
+      if (l < L) s[(q0 + cc) * L + l] = tile[(size_t)l * pitch + cc];
+    }
+  } else if (c < ncol) {
+    double *dst = s + colbase + (long long)rid * inner;
+    const double *src = col + (size_t)rid * pitch;
+    for (int l = rid; l < L; l += nrid) {
+      *dst = *src;
+      dst += (long long)nrid * inner;
+      src += (size_t)nrid * pitch;
+    }
+  }
+}
+
+int g_opt_wavelet_cols = 1;   // 0: always the generic (line, pair) kernel
+int g_opt_wavelet_tile_kb = 0;   // 0: automatic (32 KB tiles, 64 KB for axes longer than 256)
+
+// Launches the column-layout kernel when the axis length fits its tile; returns 1 when it did, 0 to fall back.
+template <int TYPE, bool FWD>
+static int launch_cols(double *d_s, int L, long long inner, long long outer, cudaStream_t st, int *launched) {
+  *launched = 0;
+  if (!g_opt_wavelet_cols || L < 2) return 0;
+  const bool transpose = (inner == 1);
+  // columns per CTA: whole warps of lines while the tile stays <= 64 KB; half-warps for long lines (<= 1024 rows)
+  // columns (lines) per CTA: the largest power of two in [8, 256] whose tile stays within the budget (small tiles: many
+  // CTAs per SM in different phases -- load / lift / store -- keep the memory pipeline busy)
+  // measured (512x512x128 Haar): 16 KB tiles 0.51 ms, 32 KB 0.46 ms, 64 KB 0.39 ms; 256x256x64: 0.086 / 0.075 / 0.078 ms
+  const size_t budget = (g_opt_wavelet_tile_kb > 0 ? (size_t)std::max(8, g_opt_wavelet_tile_kb) : (L > 256 ? 64 : 32)) * 1024;
+  int NC = 256;
+  while (NC > 8 && (size_t)L * NC * sizeof(double) > budget) NC >>= 1;
+  if ((size_t)L * (NC + 1) * sizeof(double) > 140 * 1024) return 0;   // axis too long for any tile: generic kernel
+  if (!transpose && inner < NC && inner < 16) return 0;   // tiny inner extents: lanes would not read contiguous memory
+  const long long nlines = inner * outer;
+  const int pitch = transpose ? NC + 1 : NC;
+  const size_t smem = (size_t)L * pitch * sizeof(double);
+  const long long grid = (nlines + NC - 1) / NC;
+  if (grid > 0x7fffffffLL) return 0;
+  if (transpose) {
+    auto kern = wavelet_cols_kernel<TYPE, FWD, true>;
+    TFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
+    kern<<<(unsigned)grid, 256, smem, st>>>(d_s, L, inner, nlines, NC, pitch, make_consts());
+  } else {
+    auto kern = wavelet_cols_kernel<TYPE, FWD, false>;
+    TFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
+    kern<<<(unsigned)grid, 256, smem, st>>>(d_s, L, inner, nlines, NC, pitch, make_consts());
+  }
+  ctx().launches++;
+  TFX_CUDA(cudaGetLastError());
+  *launched = 1;
+  return 0;
+}
+
 static WaveConst make_consts() {
   // wavelet_transform.F90:251-255 and the sqrt(2) of the Haar normalisation (:138-139).
   WaveConst k;
@@ -207,12 +499,19 @@ static WaveConst make_consts() {
   k.c2 = (sqrt(3.0) - 2.0) / 4.0;
   k.c3 = (sqrt(3.0) - 1.0) / sqrt(2.0);
   k.c4 = (sqrt(3.0) + 1.0) / sqrt(2.0);
+  k.isq2 = 1.0 / k.sq2;
+  k.half_sq2 = 0.4999 * k.sq2;
   return k;
 }
 
 template <int TYPE, bool FWD>
 static int launch_axis(double *d_s, int L, long long inner, long long outer, cudaStream_t st) {
   if (L < 2) return 0;  // nscale == 0: nothing to do
+  {
+    int launched = 0;
+    TFX_TRY((launch_cols<TYPE, FWD>(d_s, L, inner, outer, st, &launched)));
+    if (launched) return 0;
+  }
   const size_t kHardMax = 200 * 1024;
   // Tile budget. The passes are latency-bound (load, log2(L) block barriers, store), so for short axes many small
   // CTAs in flight win (32 KB tiles, 256 threads: measured 0.104 ms per 256x256x64 transform against 0.121 ms with
@@ -263,11 +562,25 @@ static int launch_axis(double *d_s, int L, long long inner, long long outer, cud
 
 // nvol volumes stored back to back are one volume with nvol times the outer extent for every axis pass (lines never
 // mix): one set of three launches for a whole batch, full waves of CTAs instead of 1.2 per small volume.
+// i3-slab size of the L2-blocked axis-1 / axis-2 passes; 0 (default): whole volume per pass. Measured on B200 with the
+// column kernels (gpurun_out r2_wavelet_time_e, 512x512x128 Haar): no slabs 0.405 ms, 32 MB slabs 0.537 ms, 64 MB 0.443 ms,
+// 100 MB 0.441 ms -- the small launches lose more (partial waves, launch gaps) than the L2 hits win, so it stays off.
+int g_opt_wavelet_slab_mb = 0;
+
 template <int TYPE, bool FWD>
 static int run3d(double *d_s, int n1, int n2, int n3, long long nvol, cudaStream_t st) {
-  TFX_TRY((launch_axis<TYPE, FWD>(d_s, n1, 1, (long long)n2 * n3 * nvol, st)));
-  TFX_TRY((launch_axis<TYPE, FWD>(d_s, n2, n1, (long long)n3 * nvol, st)));
-  TFX_TRY((launch_axis<TYPE, FWD>(d_s, n3, (long long)n1 * n2, nvol, st)));
+  const long long plane = (long long)n1 * n2, nplanes = (long long)n3 * nvol;
+  const long long bytes = plane * nplanes * (long long)sizeof(double);
+  long long per = nplanes;   // planes per slab
+  if (g_opt_wavelet_slab_mb > 0 && bytes > 2LL * g_opt_wavelet_slab_mb * (1 << 20))
+    per = std::max<long long>(1, (long long)g_opt_wavelet_slab_mb * (1 << 20) / (plane * (long long)sizeof(double)));
+  for (long long k0 = 0; k0 < nplanes; k0 += per) {
+    const long long nk = std::min(per, nplanes - k0);
+    double *slab = d_s + k0 * plane;
+    TFX_TRY((launch_axis<TYPE, FWD>(slab, n1, 1, (long long)n2 * nk, st)));
+    TFX_TRY((launch_axis<TYPE, FWD>(slab, n2, n1, nk, st)));
+  }
+  TFX_TRY((launch_axis<TYPE, FWD>(d_s, n3, plane, nvol, st)));
   return 0;
 }
 
