@@ -18,11 +18,15 @@ e2e    : iterations/s through the C ABI call tfx_lsqr_solve_sensit with HOST buf
          right-hand side, the initialisation before the loop, K iterations, D2H of x and u.
 roofline: the fused sweep kernel (dense_sweep_kernel): ALGORITHMIC bytes (4 B per matrix entry read
          once + the vectors) / mean launch time from CUDA events, against the measured HBM peak.
-spmv   : (extra object) the compressed half of BASELINE.json's metric: S x / S^T u on a Haar-5 % kernel of the same grid
-         assembled on the device, 10 000 stations per GPU (weak scaling), GB/s by the reference's 8 B/nnz accounting and
-         by the 6 B/nnz the T16 layouts move, wavelet transform times, assembly rate, compressed LSQR it/s.
-         --no-dense --comp-grid 512 512 128 --comp-ndata 6250 --comp-batch 5000 on 8 GPUs is BASELINE config C at full
-         size (row-blocked assembly).
+spmv   : (extra object) the compressed half of BASELINE.json's metric on BASELINE config C's shape: 512 x 512 x 128
+         cells, Haar compression 5 %, 6 250 stations PER GPU (weak scaling: 8 GPUs = the 50 000 stations of config C),
+         assembled on the device in row blocks, kept in the T16 layouts (12 B/nnz for both products, ~126 GB per GPU):
+         S x / S^T u GB/s by the reference's 8 B/nnz accounting and by the 6 B/nnz the layouts move, wavelet transform
+         times, assembly rate, compressed LSQR it/s. --comp-grid / --comp-ndata / --comp-batch change the shape.
+config_d: (extra object) parfiles/Parfile_2body_induced.txt with Daubechies-4 compression end to end (distance weights,
+         magnetic 3-component assembly, 2 x 100 LSQR iterations), column slabs over the N ranks.
+config_e: (extra object, --gpus >= 2 or --config-e) joint gravity + magnetic inversion with cross-gradient constraints
+         and the wavelet transforms inside the LSQR loop (see tomofast-x_b200/configs.py).
 cpu_baseline / --impl reference: the oracle port of the reference loops (sparse_matrix.f90:313-405,
          lsqr_solver2.F90:321-473) on the host cores, column-split over P processes like the reference's
          MPI ranks, on a bounded column sample of the same matrix shape, scaled linearly in nnz.
@@ -143,6 +147,9 @@ class Dist:
         t = torch.tensor([float(x)], dtype=torch.float64)
         self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
         return float(t[0])
+
+    def min(self, x):
+        return -self.max(-x)
 
     def sum(self, x):
         if not self.td:
@@ -323,18 +330,107 @@ def run_ours(a):
         }
         if d.world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(a, steps=2, warmup=1, seconds_hint=20.0)
-    if not a.no_compressed:
-        # free the dense block before the compressed matrix is assembled
-        del S, C, u_dev, x_dev, u_pin, x_pin
-        import gc
-        gc.collect()
-        comp = compressed_spmv(a, tfx, d)
-        if d.rank == 0:
-            line["spmv"] = comp
+    # ---- extras: the other BASELINE configurations. A failure of an extra never costs the headline line.
+    del S, C, u_dev, x_dev, u_pin, x_pin               # free the dense block first
+    import gc
+    gc.collect()
+    extras = run_extras(a, tfx, d)
     if d.rank == 0:
+        line.update(extras)
         print(json.dumps(line), flush=True)
     d.finish()
     return x_host
+
+
+def run_extras(a, tfx, d):
+    import traceback
+    out = {}
+
+    def guarded(name, fn):
+        try:
+            res = fn()
+        except Exception as e:                          # noqa: BLE001 -- reported in the JSON line
+            res = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            sys.stderr.write("bench extra %s failed:\n%s\n" % (name, traceback.format_exc()))
+        failed = d.max(1.0 if "error" in res else 0.0) > 0
+        if failed and "error" not in res:
+            res = {"error": "failed on another rank"}
+        out[name] = res
+        tfx.synchronize()
+        import gc
+        gc.collect()
+
+    if not a.no_compressed:
+        guarded("spmv", lambda: compressed_spmv(a, tfx, d))
+    if not a.no_config_d:
+        guarded("config_d", lambda: config_d_extra(a, tfx, d))
+    if (a.config_e == 1) or (a.config_e < 0 and d.world >= 2):
+        guarded("config_e", lambda: config_e_extra(a, tfx, d))
+    return out
+
+
+def config_d_extra(a, tfx, d):
+    """BASELINE config D: parfiles/Parfile_2body_induced.txt with Daubechies-4 compression, end to end."""
+    from tomofastx_b200 import configs
+    fixture = os.path.join(ROOT, "tests", "golden", "twobody_induced.npz")   # input DATA of the reference's Parfile
+    if not os.path.exists(fixture):
+        return {"skipped": "input fixture tests/golden/twobody_induced.npz not found"}
+    c = configs.load_twobody(fixture)
+    configs.run_config_d(tfx, dict(c, nmajor=1, niter=3), 2, d.rank, d.world, sync=d.barrier)   # warm-up (allocations, NCCL)
+    r = configs.run_config_d(tfx, c, 2, d.rank, d.world, sync=d.barrier)
+    loop_ms = d.max(r["loop_ms"])
+    nnz = r["nnz"]
+    peak, _ = hbm_peak()
+    return {"workload": "Parfile_2body_induced: magnetic 3-component, 67x67x30 cells, 1681 data, Daubechies-4 rate 0.3, "
+                        "distance weighting, 2 x 100 LSQR iterations, damping 1e-8",
+            "n_gpus": d.world, "nnz": nnz, "compression_error": r.get("compression_error"),
+            "depth_weight_s": round(d.max(r["depth_weight_s"]), 4), "assemble_s": round(d.max(r["assemble_s"]), 3),
+            "inversion_s": round(d.max(r["inversion_s"]), 3), "iters": r["iters"],
+            "lsqr_it_per_s": r["iters"] / (loop_ms * 1e-3), "ms_per_it": loop_ms / max(r["iters"], 1),
+            "ref_accounting_gbs": 16.0 * nnz * r["iters"] / loop_ms / 1e6, "ref_accounting_frac": 16.0 * nnz * r["iters"] / loop_ms / 1e6 / (peak * d.world),
+            "costs": [float(v) for v in r["costs"]], "residual_last": [float(h[-1]) for h in r["histories"]],
+            "column_slabs": r.get("column_slabs"),
+            "note": "launch/latency-bound at this size (2.0e8 nnz, SURVEY 8d: 3.3 GB per iteration by the reference's "
+                    "accounting); parity vs the oracle: tests/test_gpu_config_d.py"}
+
+
+def config_e_extra(a, tfx, d):
+    """BASELINE config E in shape: joint gravity + magnetic inversion, cross-gradient constraint, wavelet transforms
+    inside the LSQR loop, column slabs over the N ranks. The grid is weak-scaled with N (16.8 M cells per GPU:
+    1024 x 1024 x 128 at 8 GPUs = config E's grid); the station count is a small fraction of config E's 200 000 (the
+    assembly of the full kernel, 5.4e13 cell evaluations, does not fit a benchmark run), so the products with S are
+    timed on their own and the full-size iteration is PROJECTED from them."""
+    from tomofastx_b200 import configs
+    grids = {1: (256, 512, 128), 2: (512, 512, 128), 4: (1024, 512, 128)}
+    nx, ny, nz = a.e_grid if a.e_grid else grids.get(d.world, (1024, 1024, 128))
+    per = a.e_ndata if a.e_ndata > 0 else 500
+    nd1 = nd2 = per * d.world
+    rate = 0.002
+    r = configs.run_config_e(tfx, nx, ny, nz, nd1, nd2, rate=rate, niter=a.steps, warmup=max(3, a.warmup), rank=d.rank,
+                             world=d.world, sync=d.barrier)
+    loop_ms = d.max(r["loop_ms"])
+    it = r["iters"]
+    N = nx * ny * nz
+    fwd, trn, wav = d.max(r["S_fwd_ms"]), d.max(r["S_trans_ms"]), d.max(r["wavelet_slab_ms"])
+    ms_it = loop_ms / max(it, 1)
+    # config E proper: 200 000 stations x int(0.0025 N) entries per row on this grid (SURVEY 8a), products scale with nnz
+    full_nnz = 200000.0 * int(0.0025 * N) * (8.0 / max(d.world, 1)) if d.world < 8 else 200000.0 * int(0.0025 * N)
+    scale_up = full_nnz / max(r["nnz"], 1)
+    projected = ms_it + (scale_up - 1.0) * (fwd + trn)
+    peak, _ = hbm_peak()
+    return {"workload": "joint grav+mag %dx%dx%d cells, %d + %d data, Haar rate %g, damping + cross-gradient constraint "
+                        "(%d rows), wavelet in the LSQR loop (WAVELET_DOMAIN = F)" % (nx, ny, nz, nd1, nd2, rate, r["constraint_rows"]),
+            "n_gpus": d.world, "nnz": r["nnz"], "column_slabs": r["column_slabs"],
+            "assemble_s": round(d.max(r["assemble_s"]), 2), "constraints_s": round(d.max(r["constraints_s"]), 2),
+            "constraint_nnz": int(d.sum(float(r["constraint_nnz_local"]))),
+            "lsqr_it_per_s": it / (loop_ms * 1e-3), "ms_per_it": ms_it, "iters": it,
+            "residual_last": float(r["history"][-1]) if len(r["history"]) else None,
+            "S_fwd_ms": fwd, "S_trans_ms": trn, "wavelet_transform_ms": wav,
+            "wavelet_share": 4.0 * wav / ms_it,
+            "projected_full_config_e": {"nnz": full_nnz, "ms_per_it": projected, "it_per_s": 1e3 / projected,
+                                        "note": "measured iteration + (200 000 stations x 0.25 %% nnz / measured nnz - 1) x "
+                                                "measured product times; BASELINE.md: roofline 24 it/s, 60 %% target 14.6 it/s on 8 GPUs"},
+            "note": "4 distributed transforms per iteration: slabs all-gathered over NVLink, full volume transformed on every GPU"}
 
 
 def compressed_spmv(a, tfx, d):
@@ -347,10 +443,23 @@ def compressed_spmv(a, tfx, d):
     slabs (csrc/sensit_dist.cu) and every figure is the whole-job aggregate (total bytes / max time over ranks)."""
     from tomofastx_b200.synth import depth_weight_type1, regular_grid, station_lattice
     # weak scaling: the number of stations grows with the number of GPUs, so every GPU keeps a slab of the same nnz
-    # (2 x 12.6 GB in the T16 layouts) -- a per-GPU fraction of the HBM peak means something only at that size
+    # (config C: 2 x 63 GB in the T16 layouts) -- a per-GPU fraction of the HBM peak means something only at that size
     nx, ny, nz = (a.comp_grid if a.comp_grid else (a.nx, a.ny, a.nz))
-    nd, rate = a.comp_ndata * d.world, a.comp_rate
+    rate = a.comp_rate
     N = nx * ny * nz
+    per_rank = a.comp_ndata
+    batch = a.comp_batch if a.comp_batch >= 0 else 400 * d.world
+    # fit the layouts (12 B/nnz) + the build peak of one row block (~3x its own 12 B/nnz) + the row pipeline into the
+    # memory that is free now; a smaller station count is reported, never silently
+    free_b, _ = tfx.device_mem_info()
+    free_b = d.min(float(free_b))
+    nel_row = max(1, int(rate * N))
+    blk_rows = (batch // d.world) if batch > 0 else per_rank
+    need = lambda rows: 12.0 * nel_row * rows + 36.0 * nel_row * min(blk_rows, rows) + 40.0 * N + (3 << 30)
+    while per_rank > 16 and need(per_rank) > 0.94 * free_b:
+        per_rank = int(per_rank * 0.9)
+    nd = per_rank * d.world
+    a_comp_batch = batch
     grid = regular_grid(nx, ny, nz)
     xyz = station_lattice(nd, 100.0 * nx, 100.0 * ny, z=-0.1)
     cw = depth_weight_type1(grid, 2.0, 0.0, 4.0e3)
@@ -365,7 +474,7 @@ def compressed_spmv(a, tfx, d):
     d.barrier()
     t0 = time.perf_counter()
     t_rows = t_part = None
-    if a.comp_batch > 0:
+    if a_comp_batch > 0:
         # Row-blocked assembly (bounded build memory, csrc/sensit.cu matrix_append_block): the column partition comes
         # from a strided sample of the stations (the reference balances on the nnz counts of ALL rows, which it has on
         # disk before it reads the kernel back; the regular station lattice makes 1/16 of them representative), then
@@ -387,8 +496,8 @@ def compressed_spmv(a, tfx, d):
         S = tfx.SparseMatrix(nd, 2 * ncl, int(nd) * int(rate * N))
         nnz = 0
         cerr_sum = 0.0
-        for b0 in range(0, nd, a.comp_batch):
-            nb = min(a.comp_batch, nd - b0)
+        for b0 in range(0, nd, a_comp_batch):
+            nb = min(a_comp_batch, nd - b0)
             par_b = copy.copy(par); par_b.ndata = nb
             xb = tuple(np.ascontiguousarray(v[b0:b0 + nb]) for v in xyz)
             rows_b, _, cerr_b, tot_b = tfx.sensit_assemble_rows(par_b, grid, xb, cw, dw1[b0:b0 + nb], d.rank, d.world)
@@ -430,9 +539,11 @@ def compressed_spmv(a, tfx, d):
            "nnz": int(nnz), "compression_error": cerr, "assemble_s": round(t_asm, 2),
            "layout": "T16 (f32 value + u16 in-tile key = 6 B/nnz per product, one copy per direction)",
            "peak": peak * d.world, "peak_source": peak_src + (" x %d GPUs" % d.world if d.world > 1 else ""),
-           "unit": "GB/s", "reps": a.comp_reps, "scaling": "weak (%d stations per GPU)" % a.comp_ndata}
-    if a.comp_batch > 0:
-        out["row_blocks"] = {"stations_per_batch": a.comp_batch, "batches": (nd + a.comp_batch - 1) // a.comp_batch,
+           "unit": "GB/s", "reps": a.comp_reps, "scaling": "weak (%d stations per GPU)" % per_rank}
+    if per_rank != a.comp_ndata:
+        out["note"] = "stations per GPU reduced from %d to %d to fit the free HBM (%.0f GB)" % (a.comp_ndata, per_rank, free_b / 1e9)
+    if a_comp_batch > 0:
+        out["row_blocks"] = {"stations_per_batch": a_comp_batch, "batches": (nd + a_comp_batch - 1) // a_comp_batch,
                              "partition_sample_s": round(t_sample, 2), "device_bytes_per_rank_max": int(d.max(float(S.device_bytes())))}
     if d.world > 1:
         out["column_slabs"] = slabs
@@ -456,7 +567,7 @@ def compressed_spmv(a, tfx, d):
     lhs, rhs = d.sum(float(np.dot(q.numpy(), uh))), d.sum(float(np.dot(xh, t.numpy())))
     out["adjoint_rel_err"] = abs(lhs - rhs) / max(abs(lhs), abs(rhs), 1e-300)
     assert out["adjoint_rel_err"] < 1e-10, out["adjoint_rel_err"]
-    if d.world == 1 and a.comp_batch == 0:
+    if d.world == 1:
         # 3-D wavelet transform on a device-resident volume (SURVEY 8d metric iii: 16 B per element and transform)
         vol = tfx.Buffer(N)
         tfx.copy(vol, rng.uniform(-1.0, 1.0, N), N)
@@ -469,7 +580,8 @@ def compressed_spmv(a, tfx, d):
                 tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)
             ms = tfx.timer_stop() / 20.0
             out["wavelet"][wname] = {"ms_per_transform": ms, "achieved": 16.0 * N / ms / 1e6, "frac": 16.0 * N / ms / 1e6 / peak,
-                                     "note": "algorithmic 16 B/element; the kernel makes 3 axis passes (48 B/element moved)"}
+                                     "moved_frac": 48.0 * N / ms / 1e6 / peak,
+                                     "note": "algorithmic 16 B/element; three axis passes move 48 B/element"}
         del vol
     out["assembly"] = {"rows_per_s": nd / t_asm, "cell_evaluations_per_s": float(nd) * N / t_asm,
                        "note": "kernel line + column weight + Haar transform + exact k-th threshold + compaction per row"
@@ -585,13 +697,18 @@ def main():
     ap.add_argument("--dense-vec4", type=int, default=None, help="A/B switch of the dense sweep kernel shape (option dense_vec4)")
     ap.add_argument("--dense-f2f-rows", type=int, default=None, help="A/B switch (option dense_f2f_rows)")
     ap.add_argument("--no-compressed", action="store_true", help="skip the compressed SpMV section")
-    ap.add_argument("--comp-ndata", type=int, default=10000)
+    ap.add_argument("--comp-ndata", type=int, default=6250, help="stations per GPU of the compressed section")
     ap.add_argument("--comp-rate", type=float, default=0.05)
     ap.add_argument("--comp-reps", type=int, default=20)
-    ap.add_argument("--comp-grid", type=int, nargs=3, default=None, metavar=("NX", "NY", "NZ"),
-                    help="grid of the compressed section (default: the headline grid); BASELINE config C: 512 512 128")
-    ap.add_argument("--comp-batch", type=int, default=0,
-                    help="assemble the compressed kernel in row blocks of this many stations (all ranks together); 0 = one piece")
+    ap.add_argument("--comp-grid", type=int, nargs=3, default=(512, 512, 128), metavar=("NX", "NY", "NZ"),
+                    help="grid of the compressed section (default: BASELINE config C, 512 512 128)")
+    ap.add_argument("--comp-batch", type=int, default=-1,
+                    help="assemble the compressed kernel in row blocks of this many stations (all ranks together); "
+                         "0 = one piece, -1 (default) = 400 per rank")
+    ap.add_argument("--no-config-d", action="store_true", help="skip the config D extra")
+    ap.add_argument("--config-e", type=int, default=-1, help="1 / 0: run / skip the config E extra (default: run when --gpus >= 2)")
+    ap.add_argument("--e-grid", type=int, nargs=3, default=None, metavar=("NX", "NY", "NZ"))
+    ap.add_argument("--e-ndata", type=int, default=0, help="stations per problem and GPU of the config E extra")
     ap.add_argument("--no-dense", action="store_true", help="run only the compressed section")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup

@@ -76,6 +76,8 @@ int tfx_device_free(void *p);
 int tfx_host_alloc(void **p, int64_t bytes);
 int tfx_host_free(void *p);
 int tfx_memcpy(void *dst, const void *src, int64_t bytes);
+/* cudaMemset on the library stream (waits for it): zero-fills device-resident vectors such as b_RHS. */
+int tfx_device_memset(void *dst, int value, int64_t bytes);
 int tfx_device_mem_info(int64_t *free_bytes, int64_t *total_bytes);
 
 /* ---- communicator: stands in for MPI_COMM_WORLD on the solver's reductions ---------------------

@@ -1,0 +1,112 @@
+"""BASELINE config D (parfiles/Parfile_2body_induced.txt with Daubechies-4 compression) end to end on the device against
+the oracle: distance weighting (type 2) -> magnetic 3-component assembly -> observed data from the synthetic model ->
+2 major x 100 LSQR iterations with model damping on every component -> model update.
+
+The product side is tomofast-x_b200/configs.py:run_config_d (libtfx through the C ABI). The checker below restates the
+reference's driver (problem_joint_gravmag.F90:172-547, joint_inverse_problem.F90:393-573) on the oracle's functions. To
+finish in seconds the oracle sees every 4th station of the 41 x 41 lattice in both directions (121 stations, full
+67 x 67 x 30 grid); the full 1681-station run is checked through size-independent properties.
+The assembly (threshold flips within rounding) is compared on its own in tests/test_gpu_2body.py; here both sides
+solve with the SAME matrix (the device's, exported), so the comparison of the solve is tight."""
+import os
+
+import numpy as np
+import pytest
+
+import tomofastx_b200 as tfx
+from tomofastx_b200 import configs
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "twobody_induced.npz")
+
+
+def oracle_config_d(orc, c, S, column_weight, compression_type):
+    """The same major loop on the oracle (nbproc = 1)."""
+    N, nd, ncomp, pw = c["N"], c["ndata"], c["ncomp"], c["problem_weight"]
+    nx, ny, nz = c["nx"], c["ny"], c["nz"]
+    cw, dw = column_weight, np.ones((nd, 1))
+    shift, ncol = ncomp * N, 2 * ncomp * N
+    calc = lambda model: orc.calculate_data(S, model, nd, 1, pw, cw, dw, compression_type, nx, ny, nz, 1, shift).ravel()
+    m = np.full((ncomp, N), c["start_value"]); prior = np.zeros((ncomp, N))
+    d_obs = calc(c["m_true"]); d_calc = calc(m)
+    out = dict(d_obs=d_obs, histories=[], costs=[float(np.linalg.norm(d_calc - d_obs) / np.linalg.norm(d_obs))], rhs=[])
+    for _ in range(c["nmajor"]):
+        b = np.zeros(nd + ncomp * N)
+        b[:nd] = pw * (d_obs - d_calc)
+        Cm = orc.SparseMatrix(ncomp * N, ncol, ncomp * N)
+        cons = b[nd:]
+        for k in range(ncomp):
+            orc.damping_add(Cm, cons, c["alpha"], pw, 2.0, compression_type, nx, ny, nz, 0, N, cw, m[k], prior[k],
+                            shift + k * N, True)
+        Cm.finalize()
+        out["rhs"].append(b.copy())
+        x, h, it = orc.lsqr_solve_sensit(c["niter"], c["rmin"], 0.0, 0.0, S, Cm, b, N, nx, ny, nz, ncomp, compression_type,
+                                         True, solve_problem=(0, 1))
+        out["histories"].append(h)
+        delta = x[shift:].reshape(ncomp, N).copy()
+        for k in range(ncomp):
+            delta[k] = orc.inverse_wavelet(delta[k].copy(), nx, ny, nz, compression_type)
+        m = m + delta * cw
+        d_calc = calc(m)
+        out["costs"].append(float(np.linalg.norm(d_calc - d_obs) / np.linalg.norm(d_obs)))
+    out["model"] = m
+    return out
+
+
+def oracle_from_export(orc, nl, ncolumns, arrays):
+    """The oracle's t_sparse_matrix filled with the reference-format CSR arrays another matrix exported."""
+    sa, ija, ijl, rowptr = arrays
+    M = orc.SparseMatrix(nl, ncolumns, len(sa))
+    for i in range(len(rowptr)):
+        while M.current_row < rowptr[i] - 1:
+            M.new_row()                                                   # rows without entries are not stored
+        M.add_row(sa[ijl[i] - 1:ijl[i + 1] - 1], ija[ijl[i] - 1:ijl[i + 1] - 1])
+        M.new_row()
+    while M.current_row < nl:
+        M.new_row()
+    M.finalize()
+    return M
+
+
+def test_config_d_against_oracle(oracle):
+    c = configs.load_twobody(GOLDEN, station_stride=4)
+    assert c["ndata"] == 121 and c["N"] == 134670 and c["ncomp"] == 3
+    got = configs.run_config_d(tfx, c, compression_type=2)
+    # distance weighting (weights_gravmag.f90:81-138) on the real padded grid
+    cw_o = oracle.depth_weight(2, c["grid"], *c["data_xyz"], c["dw_power"], c["dw_beta"], 0.0)
+    assert np.allclose(got["column_weight"], cw_o, rtol=1e-12)
+    nel = int(c["rate"] * c["N"])
+    assert abs(got["nnz"] - 3 * nel * c["ndata"]) <= 12 * c["ndata"]            # 40 401 per (row, component), ties aside
+    # the same matrix on both sides
+    So = oracle_from_export(oracle, c["ndata"], 2 * 3 * c["N"], got["S"].export())
+    want = oracle_config_d(oracle, c, So, got["column_weight"], 2)
+    assert np.allclose(got["d_obs"], want["d_obs"], rtol=1e-11, atol=1e-14 * np.abs(want["d_obs"]).max())
+    assert len(got["histories"]) == 2 and all(len(h) == 100 for h in got["histories"])
+    # major iteration 1 starts from identical states: the LSQR bar (1e-6) on the residual history
+    h, ho = got["histories"][0], want["histories"][0]
+    assert len(ho) == 100
+    rel = np.abs(h - ho) / ho
+    assert rel[:10].max() < 1e-6, rel[:10]
+    assert rel.max() < 1e-4, (np.argmax(rel), rel.max())        # mid-phase iterates amplify last-bit differences
+    # free run: costs and final model after both major iterations
+    assert np.allclose(got["costs"], want["costs"], rtol=1e-4)
+    assert got["costs"][-1] < got["costs"][1] < got["costs"][0]
+    scale = np.abs(want["model"]).max()
+    assert np.abs(got["model"] - want["model"]).max() < 1e-5 * scale
+
+
+def test_config_d_full_size_properties():
+    """All 1681 stations (the Parfile): 40 401 D4 coefficients per row and component, costs decrease, the data misfit
+    of the recovered model matches the solver's last residual (||S dm - r|| consistency)."""
+    c = configs.load_twobody(GOLDEN)
+    assert c["ndata"] == 1681
+    got = configs.run_config_d(tfx, c, compression_type=2)
+    nel = int(c["rate"] * c["N"])
+    assert abs(got["nnz"] - 3 * nel * 1681) <= 12 * 1681
+    assert 1e-7 < got["compression_error"] < 1e-4
+    assert got["iters"] == 200
+    assert got["costs"][2] < got["costs"][1] < got["costs"][0] == pytest.approx(got["costs"][0])
+    assert np.all(np.isfinite(got["model"]))
+    # LSQR's r_k = |b - A x_k| / |b|: the data part of the final residual cannot exceed it
+    assert got["costs"][1] <= got["histories"][0][-1] * got["rhs_norms"][0] / np.linalg.norm(got["d_obs"]) * (1 + 1e-6) + 1e-12

@@ -187,6 +187,15 @@ def copy(dst, src, n):
     _check(L.tfx_memcpy(_ptr(dst), _ptr(src), int(n) * 8))
 
 
+def zero(buf, n=None, offset=0):
+    """Zero-fills n float64 of a device Buffer (default: all of it) starting at element `offset`."""
+    L = lib()
+    L.tfx_device_memset.argtypes = [C.c_void_p, C.c_int, C.c_int64]
+    n = buf.n - offset if n is None else n
+    _check(L.tfx_device_memset(_ptr(buf) + 8 * int(offset), 0, int(n) * 8))
+    return buf
+
+
 def device_mem_info():
     L = lib()
     f, t = C.c_int64(0), C.c_int64(0)

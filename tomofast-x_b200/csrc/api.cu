@@ -953,6 +953,12 @@ int tfx_memcpy(void *dst, const void *src, int64_t bytes) {
   TFX_CUDA(cudaStreamSynchronize(ctx().stream));
   return 0;
 }
+int tfx_device_memset(void *dst, int value, int64_t bytes) {
+  TFX_TRY(ensure_init());
+  if (bytes > 0) TFX_CUDA(cudaMemsetAsync(dst, value, (size_t)bytes, ctx().stream));
+  TFX_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
 int tfx_device_mem_info(int64_t *free_bytes, int64_t *total_bytes) {
   TFX_TRY(ensure_init());
   size_t f = 0, t = 0;
