@@ -77,6 +77,8 @@ def lib():
     L.orc_graviprism_z.argtypes = [C.c_int32, _d, _d, _d, _d, _d, _d, C.c_double, C.c_double, C.c_double, _d]
     L.orc_gradiprism_zz.argtypes = [C.c_int32, _d, _d, _d, _d, _d, _d, C.c_double, C.c_double, C.c_double, _d]
     L.orc_gradiprism_zz.restype = None
+    L.orc_gradiprism_full.argtypes = [C.c_int32, _d, _d, _d, _d, _d, _d, C.c_double, C.c_double, C.c_double, _d]
+    L.orc_gradiprism_full.restype = C.c_int32
     L.orc_magprism.argtypes = [C.c_int32, C.c_int32, C.c_int32, _d, _d, _d, _d, _d, _d,
                                C.c_double, C.c_double, C.c_double,
                                C.c_double, C.c_double, C.c_double, C.c_double, _d]
@@ -261,6 +263,19 @@ def gradiprism_zz(grid, xd, yd, zd):
     out = np.zeros(X1.size)
     lib().orc_gradiprism_zz(X1.size, X1, X2, Y1, Y2, Z1, Z2, xd, yd, zd, out)
     return out
+
+
+def gradiprism_full(grid, xd, yd, zd):
+    """gradiprism_full (gravity_field.f90:207-309): numpy shape (6, n), components XX, YY, ZZ, XY, YZ, ZX -- the order of
+    sensit_line_full(:, 1, 1..6) at sensitivity_gravmag.F90:207-209."""
+    X1, X2, Y1, Y2, Z1, Z2 = _grid6(grid)
+    out = np.zeros(6 * X1.size)
+    rc = lib().orc_gradiprism_full(X1.size, X1, X2, Y1, Y2, Z1, Z2, xd, yd, zd, out)
+    if rc == 3:
+        raise RuntimeError("Zero denominator in gradiprism_full! Adjust the model grid.")
+    if rc == 4:
+        raise RuntimeError("Bad log argument in gradiprism_full! Adjust the model grid.")
+    return out.reshape(6, X1.size)
 
 
 def magprism(grid, xd, yd, zd, nmodel_comp, ndata_comp, mi, md, theta, intensity):

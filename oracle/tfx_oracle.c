@@ -547,6 +547,57 @@ void orc_gradiprism_zz(int32_t n, const double *X1, const double *X2, const doub
   }
 }
 
+/* gradiprism_full, gravity_field.f90:207-309: the six components of the gravity gradient tensor of every prism at one
+ * station. lines[d*n + i], d = 0..5 in the order the caller stores them (sensitivity_gravmag.F90:207-209):
+ * XX, YY, ZZ, XY, YZ, ZX. Returns 3 for "Zero denominator in gradiprism_full!", 4 for "Bad log argument in
+ * gradiprism_full!" (:271-280, exit_MPI in the reference), 0 otherwise. */
+int orc_gradiprism_full(int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
+                        const double *Z1, const double *Z2, double xd, double yd, double zd, double *lines) {
+  const double twopi = 2.0 * ORC_PI;
+  const double signo[2] = {-1.0, 1.0};
+  for (int32_t i = 0; i < n; ++i) {
+    double XX[2] = {xd - X1[i], xd - X2[i]};
+    double YY[2] = {yd - Y1[i], yd - Y2[i]};
+    double ZZ[2] = {-(zd - Z1[i]), -(zd - Z2[i])};
+    double gxx = 0.0, gxy = 0.0, gyy = 0.0, gzx = 0.0, gyz = 0.0, gzz = 0.0;
+    for (int K = 0; K < 2; ++K)
+      for (int L = 0; L < 2; ++L)
+        for (int M = 0; M < 2; ++M) {
+          double dmu = signo[K] * signo[L] * signo[M];
+          double Rs = sqrt(XX[K] * XX[K] + YY[L] * YY[L] + ZZ[M] * ZZ[M]);
+          double vxx = atan2(XX[K] * YY[L], XX[K] * XX[K] + Rs * ZZ[M] + ZZ[M] * ZZ[M]);
+          double vyy = atan2(XX[K] * YY[L], Rs * Rs + Rs * ZZ[M] - XX[K] * XX[K]);
+          double vzz = -atan2(XX[K] * YY[L], Rs * ZZ[M]);
+          if (vxx < 0) vxx = vxx + twopi;
+          if (vyy < 0) vyy = vyy + twopi;
+          if (vzz < 0) vzz = vzz + twopi;
+          double arg1 = Rs + ZZ[M];
+          double arg21 = Rs - YY[L], arg22 = Rs + YY[L];
+          double arg31 = Rs - XX[K], arg32 = Rs + XX[K];
+          if (arg22 == 0. || arg32 == 0.) return 3;
+          double arg2 = arg21 / arg22;
+          double arg3 = arg31 / arg32;
+          if (arg1 <= 0. || arg2 <= 0. || arg3 <= 0.) return 4;
+          double vxy = log(arg1);
+          double vzx = 0.5 * log(arg2);
+          double vyz = 0.5 * log(arg3);
+          gxx = gxx + dmu * vxx;
+          gyy = gyy + dmu * vyy;
+          gzz = gzz + dmu * vzz;
+          gxy = gxy + dmu * vxy;
+          gyz = gyz + dmu * vyz;
+          gzx = gzx + dmu * vzx;
+        }
+    lines[0 * (size_t)n + i] = ORC_G_GRAV * gxx;
+    lines[1 * (size_t)n + i] = ORC_G_GRAV * gyy;
+    lines[2 * (size_t)n + i] = ORC_G_GRAV * gzz;
+    lines[3 * (size_t)n + i] = ORC_G_GRAV * gxy;
+    lines[4 * (size_t)n + i] = ORC_G_GRAV * gyz;
+    lines[5 * (size_t)n + i] = ORC_G_GRAV * gzx;
+  }
+  return 0;
+}
+
 /* ========================================================================== */
 /* magnetic_field -- src/forward/gravmag/mag/magnetic_field.f90                */
 /* ========================================================================== */

@@ -91,6 +91,8 @@ int  orc_graviprism_z(int32_t n, const double *X1, const double *X2, const doubl
                       const double *Z1, const double *Z2, double xd, double yd, double zd, double *lineZ);
 void orc_gradiprism_zz(int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
                        const double *Z1, const double *Z2, double xd, double yd, double zd, double *lineZZ);
+int  orc_gradiprism_full(int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
+                         const double *Z1, const double *Z2, double xd, double yd, double zd, double *lines);
 /* src/forward/gravmag/mag/magnetic_field.f90 */
 void orc_dircos(double incl, double decl, double azim, double *a, double *b, double *c);
 int  orc_sharmbox(double x0, double y0, double z0, double x1, double y1, double z1,

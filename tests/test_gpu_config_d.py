@@ -87,8 +87,12 @@ def test_config_d_against_oracle(oracle):
     h, ho = got["histories"][0], want["histories"][0]
     assert len(ho) == 100
     rel = np.abs(h - ho) / ho
-    assert rel[:10].max() < 1e-6, rel[:10]
-    assert rel.max() < 1e-4, (np.argmax(rel), rel.max())        # mid-phase iterates amplify last-bit differences
+    # 121 data rows against 404 010 unknowns: the solve reaches the rounding floor (r ~ 1e-8 ... 1e-11) within ~30
+    # iterations, below which phibar/b1 is rounding noise on both sides: the bar applies on the way down
+    descending = ho > 1.0e-6
+    assert descending.sum() >= 10
+    assert rel[descending].max() < 1e-6, rel[descending]
+    assert h[-1] < 1e-9 and ho[-1] < 1e-9
     # free run: costs and final model after both major iterations
     assert np.allclose(got["costs"], want["costs"], rtol=1e-4)
     assert got["costs"][-1] < got["costs"][1] < got["costs"][0]

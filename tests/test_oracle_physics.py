@@ -94,3 +94,57 @@ def test_magnetic_far_field_is_a_dipole(oracle):
         vals.append(oracle.magprism(box, px, py, zd, 1, 1, mi, md, theta, intensity)[0, 0, 0])
     want = 2.0 * intensity * vol / (4.0 * np.pi * r ** 3)
     assert min(abs(v - want) for v in vals) < 3e-3 * want, (vals, want)
+
+
+# ---- gradiprism_full (gravity_field.f90:207-309): the six components of the gravity gradient tensor --------------------
+def test_gradient_tensor_zz_component_is_gradiprism_zz(oracle):
+    rng = np.random.default_rng(4)
+    box = [np.array(v) for v in ([0.0, 120.0], [100.0, 250.0], [-30.0, 10.0], [60.0, 90.0], [20.0, 200.0], [80.0, 260.0])]
+    for xd, yd, zd in rng.uniform(-400, 400, (5, 3)):
+        zd = -abs(zd) - 1.0
+        full = oracle.gradiprism_full(box, xd, yd, zd)
+        assert full.shape == (6, 2)
+        assert np.array_equal(full[2], oracle.gradiprism_zz(box, xd, yd, zd))      # same expression, same order
+
+
+def test_gradient_tensor_far_field_is_a_point_mass(oracle):
+    """Far from a small prism T_ij = G m (3 r_i r_j - r^2 delta_ij) / r^5 up to the component conventions of Dubey &
+    Tiwari (2015) the routine follows; the convention-independent facts are checked: the off-diagonal magnitudes and the
+    products that do not depend on the sign convention."""
+    box = _box(0, 10, 0, 10, 100, 110)
+    cx, cy, cz, vol = 5.0, 5.0, 105.0, 1000.0
+    for xd, yd, zd in ((1500.0, -900.0, -1.0), (-700.0, 1300.0, -300.0)):
+        t = oracle.gradiprism_full(box, xd, yd, zd)[:, 0]
+        r = np.array([cx - xd, cy - yd, cz - zd]); rn = np.linalg.norm(r)
+        T = G * vol * (3.0 * np.outer(r, r) - rn ** 2 * np.eye(3)) / rn ** 5
+        gxx, gyy, gzz, gxy, gyz, gzx = t
+        assert abs(gxy) == pytest.approx(abs(T[0, 1]), rel=1e-3)
+        assert abs(gyz) == pytest.approx(abs(T[1, 2]), rel=1e-3)
+        assert abs(gzx) == pytest.approx(abs(T[0, 2]), rel=1e-3)
+        assert gzz == pytest.approx(oracle.gradiprism_zz(box, xd, yd, zd)[0], rel=1e-12)
+
+
+def test_gradient_tensor_is_additive_and_aborts_like_the_reference(oracle):
+    rng = np.random.default_rng(6)
+    xs, ys, zs = np.sort(rng.uniform(0, 300, 4)), np.sort(rng.uniform(0, 300, 3)), np.sort(rng.uniform(10, 200, 3))
+    whole = _box(xs[0], xs[-1], ys[0], ys[-1], zs[0], zs[-1])
+    parts = [[], [], [], [], [], []]
+    for i in range(3):
+        for j in range(2):
+            for k in range(2):
+                for arr, v in zip(parts, (xs[i], xs[i + 1], ys[j], ys[j + 1], zs[k], zs[k + 1])):
+                    arr.append(v)
+    parts = [np.array(a) for a in parts]
+    for xd, yd, zd in ((-55.3, 80.1, -0.1), (150.2, 140.7, -20.0), (400.0, -10.0, -5.0)):
+        total = oracle.gradiprism_full(parts, xd, yd, zd).sum(axis=1)
+        one = oracle.gradiprism_full(whole, xd, yd, zd)[:, 0]
+        # the off-diagonal components (logs) and zz are additive; xx / yy come out of atan2 shifted to [0, 2 pi) per
+        # corner, so their sums agree modulo the 2 pi G steps the reference's convention introduces
+        for d in (2, 3, 4, 5):
+            assert total[d] == pytest.approx(one[d], rel=1e-9, abs=1e-22)
+        for d in (0, 1):
+            k = (total[d] - one[d]) / (2.0 * np.pi * G)
+            assert abs(k - round(k)) < 1e-6
+    # station on the vertical line through a cell edge: Rs - YY = 0 / Rs - XX = 0 -> "Bad log argument" (:278-280)
+    with pytest.raises(RuntimeError, match="Bad log argument"):
+        oracle.gradiprism_full(_box(0, 10, 0, 10, 5, 15), 0.0, 0.0, 30.0)

@@ -1,6 +1,7 @@
 // assembly.cu -- forward-kernel evaluation on the device (right rectangular prisms).
 //
-// Replaces graviprism_z / gradiprism_zz (src/forward/gravmag/grav/gravity_field.f90:131-195, :314-364)
+// Replaces graviprism_z / gradiprism_zz / gradiprism_full (src/forward/gravmag/grav/gravity_field.f90:131-195, :314-364,
+// :207-309)
 // and magprism / sharmbox (src/forward/gravmag/mag/magnetic_field.f90:118-457) together with the
 // weighting / real(4) rounding steps of calculate_and_write_sensit (sensitivity_gravmag.F90:228,290)
 // and read_sensitivity_kernel (:837-843).
@@ -74,6 +75,52 @@ __device__ __forceinline__ double grav_gzz(double x1, double x2, double y1, doub
         gzz = __dadd_rn(gzz, __dmul_rn(dmu, vzz));
       }
   return gzz;
+}
+
+// gradiprism_full, gravity_field.f90:207-309: the six tensor components of one prism, out[] in the order the caller stores
+// them (sensitivity_gravmag.F90:207-209): XX, YY, ZZ, XY, YZ, ZX. err: 3 zero denominator (:271-273), 4 bad log argument
+// (:278-280). Same operation order as the reference, no FMA contraction.
+__device__ __forceinline__ void grav_full(double x1, double x2, double y1, double y2, double z1, double z2, double xd,
+                                          double yd, double zd, double (&out)[6], int *err) {
+  const double twopi = 2.0 * TFX_PI;
+  const double XX[2] = {xd - x1, xd - x2};
+  const double YY[2] = {yd - y1, yd - y2};
+  const double ZZ[2] = {-(zd - z1), -(zd - z2)};
+  double gxx = 0.0, gxy = 0.0, gyy = 0.0, gzx = 0.0, gyz = 0.0, gzz = 0.0;
+#pragma unroll
+  for (int K = 0; K < 2; ++K)
+#pragma unroll
+    for (int L = 0; L < 2; ++L)
+#pragma unroll
+      for (int M = 0; M < 2; ++M) {
+        const double dmu = ((K + L + M) & 1) ? 1.0 : -1.0;
+        const double xx = __dmul_rn(XX[K], XX[K]), zz = __dmul_rn(ZZ[M], ZZ[M]);
+        const double Rs = sqrt(__dadd_rn(__dadd_rn(xx, __dmul_rn(YY[L], YY[L])), zz));
+        const double xy = __dmul_rn(XX[K], YY[L]), rz = __dmul_rn(Rs, ZZ[M]);
+        double vxx = atan2(xy, __dadd_rn(__dadd_rn(xx, rz), zz));
+        double vyy = atan2(xy, __dsub_rn(__dadd_rn(__dmul_rn(Rs, Rs), rz), xx));
+        double vzz = -atan2(xy, rz);
+        if (vxx < 0) vxx = vxx + twopi;
+        if (vyy < 0) vyy = vyy + twopi;
+        if (vzz < 0) vzz = vzz + twopi;
+        const double arg1 = Rs + ZZ[M];
+        const double arg21 = Rs - YY[L], arg22 = Rs + YY[L];
+        const double arg31 = Rs - XX[K], arg32 = Rs + XX[K];
+        if (arg22 == 0. || arg32 == 0.) { *err = 3; continue; }
+        const double arg2 = __ddiv_rn(arg21, arg22);
+        const double arg3 = __ddiv_rn(arg31, arg32);
+        if (arg1 <= 0. || arg2 <= 0. || arg3 <= 0.) { *err = 4; continue; }
+        const double vxy = log(arg1);
+        const double vzx = __dmul_rn(0.5, log(arg2));
+        const double vyz = __dmul_rn(0.5, log(arg3));
+        gxx = __dadd_rn(gxx, __dmul_rn(dmu, vxx));
+        gyy = __dadd_rn(gyy, __dmul_rn(dmu, vyy));
+        gzz = __dadd_rn(gzz, __dmul_rn(dmu, vzz));
+        gxy = __dadd_rn(gxy, __dmul_rn(dmu, vxy));
+        gyz = __dadd_rn(gyz, __dmul_rn(dmu, vyz));
+        gzx = __dadd_rn(gzx, __dmul_rn(dmu, vzx));
+      }
+  out[0] = gxx; out[1] = gyy; out[2] = gzz; out[3] = gxy; out[4] = gyz; out[5] = gzx;
 }
 
 // One corner term of graviprism_z (gravity_field.f90:163-188): Z*atan2(X*Y, Z*R) - X*log(R+Y) - Y*log(R+X).
@@ -314,6 +361,36 @@ __global__ void __launch_bounds__(256) grav_lines_nodes_kernel(double *__restric
     __syncthreads();
   }
   if (e) atomicExch(err, e);
+}
+
+// Full-tensor gradiometry lines: lines[(b*6 + d)*n + p] (Fortran sensit_line(p, 1, d) of station b).
+__global__ void __launch_bounds__(256) grav_full_lines_kernel(double *__restrict__ lines, int n, int nb,
+                                                              const double *__restrict__ X1, const double *__restrict__ X2,
+                                                              const double *__restrict__ Y1, const double *__restrict__ Y2,
+                                                              const double *__restrict__ Z1, const double *__restrict__ Z2,
+                                                              const double *__restrict__ xd, const double *__restrict__ yd,
+                                                              const double *__restrict__ zd, int *err) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double x1 = X1[p], x2 = X2[p], y1 = Y1[p], y2 = Y2[p], z1 = Z1[p], z2 = Z2[p];
+  int e = 0;
+  for (int b = blockIdx.y; b < nb; b += gridDim.y) {
+    double v[6];
+    grav_full(x1, x2, y1, y2, z1, z2, xd[b], yd[b], zd[b], v, &e);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) lines[((long long)b * 6 + d) * n + p] = __dmul_rn(g_grav(), v[d]);
+  }
+  if (e) atomicExch(err, e);
+}
+
+int grav_full_lines(const GridDev &g, int32_t nb, const double *d_xd, const double *d_yd, const double *d_zd,
+                    double *d_lines, int *d_err, cudaStream_t st) {
+  dim3 grid((g.n + 255) / 256, std::min(nb, 1024));
+  grav_full_lines_kernel<<<grid, 256, 0, st>>>(d_lines, g.n, nb, g.X1.p, g.X2.p, g.Y1.p, g.Y2.p, g.Z1.p, g.Z2.p, d_xd,
+                                               d_yd, d_zd, d_err);
+  ctx().launches++;
+  TFX_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int grav_lines(const GridDev &g, int32_t nb, const double *d_xd, const double *d_yd, const double *d_zd, int data_type,

@@ -161,6 +161,10 @@ int assemble_grav_dense(DenseCM &S, const GridDev &g, int32_t cell0, int32_t nce
 int grav_lines(const GridDev &g, int32_t ndata_batch, const double *d_xd, const double *d_yd, const double *d_zd,
                int data_type, double *d_lines, int *d_err, cudaStream_t st);
 
+// Full-tensor gravity gradiometry lines (gradiprism_full): d_lines[(b*6 + d)*ncells + p], d = XX, YY, ZZ, XY, YZ, ZX.
+int grav_full_lines(const GridDev &g, int32_t ndata_batch, const double *d_xd, const double *d_yd, const double *d_zd,
+                    double *d_lines, int *d_err, cudaStream_t st);
+
 // Magnetic tensor lines: d_lines[((b*ndc + d)*nmc + k)*ncells + p] (Fortran sensit_line(p,k,d) per data b).
 int mag_lines(const GridDev &g, int32_t ndata_batch, const double *d_xd, const double *d_yd, const double *d_zd,
               int nmc, int ndc, double mi, double md, double theta, double intensity, double *d_lines,

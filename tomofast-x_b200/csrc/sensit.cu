@@ -231,6 +231,8 @@ int upload_grid_impl(GridDev &g, int32_t n, const double *X1, const double *X2, 
 int kernel_error(int e) {
   if (e == 1) return fail(-70, "Data coordinate coincides with model grid boundary (YZ). Adjust the model grid!");
   if (e == 2) return fail(-70, "Data coordinate coincides with model grid boundary (XZ). Adjust the model grid!");
+  if (e == 3) return fail(-70, "Zero denominator in gradiprism_full! Adjust the model grid.");
+  if (e == 4) return fail(-70, "Bad log argument in gradiprism_full! Adjust the model grid.");
   if (e == 11) return fail(-70, "The model grid X-boundary coincides with the data position");
   if (e == 12) return fail(-70, "The model grid Y-boundary coincides with the data position");
   return fail(-70, "forward kernel error");
@@ -242,7 +244,9 @@ int compute_lines(const tfx_sensit_params &P, const GridDev &g, int nb, const do
     if (P.nmodel_components != 1) return fail(-71, "gravity: nmodel_components must be 1");
     if (P.data_type == 1 && P.ndata_components == 1) return grav_lines(g, nb, dx, dy, dz, 1, d_lines, d_err, st);
     if (P.data_type == 2 && P.ndata_components == 1) return grav_lines(g, nb, dx, dy, dz, 2, d_lines, d_err, st);
-    return fail(-72, "gravity: only data_type 1 (gz) and 2 with one component (gzz) are available on the device");
+    if (P.data_type == 2 && P.ndata_components == 6) return grav_full_lines(g, nb, dx, dy, dz, d_lines, d_err, st);
+    if (P.data_type == 2) return fail(-72, "Wrong number of gravity gradiometry data components!");   // :210-212
+    return fail(-72, "gravity: unknown data_type (1: gz, 2: gradiometry)");
   }
   if (P.problem_type == 2)
     return mag_lines(g, nb, dx, dy, dz, P.nmodel_components, P.ndata_components, P.mi, P.md, P.theta, P.intensity,
