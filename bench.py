@@ -178,6 +178,9 @@ def run_ours(a):
 
     d = Dist()
     tfx.init(d.local_rank)
+    for kv in a.opt:
+        k, v = kv.split("=")
+        tfx.set_option(k, int(v))
     if a.dense_vec4 is not None:
         tfx.set_option("dense_vec4", a.dense_vec4)
     if a.dense_f2f_rows is not None:
@@ -449,18 +452,37 @@ def compressed_spmv(a, tfx, d):
     rate = a.comp_rate
     N = nx * ny * nz
     per_rank = a.comp_ndata
-    batch = a.comp_batch if a.comp_batch >= 0 else 400 * d.world
-    # fit the layouts (12 B/nnz) + the build peak of one row block (~3x its own 12 B/nnz) + the row pipeline into the
-    # memory that is free now; a smaller station count is reported, never silently
+    # Row blocks. A block is built from triplets: up to ~45 B per entry at the peak of its build (triplets, the two CSR
+    # copies, the scratch of the stable sort by column), 12 B per entry once its T16 layouts stand. --comp-batch -1 (default) sizes every block to the
+    # memory that is free WHEN IT IS BUILT: the first blocks are large (thousands of stations: long segments, the
+    # kernels' best case), the last ones small -- instead of equal thin blocks sized for the last one.
+    auto_blocks = a.comp_batch < 0
+    batch = a.comp_batch if a.comp_batch >= 0 else 0
     free_b, _ = tfx.device_mem_info()
     free_b = d.min(float(free_b))
     nel_row = max(1, int(rate * N))
-    blk_rows = (batch // d.world) if batch > 0 else per_rank
-    need = lambda rows: 12.0 * nel_row * rows + 36.0 * nel_row * min(blk_rows, rows) + 40.0 * N + (3 << 30)
-    while per_rank > 16 and need(per_rank) > 0.94 * free_b:
+    kBuild, kReserve = 48.0, 40.0 * N + (4 << 30)
+    if auto_blocks:
+        need = lambda rows: 12.0 * nel_row * rows + kReserve + kBuild * nel_row * 64
+    else:
+        blk_rows = (batch // d.world) if batch > 0 else per_rank
+        need = lambda rows: 12.0 * nel_row * rows + 36.0 * nel_row * min(blk_rows, rows) + kReserve
+    while per_rank > 16 and need(per_rank) > 0.94 * free_b:    # a smaller station count is reported, never silent
         per_rank = int(per_rank * 0.9)
     nd = per_rank * d.world
-    a_comp_batch = batch
+    a_comp_batch = batch if not auto_blocks else 1
+
+    def next_block(rows_left):
+        """Stations (all ranks together) of the next row block."""
+        if not auto_blocks:
+            return min(a_comp_batch, rows_left)
+        fr, _ = tfx.device_mem_info()
+        fr = d.min(float(fr))
+        fit = int((0.92 * fr - kReserve) / (kBuild * nel_row))     # rows per rank whose build fits now
+        nb = max(32, fit) * d.world
+        if rows_left - nb < 64 * d.world:                          # no crumbs at the end
+            nb = rows_left
+        return min(nb, rows_left)
     grid = regular_grid(nx, ny, nz)
     xyz = station_lattice(nd, 100.0 * nx, 100.0 * ny, z=-0.1)
     cw = depth_weight_type1(grid, 2.0, 0.0, 4.0e3)
@@ -497,14 +519,17 @@ def compressed_spmv(a, tfx, d):
         S = tfx.SparseMatrix(nd, 2 * ncl, int(nd) * int(rate * N))
         nnz = 0
         cerr_sum = 0.0
-        for b0 in range(0, nd, a_comp_batch):
-            nb = min(a_comp_batch, nd - b0)
+        b0, block_sizes = 0, []
+        while b0 < nd:
+            nb = next_block(nd - b0)
+            block_sizes.append(nb)
             par_b = copy.copy(par); par_b.ndata = nb
             xb = tuple(np.ascontiguousarray(v[b0:b0 + nb]) for v in xyz)
             rows_b, _, cerr_b, tot_b = tfx.sensit_assemble_rows(par_b, grid, xb, cw, dw1[b0:b0 + nb], d.rank, d.world)
             tfx.sensit_repartition_into(S, rows_b, 1, nel_at, d.rank, d.world)
             del rows_b
             nnz += int(tot_b); cerr_sum += cerr_b * nb
+            b0 += nb
         S.finalize()
         tfx.set_option("sensit_row_blocks", 0)
         cerr = cerr_sum / nd
@@ -544,7 +569,8 @@ def compressed_spmv(a, tfx, d):
     if per_rank != a.comp_ndata:
         out["note"] = "stations per GPU reduced from %d to %d to fit the free HBM (%.0f GB)" % (a.comp_ndata, per_rank, free_b / 1e9)
     if a_comp_batch > 0:
-        out["row_blocks"] = {"stations_per_batch": a_comp_batch, "batches": (nd + a_comp_batch - 1) // a_comp_batch,
+        out["row_blocks"] = {"stations_per_block": block_sizes, "blocks": len(block_sizes),
+                             "sizing": "each block sized to the HBM free when it is built" if auto_blocks else "fixed",
                              "partition_sample_s": round(t_sample, 2), "device_bytes_per_rank_max": int(d.max(float(S.device_bytes())))}
     if d.world > 1:
         out["column_slabs"] = slabs
@@ -707,6 +733,7 @@ def main():
                     help="assemble the compressed kernel in row blocks of this many stations (all ranks together); "
                          "0 = one piece, -1 (default) = 400 per rank")
     ap.add_argument("--no-config-d", action="store_true", help="skip the config D extra")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="tfx_set_option before the run (A/B switches)")
     ap.add_argument("--config-e", type=int, default=-1, help="1 / 0: run / skip the config E extra (default: run when --gpus >= 2)")
     ap.add_argument("--e-grid", type=int, nargs=3, default=None, metavar=("NX", "NY", "NZ"))
     ap.add_argument("--e-ndata", type=int, default=0, help="stations per problem and GPU of the config E extra")

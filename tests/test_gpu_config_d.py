@@ -41,6 +41,7 @@ def oracle_config_d(orc, c, S, column_weight, compression_type):
                             shift + k * N, True)
         Cm.finalize()
         out["rhs"].append(b.copy())
+        out.setdefault("C0", Cm)
         x, h, it = orc.lsqr_solve_sensit(c["niter"], c["rmin"], 0.0, 0.0, S, Cm, b, N, nx, ny, nz, ncomp, compression_type,
                                          True, solve_problem=(0, 1))
         out["histories"].append(h)
@@ -83,16 +84,49 @@ def test_config_d_against_oracle(oracle):
     want = oracle_config_d(oracle, c, So, got["column_weight"], 2)
     assert np.allclose(got["d_obs"], want["d_obs"], rtol=1e-11, atol=1e-14 * np.abs(want["d_obs"]).max())
     assert len(got["histories"]) == 2 and all(len(h) == 100 for h in got["histories"])
-    # major iteration 1 starts from identical states: the LSQR bar (1e-6) on the residual history
-    h, ho = got["histories"][0], want["histories"][0]
+    # ---- major iteration 1 starts from identical states: the LSQR bar (1e-6) on the residual history.
+    # 121 data rows against 404 010 unknowns: r_k falls from 1 to ~1e-8 within ~30 iterations and the iterates on the way
+    # down are chaotic under last-bit perturbations (like config A's mid-phase, tests/test_oracle_mansf.py): the oracle's
+    # own envelope under exact-invariance rescalings of b is measured, strict_order (reference summation order) must meet
+    # the bar on ALL iterations above the rounding floor, the fast kernels where the oracle itself is reproducible.
+    N, nd, ncomp = c["N"], c["ndata"], c["ncomp"]
+    b = want["rhs"][0]
+    ho = want["histories"][0]
     assert len(ho) == 100
-    rel = np.abs(h - ho) / ho
-    # 121 data rows against 404 010 unknowns: the solve reaches the rounding floor (r ~ 1e-8 ... 1e-11) within ~30
-    # iterations, below which phibar/b1 is rounding noise on both sides: the bar applies on the way down
-    descending = ho > 1.0e-6
-    assert descending.sum() >= 10
-    assert rel[descending].max() < 1e-6, rel[descending]
-    assert h[-1] < 1e-9 and ho[-1] < 1e-9
+    solve_o = lambda rhs: oracle.lsqr_solve_sensit(c["niter"], c["rmin"], 0.0, 0.0, So, want["C0"], rhs, N, c["nx"], c["ny"],
+                                                   c["nz"], ncomp, 2, True, solve_problem=(0, 1))[1]
+    env = np.zeros_like(ho)
+    for scale in (1.0 + 2.3e-16, 3.0, 1.0 / 3.0):
+        env = np.maximum(env, np.abs(solve_o(b * scale) - ho) / ho)
+    Cg = tfx.SparseMatrix(ncomp * N, 2 * ncomp * N, ncomp * N)
+    bg = np.zeros_like(b); bg[:nd] = b[:nd]
+    m0 = np.full((ncomp, N), c["start_value"]); prior = np.zeros((ncomp, N))
+    for k in range(ncomp):
+        tfx.damping_add(Cg, bg[nd:], c["alpha"], 1.0, 2.0, 2, c["nx"], c["ny"], c["nz"], got["column_weight"], m0[k], prior[k],
+                        ncomp * N + k * N, True)
+    Cg.finalize()
+    assert np.array_equal(bg, b)                                       # device-built constraint RHS: bit-identical
+    hist = {}
+    for mode in (1, 0):
+        tfx.set_option("strict_order", mode)
+        try:
+            u = b.copy(); x = np.zeros(2 * ncomp * N)
+            tfx.lsqr_solve_sensit(len(u), x.size, c["niter"], c["rmin"], 0.0, 0.0, got["S"], Cg, u, x, [0, 1], N, c["nx"],
+                                  c["ny"], c["nz"], ncomp, 2, True)
+        finally:
+            tfx.set_option("strict_order", 0)
+        hist[mode] = tfx.last_history()[0]
+    floor = ho > 1.0e-7                                                # below: phibar/b1 is rounding noise on every side
+    rel_s = np.abs(hist[1] - ho) / ho
+    rel_f = np.abs(hist[0] - ho) / ho
+    assert floor.sum() >= 15
+    assert rel_s[floor].max() < 1e-6, (rel_s[floor].max(), rel_s[floor].argmax())
+    # fast kernels (tree-order sums, deferred normalisation): the bar holds while the residual is well above the floor and
+    # the oracle itself is reproducible; the last decades before the floor amplify last-bit differences to O(1)
+    stable = (ho > 1.0e-5) & (env < 1e-8)
+    assert stable.sum() >= 10 and rel_f[stable].max() < 1e-6, (stable.sum(), rel_f[stable])
+    assert np.array_equal(hist[0], got["histories"][0])                # run_config_d's own first solve: same kernels
+    assert hist[0][-1] < 1e-9 and ho[-1] < 1e-9
     # free run: costs and final model after both major iterations
     assert np.allclose(got["costs"], want["costs"], rtol=1e-4)
     assert got["costs"][-1] < got["costs"][1] < got["costs"][0]

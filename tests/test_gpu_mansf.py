@@ -107,3 +107,39 @@ def test_device_resident_major_loop(oracle):
     m_dev = idev.m.numpy()
     assert np.abs(m_dev - io.m).max() < 1e-3 * np.abs(io.m).max()
     assert len(idev.admm_costs) == 10 and all(np.isfinite(idev.admm_costs))
+
+
+def test_all_60_major_iterations(oracle):
+    """Config A in full: 60 major x 100 LSQR iterations (parfiles/Parfile_mansf_slice.txt:58-59).
+    (1) teacher-forced, strict_order: ALL 6000 residuals r_k within 1e-6 relative of the oracle -- the north-star bar on
+        the whole Parfile, not on its first major iterations;
+    (2) free run on the benchmarked fast kernels: final data cost and model against the oracle's own free run and the
+        surveyor's figures (cost ~9e-11, model range [-19.95, 260.0])."""
+    cfg = mansf.Config()
+    io = mansf.Inversion(mansf.OracleBackend(oracle), cfg, oracle.admm_iterate)
+    ig = mansf.Inversion(mansf.TfxBackend(tfx), cfg, oracle.admm_iterate)
+    Sg = tfx.SparseMatrix.from_arrays(cfg.ndata, cfg.ncolumns, *io.S.arrays())
+    worst = 0.0
+    tfx.set_option("strict_order", 1)
+    try:
+        for major in range(60):
+            b = io.build_rhs()
+            xo, ho = io.be.solve(cfg, io.S, io.C, b)
+            xs, hs = ig.be.solve(cfg, Sg, ig.C, b)
+            assert len(hs) == len(ho) == cfg.niter
+            rel = np.abs(hs - ho) / ho
+            worst = max(worst, rel.max())
+            assert rel.max() < 1e-6, (major, rel.max(), rel.argmax())
+            assert np.allclose(xs, xo, rtol=1e-6, atol=1e-9 * np.abs(xo).max())
+            io.histories.append(ho)
+            io.apply(xo)
+    finally:
+        tfx.set_option("strict_order", 0)
+    assert 5e-11 < io.costs[-1] < 2e-10
+    print("config A, 60 x 100 iterations, strict_order: worst relative residual difference %.3e" % worst)
+    # free run, fast kernels
+    for major in range(60):
+        ig.step()
+    assert ig.costs[-1] < 1e-9 and ig.costs[-1] == pytest.approx(io.costs[-1], rel=0.5)
+    assert -19.96 < ig.m.min() < -19.9 and 259.9 < ig.m.max() < 260.0
+    assert np.abs(ig.m - io.m).max() < 2e-2 * np.abs(io.m).max()

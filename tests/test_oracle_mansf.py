@@ -44,3 +44,15 @@ def test_residual_history_is_chaotic_under_rounding(oracle):
     assert rel[12:40].max() > 1e-5
     assert rel[60:].max() < 1e-6
     assert np.abs(x1 - x0).max() < 1e-8 * np.abs(x0).max()
+
+
+def test_all_60_major_iterations(oracle):
+    """Parfile_mansf_slice in full (60 major x 100 LSQR iterations, parfiles/Parfile_mansf_slice.txt:58-59): the
+    surveyor's end-of-run figures: relative data cost ~9e-11, model inside the ADMM bounds [-20, 260]."""
+    cfg = mansf.Config()
+    io = mansf.Inversion(mansf.OracleBackend(oracle), cfg, oracle.admm_iterate)
+    for _ in range(60):
+        io.step()
+    assert all(len(h) == 100 for h in io.histories)          # every solve hits niter
+    assert 5e-11 < io.costs[-1] < 2e-10
+    assert -19.96 < io.m.min() < -19.9 and 259.9 < io.m.max() < 260.0

@@ -356,6 +356,14 @@ int tfx_set_option(const char *name, int value) {
     g_opt_lsqr_graph = value;
     return 0;
   }
+  if (name && strcmp(name, "t16_blk") == 0) {
+    g_opt_t16_blk = value;
+    return 0;
+  }
+  if (name && strcmp(name, "t16_long_seg") == 0) {
+    g_opt_t16_long_seg = value;
+    return 0;
+  }
   if (name && strcmp(name, "wavelet_tile_kb") == 0) {
     g_opt_wavelet_tile_kb = value;
     return 0;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <exception>
 #include <string>
 
 namespace tfx {
@@ -24,6 +25,18 @@ int fail(int code, const std::string &msg);
       return ::tfx::fail(-100, std::string("CUDA error: ") + cudaGetErrorString(_e) +       \
                                    " at " __FILE__ ":" + std::to_string(__LINE__));         \
     }                                                                                       \
+  } while (0)
+
+// Thrust / CUB signal failures (typically cudaErrorMemoryAllocation of their scratch space) with C++ exceptions; no
+// exception may cross the C ABI (a Fortran / C host would abort without the library's message).
+#define TFX_THRUST(stmt)                                                                           \
+  do {                                                                                             \
+    try {                                                                                          \
+      stmt;                                                                                        \
+    } catch (const std::exception &_ex) {                                                          \
+      cudaGetLastError();                                                                          \
+      return ::tfx::fail(-101, std::string("device scratch allocation failed (thrust): ") + _ex.what()); \
+    }                                                                                              \
   } while (0)
 
 #define TFX_TRY(expr)              \

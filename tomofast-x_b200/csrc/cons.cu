@@ -69,7 +69,7 @@ int emit_rows(Matrix &M, const Gen &g, int64_t nrows) {
   TFX_CUDA(cudaMemsetAsync(cnt.p + nrows, 0, 4, st));
   k_cons_count<<<cons_grid(nrows), kCT, 0, st>>>(g, nrows, cnt.p);
   auto first = thrust::make_transform_iterator(thrust::device_pointer_cast(cnt.p), ToI64());
-  thrust::exclusive_scan(thrust::cuda::par.on(st), first, first + nrows + 1, thrust::device_pointer_cast(off.p));
+  TFX_THRUST(thrust::exclusive_scan(thrust::cuda::par.on(st), first, first + nrows + 1, thrust::device_pointer_cast(off.p)));
   int64_t nnz = 0;
   TFX_CUDA(cudaMemcpyAsync(&nnz, off.p + nrows, 8, cudaMemcpyDeviceToHost, st));
   TFX_CUDA(cudaStreamSynchronize(st));

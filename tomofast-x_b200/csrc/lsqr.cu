@@ -486,10 +486,10 @@ int build_plan(ConsPlan &P, Matrix *C, int nranks, int rank, cudaStream_t st) {
   if (nranks > 1) TFX_TRY(comm_allreduce_sum_u8(P.cnt.p, (size_t)P.ncons, st));
   thrust::counting_iterator<int> first(0);
   if (nranks > 1) {
-    P.nshared = (int32_t)thrust::count_if(pol, first, first + P.ncons, CntIs{P.cnt.p, 2, 255});
+    TFX_THRUST(P.nshared = (int32_t)thrust::count_if(pol, first, first + P.ncons, CntIs{P.cnt.p, 2, 255}));
     TFX_TRY(P.shared_rows.alloc((size_t)P.nshared));
     thrust::device_ptr<int32_t> out(P.shared_rows.p);
-    if (P.nshared > 0) thrust::copy_if(pol, first, first + P.ncons, out, CntIs{P.cnt.p, 2, 255});
+    if (P.nshared > 0) TFX_THRUST(thrust::copy_if(pol, first, first + P.ncons, out, CntIs{P.cnt.p, 2, 255}));
     c.launches += 2;
     if (P.nseg > 0) {
       TFX_TRY(P.seg_slot.alloc((size_t)P.nseg));
@@ -499,10 +499,10 @@ int build_plan(ConsPlan &P, Matrix *C, int nranks, int rank, cudaStream_t st) {
     }
   }
   if (rank == 0) {
-    P.nempty = (int32_t)thrust::count_if(pol, first, first + P.ncons, CntIs{P.cnt.p, 0, 0});
+    TFX_THRUST(P.nempty = (int32_t)thrust::count_if(pol, first, first + P.ncons, CntIs{P.cnt.p, 0, 0}));
     TFX_TRY(P.empty_rows.alloc((size_t)P.nempty));
     thrust::device_ptr<int32_t> out(P.empty_rows.p);
-    if (P.nempty > 0) thrust::copy_if(pol, first, first + P.ncons, out, CntIs{P.cnt.p, 0, 0});
+    if (P.nempty > 0) TFX_THRUST(thrust::copy_if(pol, first, first + P.ncons, out, CntIs{P.cnt.p, 0, 0}));
     c.launches += 2;
   }
   TFX_CUDA(cudaStreamSynchronize(st));

@@ -514,8 +514,8 @@ static int runs_of_sorted_keys(const int32_t *d_keys, int64_t n, int32_t max_uni
   TFX_TRY(ucols.alloc(cap)); TFX_TRY(ucnt.alloc(cap));
   thrust::device_ptr<const int32_t> K(d_keys);
   thrust::device_ptr<int32_t> UC(ucols.p), UN(ucnt.p);
-  auto ends = thrust::reduce_by_key(pol, K, K + n, thrust::make_constant_iterator<int32_t>(1), UC, UN);
-  const size_t nu = (size_t)(ends.first - UC);
+  size_t nu = 0;
+  TFX_THRUST(nu = (size_t)(thrust::reduce_by_key(pol, K, K + n, thrust::make_constant_iterator<int32_t>(1), UC, UN).first - UC));
   uniq.resize(nu);
   std::vector<int32_t> cnt(nu);
   TFX_CUDA(cudaMemcpyAsync(uniq.data(), ucols.p, nu * 4, cudaMemcpyDeviceToHost, st));
@@ -564,7 +564,7 @@ int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R
     TFX_CUDA(cudaMemcpyAsync(T.val.p, F.val.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
     thrust::device_ptr<int32_t> K(keys.p), Rw(T.idx.p);
     thrust::device_ptr<float> V(T.val.p);
-    thrust::stable_sort_by_key(pol, K, K + nnz, thrust::make_zip_iterator(thrust::make_tuple(Rw, V)));
+    TFX_THRUST(thrust::stable_sort_by_key(pol, K, K + nnz, thrust::make_zip_iterator(thrust::make_tuple(Rw, V))));
     c.launches += 2;
     TFX_TRY(runs_of_sorted_keys(keys.p, nnz, ncolumns, tmap, tptr));
   }

@@ -306,7 +306,7 @@ static int repartition_core(tfx_sensit_rows *rows, int32_t problem_slot, const i
     k_piece_counts<<<g1, 256, 0, st>>>(d_bound.p, nseg, nbproc, d_off.p);
     TFX_CUDA(cudaMemsetAsync(d_off.p + nseg * nbproc, 0, 8, st));
     thrust::device_ptr<int64_t> O(d_off.p);
-    thrust::exclusive_scan(thrust::cuda::par.on(st), O, O + nseg * nbproc + 1, O);
+    TFX_THRUST(thrust::exclusive_scan(thrust::cuda::par.on(st), O, O + nseg * nbproc + 1, O));
     c.launches += 4;
     for (int32_t r = 0; r <= nbproc; ++r)
       TFX_CUDA(cudaMemcpyAsync(&send_off[r], d_off.p + (int64_t)r * nseg, 8, cudaMemcpyDeviceToHost, st));

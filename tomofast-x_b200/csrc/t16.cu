@@ -44,6 +44,8 @@ int g_opt_t16_tile = 0;            // 0: automatic; otherwise forced tile size (
 // segment order of the builder; transposed 2.45 (registers) -> 2.56 (ring alone) -> 2.28 ms (ring + bank dealing).
 int g_opt_t16_async = 3;
 int g_opt_t16_bank_deal = 1;       // 1: long segments are dealt over the shared-memory banks by the builder
+int g_opt_t16_blk = 0;            // 0: automatic (32 / 16 / 8 outputs per warp task by the number of outputs)
+int g_opt_t16_long_seg = 256;     // segments longer than this take the whole-warp path (<= 256)
 int g_opt_t16_direct_max = 16384;   // gathered ranges up to this many elements use one DIRECT tile; longer ones TILES
 
 static const int kT16Threads = 768;      // DIRECT: one CTA per SM
@@ -78,6 +80,9 @@ struct T16Args {
   int accumulate;          // DIRECT: y += instead of y =
   int async_ring;          // long segments go through the cp.async ring (the warp strip holds kAsyncRingBytes)
   int wstrip;              // doubles per warp strip (flat-run products / cp.async ring)
+  int blk;                 // outputs a warp takes at a time (32; 16 or 8 when a tile has few outputs, so that every warp
+                           // of the CTA parked on it finds work -- row blocks of a few hundred stations)
+  int long_seg;            // segments longer than this are summed by the whole warp (<= kLongSeg)
   const int *done;
 };
 
@@ -227,10 +232,12 @@ __device__ __forceinline__ double t16_long_async(const float *__restrict__ val, 
 __device__ __forceinline__ double t16_block32(const T16Args &a, const double *xs, double *wbuf, int64_t tbase, int o0,
                                               int lane) {
   const int o = o0 + lane;
-  // lanes past the last output read the end pointer: empty segments, offsets stay monotone
-  const int64_t pb = __ldg(a.ptr + tbase + min(o, a.nseg));
+  // lanes past the last output of the block (o0 + blk) or of the layout read the end pointer: empty segments, offsets
+  // stay monotone
+  const int olim = min(o0 + a.blk, a.nseg);
+  const int64_t pb = __ldg(a.ptr + tbase + min(o, olim));
   int64_t pe = __shfl_down_sync(0xffffffffu, pb, 1);
-  if (lane == 31) pe = __ldg(a.ptr + tbase + min(o + 1, a.nseg));
+  if (lane == 31) pe = __ldg(a.ptr + tbase + min(o + 1, olim));
   const int64_t pb0 = __shfl_sync(0xffffffffu, pb, 0);
   const int len = (int)(pe - pb);                              // a segment never exceeds the tile size
   const int rel = (int)(pb - pb0);                             // 32 segments span < 2^31 entries
@@ -238,7 +245,7 @@ __device__ __forceinline__ double t16_block32(const T16Args &a, const double *xs
   if (__ballot_sync(0xffffffffu, len > 0) == 0u) return result;
   const float *__restrict__ val = a.val + pb0;                 // pb0 is even: 8-byte aligned packets
   const uint16_t *__restrict__ key = a.key + pb0;
-  const bool is_long = len > kLongSeg;
+  const bool is_long = len > a.long_seg;
   unsigned longmask = __ballot_sync(0xffffffffu, is_long);
   const unsigned flatmask = ~longmask;
   if (a.async_ring) {
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(kT16Threads, 1) t16_direct_kernel(T16Args a) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double *wbuf = xs + ((a.tile + 15) & ~15) + wid * a.wstrip;
   const int64_t tbase = (int64_t)a.t0 * a.nseg;
-  const int nblk = (a.nseg + 31) / 32;
+  const int nblk = (a.nseg + a.blk - 1) / a.blk;
   __syncthreads();
   for (;;) {
     int base = 0;
@@ -317,9 +324,9 @@ __global__ void __launch_bounds__(kT16Threads, 1) t16_direct_kernel(T16Args a) {
     if (base >= nblk) break;
     const int b_hi = min(nblk, base + kDirectChunk);
     for (int blk = base; blk < b_hi; ++blk) {
-      const double r = t16_block32(a, xs, wbuf, tbase, blk * 32, lane);
-      const int o = blk * 32 + lane;
-      if (o < a.nseg) a.y[o] = a.accumulate ? (a.y[o] + r) : r;
+      const double r = t16_block32(a, xs, wbuf, tbase, blk * a.blk, lane);
+      const int o = blk * a.blk + lane;
+      if (lane < a.blk && o < a.nseg) a.y[o] = a.accumulate ? (a.y[o] + r) : r;
     }
   }
 }
@@ -335,7 +342,7 @@ __global__ void __launch_bounds__(NT, MINB) t16_tiles_kernel(T16Args a) {
   __shared__ int s_next;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double *wbuf = xs + ((a.tile + 15) & ~15) + wid * a.wstrip;
-  const int nblk = (a.nseg + 31) / 32;
+  const int nblk = (a.nseg + a.blk - 1) / a.blk;
   const int start = (int)((int64_t)blockIdx.x * a.ntiles / gridDim.x);
   int i = 0;   // tiles visited so far (relative to start)
   for (;;) {
@@ -368,9 +375,9 @@ __global__ void __launch_bounds__(NT, MINB) t16_tiles_kernel(T16Args a) {
       if (lane == 0) blk = atomicAdd(a.counter + t, 1);
       blk = __shfl_sync(0xffffffffu, blk, 0);
       if (blk >= nblk) break;
-      const double r = t16_block32(a, xs, wbuf, tbase, blk * 32, lane);
-      const int o = blk * 32 + lane;
-      if (o < a.nseg) a.partial[tbase + o] = r;
+      const double r = t16_block32(a, xs, wbuf, tbase, blk * a.blk, lane);
+      const int o = blk * a.blk + lane;
+      if (lane < a.blk && o < a.nseg) a.partial[tbase + o] = r;
     }
     ++i;
   }
@@ -425,7 +432,11 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
   a.partial = m.partial.p; a.counter = m.counter.p;
   a.nseg = m.nseg; a.tile = m.tile; a.ntiles = m.ntiles; a.nin = m.nin; a.nsplit = m.nsplit;
   a.t0 = 0; a.accumulate = accumulate ? 1 : 0; a.done = d_done;
-  const int nblk = (m.nseg + 31) / 32;
+  // outputs per warp task: fewer when the layout has few outputs (every tile visit must feed all 24 warps of a CTA)
+  a.blk = (m.nseg >= 32 * 48) ? 32 : (m.nseg >= 16 * 48 ? 16 : 8);
+  if (g_opt_t16_blk > 0) a.blk = g_opt_t16_blk;
+  a.long_seg = std::max(8, std::min(g_opt_t16_long_seg, kLongSeg));
+  const int nblk = (m.nseg + a.blk - 1) / a.blk;
   const size_t tile_bytes = (size_t)((m.tile + 15) & ~15) * sizeof(double);
   const size_t smem_max = 227 * 1024 - 64;
   const size_t strip_flat = (size_t)(kFlatMax / 2) * sizeof(double), strip_async = (size_t)kAsyncRingBytes;
@@ -685,7 +696,7 @@ int t16_build(const SegMatrix &src, T16Matrix &T, cudaStream_t st) {
   TFX_CUDA(cudaMemsetAsync(T.ptr.p + table, 0, 8, st));
   {
     thrust::device_ptr<int64_t> P(T.ptr.p);
-    thrust::exclusive_scan(thrust::cuda::par.on(st), P, P + table + 1, P);
+    TFX_THRUST(thrust::exclusive_scan(thrust::cuda::par.on(st), P, P + table + 1, P));
     c.launches += 2;
   }
   int64_t padded = 0;
