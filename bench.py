@@ -684,7 +684,10 @@ def cpu_reference(a, steps, warmup, seconds_hint=20.0):
     full_entries = float(a.ndata) * a.nx * a.ny * a.nz
     its_per_s_sample = 1.0 / t_iter
     value = its_per_s_sample * sample_entries / full_entries          # SpMV cost is linear in nnz
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "projected": True,
+            "projection": "measured on a column sample that fits the host RAM (the full CSR is 335 GB), scaled linearly in "
+                          "nnz; workers are independent column slabs WITHOUT the per-iteration all-reduce of u and without "
+                          "the damping block (both favour the CPU arm)",
             "value_1core": (its1 / dt1) * ent1 / full_entries,
             "sample": "oracle lsqr_solve (C port of lsqr_solver2.F90:321-473 + sparse_matrix.f90:313-405), "
                       "%d column-slab processes x (%d rows x %d dense columns, CSR f32+i32), %d iterations each; "
@@ -705,8 +708,9 @@ def run_reference(a):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "reference = Fortran 2008 + MPI, not buildable in this image (no Fortran compiler, no MPI): "
-                    "timed arm is the line-faithful C port (oracle/)"}
+            "note": "reference = Fortran 2008 + MPI, not buildable in this image nor on the GPU box (no Fortran compiler, no "
+                    "MPI: profiles/r2_probe_fortran_gpubox.txt): the timed arm is the line-faithful C port (oracle/) and its "
+                    "value is PROJECTED from a column sample (cpu_baseline.projection)"}
     print(json.dumps(line), flush=True)
 
 

@@ -87,17 +87,20 @@ def test_config_d_against_oracle(oracle):
     # ---- major iteration 1 starts from identical states: the LSQR bar (1e-6) on the residual history.
     # 121 data rows against 404 010 unknowns: r_k falls from 1 to ~1e-8 within ~30 iterations and the iterates on the way
     # down are chaotic under last-bit perturbations (like config A's mid-phase, tests/test_oracle_mansf.py): the oracle's
-    # own envelope under exact-invariance rescalings of b is measured, strict_order (reference summation order) must meet
-    # the bar on ALL iterations above the rounding floor, the fast kernels where the oracle itself is reproducible.
+    # own envelope under tiny perturbations of b is measured, strict_order (reference summation order) must meet the bar
+    # on ALL iterations above the rounding floor, the fast kernels where the oracle itself is reproducible.
     N, nd, ncomp = c["N"], c["ndata"], c["ncomp"]
     b = want["rhs"][0]
     ho = want["histories"][0]
     assert len(ho) == 100
     solve_o = lambda rhs: oracle.lsqr_solve_sensit(c["niter"], c["rmin"], 0.0, 0.0, So, want["C0"], rhs, N, c["nx"], c["ny"],
                                                    c["nz"], ncomp, 2, True, solve_problem=(0, 1))[1]
+    # envelope of the oracle under random relative perturbations of b of 1e-12 -- the size of the difference between a
+    # sequential and a tree-order sum over the 4e5 terms of |v|^2 (measured: the fast kernels' r_1 differs by 4e-14)
     env = np.zeros_like(ho)
-    for scale in (1.0 + 2.3e-16, 3.0, 1.0 / 3.0):
-        env = np.maximum(env, np.abs(solve_o(b * scale) - ho) / ho)
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        env = np.maximum(env, np.abs(solve_o(b * (1.0 + 1e-12 * rng.standard_normal(b.size))) - ho) / ho)
     Cg = tfx.SparseMatrix(ncomp * N, 2 * ncomp * N, ncomp * N)
     bg = np.zeros_like(b); bg[:nd] = b[:nd]
     m0 = np.full((ncomp, N), c["start_value"]); prior = np.zeros((ncomp, N))
@@ -123,8 +126,9 @@ def test_config_d_against_oracle(oracle):
     assert rel_s[floor].max() < 1e-6, (rel_s[floor].max(), rel_s[floor].argmax())
     # fast kernels (tree-order sums, deferred normalisation): the bar holds while the residual is well above the floor and
     # the oracle itself is reproducible; the last decades before the floor amplify last-bit differences to O(1)
-    stable = (ho > 1.0e-5) & (env < 1e-8)
+    stable = (ho > 1.0e-5) & (env < 1e-9)
     assert stable.sum() >= 10 and rel_f[stable].max() < 1e-6, (stable.sum(), rel_f[stable])
+    assert env[ho > 1.0e-5].max() > 1e-6          # ... and the oracle itself is not reproducible beyond (chaotic mid-phase)
     assert np.array_equal(hist[0], got["histories"][0])                # run_config_d's own first solve: same kernels
     assert hist[0][-1] < 1e-9 and ho[-1] < 1e-9
     # free run: costs and final model after both major iterations

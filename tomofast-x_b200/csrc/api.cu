@@ -356,6 +356,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_lsqr_graph = value;
     return 0;
   }
+  if (name && strcmp(name, "t16_tma") == 0) {
+    g_opt_t16_tma = value;
+    return 0;
+  }
   if (name && strcmp(name, "t16_blk") == 0) {
     g_opt_t16_blk = value;
     return 0;

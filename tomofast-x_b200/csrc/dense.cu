@@ -427,7 +427,9 @@ int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v
     return fail(-30, "dense sweep: more than " + std::to_string(kDenseMaxRows) + " data rows per block is not supported yet");
   if (S.fastcvt_ok < 0) TFX_TRY(dense_scan_fastcvt(S, st));
   const bool vec4 = g_opt_dense_vec4 != 0;
-  const int NT = vec4 ? 512 : kThreads, VW = vec4 ? 4 : 2;
+  // dense_vec4 = 2: 640 threads x float4 rows (20 warps per SM instead of 16, 16 rows per thread at 10^4 rows)
+  const bool wide = g_opt_dense_vec4 == 2 && S.nrows > 4 * 512 * 3;
+  const int NT = wide ? 640 : (vec4 ? 512 : kThreads), VW = vec4 ? 4 : 2;
   const int KV = (S.nrows + VW * NT - 1) / (VW * NT);                       // row vectors per thread
   const int K = VW * KV;
   const unsigned col_bytes = (unsigned)(S.ld * sizeof(float));
@@ -451,7 +453,12 @@ int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v
   a.ns = ns; a.col_bytes = col_bytes; a.ring_bytes = (unsigned)ring_bytes; a.done = d_done;
   const bool fast = S.fastcvt_ok == 1;
   int rc;
-  if (vec4) {
+  if (wide) {
+    switch (KV) {
+      case 3: rc = launch_kf<3, 640, 4>(mode, a, S.grid, smem, fast, st); break;
+      default: rc = launch_kf<4, 640, 4>(mode, a, S.grid, smem, fast, st); break;
+    }
+  } else if (vec4) {
     switch (KV) {
       case 1: rc = launch_kf<1, 512, 4>(mode, a, S.grid, smem, fast, st); break;
       case 2: rc = launch_kf<2, 512, 4>(mode, a, S.grid, smem, fast, st); break;

@@ -94,6 +94,7 @@ extern int g_opt_t16_async;
 extern int g_opt_t16_direct_max;
 extern int g_opt_t16_bank_deal;
 extern int g_opt_t16_blk;
+extern int g_opt_t16_tma;
 extern int g_opt_t16_long_seg;
 // Builds the layout from a compressed-segment matrix (segments = outputs, idx = gathered index). Leaves
 // T.valid == false (and returns 0) when the source does not qualify (indices not strictly ascending).

@@ -44,6 +44,13 @@ int g_opt_t16_tile = 0;            // 0: automatic; otherwise forced tile size (
 // segment order of the builder; transposed 2.45 (registers) -> 2.56 (ring alone) -> 2.28 ms (ring + bank dealing).
 int g_opt_t16_async = 3;
 int g_opt_t16_bank_deal = 1;       // 1: long segments are dealt over the shared-memory banks by the builder
+// 1: long segments through the TMA (cp.async.bulk + mbarrier) ring, 0 (default): per-lane cp.async ring. Measured on B200
+// (gpurun_out/r2_t16_ab.txt, 256x256x64 / 10 000 stations, 2.1e9 nnz): forward 2.31 ms with the cp.async ring, 3.45 ms
+// with the TMA ring; transposed 2.36 / 2.40 ms. A round is 1.5 KB -- two bulk copies of 1 KB + 0.5 KB issued by one lane
+// and a 32-lane mbarrier spin per round cost more than the 128 LDGSTS they replace; TMA pays from several KB per copy
+// (the dense sweep's 40 KB columns), which this per-warp, per-segment streaming cannot offer without giving up the
+// fixed summation order. Kept as an option for the record and for the tests (bit-identical results).
+int g_opt_t16_tma = 0;
 int g_opt_t16_blk = 0;            // 0: automatic (32 / 16 / 8 outputs per warp task by the number of outputs)
 int g_opt_t16_long_seg = 256;     // segments longer than this take the whole-warp path (<= 256)
 int g_opt_t16_direct_max = 16384;   // gathered ranges up to this many elements use one DIRECT tile; longer ones TILES
@@ -224,13 +231,139 @@ __device__ __forceinline__ double t16_long_async(const float *__restrict__ val, 
   return result;
 }
 
+// ---- TMA long path -----------------------------------------------------------------------------------------------
+// Same ring, filled by the TMA engine: one elected lane issues ONE cp.async.bulk (UBLKCP) for the 256 values of a round
+// and one for their keys, completion is signalled on an mbarrier per ring slot (complete_tx), all lanes wait on the
+// slot's phase and read their packets. 2 bulk copies per round replace 128 LDGSTS of the warp; the producer cursor
+// still runs kAsyncW rounds ahead across segment ends. Value packets are 16-byte aligned (segments are padded to 4
+// entries); key ranges are 8-byte aligned, so the key copy starts at the 16-byte boundary below (<= 8 bytes early) and
+// the readers add the offset. Ring strip per warp: [kAsyncW x 1024 B values][kAsyncW x 528 B keys][kAsyncW mbarriers].
+static const int kBulkKeySlot = 512 + 16;
+static const int kBulkRingBytes = kAsyncW * 1024 + kAsyncW * kBulkKeySlot + kAsyncW * 8 + 32;   // 6272 B per warp
+
+__device__ __forceinline__ void t16_mbar_init(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void t16_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void t16_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void t16_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// Once per warp and kernel: the slot barriers of the warp's strip.
+__device__ __forceinline__ void t16_bulk_ring_init(unsigned char *ring, int lane) {
+  if (lane == 0) {
+    const uint32_t bars = t16_smem_u32(ring) + kAsyncW * 1024 + kAsyncW * kBulkKeySlot;
+#pragma unroll
+    for (int s = 0; s < kAsyncW; ++s) t16_mbar_init(bars + 8 * s);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+}
+
+// `rounds` counts the rounds this warp has pushed through its ring since the kernel started (slot = rounds % kAsyncW,
+// phase parity = (rounds / kAsyncW) & 1); every call drains what it issued, so the count is the same for producer and
+// consumer between calls.
+__device__ __forceinline__ double t16_long_bulk(const float *__restrict__ val, const uint16_t *__restrict__ key,
+                                                const double *xs, unsigned char *ring, unsigned longmask, int rel,
+                                                int len, int lane, double result, unsigned &rounds) {
+  const uint32_t rbase = t16_smem_u32(ring);
+  const uint32_t kbase = rbase + kAsyncW * 1024;
+  const uint32_t bars = kbase + kAsyncW * kBulkKeySlot;
+  // the strip may hold flat-run products written through the generic proxy: order them before the async-proxy writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  unsigned pm = longmask, cm = longmask;
+  int pj = __ffs(pm) - 1;
+  int pk = __shfl_sync(0xffffffffu, rel, pj);
+  int p_end = pk + __shfl_sync(0xffffffffu, len, pj);
+  int cj = pj, ck = pk, c_end = p_end;
+  unsigned pr = rounds, cr = rounds;   // producer / consumer round counters
+  auto issue = [&]() {
+    if (pm == 0u) return;
+    const int n = min(256, p_end - pk);                 // entries of this round (a multiple of 4)
+    const unsigned slot = pr & (kAsyncW - 1);
+    if (lane == 0) {
+      const uint16_t *ksrc = key + pk;
+      const uint32_t kal = (uint32_t)((uintptr_t)ksrc & 15u);           // 0 or 8
+      const uint32_t vbytes = (uint32_t)n * 4u, kbytes = (kal + (uint32_t)n * 2u + 15u) & ~15u;
+      const uint32_t bar = bars + 8 * slot;
+      t16_mbar_expect_tx(bar, vbytes + kbytes);
+      t16_bulk_load(rbase + slot * 1024, val + pk, vbytes, bar);
+      t16_bulk_load(kbase + slot * kBulkKeySlot, (const unsigned char *)ksrc - kal, kbytes, bar);
+    }
+    ++pr;
+    pk += 256;
+    if (pk >= p_end) {
+      pm &= pm - 1;
+      if (pm != 0u) {
+        pj = __ffs(pm) - 1;
+        pk = __shfl_sync(0xffffffffu, rel, pj);
+        p_end = pk + __shfl_sync(0xffffffffu, len, pj);
+      }
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < kAsyncW; ++s) issue();
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  while (cm != 0u) {
+    const unsigned slot = cr & (kAsyncW - 1);
+    t16_mbar_wait(bars + 8 * slot, (cr / kAsyncW) & 1u);
+    const unsigned char *vs = ring + slot * 1024 + lane * 16;
+    const unsigned char *ks = ring + kAsyncW * 1024 + slot * kBulkKeySlot + (((uintptr_t)(key + ck)) & 15u) + lane * 8;
+#pragma unroll
+    for (int i = 0; i < kAsyncR; ++i) {
+      const int e = ck + 128 * i + 4 * lane;
+      if (e < c_end) {
+        const float4 v = *(const float4 *)(vs + 512 * i);
+        const uint2 k = *(const uint2 *)(ks + 256 * i);
+        a0 = fma((double)v.x, xs[k.x & 0xffffu], a0);
+        a1 = fma((double)v.y, xs[k.x >> 16], a1);
+        a2 = fma((double)v.z, xs[k.y & 0xffffu], a2);
+        a3 = fma((double)v.w, xs[k.y >> 16], a3);
+      }
+    }
+    ++cr;
+    __syncwarp();                                  // every lane has read the slot: it may be refilled
+    issue();
+    ck += 256;
+    if (ck >= c_end) {                             // end of the consumed segment: reduce, hand the sum to its lane
+      const double t = warp_sum((a0 + a1) + (a2 + a3));
+      if (lane == cj) result = t;
+      a0 = a1 = a2 = a3 = 0.0;
+      cm &= cm - 1;
+      if (cm != 0u) {
+        cj = __ffs(cm) - 1;
+        ck = __shfl_sync(0xffffffffu, rel, cj);
+        c_end = ck + __shfl_sync(0xffffffffu, len, cj);
+      }
+    }
+  }
+  rounds = cr;
+  return result;
+}
+
 // 32 consecutive outputs [o0, o0 + 32) of tile t: lane j returns the sum of segment o0 + j.
 //  * segments longer than kLongSeg entries: one at a time with the whole warp (t16_long_partial);
 //  * all others: FLAT -- maximal runs of consecutive segments spanning <= kFlatMax entries are streamed as
 //    one contiguous range (every lane loads packets, all loads independent and coalesced), the packet
 //    products are parked in the warp's shared-memory strip and every lane then adds up its own segment.
 __device__ __forceinline__ double t16_block32(const T16Args &a, const double *xs, double *wbuf, int64_t tbase, int o0,
-                                              int lane) {
+                                              int lane, unsigned &rounds) {
   const int o = o0 + lane;
   // lanes past the last output of the block (o0 + blk) or of the layout read the end pointer: empty segments, offsets
   // stay monotone
@@ -248,7 +381,9 @@ __device__ __forceinline__ double t16_block32(const T16Args &a, const double *xs
   const bool is_long = len > a.long_seg;
   unsigned longmask = __ballot_sync(0xffffffffu, is_long);
   const unsigned flatmask = ~longmask;
-  if (a.async_ring) {
+  if (a.async_ring == 2) {
+    if (longmask) result = t16_long_bulk(val, key, xs, (unsigned char *)wbuf, longmask, rel, len, lane, result, rounds);
+  } else if (a.async_ring) {
     if (longmask) result = t16_long_async(val, key, xs, (unsigned char *)wbuf, longmask, rel, len, lane, result);
   } else {
     while (longmask) {
@@ -314,6 +449,8 @@ __global__ void __launch_bounds__(kT16Threads, 1) t16_direct_kernel(T16Args a) {
   t16_load_tile(a, xs, a.t0);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double *wbuf = xs + ((a.tile + 15) & ~15) + wid * a.wstrip;
+  unsigned rounds = 0;
+  if (a.async_ring == 2) t16_bulk_ring_init((unsigned char *)wbuf, lane);
   const int64_t tbase = (int64_t)a.t0 * a.nseg;
   const int nblk = (a.nseg + a.blk - 1) / a.blk;
   __syncthreads();
@@ -324,7 +461,7 @@ __global__ void __launch_bounds__(kT16Threads, 1) t16_direct_kernel(T16Args a) {
     if (base >= nblk) break;
     const int b_hi = min(nblk, base + kDirectChunk);
     for (int blk = base; blk < b_hi; ++blk) {
-      const double r = t16_block32(a, xs, wbuf, tbase, blk * a.blk, lane);
+      const double r = t16_block32(a, xs, wbuf, tbase, blk * a.blk, lane, rounds);
       const int o = blk * a.blk + lane;
       if (lane < a.blk && o < a.nseg) a.y[o] = a.accumulate ? (a.y[o] + r) : r;
     }
@@ -342,6 +479,8 @@ __global__ void __launch_bounds__(NT, MINB) t16_tiles_kernel(T16Args a) {
   __shared__ int s_next;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double *wbuf = xs + ((a.tile + 15) & ~15) + wid * a.wstrip;
+  unsigned rounds = 0;
+  if (a.async_ring == 2) t16_bulk_ring_init((unsigned char *)wbuf, lane);
   const int nblk = (a.nseg + a.blk - 1) / a.blk;
   const int start = (int)((int64_t)blockIdx.x * a.ntiles / gridDim.x);
   int i = 0;   // tiles visited so far (relative to start)
@@ -375,7 +514,7 @@ __global__ void __launch_bounds__(NT, MINB) t16_tiles_kernel(T16Args a) {
       if (lane == 0) blk = atomicAdd(a.counter + t, 1);
       blk = __shfl_sync(0xffffffffu, blk, 0);
       if (blk >= nblk) break;
-      const double r = t16_block32(a, xs, wbuf, tbase, blk * a.blk, lane);
+      const double r = t16_block32(a, xs, wbuf, tbase, blk * a.blk, lane, rounds);
       const int o = blk * a.blk + lane;
       if (lane < a.blk && o < a.nseg) a.partial[tbase + o] = r;
     }
@@ -403,7 +542,7 @@ static bool t16_uses_ring(T16Mode mode, int tile) {
   const size_t tile_bytes = (size_t)((tile + 15) & ~15) * sizeof(double);
   const size_t smem_max = 227 * 1024 - 64;
   const int bit = (mode == T16_TILES) ? 1 : 2;
-  return (g_opt_t16_async & bit) && tile_bytes + (size_t)(kT16Threads / 32) * kAsyncRingBytes <= smem_max;
+  return (g_opt_t16_async & bit) && tile_bytes + (size_t)(kT16Threads / 32) * kBulkRingBytes <= smem_max;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -439,13 +578,14 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
   const int nblk = (m.nseg + a.blk - 1) / a.blk;
   const size_t tile_bytes = (size_t)((m.tile + 15) & ~15) * sizeof(double);
   const size_t smem_max = 227 * 1024 - 64;
-  const size_t strip_flat = (size_t)(kFlatMax / 2) * sizeof(double), strip_async = (size_t)kAsyncRingBytes;
+  // option t16_tma (default 1): the ring is filled by cp.async.bulk (TMA) instead of per-lane cp.async
+  const size_t strip_flat = (size_t)(kFlatMax / 2) * sizeof(double), strip_async = g_opt_t16_tma ? (size_t)kBulkRingBytes : (size_t)kAsyncRingBytes;
   if (m.mode == T16_DIRECT) {
     const int warps = kT16Threads / 32;
     const bool use_async = t16_uses_ring(T16_DIRECT, m.tile);
     const size_t strip = use_async ? strip_async : strip_flat;
     const size_t smem = tile_bytes + warps * strip;
-    a.async_ring = use_async ? 1 : 0;
+    a.async_ring = use_async ? (g_opt_t16_tma ? 2 : 1) : 0;
     a.wstrip = (int)(strip / sizeof(double));
     static bool attr = false;
     if (!attr) {
@@ -468,7 +608,7 @@ int t16_spmv(T16Matrix &m, const double *d_x, double *d_y, bool accumulate, int3
     TFX_CUDA(cudaMemsetAsync(m.counter.p, 0, sizeof(int) * (size_t)m.ntiles, st));
     if (use_async) {
       const size_t smem = tile_bytes + (kT16Threads / 32) * strip_async;
-      a.async_ring = 1;
+      a.async_ring = g_opt_t16_tma ? 2 : 1;
       a.wstrip = (int)(strip_async / sizeof(double));
       static bool attr = false;
       if (!attr) {
