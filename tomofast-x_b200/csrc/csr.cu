@@ -124,6 +124,26 @@ __global__ void __launch_bounds__(256) seg_items_warp_kernel(SegArgs a) {
   }
 }
 
+// G lanes per item (G = 4, 8, 16): segments of a few to a few dozen entries -- the columns of a cross-gradient /
+// gradient-damping block (each cell is touched by ~20 rows), short sensitivity columns. A full warp per item leaves most
+// lanes idle there (config E, ncu: 4.0 ms per C^T product with one warp per column, 81 % of the iteration).
+template <int G>
+__global__ void __launch_bounds__(256) seg_items_group_kernel(SegArgs a) {
+  if (a.done && *a.done) return;
+  const int sub = threadIdx.x & (G - 1);
+  const int gpw = 32 / G, wpb = blockDim.x >> 5;   // groups per warp; the loop bound is uniform over the warp (shuffles)
+  for (int item0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * gpw; item0 < a.nitems; item0 += gridDim.x * wpb * gpw) {
+    const int item = item0 + ((threadIdx.x & 31) / G);
+    const bool valid = item < a.nitems;
+    const int out = valid ? a.segmap[a.item_seg[item]] : -1;
+    const bool in = valid && !(out < a.out_lo || out >= a.out_hi);
+    double s = in ? item_partial_sum(a, a.item_beg[item], a.item_end[item], sub, G) : 0.0;
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (in && sub == 0) item_store(a, item, out, s);
+  }
+}
+
 // One thread per item: very short segments (constraint matrices: 1..12 entries per row).
 __global__ void __launch_bounds__(256) seg_items_thread_kernel(SegArgs a) {
   if (a.done && *a.done) return;
@@ -178,9 +198,16 @@ int seg_spmv(SegMatrix &m, const double *d_x, double *d_y, bool accumulate, int3
   if (m.avg_len >= 1024.0) {
     int blocks = std::min(m.nitems, c.num_sms * 16);
     seg_items_block_kernel<<<blocks, 256, 0, st>>>(a);
-  } else if (m.avg_len >= 6.0) {
+  } else if (m.avg_len >= 96.0) {
     int blocks = std::min((m.nitems + 7) / 8, c.num_sms * 16);
     seg_items_warp_kernel<<<blocks, 256, 0, st>>>(a);
+  } else if (m.avg_len >= 6.0) {
+    // lanes per item ~ a third of the average length: 4 (6-24 entries), 8 (24-48), 16 (48-96)
+    const int G = m.avg_len >= 48.0 ? 16 : (m.avg_len >= 24.0 ? 8 : 4);
+    const int blocks = (int)std::min<int64_t>(((int64_t)m.nitems * G + 255) / 256, (int64_t)c.num_sms * 32);
+    if (G == 16) seg_items_group_kernel<16><<<blocks, 256, 0, st>>>(a);
+    else if (G == 8) seg_items_group_kernel<8><<<blocks, 256, 0, st>>>(a);
+    else seg_items_group_kernel<4><<<blocks, 256, 0, st>>>(a);
   } else {
     int blocks = std::min((m.nitems + 255) / 256, c.num_sms * 16);
     seg_items_thread_kernel<<<blocks, 256, 0, st>>>(a);
