@@ -10,7 +10,7 @@ for (nx, ny, nz) in ((256, 256, 64), (512, 512, 128), (1024, 1024, 128)):
     N = nx * ny * nz
     vol = tfx.Buffer(N)
     tfx.copy(vol, rng.uniform(-1, 1, N), N)
-    for slab, tile in ((0, 0), (32, 0), (64, 0), (100, 0)):
+    for slab, tile in ((0, 0),):
         tfx.set_option("wavelet_slab_mb", slab)
         tfx.set_option("wavelet_tile_kb", tile)
         for wname, wtype in (("haar", 1), ("d4", 2)):

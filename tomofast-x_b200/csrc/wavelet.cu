@@ -266,7 +266,7 @@ __device__ __forceinline__ void haar_pair(double &lo, double &hi, const WaveCons
 }
 
 template <int TYPE, bool FWD, bool TRANSPOSE>
-__global__ void __launch_bounds__(256) wavelet_cols_kernel(double *__restrict__ s, int L, long long inner, long long nlines,
+__global__ void __launch_bounds__(256, 4) wavelet_cols_kernel(double *__restrict__ s, int L, long long inner, long long nlines,
                                                            int NC, int pitch, WaveConst k) {
   extern __shared__ double tile[];
   const int nt = (int)blockDim.x;
@@ -277,15 +277,19 @@ __global__ void __launch_bounds__(256) wavelet_cols_kernel(double *__restrict__ 
 
   // ---- load
   long long colbase = 0;
-  if (TRANSPOSE) {   // inner == 1: line q = s[q*L .. q*L + L); lanes along l
+  if (TRANSPOSE) {   // inner == 1: line q = s[q*L .. q*L + L); lanes along l, a warp takes whole lines
+    // (running pointers only: the (job / chunk) index arithmetic of the first version was 2/3 of the kernel's
+    // instructions, profiles/r2_wavelet_cols_v1_ncu_summary.csv)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nt >> 5;
-    const int nchunk = (L + 31) >> 5;
-    for (int job = w; job < ncol * nchunk; job += nw) {
-      const int cc = job / nchunk, l = ((job - cc * nchunk) << 5) + lane;
-      if (l < L) {
-        const double *src = s + (q0 + cc) * L + l;
-        const uint32_t dst = tile_s + (uint32_t)((l * pitch + cc) * (int)sizeof(double));
+    const uint32_t dstep = (uint32_t)(32 * pitch * (int)sizeof(double));
+    for (int cc = w; cc < ncol; cc += nw) {
+      const double *src = s + (q0 + cc) * L + lane;
+      uint32_t dst = tile_s + (uint32_t)((lane * pitch + cc) * (int)sizeof(double));
+#pragma unroll 4
+      for (int l = lane; l < L; l += 32) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+        src += 32;
+        dst += dstep;
       }
     }
   } else {
@@ -295,6 +299,7 @@ __global__ void __launch_bounds__(256) wavelet_cols_kernel(double *__restrict__ 
     if (c < ncol) {
       const double *src = s + colbase + (long long)rid * inner;
       uint32_t dst = tile_s + (uint32_t)((rid * pitch + c) * (int)sizeof(double));
+#pragma unroll 4
       for (int l = rid; l < L; l += nrid) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
         src += (long long)nrid * inner;
@@ -436,14 +441,20 @@ __global__ void __launch_bounds__(256) wavelet_cols_kernel(double *__restrict__ 
   // ---- store
   if (TRANSPOSE) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nt >> 5;
-    const int nchunk = (L + 31) >> 5;
-    for (int job = w; job < ncol * nchunk; job += nw) {
-      const int cc = job / nchunk, l = ((job - cc * nchunk) << 5) + lane;
-      if (l < L) s[(q0 + cc) * L + l] = tile[(size_t)l * pitch + cc];
+    for (int cc = w; cc < ncol; cc += nw) {
+      double *dst = s + (q0 + cc) * L + lane;
+      const double *src = tile + (size_t)lane * pitch + cc;
+#pragma unroll 4
+      for (int l = lane; l < L; l += 32) {
+        *dst = *src;
+        dst += 32;
+        src += (size_t)32 * pitch;
+      }
     }
   } else if (c < ncol) {
     double *dst = s + colbase + (long long)rid * inner;
     const double *src = col + (size_t)rid * pitch;
+#pragma unroll 4
     for (int l = rid; l < L; l += nrid) {
       *dst = *src;
       dst += (long long)nrid * inner;
