@@ -150,12 +150,16 @@ int comm_alltoallv_4b(const void *d_send, const int64_t *send_off, void *d_recv,
 }
 
 // In-place all-gather of slabs of different lengths: rank r's slab already sits at d_full + offsets[r]
-// (offsets has nranks + 1 entries); one grouped ncclBroadcast per rank. Replaces get_full_array (MPI_Gatherv to
+// (offsets has nranks + 1 entries). Replaces get_full_array (MPI_Gatherv to
 // rank 0, parallel_tools.f90:147) + the scatter back: every GPU ends up with the whole vector, moving half the bytes of
 // the all-reduce-into-zeros it replaces.
 int comm_allgatherv_f64(double *d_full, const int64_t *offsets, cudaStream_t st) {
   Nccl &n = N();
   if (!n.comm || n.nranks <= 1) return 0;
+  // One grouped ncclBroadcast per slab. Measured at 8 GPUs on a 1.07 GB volume with nnz-balanced (unequal) slabs
+  // (profiles/r2_bench_8gpu_a.jsonl vs gpurun_out/r2_bench_8gpu_e.jsonl): 3.8 ms this way, 5.8 ms as grouped
+  // ncclSend/ncclRecv pairs -- the rank with the largest slab would have to push it to 7 peers itself, the broadcast lets
+  // the NVSwitch replicate it.
   ncclResult_t r = n.GroupStart();
   if (r != ncclSuccess) return nccl_fail("ncclGroupStart", r);
   for (int q = 0; q < n.nranks; ++q) {
