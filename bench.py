@@ -434,14 +434,16 @@ def config_e_extra(a, tfx, d):
             "lsqr_it_per_s": it / (loop_ms * 1e-3), "ms_per_it": ms_it, "iters": it,
             "residual_last": float(r["history"][-1]) if len(r["history"]) else None,
             "S_fwd_ms": fwd, "S_trans_ms": trn, "wavelet_transform_ms": wav,
-            "wavelet_share": 4.0 * wav / ms_it,
+            "wavelet_share": 4.0 * wav / ms_it, "wavelet_distributed": r.get("wavelet_distributed"),
             "non_product_ms_per_it": non_product,
             "projected_full_config_e": {"nnz": full_nnz, "ms_per_it": projected, "it_per_s": 1e3 / projected,
                                         "note": "measured non-product part of the iteration (wavelets, constraint block, vectors, "
                                                 "collectives) + the two products of a 25 000-stations-per-GPU, 0.25 %% kernel at "
                                                 "0.75 of the HBM peak by bytes moved (the config C section's measured rate); "
                                                 "BASELINE.md: roofline 24 it/s, 60 %% target 14.6 it/s on 8 GPUs"},
-            "note": "4 distributed transforms per iteration: slabs all-gathered over NVLink, full volume transformed on every GPU"}
+            "note": "4 transforms of distributed vectors per iteration: axis-1/2 passes on the planes a rank owns, one all-to-all, "
+                    "axis-3 pass on its columns, one all-to-all back (wavelet_distributed = true); falls back to all-gather + "
+                    "full transform when a slab is thinner than a plane"}
 
 
 def compressed_spmv(a, tfx, d):

@@ -155,6 +155,9 @@ int tfx_iDaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3);               
  * tfx_comm_init) the slabs are assembled on every GPU by one all-reduce, transformed, and the own slab is kept --
  * the reference's gather to rank 0 / serial transform / scatter (:57-67) without the serial section; model_full
  * is not needed. */
+/* Diagnostic: 1 when the last transform of a distributed vector ran on the plane-owner / column-owner layouts (two
+ * all-to-all exchanges), 0 when it gathered the slabs into a full volume on every GPU (slab layout did not qualify). */
+int tfx_wavelet_last_distributed(void);
 int tfx_apply_wavelet_transform(int32_t nelements, int32_t nx, int32_t ny, int32_t nz, int32_t ncomponents,
                                 double *v, int32_t fwd, int32_t compression_type, int32_t nproblems,
                                 const int32_t *solve_problem, int32_t myrank, int32_t nbproc);

@@ -368,6 +368,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_t16_long_seg = value;
     return 0;
   }
+  if (name && strcmp(name, "wavelet_dist") == 0) {
+    g_opt_wavelet_dist = value;
+    return 0;
+  }
   if (name && strcmp(name, "wavelet_tile_kb") == 0) {
     g_opt_wavelet_tile_kb = value;
     return 0;

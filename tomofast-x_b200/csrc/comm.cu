@@ -172,6 +172,29 @@ int comm_allgatherv_f64(double *d_full, const int64_t *offsets, cudaStream_t st)
   return r == ncclSuccess ? 0 : nccl_fail("ncclGroupEnd", r);
 }
 
+// Grouped point-to-point exchange of doubles: for every peer q, send_cnt[q] doubles from d_send + send_off[q] and
+// recv_cnt[q] doubles into d_recv + recv_off[q] (the own block is NOT copied: callers place it themselves).
+int comm_exchange_f64(const double *d_send, const int64_t *send_off, const int64_t *send_cnt, double *d_recv,
+                      const int64_t *recv_off, const int64_t *recv_cnt, cudaStream_t st) {
+  Nccl &n = N();
+  if (!n.comm || n.nranks <= 1) return 0;
+  ncclResult_t r = n.GroupStart();
+  if (r != ncclSuccess) return nccl_fail("ncclGroupStart", r);
+  for (int q = 0; q < n.nranks; ++q) {
+    if (q == n.rank) continue;
+    if (send_cnt[q] > 0) {
+      r = n.Send(d_send + send_off[q], (size_t)send_cnt[q], ncclDouble, q, n.comm, st);
+      if (r != ncclSuccess) { n.GroupEnd(); return nccl_fail("ncclSend", r); }
+    }
+    if (recv_cnt[q] > 0) {
+      r = n.Recv(d_recv + recv_off[q], (size_t)recv_cnt[q], ncclDouble, q, n.comm, st);
+      if (r != ncclSuccess) { n.GroupEnd(); return nccl_fail("ncclRecv", r); }
+    }
+  }
+  r = n.GroupEnd();
+  return r == ncclSuccess ? 0 : nccl_fail("ncclGroupEnd", r);
+}
+
 // Slab lengths of all ranks as prefix offsets (nranks + 1 entries): one small all-gather + host read.
 int comm_slab_offsets(int64_t mine, std::vector<int64_t> &offsets) {
   Nccl &n = N();

@@ -3,6 +3,7 @@
 // the device so the model never leaves HBM between solves.
 #include "../../include/tfx.h"
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -43,6 +44,144 @@ __global__ void __launch_bounds__(256) k_model_update(double *__restrict__ v, co
 }
 }  // namespace
 
+int g_opt_wavelet_dist = 1;   // 1: plane-owner / column-owner transform when the slabs allow it, 0: always gather
+int g_wavelet_last_dist = 0;  // diagnostic: 1 when the last slab transform ran distributed (tfx_wavelet_last_distributed)
+
+namespace {
+struct DistBufs {
+  DevBuf<double> A, B, stage;
+};
+DistBufs &dist_bufs() {
+  static DistBufs b;
+  return b;
+}
+inline int64_t clampi(int64_t v, int64_t lo, int64_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+}  // namespace
+
+// Distributed 3-D transform of a volume held as contiguous cell slabs (i fastest, then j, then k; slab r = cells
+// [off[r], off[r+1])), WITHOUT assembling the volume anywhere:
+//   layout A: rank r holds the complete k-planes whose first cell lies in its slab -> the axis-1 and axis-2 passes are
+//             local (they never leave a plane); only the piece of a plane that straddles a slab boundary moves
+//             (<= one plane, to the neighbouring rank);
+//   layout B: rank q holds, for ALL k, the cells p in [pa[q], pa[q+1]) of every plane -> the axis-3 pass is local;
+//   A -> B and B -> slabs are two all-to-all exchanges over NVLink: ~2 V/N doubles per GPU instead of the (N-1) V/N an
+//   all-gather receives, and every GPU transforms V/N cells instead of V.
+// Same kernels on the same lines in the same order: bit-identical to the serial transform. Returns 1 in *done when the
+// slab layout qualifies (every slab starts at most one plane before a plane it owns), 0 to fall back to the gather.
+static int wavelet_slab_dist(double *d_slab, const std::vector<int64_t> &off, int nx, int ny, int nz, int wavelet_type,
+                             bool forward, cudaStream_t st, int *done) {
+  *done = 0;
+  const int nr = comm_nranks(), me = comm_rank();
+  const int64_t plane = (int64_t)nx * ny, n3 = nz;
+  if (!g_opt_wavelet_dist || nr <= 1 || plane < nr || n3 < 1) return 0;
+  // ---- ownership of planes (A) and of plane columns (B)
+  std::vector<int64_t> ka((size_t)nr + 1), pa((size_t)nr + 1);
+  for (int r = 0; r <= nr; ++r) {
+    ka[r] = (r == nr) ? n3 : (off[r] + plane - 1) / plane;      // first plane whose first cell is >= off[r]
+    pa[r] = plane * r / nr;
+  }
+  for (int r = 0; r < nr; ++r) {
+    if (ka[r] >= ka[r + 1]) return 0;                              // a rank without a plane of its own
+    if (r > 0 && (ka[r] - 1) * plane < off[r - 1]) return 0;       // its leading piece would skip a rank
+  }
+  const int64_t nk = ka[me + 1] - ka[me];                          // planes this rank owns
+  const int64_t lead = ka[me] * plane - off[me];                   // cells of my slab that belong to rank me-1's plane
+  const int64_t own = off[me + 1] - ka[me] * plane;                // cells of my planes I hold myself
+  const int64_t trail = ka[me + 1] * plane - off[me + 1];          // ... and the rest comes from rank me+1
+  const int64_t W = pa[me + 1] - pa[me];
+  DistBufs &D = dist_bufs();
+  TFX_TRY(D.A.alloc((size_t)(nk * plane)));
+  TFX_TRY(D.B.alloc((size_t)(n3 * W)));
+  TFX_TRY(D.stage.alloc((size_t)std::max<int64_t>(nk * plane, off[me + 1] - off[me])));
+  std::vector<int64_t> soff((size_t)nr, 0), scnt((size_t)nr, 0), roff((size_t)nr, 0), rcnt((size_t)nr, 0);
+
+  // ---- slabs -> layout A
+  TFX_CUDA(cudaMemcpyAsync(D.A.p, d_slab + lead, (size_t)own * 8, cudaMemcpyDeviceToDevice, st));
+  if (me > 0) { soff[me - 1] = 0; scnt[me - 1] = lead; }
+  if (me + 1 < nr) { roff[me + 1] = own; rcnt[me + 1] = trail; }
+  TFX_TRY(comm_exchange_f64(d_slab, soff.data(), scnt.data(), D.A.p, roff.data(), rcnt.data(), st));
+
+  // ---- axes 1 and 2 on my planes
+  TFX_TRY(wavelet_axis_device(D.A.p, nx, 1, (long long)ny * nk, wavelet_type, forward, st));
+  TFX_TRY(wavelet_axis_device(D.A.p, ny, nx, nk, wavelet_type, forward, st));
+
+  // ---- A -> B: to rank q the columns [pa[q], pa[q+1]) of my planes (packed); what arrives from rank r are the rows
+  // [ka[r], ka[r+1]) of B, already in place
+  {
+    int64_t pos = 0;
+    for (int q = 0; q < nr; ++q) {
+      const int64_t Wq = pa[q + 1] - pa[q];
+      if (q == me) {
+        TFX_CUDA(cudaMemcpy2DAsync(D.B.p + ka[me] * W, (size_t)W * 8, D.A.p + pa[me], (size_t)plane * 8, (size_t)W * 8,
+                                   (size_t)nk, cudaMemcpyDeviceToDevice, st));
+        scnt[q] = rcnt[q] = 0;
+        continue;
+      }
+      TFX_CUDA(cudaMemcpy2DAsync(D.stage.p + pos, (size_t)Wq * 8, D.A.p + pa[q], (size_t)plane * 8, (size_t)Wq * 8,
+                                 (size_t)nk, cudaMemcpyDeviceToDevice, st));
+      soff[q] = pos; scnt[q] = nk * Wq;
+      pos += nk * Wq;
+      roff[q] = ka[q] * W; rcnt[q] = (ka[q + 1] - ka[q]) * W;
+    }
+    TFX_TRY(comm_exchange_f64(D.stage.p, soff.data(), scnt.data(), D.B.p, roff.data(), rcnt.data(), st));
+  }
+
+  // ---- axis 3 on my columns
+  TFX_TRY(wavelet_axis_device(D.B.p, nz, W, 1, wavelet_type, forward, st));
+
+  // ---- B -> slabs: the cells of slab r inside my columns are ONE contiguous range of B (suffix of the first row, whole
+  // rows, prefix of the last row); the receiver unpacks rows of width W_q at stride `plane`.
+  auto range_in = [&](int q, int r, int64_t *b0, int64_t *b1) {     // range of rank q's B that belongs to slab r
+    const int64_t Wq = pa[q + 1] - pa[q];
+    const int64_t k0 = off[r] / plane, s0 = off[r] - k0 * plane;
+    const int64_t k1 = (off[r + 1] - 1) / plane, e1 = off[r + 1] - k1 * plane;
+    *b0 = k0 * Wq + clampi(s0, pa[q], pa[q + 1]) - pa[q];
+    *b1 = k1 * Wq + clampi(e1, pa[q], pa[q + 1]) - pa[q];
+    if (*b1 < *b0) *b1 = *b0;
+  };
+  {
+    int64_t pos = 0;
+    for (int q = 0; q < nr; ++q) {
+      int64_t b0, b1;
+      range_in(me, q, &b0, &b1);                                       // what I send to rank q
+      soff[q] = b0; scnt[q] = (q == me) ? 0 : b1 - b0;
+      range_in(q, me, &b0, &b1);                                       // what rank q sends to me
+      roff[q] = pos; rcnt[q] = (q == me) ? 0 : b1 - b0;
+      if (q != me) pos += b1 - b0;
+    }
+    TFX_TRY(comm_exchange_f64(D.B.p, soff.data(), scnt.data(), D.stage.p, roff.data(), rcnt.data(), st));
+    // unpack (the own block straight from B)
+    const int64_t k0 = off[me] / plane, s0 = off[me] - k0 * plane;
+    const int64_t k1 = (off[me + 1] - 1) / plane, e1 = off[me + 1] - k1 * plane;
+    for (int q = 0; q < nr; ++q) {
+      const int64_t Wq = pa[q + 1] - pa[q];
+      int64_t b0, b1;
+      range_in(q, me, &b0, &b1);
+      if (b1 <= b0) continue;
+      const double *src = (q == me) ? D.B.p + b0 : D.stage.p + roff[q];
+      int64_t consumed = 0;
+      for (int part = 0; part < 3; ++part) {
+        // part 0: row k0 (partial), part 1: rows k0+1 .. k1-1 (whole), part 2: row k1 (partial, when k1 > k0)
+        int64_t ka_ = 0, nrows = 0, plo = 0, phi = 0;
+        if (part == 0) { ka_ = k0; nrows = 1; plo = clampi(s0, pa[q], pa[q + 1]); phi = (k1 == k0) ? clampi(e1, pa[q], pa[q + 1]) : pa[q + 1]; }
+        else if (part == 1) { ka_ = k0 + 1; nrows = k1 - k0 - 1; plo = pa[q]; phi = pa[q + 1]; }
+        else { if (k1 == k0) break; ka_ = k1; nrows = 1; plo = pa[q]; phi = clampi(e1, pa[q], pa[q + 1]); }
+        const int64_t w = phi - plo;
+        if (nrows <= 0 || w <= 0) continue;
+        double *dst = d_slab + (ka_ * plane + plo - off[me]);
+        // inside the source range the rows keep B's pitch W_q except that the first / last row are shortened
+        const size_t spitch = (size_t)Wq * 8;
+        TFX_CUDA(cudaMemcpy2DAsync(dst, (size_t)plane * 8, src + consumed, nrows > 1 ? spitch : (size_t)w * 8, (size_t)w * 8,
+                                   (size_t)nrows, cudaMemcpyDeviceToDevice, st));
+        consumed += (nrows > 1 || part == 1) ? nrows * Wq : w;
+      }
+    }
+  }
+  *done = 1;
+  g_wavelet_last_dist = 1;
+  return 0;
+}
+
 // Every rank drops its slab at its place in a full volume, the slabs are all-gathered over NVLink (each GPU receives the
 // other ranks' cells once: half the bytes of an all-reduce into a zeroed volume, no additions), every GPU transforms the
 // identical volume and keeps its own cells: get_full_array + scatter_full_array (parallel_tools.f90:147,250) without the
@@ -58,6 +197,12 @@ int wavelet_slab_device_off(double *d_slab, const std::vector<int64_t> &offsets,
   }
   if ((int)offsets.size() != nranks + 1 || offsets[(size_t)nranks] != N)
     return fail(-24, "apply_wavelet_transform: the ranks' nelements must add up to nx*ny*nz");
+  {
+    int done = 0;
+    TFX_TRY(wavelet_slab_dist(d_slab, offsets, nx, ny, nz, wavelet_type, forward, st, &done));
+    if (done) return 0;
+  }
+  g_wavelet_last_dist = 0;
   const int64_t nsmaller = offsets[(size_t)rank], nelements = offsets[(size_t)rank + 1] - nsmaller;
   DevBuf<double> &F = full_scratch();
   TFX_TRY(F.alloc((size_t)N));
@@ -79,6 +224,8 @@ int wavelet_slab_device(double *d_slab, int64_t nelements, int64_t nsmaller, int
 }  // namespace tfx
 
 using namespace tfx;
+
+extern "C" int tfx_wavelet_last_distributed(void) { return tfx::g_wavelet_last_dist; }
 
 extern "C" int tfx_apply_wavelet_transform(int32_t nelements, int32_t nx, int32_t ny, int32_t nz, int32_t ncomponents,
                                            double *v, int32_t fwd, int32_t compression_type, int32_t nproblems,

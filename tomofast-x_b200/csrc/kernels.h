@@ -19,6 +19,10 @@ extern int g_opt_wavelet_slab_mb;
 extern int g_opt_wavelet_cols;
 extern int g_opt_wavelet_tile_kb;
 
+int wavelet_axis_device(double *d_s, int L, long long inner, long long outer, int wavelet_type, bool forward,
+                        cudaStream_t st);
+extern int g_opt_wavelet_dist;
+
 // ---- csr.cu -----------------------------------------------------------------------------------
 // A compressed-segment matrix view on the device. For the forward product it is the CSR of A
 // (segments = stored rows, idx = column); for the transposed product it is the CSR of A^T

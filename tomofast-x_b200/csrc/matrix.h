@@ -152,6 +152,8 @@ int wavelet_slab_device_off(double *d_slab, const std::vector<int64_t> &offsets,
                             bool forward, cudaStream_t st);
 int comm_slab_offsets(int64_t mine, std::vector<int64_t> &offsets);
 int comm_allgatherv_f64(double *d_full, const int64_t *offsets, cudaStream_t st);
+int comm_exchange_f64(const double *d_send, const int64_t *send_off, const int64_t *send_cnt, double *d_recv,
+                      const int64_t *recv_off, const int64_t *recv_cnt, cudaStream_t st);
 int comm_allreduce_sum(double *d_buf, size_t count, cudaStream_t st);
 int comm_allreduce_sum_i32(int32_t *d_buf, size_t count, cudaStream_t st);
 int comm_allreduce_sum_u8(uint8_t *d_buf, size_t count, cudaStream_t st);

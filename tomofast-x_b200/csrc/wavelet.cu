@@ -609,4 +609,16 @@ int wavelet3d_device(double *d_s, int n1, int n2, int n3, int wavelet_type, bool
   return wavelet3d_device_batch(d_s, n1, n2, n3, 1, wavelet_type, forward, st);
 }
 
+// One axis pass (all scales of that axis) over lines A[outer][L][inner]: the building block of the distributed
+// transform (data.cu), which runs axes 1 / 2 on the planes a rank owns and axis 3 on its share of the k-lines.
+int wavelet_axis_device(double *d_s, int L, long long inner, long long outer, int wavelet_type, bool forward,
+                        cudaStream_t st) {
+  if (L < 1 || inner < 1 || outer < 1) return 0;
+  if (wavelet_type == 1)
+    return forward ? launch_axis<1, true>(d_s, L, inner, outer, st) : launch_axis<1, false>(d_s, L, inner, outer, st);
+  if (wavelet_type == 2)
+    return forward ? launch_axis<2, true>(d_s, L, inner, outer, st) : launch_axis<2, false>(d_s, L, inner, outer, st);
+  return fail(-22, "Unknown wavelet type!");
+}
+
 }  // namespace tfx
