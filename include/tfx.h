@@ -150,14 +150,15 @@ int tfx_Haar3D(double *s, int32_t n1, int32_t n2, int32_t n3);                  
 int tfx_iHaar3D(double *s, int32_t n1, int32_t n2, int32_t n3);                                 /* :158-236 */
 int tfx_DaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3);                                /* :243-367 */
 int tfx_iDaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3);                               /* :374-498 */
-/* module wavelet_utils: apply_wavelet_transform (src/inversion/wavelet_utils.F90:37-72):
- * v(nelements, ncomponents, nproblems) holds this rank's cell slab of every volume. With nbproc > 1 (needs
- * tfx_comm_init) the slabs are assembled on every GPU by one all-reduce, transformed, and the own slab is kept --
- * the reference's gather to rank 0 / serial transform / scatter (:57-67) without the serial section; model_full
- * is not needed. */
 /* Diagnostic: 1 when the last transform of a distributed vector ran on the plane-owner / column-owner layouts (two
  * all-to-all exchanges), 0 when it gathered the slabs into a full volume on every GPU (slab layout did not qualify). */
 int tfx_wavelet_last_distributed(void);
+/* module wavelet_utils: apply_wavelet_transform (src/inversion/wavelet_utils.F90:37-72):
+ * v(nelements, ncomponents, nproblems) holds this rank's cell slab of every volume. With nbproc > 1 (needs
+ * tfx_comm_init) the volume is transformed in place across the GPUs -- axis-1/2 passes on the k-planes a rank owns, one
+ * NVLink all-to-all, the axis-3 pass on its share of the k-lines, one all-to-all back (or, when a slab is thinner than a
+ * plane: slabs all-gathered on every GPU, transformed, own slab kept) -- the reference's gather to rank 0 / serial
+ * transform / scatter (:57-67) without the serial section, bit-identical; model_full is not needed. */
 int tfx_apply_wavelet_transform(int32_t nelements, int32_t nx, int32_t ny, int32_t nz, int32_t ncomponents,
                                 double *v, int32_t fwd, int32_t compression_type, int32_t nproblems,
                                 const int32_t *solve_problem, int32_t myrank, int32_t nbproc);
