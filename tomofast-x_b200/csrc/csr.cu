@@ -18,7 +18,22 @@ namespace tfx {
 // ---------------------------------------------------------------------------------------------
 // Item table
 // ---------------------------------------------------------------------------------------------
+int seg_set_identity_items(SegMatrix &m) {
+  m.identity_items = true;
+  m.item_seg.release(); m.item_beg.release(); m.item_end.release(); m.seg_item0.release(); m.partial.release();
+  m.nitems = m.nseg;
+  m.max_items_per_seg = m.nseg > 0 ? 1 : 0;
+  m.avg_len = m.nseg ? (double)m.nnz / (double)m.nseg : 0.0;
+  return 0;
+}
+
 int seg_build_items(SegMatrix &m, const int64_t *h_ptr) {
+  {
+    int64_t longest = 0;
+    for (int32_t s = 0; s < m.nseg; ++s) longest = std::max(longest, h_ptr[s + 1] - h_ptr[s]);
+    if (longest <= kItemLen) return seg_set_identity_items(m);
+  }
+  m.identity_items = false;
   std::vector<int32_t> item_seg;
   std::vector<int64_t> item_beg, item_end;
   std::vector<int32_t> seg_item0((size_t)m.nseg + 1);
@@ -58,6 +73,7 @@ int seg_build_items(SegMatrix &m, const int64_t *h_ptr) {
 // Kernels
 // ---------------------------------------------------------------------------------------------
 struct SegArgs {
+  const int64_t *ptr;        // identity items (item_seg == nullptr): item i = segment i = [ptr[i], ptr[i+1])
   const int64_t *item_beg, *item_end;
   const int32_t *item_seg, *segmap, *idx;
   const float *val;
@@ -90,6 +106,10 @@ __device__ __forceinline__ double item_partial_sum(const SegArgs &a, int64_t b, 
   return (s0 + s1) + (s2 + s3);
 }
 
+__device__ __forceinline__ int item_segment(const SegArgs &a, int item) { return a.item_seg ? a.item_seg[item] : item; }
+__device__ __forceinline__ int64_t item_begin(const SegArgs &a, int item) { return a.item_seg ? a.item_beg[item] : a.ptr[item]; }
+__device__ __forceinline__ int64_t item_finish(const SegArgs &a, int item) { return a.item_seg ? a.item_end[item] : a.ptr[item + 1]; }
+
 __device__ __forceinline__ void item_store(const SegArgs &a, int item, int out, double sum) {
   if (a.direct) a.y[out - a.out_lo] += sum;   // one writer per output element
   else a.partial[item] = sum;
@@ -100,10 +120,10 @@ __global__ void __launch_bounds__(256) seg_items_block_kernel(SegArgs a) {
   if (a.done && *a.done) return;
   __shared__ double red[32];
   for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-    const int seg = a.item_seg[item];
+    const int seg = item_segment(a, item);
     const int out = a.segmap[seg];
     if (out < a.out_lo || out >= a.out_hi) continue;
-    double s = item_partial_sum(a, a.item_beg[item], a.item_end[item], threadIdx.x, blockDim.x);
+    double s = item_partial_sum(a, item_begin(a, item), item_finish(a, item), threadIdx.x, blockDim.x);
     s = block_sum(s, red);
     if (threadIdx.x == 0) item_store(a, item, out, s);
   }
@@ -115,10 +135,10 @@ __global__ void __launch_bounds__(256) seg_items_warp_kernel(SegArgs a) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < a.nitems; item += gridDim.x * wpb) {
-    const int seg = a.item_seg[item];
+    const int seg = item_segment(a, item);
     const int out = a.segmap[seg];
     if (out < a.out_lo || out >= a.out_hi) continue;
-    double s = item_partial_sum(a, a.item_beg[item], a.item_end[item], lane, 32);
+    double s = item_partial_sum(a, item_begin(a, item), item_finish(a, item), lane, 32);
     s = warp_sum(s);
     if (lane == 0) item_store(a, item, out, s);
   }
@@ -135,9 +155,9 @@ __global__ void __launch_bounds__(256) seg_items_group_kernel(SegArgs a) {
   for (int item0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * gpw; item0 < a.nitems; item0 += gridDim.x * wpb * gpw) {
     const int item = item0 + ((threadIdx.x & 31) / G);
     const bool valid = item < a.nitems;
-    const int out = valid ? a.segmap[a.item_seg[item]] : -1;
+    const int out = valid ? a.segmap[item_segment(a, item)] : -1;
     const bool in = valid && !(out < a.out_lo || out >= a.out_hi);
-    double s = in ? item_partial_sum(a, a.item_beg[item], a.item_end[item], sub, G) : 0.0;
+    double s = in ? item_partial_sum(a, item_begin(a, item), item_finish(a, item), sub, G) : 0.0;
 #pragma unroll
     for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (in && sub == 0) item_store(a, item, out, s);
@@ -148,12 +168,13 @@ __global__ void __launch_bounds__(256) seg_items_group_kernel(SegArgs a) {
 __global__ void __launch_bounds__(256) seg_items_thread_kernel(SegArgs a) {
   if (a.done && *a.done) return;
   for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < a.nitems; item += gridDim.x * blockDim.x) {
-    const int seg = a.item_seg[item];
+    const int seg = item_segment(a, item);
     const int out = a.segmap[seg];
     if (out < a.out_lo || out >= a.out_hi) continue;
     const double *x = a.x - a.xshift;
     double s = 0.0;
-    for (int64_t k = a.item_beg[item]; k < a.item_end[item]; ++k)
+    const int64_t kend = item_finish(a, item);
+    for (int64_t k = item_begin(a, item); k < kend; ++k)
       s = fma((double)__ldg(a.val + k), __ldg(x + __ldg(a.idx + k)), s);
     item_store(a, item, out, s);
   }
@@ -190,7 +211,9 @@ int seg_spmv(SegMatrix &m, const double *d_x, double *d_y, bool accumulate, int3
   }
   if (m.empty() || m.nitems == 0) return 0;
   SegArgs a;
-  a.item_beg = m.item_beg.p; a.item_end = m.item_end.p; a.item_seg = m.item_seg.p; a.segmap = m.segmap.p;
+  a.ptr = m.ptr.p;
+  a.item_beg = m.identity_items ? nullptr : m.item_beg.p; a.item_end = m.identity_items ? nullptr : m.item_end.p;
+  a.item_seg = m.identity_items ? nullptr : m.item_seg.p; a.segmap = m.segmap.p;
   a.idx = m.idx.p; a.val = m.val.p; a.x = d_x; a.partial = m.partial.p; a.y = d_y;
   a.nitems = m.nitems; a.out_lo = out_lo; a.out_hi = out_hi; a.xshift = xshift;
   a.direct = (m.max_items_per_seg <= 1) ? 1 : 0;

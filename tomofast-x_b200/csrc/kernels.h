@@ -46,11 +46,15 @@ struct SegMatrix {
   DevBuf<int64_t> item_end;    // [nitems]
   DevBuf<int32_t> seg_item0;   // [nseg+1] first item of each segment
   DevBuf<double> partial;      // [nitems]
+  // identity_items: no segment is longer than kItemLen, so item i IS segment i (beg = ptr[i], end = ptr[i+1]) and the
+  // four item tables are not materialised -- the case of every constraint matrix and of the column-major copies of
+  // compressed kernels (tens of millions of short segments: the tables cost 24 B per segment and a host loop to build).
+  bool identity_items = false;
   bool empty() const { return nnz == 0 || nseg == 0; }
   void release() {
     ptr.release(); idx.release(); val.release(); segmap.release(); item_seg.release(); item_beg.release();
     item_end.release(); seg_item0.release(); partial.release();
-    nnz = 0; nseg = 0; nitems = 0;
+    nnz = 0; nseg = 0; nitems = 0; identity_items = false;
   }
 };
 
@@ -58,6 +62,8 @@ static const int kItemLen = 8192;
 
 // Builds the item table from host copies of ptr (0-based, nseg+1 entries).
 int seg_build_items(SegMatrix &m, const int64_t *h_ptr);
+// The same when ptr only exists on the device and the longest segment (max_len) is known.
+int seg_set_identity_items(SegMatrix &m);
 
 // y[segmap[s] - out_lo] (+)= sum_k val[k] * x[idx[k] - xshift], restricted to segments whose output
 // index lies in [out_lo, out_hi). accumulate == false zeroes y[0 .. out_hi-out_lo) first.

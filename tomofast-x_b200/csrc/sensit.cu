@@ -527,6 +527,37 @@ static int runs_of_sorted_keys(const int32_t *d_keys, int64_t n, int32_t max_uni
   return 0;
 }
 
+// keys (sorted, n entries) -> S.segmap (unique keys), S.ptr (offsets) and identity items, all on the device: no host
+// loop over the segments (a cross-gradient block has 10^8 of them per rank, the column-major copy of a compressed kernel
+// 3e7 per row block). *ok = false (nothing built) when some run is longer than kItemLen: the caller takes the host path.
+static int seg_from_sorted_keys_device(const int32_t *d_keys, int64_t n, int32_t max_unique, SegMatrix &S, bool *ok) {
+  cudaStream_t st = ctx().stream;
+  auto pol = thrust::cuda::par.on(st);
+  *ok = false;
+  if (n <= 0) return 0;
+  DevBuf<int32_t> ucnt;
+  const size_t cap = (size_t)std::min<int64_t>(n, max_unique);
+  TFX_TRY(S.segmap.alloc(cap)); TFX_TRY(ucnt.alloc(cap));
+  thrust::device_ptr<const int32_t> K(d_keys);
+  thrust::device_ptr<int32_t> UC(S.segmap.p), UN(ucnt.p);
+  size_t nu = 0;
+  int longest = 0;
+  TFX_THRUST(nu = (size_t)(thrust::reduce_by_key(pol, K, K + n, thrust::make_constant_iterator<int32_t>(1), UC, UN).first - UC));
+  TFX_THRUST(longest = thrust::reduce(pol, UN, UN + nu, 0, thrust::maximum<int32_t>()));
+  ctx().launches += 3;
+  if (longest > kItemLen) return 0;
+  TFX_TRY(S.ptr.alloc(nu + 1));
+  thrust::device_ptr<int64_t> P(S.ptr.p);
+  TFX_THRUST(thrust::exclusive_scan(pol, UN, UN + nu, P, (int64_t)0));
+  TFX_CUDA(cudaMemcpyAsync(S.ptr.p + nu, &n, 8, cudaMemcpyHostToDevice, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  ctx().launches += 1;
+  S.nseg = (int32_t)nu;
+  TFX_TRY(seg_set_identity_items(S));
+  *ok = true;
+  return 0;
+}
+
 // Finalized device matrix from entries sorted by (row, column). Takes ownership of R's buffers.
 // Matrix rows without entries are not stored (new_row(), sparse_matrix.f90:266-274).
 int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R) {
@@ -539,15 +570,20 @@ int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R
 
   // ---- forward representation: runs of equal row ids
   SegMatrix &F = M.fwd;
+  F.nnz = nnz; F.nout = nl; F.nin = ncolumns;
+  bool on_device = false;
+  TFX_TRY(seg_from_sorted_keys_device(R.rowid.p, nnz, nl, F, &on_device));
   std::vector<int64_t> ptr;
   std::vector<int32_t> segmap;
-  TFX_TRY(runs_of_sorted_keys(R.rowid.p, nnz, nl, segmap, ptr));
+  if (!on_device) TFX_TRY(runs_of_sorted_keys(R.rowid.p, nnz, nl, segmap, ptr));
   std::swap(F.idx.p, R.idx.p); std::swap(F.idx.n, R.idx.n);
   std::swap(F.val.p, R.val.p); std::swap(F.val.n, R.val.n);
-  F.nnz = nnz; F.nseg = (int32_t)segmap.size(); F.nout = nl; F.nin = ncolumns;
-  TFX_TRY(up(F.ptr, ptr.data(), ptr.size()));
-  TFX_TRY(up(F.segmap, segmap.data(), segmap.size()));
-  TFX_TRY(seg_build_items(F, ptr.data()));
+  if (!on_device) {
+    F.nseg = (int32_t)segmap.size();
+    TFX_TRY(up(F.ptr, ptr.data(), ptr.size()));
+    TFX_TRY(up(F.segmap, segmap.data(), segmap.size()));
+    TFX_TRY(seg_build_items(F, ptr.data()));
+  }
 
   // ---- transpose on the device: stable sort by column keeps the row order inside each column
   SegMatrix &T = M.trn;
@@ -566,13 +602,18 @@ int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R
     thrust::device_ptr<float> V(T.val.p);
     TFX_THRUST(thrust::stable_sort_by_key(pol, K, K + nnz, thrust::make_zip_iterator(thrust::make_tuple(Rw, V))));
     c.launches += 2;
-    TFX_TRY(runs_of_sorted_keys(keys.p, nnz, ncolumns, tmap, tptr));
+    TFX_TRY(seg_from_sorted_keys_device(keys.p, nnz, ncolumns, T, &on_device));
+    if (!on_device) TFX_TRY(runs_of_sorted_keys(keys.p, nnz, ncolumns, tmap, tptr));
+  } else {
+    on_device = false;
   }
   keys.release();
-  T.nseg = (int32_t)tmap.size();
-  TFX_TRY(up(T.ptr, tptr.data(), tptr.size()));
-  TFX_TRY(up(T.segmap, tmap.data(), tmap.size()));
-  TFX_TRY(seg_build_items(T, tptr.data()));
+  if (!on_device) {
+    T.nseg = (int32_t)tmap.size();
+    TFX_TRY(up(T.ptr, tptr.data(), tptr.size()));
+    TFX_TRY(up(T.segmap, tmap.data(), tmap.size()));
+    TFX_TRY(seg_build_items(T, tptr.data()));
+  }
 
   M.has_seg = true;
   TFX_TRY(matrix_build_t16(M));
