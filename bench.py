@@ -461,8 +461,8 @@ def compressed_spmv(a, tfx, d):
     rate = a.comp_rate
     N = nx * ny * nz
     per_rank = a.comp_ndata
-    # Row blocks. A block is built from triplets: up to ~45 B per entry at the peak of its build (triplets, the two CSR
-    # copies, the scratch of the stable sort by column), 12 B per entry once its T16 layouts stand. --comp-batch -1 (default) sizes every block to the
+    # Row blocks. A block is built from triplets: ~28 B per entry at the peak of its build (the CSR, the row ids, the
+    # double-buffered (column, position) pairs of the transpose sort), 12 B per entry once its T16 layouts stand. --comp-batch -1 (default) sizes every block to the
     # memory that is free WHEN IT IS BUILT: the first blocks are large (thousands of stations: long segments, the
     # kernels' best case), the last ones small -- instead of equal thin blocks sized for the last one.
     auto_blocks = a.comp_batch < 0
@@ -470,7 +470,7 @@ def compressed_spmv(a, tfx, d):
     free_b, _ = tfx.device_mem_info()
     free_b = d.min(float(free_b))
     nel_row = max(1, int(rate * N))
-    kBuild, kReserve = 48.0, 40.0 * N + (4 << 30)
+    kBuild, kReserve = 32.0, 40.0 * N + (4 << 30)
     if auto_blocks:
         need = lambda rows: 12.0 * nel_row * rows + kReserve + kBuild * nel_row * 64
     else:
@@ -488,6 +488,7 @@ def compressed_spmv(a, tfx, d):
         fr, _ = tfx.device_mem_info()
         fr = d.min(float(fr))
         fit = int((0.92 * fr - kReserve) / (kBuild * nel_row))     # rows per rank whose build fits now
+        fit = min(fit, int(4.0e9 / nel_row))                       # 32-bit positions inside a block's transpose sort
         nb = max(32, fit) * d.world
         if rows_left - nb < 64 * d.world:                          # no crumbs at the end
             nb = rows_left

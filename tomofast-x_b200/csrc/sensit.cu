@@ -9,6 +9,7 @@
 // concatenated at column shift param_shift + (k-1)*nelements (:759-856).
 #include "../../include/tfx.h"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/copy.h>
 #include <thrust/device_ptr.h>
@@ -527,6 +528,16 @@ static int runs_of_sorted_keys(const int32_t *d_keys, int64_t n, int32_t max_uni
   return 0;
 }
 
+__global__ void __launch_bounds__(256) k_iota(int32_t *__restrict__ p, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = (int32_t)i;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather(const T *__restrict__ src, const int32_t *__restrict__ perm, int64_t n,
+                                                T *__restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[(uint32_t)perm[i]];
+}
+
 // keys (sorted, n entries) -> S.segmap (unique keys), S.ptr (offsets) and identity items, all on the device: no host
 // loop over the segments (a cross-gradient block has 10^8 of them per rank, the column-major copy of a compressed kernel
 // 3e7 per row block). *ok = false (nothing built) when some run is longer than kItemLen: the caller takes the host path.
@@ -585,17 +596,22 @@ int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R
     TFX_TRY(seg_build_items(F, ptr.data()));
   }
 
-  // ---- transpose on the device: stable sort by column keeps the row order inside each column
+  // ---- transpose on the device: stable sort by column keeps the row order inside each column.
+  // (r2) The sort moves (column, position) pairs only -- a CUB radix sort over the significant column bits with double
+  // buffers -- and the row ids / values are gathered through the permutation afterwards, one array at a time: 28 B per
+  // entry at the peak instead of ~45 B with thrust::stable_sort_by_key on zipped values. Row blocks near the HBM
+  // capacity can be 1.6x larger for the same memory.
   SegMatrix &T = M.trn;
   T.nnz = nnz; T.nout = ncolumns; T.nin = nl;
-  DevBuf<int32_t> keys;
-  TFX_TRY(keys.alloc((size_t)std::max<int64_t>(nnz, 1)));
-  TFX_TRY(T.val.alloc((size_t)std::max<int64_t>(nnz, 1)));
-  std::swap(T.idx.p, R.rowid.p); std::swap(T.idx.n, R.rowid.n);   // row ids become the gathered index of A^T
-  if (!T.idx.p) TFX_TRY(T.idx.alloc(1));
   std::vector<int64_t> tptr(1, 0);
   std::vector<int32_t> tmap;
-  if (nnz > 0) {
+  on_device = false;
+  if (nnz >= (int64_t)0xFFFFFFF0LL) {
+    // more entries than a 32-bit position can address: the (memory-hungrier) zipped sort
+    DevBuf<int32_t> keys;
+    TFX_TRY(keys.alloc((size_t)nnz));
+    TFX_TRY(T.val.alloc((size_t)nnz));
+    std::swap(T.idx.p, R.rowid.p); std::swap(T.idx.n, R.rowid.n);
     TFX_CUDA(cudaMemcpyAsync(keys.p, F.idx.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
     TFX_CUDA(cudaMemcpyAsync(T.val.p, F.val.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
     thrust::device_ptr<int32_t> K(keys.p), Rw(T.idx.p);
@@ -604,10 +620,42 @@ int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R
     c.launches += 2;
     TFX_TRY(seg_from_sorted_keys_device(keys.p, nnz, ncolumns, T, &on_device));
     if (!on_device) TFX_TRY(runs_of_sorted_keys(keys.p, nnz, ncolumns, tmap, tptr));
+  } else if (nnz > 0) {
+    DevBuf<int32_t> keys, keys_alt, perm, perm_alt;   // perm holds 32-bit UNSIGNED positions
+    TFX_TRY(keys.alloc((size_t)nnz)); TFX_TRY(keys_alt.alloc((size_t)nnz));
+    TFX_TRY(perm.alloc((size_t)nnz)); TFX_TRY(perm_alt.alloc((size_t)nnz));
+    TFX_CUDA(cudaMemcpyAsync(keys.p, F.idx.p, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st));
+    k_iota<<<(int)std::min<int64_t>((nnz + 255) / 256, (int64_t)c.num_sms * 16), 256, 0, st>>>(perm.p, nnz);
+    cub::DoubleBuffer<int32_t> dk(keys.p, keys_alt.p), dv(perm.p, perm_alt.p);
+    int end_bit = 1;
+    while (end_bit < 31 && ((int64_t)1 << end_bit) < (int64_t)ncolumns) ++end_bit;
+    size_t tb = 0;
+    TFX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, nnz, 0, end_bit, st));
+    DevBuf<unsigned char> tmp;
+    TFX_TRY(tmp.alloc(tb + 16));
+    TFX_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, nnz, 0, end_bit, st));
+    c.launches += 5;
+    TFX_CUDA(cudaStreamSynchronize(st));
+    tmp.release();
+    if (dk.Current() == keys.p) keys_alt.release(); else keys.release();
+    if (dv.Current() == perm.p) perm_alt.release(); else perm.release();
+    const int32_t *skeys = dk.Current(), *sperm = dv.Current();
+    TFX_TRY(seg_from_sorted_keys_device(skeys, nnz, ncolumns, T, &on_device));
+    if (!on_device) TFX_TRY(runs_of_sorted_keys(skeys, nnz, ncolumns, tmap, tptr));
+    keys.release(); keys_alt.release();
+    const int gg = (int)std::min<int64_t>((nnz + 255) / 256, (int64_t)c.num_sms * 16);
+    TFX_TRY(T.idx.alloc((size_t)nnz));
+    k_gather<int32_t><<<gg, 256, 0, st>>>(R.rowid.p, sperm, nnz, T.idx.p);     // row ids become the gathered index of A^T
+    TFX_CUDA(cudaStreamSynchronize(st));
+    R.rowid.release();
+    TFX_TRY(T.val.alloc((size_t)nnz));
+    k_gather<float><<<gg, 256, 0, st>>>(F.val.p, sperm, nnz, T.val.p);
+    c.launches += 2;
+    TFX_CUDA(cudaStreamSynchronize(st));
   } else {
-    on_device = false;
+    TFX_TRY(T.idx.alloc(1)); TFX_TRY(T.val.alloc(1));
+    R.rowid.release();
   }
-  keys.release();
   if (!on_device) {
     T.nseg = (int32_t)tmap.size();
     TFX_TRY(up(T.ptr, tptr.data(), tptr.size()));
