@@ -420,6 +420,84 @@ def dist_sensit_model(rank, world, td):
     print("multi_rank_case ok: backend=model kind=dist_sensit world=%d slabs=%s" % (world, list(map(int, nel_at))), flush=True)
 
 
+def dist_wavelet_model(rank, world, td):
+    """Host model of csrc/data.cu:wavelet_slab_dist on CPU (gloo): the 3-D transform of a volume held as contiguous cell
+    slabs WITHOUT assembling it anywhere -- layout A (whole k-planes: axes 1 and 2 local), one all-to-all, layout B (all k
+    for a range of plane cells: axis 3 local), one all-to-all back to the slabs. Same plan arithmetic (ka, pa, the
+    contiguous B range of a slab) as the C++; the per-axis passes are the oracle's 3-D transform applied to shapes with
+    the other axes' lengths 1. Result must be bit-identical to the oracle's transform of the whole volume."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(99)
+    for (nx, ny, nz), wtype in (((12, 10, 9), 1), ((7, 9, 11), 2), ((16, 8, 6), 1)):
+        plane, N = nx * ny, nx * ny * nz
+        vol = rng.standard_normal(N)
+        # unequal slabs (nnz-balanced in the product): cut points not aligned with planes
+        cuts = np.sort(rng.choice(np.arange(plane, N - plane), size=world - 1, replace=False)) if world > 1 else np.array([], int)
+        off = np.concatenate([[0], cuts, [N]]).astype(np.int64)
+        ka = [(int(off[r]) + plane - 1) // plane for r in range(world)] + [nz]
+        pa = [plane * r // world for r in range(world + 1)]
+        qualifies = all(ka[r] < ka[r + 1] for r in range(world)) and all(
+            (ka[r] - 1) * plane >= off[r - 1] for r in range(1, world))
+        for fwd in (True, False):
+            want = (orc.forward_wavelet if fwd else orc.inverse_wavelet)(vol.copy(), nx, ny, nz, wtype)
+            if not qualifies:
+                continue                                   # the product falls back to the gather path
+            t = orc.forward_wavelet if fwd else orc.inverse_wavelet
+            slab = vol[off[rank]:off[rank + 1]].copy()
+            me = rank
+            nk = ka[me + 1] - ka[me]
+            lead = ka[me] * plane - int(off[me])
+            # slabs -> A: my planes = my cells from `lead` on + the leading piece of rank me+1's slab
+            pieces = [None] * world
+            td.all_gather_object(pieces, slab[:lead])
+            A = np.concatenate([slab[lead:], pieces[me + 1] if me + 1 < world else np.zeros(0)])
+            assert A.size == nk * plane
+            # axes 1 and 2 on my planes: a (nx, ny, nk) volume transformed along axis 1, then along axis 2
+            A = A.reshape(nk, ny, nx)
+            for k in range(nk):
+                for j in range(ny):
+                    A[k, j] = t(A[k, j].copy(), nx, 1, 1, wtype)
+                for i in range(nx):
+                    A[k, :, i] = t(A[k, :, i].copy(), 1, ny, 1, wtype)
+            A = A.reshape(nk, plane)
+            # A -> B: rank q receives the columns [pa[q], pa[q+1]) of everybody's planes, plane order = rank order
+            send = [A[:, pa[q]:pa[q + 1]].copy() for q in range(world)]
+            allsend = [None] * world
+            td.all_gather_object(allsend, send)
+            B = np.concatenate([allsend[r][me] for r in range(world)], axis=0)      # (nz, W)
+            W = pa[me + 1] - pa[me]
+            assert B.shape == (nz, W)
+            for p in range(W):
+                B[:, p] = t(B[:, p].copy(), 1, 1, nz, wtype)
+            # B -> slabs: the cells of slab r inside my columns are ONE contiguous range of B
+            Bf = B.ravel()
+
+            def rng_in(q, r):
+                Wq = pa[q + 1] - pa[q]
+                k0, k1 = int(off[r]) // plane, (int(off[r + 1]) - 1) // plane
+                s0, e1 = int(off[r]) - k0 * plane, int(off[r + 1]) - k1 * plane
+                b0 = k0 * Wq + min(max(s0, pa[q]), pa[q + 1]) - pa[q]
+                b1 = k1 * Wq + min(max(e1, pa[q]), pa[q + 1]) - pa[q]
+                return b0, max(b0, b1)
+            send = [Bf[slice(*rng_in(me, r))].copy() for r in range(world)]
+            td.all_gather_object(allsend, send)
+            out = np.full(off[me + 1] - off[me], np.nan)
+            k0, k1 = int(off[me]) // plane, (int(off[me + 1]) - 1) // plane
+            for q in range(world):
+                msg = allsend[q][me]
+                pos = 0
+                for k in range(k0, k1 + 1):
+                    lo = max(pa[q], int(off[me]) - k * plane if k == k0 else 0)
+                    hi = min(pa[q + 1], int(off[me + 1]) - k * plane if k == k1 else plane)
+                    if hi > lo:
+                        d0 = k * plane + lo - int(off[me])
+                        out[d0:d0 + hi - lo] = msg[pos:pos + hi - lo]
+                        pos += hi - lo
+                assert pos == msg.size
+            assert np.array_equal(out, want[off[me]:off[me + 1]]), ((nx, ny, nz), wtype, fwd)
+    print("multi_rank_case ok: backend=model kind=dist_wavelet world=%d" % world, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--backend", default="nccl", choices=["nccl", "model"])
@@ -457,6 +535,7 @@ def main():
         dist_sensit_case(rank, world, td, a.niter)
     else:
         dist_sensit_model(rank, world, td)
+        dist_wavelet_model(rank, world, td)
     td.barrier()
     td.destroy_process_group()
     if not ok:

@@ -27,5 +27,5 @@ def run_case(backend, world, timeout=600):
 def test_column_split_model_matches_oracle(world):
     r = run_case("model", world)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    # dense + sparse solves on rank 0, the re-partitioning model on every rank
-    assert r.stdout.count("multi_rank_case ok") == 5 + world, r.stdout
+    # five solves on rank 0; the re-partitioning model and the distributed-wavelet model on every rank
+    assert r.stdout.count("multi_rank_case ok") == 5 + 2 * world, r.stdout
