@@ -374,6 +374,11 @@ int tfx_sensit_lines(const tfx_sensit_params *par, const double *X1, const doubl
                      const double *Y2, const double *Z1, const double *Z2, int32_t ndata_batch,
                      const double *data_X, const double *data_Y, const double *data_Z, double *lines);
 
+/* Diagnostics for tests/test_gpu_mathx.py: the forward kernels' own log / atan2 (csrc/mathx.cuh: CUDA's algorithms with
+ * the polynomial coefficients read from the constant bank) next to the CUDA library's, element by element (host arrays):
+ * out = [tfx_log(x) | log(x) | tfx_atan2(y, x) | atan2(y, x)], 4 * n doubles. */
+int tfx_debug_math(int64_t n, const double *y, const double *x, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,10 +1,15 @@
-"""Compressed row pipeline on a few stations (for an ncu launch list): python scratch/assembly_breakdown.py [nz] [ndata]"""
+"""Compressed row pipeline on a few stations (for an ncu launch list):
+    python scratch/assembly_breakdown.py [nz] [ndata] [problem_type] [option=value | nx=.. | ny=.. | wt=..] ..."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import tomofastx_b200 as tfx
-from tests.synth import depth_weight_type1, regular_grid, station_lattice
-nx, ny = 256, 256
+from tomofastx_b200.synth import depth_weight_type1, regular_grid, station_lattice
+nx, ny, wt = 256, 256, 1
+for kv in list(sys.argv[4:]):
+    k, v = kv.split('=')
+    if k in ('nx', 'ny', 'wt'):
+        globals()[k] = int(v); sys.argv.remove(kv)
 nz = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 nd = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 N = nx * ny * nz
@@ -20,7 +25,7 @@ par.problem_type = ptype
 par.nx, par.ny, par.nz = nx, ny, nz
 par.ndata, par.ndata_components, par.nmodel_components, par.data_type = nd, 1, 1, 1
 par.mi, par.md, par.theta, par.intensity = 60.0, 10.0, 0.0, 50000.0
-par.compression_type, par.compression_rate = 1, 0.05
+par.compression_type, par.compression_rate = wt, 0.05
 par.problem_weight = 1.0
 par.cell0, par.ncells_local, par.param_shift, par.ncolumns = 0, N, 0, 2 * N
 for rep in range(2):

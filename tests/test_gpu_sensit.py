@@ -144,6 +144,54 @@ def test_compressed_assembly_vs_oracle(oracle, ctype):
     assert np.allclose(d_got, d_want, rtol=1e-6, atol=1e-8 * np.abs(d_want).max())
 
 
+@pytest.mark.parametrize("ctype", [1, 2])
+def test_compressed_assembly_many_chunks_vs_oracle(oracle, ctype):
+    """A grid that spans several 4096-element compaction chunks and several CTAs per line in the select passes
+    (csrc/sensit.cu k_sel_* / k_cmp_*): pattern, values and per-cell counts vs the oracle."""
+    pb = make_problem(nx=48, ny=40, nz=10, ndata=6, compression_type=ctype, rate=0.07)
+    S, nnz_col, cerr, tot = tfx.calculate_sensit(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+    So = pb.oracle_matrix(oracle)
+    want = _rows(*So.arrays())
+    got = _rows(*S.export())
+    assert set(want) == set(got)
+    mismatched = 0
+    for r in want:
+        assert np.all(np.diff(got[r][0]) > 0)                 # columns ascending inside a row
+        if np.array_equal(got[r][0], want[r][0]):
+            assert np.allclose(got[r][1], want[r][1], rtol=3e-6, atol=1e-6 * np.abs(want[r][1]).max())
+        else:
+            mismatched += len(set(got[r][0]) ^ set(want[r][0]))
+    assert mismatched <= 2 * pb.ndata, mismatched
+    assert abs(tot - So.nel) <= mismatched
+    assert int(nnz_col.sum()) == tot
+    # compression error = mean over the lines of sqrt(discarded cost / full cost) (sensitivity_gravmag.F90:283-285, :346-353)
+    errs = []
+    for i in range(pb.ndata):
+        line = oracle.graviprism_z(pb.grid, *(float(a[i]) for a in pb.data_xyz)) * pb.cw
+        r = oracle.compress_row(line, pb.par.nx, pb.par.ny, pb.par.nz, ctype, pb.nel_compressed)
+        errs.append(np.sqrt(r["cost_discarded"] / r["cost_full"]))
+    assert cerr == pytest.approx(np.mean(errs), rel=1e-3)
+
+
+def test_kth_select_fallback_passes_give_the_same_rows():
+    """The k-th order statistic resolves its low 39 bits on a candidate list; a bucket that does not fit the list goes on
+    with radix passes over the whole line. Forcing that path (sensit_cand_cap = 1) must not change a single entry."""
+    pb = make_problem(nx=40, ny=32, nz=16, ndata=5, compression_type=1, rate=0.05)
+    rows_a, nnz_a, cerr_a, tot_a = tfx.sensit_assemble_rows(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+    S_a, _, _, _ = tfx.calculate_sensit(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+    try:
+        tfx.set_option("sensit_cand_cap", 1)
+        S_b, nnz_b, cerr_b, tot_b = tfx.calculate_sensit(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+    finally:
+        tfx.set_option("sensit_cand_cap", 0)
+    assert tot_a == tot_b and cerr_a == cerr_b and np.array_equal(nnz_a, nnz_b)
+    for x, y in zip(S_a.export(), S_b.export()):
+        assert np.array_equal(x, y)
+    # exactly nel_compressed entries per row unless values tie at the threshold
+    nel = int(pb.par.compression_rate * pb.N)
+    assert tot_a <= nel * pb.ndata and tot_a >= (nel - 2) * pb.ndata
+
+
 def test_magnetic_compressed_assembly_three_components(oracle):
     # config D shape in miniature: magnetisation model (3 comps), TMI data, columns shifted to problem 2
     pb = make_problem(nx=8, ny=7, nz=4, ndata=6, compression_type=2, rate=0.3, problem_type=2, nmodel_components=3)

@@ -64,19 +64,21 @@ def test_wavelet_diagonal_matrix_46656():
     assert nnz == 46656
 
 
-@pytest.mark.parametrize("shape", [(256, 256, 64), (512, 512, 16), (1024, 96, 40)])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (512, 512, 16), (1024, 96, 40), (1024, 1024, 3), (512, 100, 7),
+                                   (128, 1000, 5), (40, 24, 200)])
 @pytest.mark.parametrize("wtype", [1, 2])
 def test_large_volume_kernels_agree_bit_for_bit(shape, wtype):
-    """At sizes the oracle does not visit in seconds: column-layout kernel (with and without the L2-blocked slabs) ==
-    generic kernel, bit for bit, forward and inverse."""
+    """At sizes the oracle does not visit in seconds: column-layout kernel (with and without the L2-blocked slabs, with
+    and without the fused Haar axis-1 + low axis-2 scales pass) == generic kernel, bit for bit, forward and inverse."""
     import torch
     n1, n2, n3 = shape
     g = torch.Generator(device="cuda").manual_seed(11)
     x = torch.randn(n1 * n2 * n3, dtype=torch.float64, device="cuda", generator=g)
     outs = []
     try:
-        for cols, slab in ((0, 0), (1, 0), (1, 4)):
+        for cols, slab, fuse in ((0, 0, 1), (1, 0, 0), (1, 0, 1), (1, 4, 1)):
             tfx.set_option("wavelet_cols", cols); tfx.set_option("wavelet_slab_mb", slab)
+            tfx.set_option("wavelet_fuse12", fuse)
             y = x.clone()
             torch.cuda.synchronize()      # libtfx runs on its own non-blocking stream: order torch's work first
             tfx.forward_wavelet(y, n1, n2, n3, wtype)
@@ -85,7 +87,7 @@ def test_large_volume_kernels_agree_bit_for_bit(shape, wtype):
             tfx.inverse_wavelet(z, n1, n2, n3, wtype)
             outs.append((y, z))
     finally:
-        tfx.set_option("wavelet_cols", 1); tfx.set_option("wavelet_slab_mb", 0)
+        tfx.set_option("wavelet_cols", 1); tfx.set_option("wavelet_slab_mb", 0); tfx.set_option("wavelet_fuse12", 1)
     for y, z in outs[1:]:
         assert torch.equal(y, outs[0][0]) and torch.equal(z, outs[0][1])
     assert float((outs[0][1] - x).abs().max()) < 1e-11

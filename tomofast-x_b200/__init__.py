@@ -107,6 +107,7 @@ def lib():
     L.tfx_get_load_balancing_nelements.argtypes = [i32, vp, i32, vp, vp]
     L.tfx_sensit_repartition.argtypes = [C.POINTER(vp), vp, i32, vp, i32, i32]
     L.tfx_sensit_lines.argtypes = [C.POINTER(SensitParams)] + [vp] * 6 + [i32] + [vp] * 4
+    L.tfx_debug_math.argtypes = [i64, vp, vp, vp]
     _lib = L
     return L
 
@@ -522,6 +523,16 @@ def sensit_lines(par, grid, data_xyz):
     out = np.zeros((dx.size, par.ndata_components, par.nmodel_components, n))
     _check(lib().tfx_sensit_lines(C.byref(par), *gp, dx.size, dx.ctypes.data, dy.ctypes.data, dz.ctypes.data,
                                   out.ctypes.data))
+    return out
+
+
+def debug_math(y, x):
+    """(tfx_log(x), log(x), tfx_atan2(y, x), atan2(y, x)) evaluated on the device (csrc/mathx.cuh vs the CUDA library)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    assert y.shape == x.shape and x.ndim == 1
+    out = np.zeros((4, x.size))
+    _check(lib().tfx_debug_math(x.size, y.ctypes.data, x.ctypes.data, out.ctypes.data))
     return out
 
 

@@ -380,6 +380,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_wavelet_cols = value;
     return 0;
   }
+  if (name && strcmp(name, "wavelet_fuse12") == 0) {
+    g_opt_wavelet_fuse12 = value;
+    return 0;
+  }
   if (name && strcmp(name, "wavelet_slab_mb") == 0) {
     g_opt_wavelet_slab_mb = value;
     return 0;
@@ -414,6 +418,10 @@ int tfx_set_option(const char *name, int value) {
   }
   if (name && strcmp(name, "sensit_row_blocks") == 0) {
     g_opt_sensit_row_blocks = value;
+    return 0;
+  }
+  if (name && strcmp(name, "sensit_cand_cap") == 0) {
+    g_opt_sensit_cand_cap = value;
     return 0;
   }
   if (name && strcmp(name, "t16_bank_deal") == 0) {

@@ -12,6 +12,7 @@
 // load and the column-major store of the dense block is coalesced.
 #include "common.cuh"
 #include "kernels.h"
+#include "mathx.cuh"
 
 #include <math.h>
 
@@ -39,14 +40,14 @@ __device__ __forceinline__ double grav_gz(double x1, double x2, double y1, doubl
         const double dmu = ((K + L + M) & 1) ? 1.0 : -1.0;   // signo(K)*signo(L)*signo(M), signo = (-1, +1)
         const double Rs =
             sqrt(__dadd_rn(__dadd_rn(__dmul_rn(XX[K], XX[K]), __dmul_rn(YY[L], YY[L])), __dmul_rn(ZZ[M], ZZ[M])));
-        double arg3 = atan2(__dmul_rn(XX[K], YY[L]), __dmul_rn(ZZ[M], Rs));
+        double arg3 = tfx_atan2(__dmul_rn(XX[K], YY[L]), __dmul_rn(ZZ[M], Rs));
         if (arg3 < 0) arg3 = arg3 + twopi;
         double arg4 = Rs + XX[K];
         double arg5 = Rs + YY[L];
         if (arg4 <= 0.) *err = 1;   // "Data coordinate coincides with model grid boundary (YZ)"
         if (arg5 <= 0.) *err = 2;   // "... (XZ)"
-        arg4 = log(arg4);
-        arg5 = log(arg5);
+        arg4 = tfx_log(arg4);
+        arg5 = tfx_log(arg5);
         const double term = __dsub_rn(__dsub_rn(__dmul_rn(ZZ[M], arg3), __dmul_rn(XX[K], arg5)), __dmul_rn(YY[L], arg4));
         gz = __dadd_rn(gz, __dmul_rn(dmu, term));
       }
@@ -70,7 +71,7 @@ __device__ __forceinline__ double grav_gzz(double x1, double x2, double y1, doub
         const double dmu = ((K + L + M) & 1) ? 1.0 : -1.0;
         const double Rs =
             sqrt(__dadd_rn(__dadd_rn(__dmul_rn(XX[K], XX[K]), __dmul_rn(YY[L], YY[L])), __dmul_rn(ZZ[M], ZZ[M])));
-        double vzz = -atan2(__dmul_rn(XX[K], YY[L]), __dmul_rn(Rs, ZZ[M]));
+        double vzz = -tfx_atan2(__dmul_rn(XX[K], YY[L]), __dmul_rn(Rs, ZZ[M]));
         if (vzz < 0) vzz = vzz + twopi;
         gzz = __dadd_rn(gzz, __dmul_rn(dmu, vzz));
       }
@@ -97,9 +98,9 @@ __device__ __forceinline__ void grav_full(double x1, double x2, double y1, doubl
         const double xx = __dmul_rn(XX[K], XX[K]), zz = __dmul_rn(ZZ[M], ZZ[M]);
         const double Rs = sqrt(__dadd_rn(__dadd_rn(xx, __dmul_rn(YY[L], YY[L])), zz));
         const double xy = __dmul_rn(XX[K], YY[L]), rz = __dmul_rn(Rs, ZZ[M]);
-        double vxx = atan2(xy, __dadd_rn(__dadd_rn(xx, rz), zz));
-        double vyy = atan2(xy, __dsub_rn(__dadd_rn(__dmul_rn(Rs, Rs), rz), xx));
-        double vzz = -atan2(xy, rz);
+        double vxx = tfx_atan2(xy, __dadd_rn(__dadd_rn(xx, rz), zz));
+        double vyy = tfx_atan2(xy, __dsub_rn(__dadd_rn(__dmul_rn(Rs, Rs), rz), xx));
+        double vzz = -tfx_atan2(xy, rz);
         if (vxx < 0) vxx = vxx + twopi;
         if (vyy < 0) vyy = vyy + twopi;
         if (vzz < 0) vzz = vzz + twopi;
@@ -110,9 +111,9 @@ __device__ __forceinline__ void grav_full(double x1, double x2, double y1, doubl
         const double arg2 = __ddiv_rn(arg21, arg22);
         const double arg3 = __ddiv_rn(arg31, arg32);
         if (arg1 <= 0. || arg2 <= 0. || arg3 <= 0.) { *err = 4; continue; }
-        const double vxy = log(arg1);
-        const double vzx = __dmul_rn(0.5, log(arg2));
-        const double vyz = __dmul_rn(0.5, log(arg3));
+        const double vxy = tfx_log(arg1);
+        const double vzx = __dmul_rn(0.5, tfx_log(arg2));
+        const double vyz = __dmul_rn(0.5, tfx_log(arg3));
         gxx = __dadd_rn(gxx, __dmul_rn(dmu, vxx));
         gyy = __dadd_rn(gyy, __dmul_rn(dmu, vyy));
         gzz = __dadd_rn(gzz, __dmul_rn(dmu, vzz));
@@ -127,14 +128,14 @@ __device__ __forceinline__ void grav_full(double x1, double x2, double y1, doubl
 __device__ __forceinline__ double grav_corner_term(double X, double Y, double Z, int *err) {
   const double twopi = 2.0 * TFX_PI;
   const double Rs = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(X, X), __dmul_rn(Y, Y)), __dmul_rn(Z, Z)));
-  double arg3 = atan2(__dmul_rn(X, Y), __dmul_rn(Z, Rs));
+  double arg3 = tfx_atan2(__dmul_rn(X, Y), __dmul_rn(Z, Rs));
   if (arg3 < 0) arg3 = arg3 + twopi;
   double arg4 = Rs + X;
   double arg5 = Rs + Y;
   if (arg4 <= 0.) *err = 1;   // "Data coordinate coincides with model grid boundary (YZ)"
   if (arg5 <= 0.) *err = 2;   // "... (XZ)"
-  arg4 = log(arg4);
-  arg5 = log(arg5);
+  arg4 = tfx_log(arg4);
+  arg5 = tfx_log(arg5);
   return __dsub_rn(__dsub_rn(__dmul_rn(Z, arg3), __dmul_rn(X, arg5)), __dmul_rn(Y, arg4));
 }
 
@@ -328,14 +329,14 @@ __global__ void __launch_bounds__(256) grav_lines_nodes_kernel(double *__restric
       if (gi <= nx && gj <= ny && gk <= nz) {
         const double X = px - xn[gi], Y = py - yn[gj], Z = pz - zn[gk];
         const double Rs = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(X, X), __dmul_rn(Y, Y)), __dmul_rn(Z, Z)));
-        double arg3 = atan2(__dmul_rn(X, Y), __dmul_rn(Z, Rs));
+        double arg3 = tfx_atan2(__dmul_rn(X, Y), __dmul_rn(Z, Rs));
         if (arg3 < 0) arg3 = arg3 + twopi;
         double arg4 = Rs + X;
         double arg5 = Rs + Y;
         if (arg4 <= 0.) e = 1;   // "Data coordinate coincides with model grid boundary (YZ)"
         if (arg5 <= 0.) e = 2;   // "... (XZ)"
-        arg4 = log(arg4);
-        arg5 = log(arg5);
+        arg4 = tfx_log(arg4);
+        arg5 = tfx_log(arg5);
         term = __dsub_rn(__dsub_rn(__dmul_rn(Z, arg3), __dmul_rn(X, arg5)), __dmul_rn(Y, arg4));
       }
       T[c][bb][a] = term;
@@ -428,50 +429,50 @@ __device__ void sharmbox_dev(double x0, double y0, double z0, double x1, double 
          a4 = sqrt(__dadd_rn(rz1sq, R2)), a5 = sqrt(__dadd_rn(rz2sq, R3)), a6 = sqrt(__dadd_rn(rz2sq, R4)),
          a7 = sqrt(__dadd_rn(rz1sq, R4)), a8 = sqrt(__dadd_rn(rz1sq, R3));
   // ts_xx (:376-383)
-  double t = atan2(__dmul_rn(ry1, rz2), __dmul_rn(rx2, a5));
-  t = __dsub_rn(t, atan2(__dmul_rn(ry2, rz2), __dmul_rn(rx2, a2)));
-  t = __dadd_rn(t, atan2(__dmul_rn(ry2, rz1), __dmul_rn(rx2, a3)));
-  t = __dsub_rn(t, atan2(__dmul_rn(ry1, rz1), __dmul_rn(rx2, a8)));
-  t = __dadd_rn(t, atan2(__dmul_rn(ry2, rz2), __dmul_rn(rx1, a1)));
-  t = __dsub_rn(t, atan2(__dmul_rn(ry1, rz2), __dmul_rn(rx1, a6)));
-  t = __dadd_rn(t, atan2(__dmul_rn(ry1, rz1), __dmul_rn(rx1, a7)));
-  t = __dsub_rn(t, atan2(__dmul_rn(ry2, rz1), __dmul_rn(rx1, a4)));
+  double t = tfx_atan2(__dmul_rn(ry1, rz2), __dmul_rn(rx2, a5));
+  t = __dsub_rn(t, tfx_atan2(__dmul_rn(ry2, rz2), __dmul_rn(rx2, a2)));
+  t = __dadd_rn(t, tfx_atan2(__dmul_rn(ry2, rz1), __dmul_rn(rx2, a3)));
+  t = __dsub_rn(t, tfx_atan2(__dmul_rn(ry1, rz1), __dmul_rn(rx2, a8)));
+  t = __dadd_rn(t, tfx_atan2(__dmul_rn(ry2, rz2), __dmul_rn(rx1, a1)));
+  t = __dsub_rn(t, tfx_atan2(__dmul_rn(ry1, rz2), __dmul_rn(rx1, a6)));
+  t = __dadd_rn(t, tfx_atan2(__dmul_rn(ry1, rz1), __dmul_rn(rx1, a7)));
+  t = __dsub_rn(t, tfx_atan2(__dmul_rn(ry2, rz1), __dmul_rn(rx1, a4)));
   tsx[0] = t;
   // ts_yx (:386-389)
-  t = log(__ddiv_rn(rz2 + a2, rz1 + a3));
-  t = __dsub_rn(t, log(__ddiv_rn(rz2 + a1, rz1 + a4)));
-  t = __dadd_rn(t, log(__ddiv_rn(rz2 + a6, rz1 + a7)));
-  t = __dsub_rn(t, log(__ddiv_rn(rz2 + a5, rz1 + a8)));
+  t = tfx_log(__ddiv_rn(rz2 + a2, rz1 + a3));
+  t = __dsub_rn(t, tfx_log(__ddiv_rn(rz2 + a1, rz1 + a4)));
+  t = __dadd_rn(t, tfx_log(__ddiv_rn(rz2 + a6, rz1 + a7)));
+  t = __dsub_rn(t, tfx_log(__ddiv_rn(rz2 + a5, rz1 + a8)));
   tsy[0] = t;
   // ts_yy (:392-399)
-  t = atan2(__dmul_rn(rx1, rz2), __dmul_rn(ry2, a1));
-  t = __dsub_rn(t, atan2(__dmul_rn(rx2, rz2), __dmul_rn(ry2, a2)));
-  t = __dadd_rn(t, atan2(__dmul_rn(rx2, rz1), __dmul_rn(ry2, a3)));
-  t = __dsub_rn(t, atan2(__dmul_rn(rx1, rz1), __dmul_rn(ry2, a4)));
-  t = __dadd_rn(t, atan2(__dmul_rn(rx2, rz2), __dmul_rn(ry1, a5)));
-  t = __dsub_rn(t, atan2(__dmul_rn(rx1, rz2), __dmul_rn(ry1, a6)));
-  t = __dadd_rn(t, atan2(__dmul_rn(rx1, rz1), __dmul_rn(ry1, a7)));
-  t = __dsub_rn(t, atan2(__dmul_rn(rx2, rz1), __dmul_rn(ry1, a8)));
+  t = tfx_atan2(__dmul_rn(rx1, rz2), __dmul_rn(ry2, a1));
+  t = __dsub_rn(t, tfx_atan2(__dmul_rn(rx2, rz2), __dmul_rn(ry2, a2)));
+  t = __dadd_rn(t, tfx_atan2(__dmul_rn(rx2, rz1), __dmul_rn(ry2, a3)));
+  t = __dsub_rn(t, tfx_atan2(__dmul_rn(rx1, rz1), __dmul_rn(ry2, a4)));
+  t = __dadd_rn(t, tfx_atan2(__dmul_rn(rx2, rz2), __dmul_rn(ry1, a5)));
+  t = __dsub_rn(t, tfx_atan2(__dmul_rn(rx1, rz2), __dmul_rn(ry1, a6)));
+  t = __dadd_rn(t, tfx_atan2(__dmul_rn(rx1, rz1), __dmul_rn(ry1, a7)));
+  t = __dsub_rn(t, tfx_atan2(__dmul_rn(rx2, rz1), __dmul_rn(ry1, a8)));
   tsy[1] = t;
   // ts_yz (:404-422)
   R1 = __dadd_rn(ry2sq, rz1sq); R2 = __dadd_rn(ry2sq, rz2sq); R3 = __dadd_rn(ry1sq, rz1sq); R4 = __dadd_rn(ry1sq, rz2sq);
   a1 = sqrt(__dadd_rn(rx1sq, R1)); a2 = sqrt(__dadd_rn(rx2sq, R1)); a3 = sqrt(__dadd_rn(rx1sq, R2));
   a4 = sqrt(__dadd_rn(rx2sq, R2)); a5 = sqrt(__dadd_rn(rx1sq, R3)); a6 = sqrt(__dadd_rn(rx2sq, R3));
   a7 = sqrt(__dadd_rn(rx1sq, R4)); a8 = sqrt(__dadd_rn(rx2sq, R4));
-  t = log(__ddiv_rn(rx1 + a1, rx2 + a2));
-  t = __dsub_rn(t, log(__ddiv_rn(rx1 + a3, rx2 + a4)));
-  t = __dadd_rn(t, log(__ddiv_rn(rx1 + a7, rx2 + a8)));
-  t = __dsub_rn(t, log(__ddiv_rn(rx1 + a5, rx2 + a6)));
+  t = tfx_log(__ddiv_rn(rx1 + a1, rx2 + a2));
+  t = __dsub_rn(t, tfx_log(__ddiv_rn(rx1 + a3, rx2 + a4)));
+  t = __dadd_rn(t, tfx_log(__ddiv_rn(rx1 + a7, rx2 + a8)));
+  t = __dsub_rn(t, tfx_log(__ddiv_rn(rx1 + a5, rx2 + a6)));
   tsy[2] = t;
   // ts_xz (:424-442)
   R1 = __dadd_rn(rx2sq, rz1sq); R2 = __dadd_rn(rx2sq, rz2sq); R3 = __dadd_rn(rx1sq, rz1sq); R4 = __dadd_rn(rx1sq, rz2sq);
   a1 = sqrt(__dadd_rn(ry1sq, R1)); a2 = sqrt(__dadd_rn(ry2sq, R1)); a3 = sqrt(__dadd_rn(ry1sq, R2));
   a4 = sqrt(__dadd_rn(ry2sq, R2)); a5 = sqrt(__dadd_rn(ry1sq, R3)); a6 = sqrt(__dadd_rn(ry2sq, R3));
   a7 = sqrt(__dadd_rn(ry1sq, R4)); a8 = sqrt(__dadd_rn(ry2sq, R4));
-  t = log(__ddiv_rn(ry1 + a1, ry2 + a2));
-  t = __dsub_rn(t, log(__ddiv_rn(ry1 + a3, ry2 + a4)));
-  t = __dadd_rn(t, log(__ddiv_rn(ry1 + a7, ry2 + a8)));
-  t = __dsub_rn(t, log(__ddiv_rn(ry1 + a5, ry2 + a6)));
+  t = tfx_log(__ddiv_rn(ry1 + a1, ry2 + a2));
+  t = __dsub_rn(t, tfx_log(__ddiv_rn(ry1 + a3, ry2 + a4)));
+  t = __dadd_rn(t, tfx_log(__ddiv_rn(ry1 + a7, ry2 + a8)));
+  t = __dsub_rn(t, tfx_log(__ddiv_rn(ry1 + a5, ry2 + a6)));
   tsx[2] = t;
   tsz[2] = -1 * (tsx[0] + tsy[1]);   // Gauss (:446)
   tsz[1] = tsy[2];
@@ -552,6 +553,32 @@ __global__ void __launch_bounds__(128) mag_lines_kernel(double *__restrict__ lin
   if (e) atomicExch(err, e);
 }
 
+// The cell that contains the station: six sub-prisms around it (magnetic_field.f90:139-224). Out of line: one cell per
+// station at most takes this path, and inlined it sets the register count of the whole kernel.
+__device__ __noinline__ void mag_incell_dev(double Xd, double Yd, double Zd, double gx1, double gy1, double gz1, double gx2,
+                                            double gy2, double gz2, double *tx, double *ty, double *tz, int *e) {
+  double width = (double)0.1f;
+  const double min_clr = fmin(fmin(fmin(fabs(Xd - gx1), fabs(Xd - gx2)), fmin(fabs(Yd - gy1), fabs(Yd - gy2))),
+                              fmin(fabs(Zd - gz1), fabs(Zd - gz2)));
+  if (width > min_clr) width = 0.5 * min_clr;
+  const double bx1[6] = {gx1, gx1, gx1, Xd + width, Xd - width, Xd - width};
+  const double bx2[6] = {gx2, gx2, Xd - width, gx2, Xd + width, Xd + width};
+  const double by1[6] = {gy1, gy1, gy1, gy1, gy1, Yd + width};
+  const double by2[6] = {gy2, gy2, gy2, gy2, Yd - width, gy2};
+  const double bz1[6] = {gz1, Zd + width, Zd - width, Zd - width, Zd - width, Zd - width};
+  const double bz2[6] = {Zd - width, gz2, Zd + width, Zd + width, Zd + width, Zd + width};
+  for (int q = 0; q < 3; ++q) tx[q] = ty[q] = tz[q] = 0.0;
+  for (int j = 0; j < 6; ++j) {
+    double ax[3], ay[3], az[3];
+    sharmbox_dev(Xd, Yd, Zd, bx1[j], by1[j], bz1[j], bx2[j], by2[j], bz2[j], ax, ay, az, e);
+    for (int q = 0; q < 3; ++q) {
+      tx[q] = __dadd_rn(tx[q], ax[q]);
+      ty[q] = __dadd_rn(ty[q], ay[q]);
+      tz[q] = __dadd_rn(tz[q], az[q]);
+    }
+  }
+}
+
 // ---- structured grids: shared corner / edge terms -------------------------------------------------
 // sharmbox (magnetic_field.f90:321-457) is a signed sum of terms that belong either to ONE corner of the prism
 //   A = atan2(ry*rz, rx*a)  (ts_xx),   B = atan2(rx*rz, ry*a)  (ts_yy),        a = sqrt(rz^2 + (ry^2 + rx^2))
@@ -567,10 +594,11 @@ namespace {
 constexpr int kMTX = 32, kMTY = 8, kMTZ = 8;
 constexpr int kMNodes = (kMTX + 1) * (kMTY + 1) * (kMTZ + 1);
 constexpr int kMEz = (kMTX + 1) * (kMTY + 1) * kMTZ, kMEx = kMTX * (kMTY + 1) * (kMTZ + 1), kMEy = (kMTX + 1) * kMTY * (kMTZ + 1);
+constexpr int kMagThreads = 512;   // 2 CTAs of 512 threads per SM (shared memory: 2 x 101 KB), 64 registers
 constexpr size_t kMagSmem = (size_t)(2 * kMNodes + kMEz + kMEx + kMEy) * sizeof(double);
 }
 
-__global__ void __launch_bounds__(256) mag_lines_nodes_kernel(double *__restrict__ lines, int nx, int ny, int nz, int nb,
+__global__ void __launch_bounds__(kMagThreads, 2) mag_lines_nodes_kernel(double *__restrict__ lines, int nx, int ny, int nz, int nb,
                                                               const double *__restrict__ xn, const double *__restrict__ yn,
                                                               const double *__restrict__ zn, const double *__restrict__ xd,
                                                               const double *__restrict__ yd, const double *__restrict__ zd,
@@ -590,7 +618,7 @@ __global__ void __launch_bounds__(256) mag_lines_nodes_kernel(double *__restrict
   for (int b_ = blockIdx.y; b_ < nb; b_ += gridDim.y) {
     const double Xd = xd[b_], Yd = yd[b_], Zd = zd[b_];
     // ---- corner terms
-    for (int idx = threadIdx.x; idx < kMNodes; idx += 256) {
+    for (int idx = threadIdx.x; idx < kMNodes; idx += kMagThreads) {
       const int a = idx % (kMTX + 1), b = (idx / (kMTX + 1)) % (kMTY + 1), c = idx / ((kMTX + 1) * (kMTY + 1));
       const int gi = min(i0 + a, nx), gj = min(j0 + b, ny), gk = min(k0 + c, nz);
       const double rx = xn[gi] - Xd, ry = yn[gj] - Yd, rz = zn[gk] - Zd;
@@ -599,63 +627,44 @@ __global__ void __launch_bounds__(256) mag_lines_nodes_kernel(double *__restrict
         if (ry == 0.) e = 12;
       }
       const double as1 = sqrt(__dadd_rn(__dmul_rn(rz, rz), __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rx, rx))));
-      sA[idx] = atan2(__dmul_rn(ry, rz), __dmul_rn(rx, as1));
-      sB[idx] = atan2(__dmul_rn(rx, rz), __dmul_rn(ry, as1));
+      sA[idx] = tfx_atan2(__dmul_rn(ry, rz), __dmul_rn(rx, as1));
+      sB[idx] = tfx_atan2(__dmul_rn(rx, rz), __dmul_rn(ry, as1));
     }
     // ---- edge terms
-    for (int idx = threadIdx.x; idx < kMEz; idx += 256) {
+    for (int idx = threadIdx.x; idx < kMEz; idx += kMagThreads) {
       const int a = idx % (kMTX + 1), b = (idx / (kMTX + 1)) % (kMTY + 1), c = idx / ((kMTX + 1) * (kMTY + 1));
       const int gi = min(i0 + a, nx), gj = min(j0 + b, ny), g1 = min(k0 + c, nz), g2 = min(k0 + c + 1, nz);
       const double rx = xn[gi] - Xd, ry = yn[gj] - Yd, rz1 = zn[g1] - Zd, rz2 = zn[g2] - Zd;
       const double R = __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rx, rx));
       const double a_lo = sqrt(__dadd_rn(__dmul_rn(rz1, rz1), R)), a_hi = sqrt(__dadd_rn(__dmul_rn(rz2, rz2), R));
-      sEz[idx] = log(__ddiv_rn(rz2 + a_hi, rz1 + a_lo));
+      sEz[idx] = tfx_log(__ddiv_rn(rz2 + a_hi, rz1 + a_lo));
     }
-    for (int idx = threadIdx.x; idx < kMEx; idx += 256) {
+    for (int idx = threadIdx.x; idx < kMEx; idx += kMagThreads) {
       const int a = idx % kMTX, b = (idx / kMTX) % (kMTY + 1), c = idx / (kMTX * (kMTY + 1));
       const int g1 = min(i0 + a, nx), g2 = min(i0 + a + 1, nx), gj = min(j0 + b, ny), gk = min(k0 + c, nz);
       const double rx1 = xn[g1] - Xd, rx2 = xn[g2] - Xd, ry = yn[gj] - Yd, rz = zn[gk] - Zd;
       const double R = __dadd_rn(__dmul_rn(ry, ry), __dmul_rn(rz, rz));
       const double a1 = sqrt(__dadd_rn(__dmul_rn(rx1, rx1), R)), a2 = sqrt(__dadd_rn(__dmul_rn(rx2, rx2), R));
-      sEx[idx] = log(__ddiv_rn(rx1 + a1, rx2 + a2));
+      sEx[idx] = tfx_log(__ddiv_rn(rx1 + a1, rx2 + a2));
     }
-    for (int idx = threadIdx.x; idx < kMEy; idx += 256) {
+    for (int idx = threadIdx.x; idx < kMEy; idx += kMagThreads) {
       const int a = idx % (kMTX + 1), b = (idx / (kMTX + 1)) % kMTY, c = idx / ((kMTX + 1) * kMTY);
       const int gi = min(i0 + a, nx), g1 = min(j0 + b, ny), g2 = min(j0 + b + 1, ny), gk = min(k0 + c, nz);
       const double rx = xn[gi] - Xd, ry1 = yn[g1] - Yd, ry2 = yn[g2] - Yd, rz = zn[gk] - Zd;
       const double R = __dadd_rn(__dmul_rn(rx, rx), __dmul_rn(rz, rz));
       const double a1 = sqrt(__dadd_rn(__dmul_rn(ry1, ry1), R)), a2 = sqrt(__dadd_rn(__dmul_rn(ry2, ry2), R));
-      sEy[idx] = log(__ddiv_rn(ry1 + a1, ry2 + a2));
+      sEy[idx] = tfx_log(__ddiv_rn(ry1 + a1, ry2 + a2));
     }
     __syncthreads();
     // ---- cells
-    for (int idx = threadIdx.x; idx < kMTX * kMTY * kMTZ; idx += 256) {
+    for (int idx = threadIdx.x; idx < kMTX * kMTY * kMTZ; idx += kMagThreads) {
       const int a = idx % kMTX, b = (idx / kMTX) % kMTY, c = idx / (kMTX * kMTY);
       const int gi = i0 + a, gj = j0 + b, gk = k0 + c;
       if (gi >= nx || gj >= ny || gk >= nz) continue;
       const double gx1 = xn[gi], gx2 = xn[gi + 1], gy1 = yn[gj], gy2 = yn[gj + 1], gz1 = zn[gk], gz2 = zn[gk + 1];
       double tx[3], ty[3], tz[3];
       if ((gx1 < Xd) && (gx2 > Xd) && (gy1 < Yd) && (gy2 > Yd) && (gz1 < Zd) && (gz2 > Zd)) {
-        double width = (double)0.1f;
-        const double min_clr = fmin(fmin(fmin(fabs(Xd - gx1), fabs(Xd - gx2)), fmin(fabs(Yd - gy1), fabs(Yd - gy2))),
-                                    fmin(fabs(Zd - gz1), fabs(Zd - gz2)));
-        if (width > min_clr) width = 0.5 * min_clr;
-        const double bx1[6] = {gx1, gx1, gx1, Xd + width, Xd - width, Xd - width};
-        const double bx2[6] = {gx2, gx2, Xd - width, gx2, Xd + width, Xd + width};
-        const double by1[6] = {gy1, gy1, gy1, gy1, gy1, Yd + width};
-        const double by2[6] = {gy2, gy2, gy2, gy2, Yd - width, gy2};
-        const double bz1[6] = {gz1, Zd + width, Zd - width, Zd - width, Zd - width, Zd - width};
-        const double bz2[6] = {Zd - width, gz2, Zd + width, Zd + width, Zd + width, Zd + width};
-        for (int q = 0; q < 3; ++q) tx[q] = ty[q] = tz[q] = 0.0;
-        for (int j = 0; j < 6; ++j) {
-          double ax[3], ay[3], az[3];
-          sharmbox_dev(Xd, Yd, Zd, bx1[j], by1[j], bz1[j], bx2[j], by2[j], bz2[j], ax, ay, az, &e);
-          for (int q = 0; q < 3; ++q) {
-            tx[q] = __dadd_rn(tx[q], ax[q]);
-            ty[q] = __dadd_rn(ty[q], ay[q]);
-            tz[q] = __dadd_rn(tz[q], az[q]);
-          }
-        }
+        mag_incell_dev(Xd, Yd, Zd, gx1, gy1, gz1, gx2, gy2, gz2, tx, ty, tz, &e);
       } else {
         // corner (x, y, z) in {1, 2}^3  ->  node (a + x - 1, b + y - 1, c + z - 1); orders and signs of :376-442
         double t = NA(a + 1, b, c + 1);
@@ -758,7 +767,7 @@ int mag_lines(const GridDev &g, int32_t nb, const double *d_xd, const double *d_
     }
     const int tiles = ((g.nx + kMTX - 1) / kMTX) * ((g.ny + kMTY - 1) / kMTY) * ((g.nz + kMTZ - 1) / kMTZ);
     dim3 grid(tiles, std::min(nb, 1024));
-    mag_lines_nodes_kernel<<<grid, 256, kMagSmem, st>>>(d_lines, g.nx, g.ny, g.nz, nb, g.xn.p, g.yn.p, g.zn.p, d_xd, d_yd, d_zd,
+    mag_lines_nodes_kernel<<<grid, kMagThreads, kMagSmem, st>>>(d_lines, g.nx, g.ny, g.nz, nb, g.xn.p, g.yn.p, g.zn.p, d_xd, d_yd, d_zd,
                                                         mp, d_err);
     ctx().launches++;
     TFX_CUDA(cudaGetLastError());
@@ -767,6 +776,22 @@ int mag_lines(const GridDev &g, int32_t nb, const double *d_xd, const double *d_
   dim3 grid((g.n + 127) / 128, std::min(nb, 1024));
   mag_lines_kernel<<<grid, 128, 0, st>>>(d_lines, g.n, nb, g.X1.p, g.X2.p, g.Y1.p, g.Y2.p, g.Z1.p, g.Z2.p, d_xd, d_yd,
                                          d_zd, mp, d_err);
+  ctx().launches++;
+  TFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) debug_math_kernel(long long n, const double *__restrict__ y,
+                                                         const double *__restrict__ x, double *__restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    out[i] = tfx_log(x[i]);
+    out[n + i] = log(x[i]);
+    out[2 * n + i] = tfx_atan2(y[i], x[i]);
+    out[3 * n + i] = atan2(y[i], x[i]);
+  }
+}
+int debug_math(long long n, const double *d_y, const double *d_x, double *d_out, cudaStream_t st) {
+  debug_math_kernel<<<ctx().num_sms * 4, 256, 0, st>>>(n, d_y, d_x, d_out);
   ctx().launches++;
   TFX_CUDA(cudaGetLastError());
   return 0;

@@ -16,6 +16,7 @@ int wavelet3d_device_batch(double *d_s, int n1, int n2, int n3, long long nvol, 
                            cudaStream_t st);
 
 extern int g_opt_wavelet_slab_mb;
+extern int g_opt_wavelet_fuse12;
 extern int g_opt_wavelet_cols;
 extern int g_opt_wavelet_tile_kb;
 
@@ -161,6 +162,7 @@ struct GridDev {
 };
 int grid_detect_structured(GridDev &g, int32_t nx, int32_t ny, int32_t nz, cudaStream_t st);
 extern int g_opt_grav_shared_nodes;
+int debug_math(long long n, const double *d_y, const double *d_x, double *d_out, cudaStream_t st);
 extern int g_opt_mag_shared_nodes;
 
 // Fills a dense column-major block with the depth-weighted gravity kernel, reproducing

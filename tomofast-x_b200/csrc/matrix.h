@@ -77,6 +77,7 @@ int matrix_trans(Matrix &m, const double *d_u, double *d_y, bool accumulate, con
 // Appends the rows held as device triplets (row ids relative to the batch) as one more row block.
 int matrix_append_block(Matrix &M, RowTriplets &R, int32_t nrows, int32_t ncolumns);
 extern int g_opt_sensit_row_blocks;
+extern int g_opt_sensit_cand_cap;   // > 0: candidate-list capacity of the k-th select (tests force the fallback passes with 1)
 
 int matrix_upload(Matrix &m, bool allow_dense);
 // Builds the T16 layouts from fwd/trn when the matrix is big enough (option "t16_min_nnz").

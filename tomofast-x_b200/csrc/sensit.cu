@@ -10,7 +10,6 @@
 #include "../../include/tfx.h"
 
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_select.cuh>
 #include <thrust/copy.h>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
@@ -39,37 +38,7 @@ __global__ void __launch_bounds__(256) k_apply_cw(double *__restrict__ lines, co
     lines[i] = __dmul_rn(lines[i], cw[i % n]);   // apply_column_weight, sensitivity_gravmag.F90:1042-1054
 }
 
-struct AbsOp {
-  __device__ double operator()(double x) const { return fabs(x); }
-};
-struct SqOp {
-  __device__ double operator()(double x) const { return x * x; }
-};
-struct DiscardedSq {
-  double thr;
-  __device__ double operator()(double x) const { return (fabs(x) > thr) ? 0.0 : x * x; }
-};
-struct KeepPred {
-  const double *line;
-  double thr;
-  __device__ bool operator()(int p) const { return fabs(line[p]) > thr; }
-};
-
-// vals = real(line(col), 4) * wgt (f32 multiply); idx = col + shift; rowid = row; nnz_count[col]++.
-__global__ void __launch_bounds__(256) k_finish_segment(const int32_t *__restrict__ cols, int nel,
-                                                         const double *__restrict__ line, float wgt, int32_t shift,
-                                                         int32_t row, int32_t *__restrict__ idx_out,
-                                                         float *__restrict__ val_out, int32_t *__restrict__ rowid_out,
-                                                         int32_t *__restrict__ nnz_count) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nel; i += gridDim.x * blockDim.x) {
-    const int p = cols[i];
-    idx_out[i] = p + shift;
-    val_out[i] = __fmul_rn((float)line[p], wgt);
-    rowid_out[i] = row;
-    if (nnz_count) atomicAdd(&nnz_count[p], 1);
-  }
-}
-
+// vals = real(line(col), 4) * wgt (f32 multiply); idx = col + shift; rowid = row; nnz_count[col]++ (uncompressed path).
 __global__ void __launch_bounds__(256) k_dense_segment(const double *__restrict__ line, int n, float wgt, int32_t shift,
                                                         int32_t row, int32_t *__restrict__ idx_out,
                                                         float *__restrict__ val_out, int32_t *__restrict__ rowid_out,
@@ -82,132 +51,433 @@ __global__ void __launch_bounds__(256) k_dense_segment(const double *__restrict_
   }
 }
 
-// ---- device-resident row state: the whole row pipeline runs without a host round trip ---------------
+// ---------------------------------------------------------------------------------------------------------------------
+// Compressed row pipeline, batched (r2): every kernel below works on ALL the lines of a batch (blockIdx.y = line), the
+// state of a line lives in device arrays, nothing returns to the host inside a batch. Per line, after the batched
+// wavelet transform:
+//   threshold = (N - nel_compressed)-th smallest |x|  (sensitivity_gravmag.F90:240-256): exact k-th order statistic by
+//     MSD radix select on the IEEE bit patterns (monotone for x >= 0): two 12-bit passes over the line fix the top 24
+//     bits (exponent + 13 mantissa bits); the few elements that share them are collected and the remaining 39 bits
+//     are resolved on that list by one CTA. (Round 1: eight 8-bit passes over the whole line.) A bucket with more than
+//     kCandCap members (massive ties, e.g. a line of zeros) falls back to further passes over the line.
+//   keep |x| > threshold (strict), columns ascending (:258-272): chunk counts + discarded cost in one pass, an exclusive
+//     scan per line, one ordered write pass (ballot ranks) -- replaces cub::DeviceSelect + a separate cost pass.
+// ---------------------------------------------------------------------------------------------------------------------
 struct RowState {
-  unsigned long long prefix;   // radix select: bits of the k-th smallest |x| found so far
-  long long rank;              // 0-based rank still to locate inside the current prefix bucket
-  int shift;                   // bit position of the digit examined by the current pass
-  int nsel;                    // entries kept in the current segment (cub::DeviceSelect output)
-  double thr;                  // threshold (sensitivity_gravmag.F90:240-256)
-  double cost_full, cost_disc; // sum x^2 before compression / over the discarded entries (:234, :283)
   double err_sum;              // sum over segments of sqrt(cost_disc / cost_full) (:285)
   long long nnz;               // entries written so far == offset of the next segment
   int bad;                     // 1: a segment kept more than nel_compressed entries (:273-275)
 };
 
-static const int kRedBlocks = 592;   // fixed grid of the two-stage sums -> fixed summation order
-
-// partial[b] = sum over this block's elements of f(x): mode 0: x^2 ; mode 1: x^2 where |x| <= thr.
-__global__ void __launch_bounds__(256) k_row_sumsq(const double *__restrict__ line, int n, int mode, const RowState *st,
-                                                    double *__restrict__ partial) {
-  __shared__ double red[32];
-  const double thr = mode ? st->thr : 0.0;
-  double s = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double x = line[i];
-    if (!mode || !(fabs(x) > thr)) s = fma(x, x, s);
-  }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) partial[blockIdx.x] = s;
-}
-__global__ void __launch_bounds__(256) k_row_sum_final(const double *__restrict__ partial, int nb, double *target) {
-  __shared__ double red[32];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partial[i];
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) *target = s;
-}
-
-// Exact k-th order statistic of |x| by MSD radix select on the IEEE bit patterns (monotone for x >= 0):
-// 8 passes of 8 bits, 256-bin histogram per pass (warp-aggregated shared-memory atomics).
-__global__ void k_select_begin(RowState *st, long long rank, unsigned *hist) {
-  if (threadIdx.x == 0) {
-    st->prefix = 0ull;
-    st->rank = rank;
-    st->shift = 56;
-  }
-  hist[threadIdx.x] = 0u;
-}
-__global__ void __launch_bounds__(256) k_select_hist(const double *__restrict__ line, int n, const RowState *st,
-                                                      unsigned *__restrict__ hist) {
-  __shared__ unsigned sh[256];
-  sh[threadIdx.x] = 0u;
-  __syncthreads();
-  const int shift = st->shift;
-  const unsigned long long prefix = st->prefix;
-  const unsigned long long himask = (shift >= 56) ? 0ull : (~0ull << (shift + 8));
-  const int nround = (n + 255) / 256 * 256;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
-    bool act = false;
-    unsigned bin = 0;
-    if (i < n) {
-      const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(line[i]));
-      act = ((b & himask) == prefix);
-      bin = (unsigned)(b >> shift) & 255u;
-    }
-    const unsigned amask = __ballot_sync(0xffffffffu, act);
-    if (act) {
-      const unsigned peers = __match_any_sync(amask, bin);
-      if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bin], __popc(peers));
-    }
-  }
-  __syncthreads();
-  if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
-}
-__global__ void k_select_pick(RowState *st, unsigned *hist) {   // <<<1, 256>>>
-  __shared__ unsigned sh[256];
-  sh[threadIdx.x] = hist[threadIdx.x];
-  hist[threadIdx.x] = 0u;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    long long r = st->rank;
-    int d = 0;
-    for (; d < 255; ++d) {
-      if (r < (long long)sh[d]) break;
-      r -= sh[d];
-    }
-    st->prefix |= (unsigned long long)d << st->shift;
-    st->rank = r;
-    st->shift -= 8;
-  }
-}
-// threshold = |k-th value|, floored at 1e-30 (:252-256); no_select: every entry above the floor is kept.
-__global__ void k_select_end(RowState *st, int no_select) {
-  double t = no_select ? -1.0 : __longlong_as_double((long long)st->prefix);
-  if (t < 1.e-30) t = 1.e-30;
-  st->thr = t;
-}
-
-struct KeepPredDev {
-  const double *line;
-  const RowState *st;
-  __device__ bool operator()(int p) const { return fabs(line[p]) > st->thr; }
+struct LineSel {
+  unsigned long long prefix;   // bits of the k-th smallest |x| found so far
+  long long rank;              // 0-based rank still to locate inside the current bucket
+  unsigned count;              // members of the current bucket
+  unsigned ncand;              // candidates collected
+  int mode;                    // 0: passes over the line; 1: finished
 };
 
-// Writes the kept entries of one segment at the running offset: value = real(line(col), 4) * wgt in real(4)
-// (:265 / :837-843), column = p + shift, and counts the entry for sensit_nnz (:267).
-__global__ void __launch_bounds__(256) k_finish_segment_dev(const int32_t *__restrict__ cols, const double *__restrict__ line,
-                                                             float wgt, int32_t shift, int32_t row, const RowState *st,
-                                                             int64_t cap, int32_t *__restrict__ idx_out,
-                                                             float *__restrict__ val_out, int32_t *__restrict__ rowid_out,
-                                                             int32_t *__restrict__ nnz_count) {
-  const int nel = st->nsel;
-  const long long off = st->nnz;
-  if (off + nel > cap) return;   // flagged by k_advance
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nel; i += gridDim.x * blockDim.x) {
-    const int p = cols[i];
-    idx_out[off + i] = p + shift;
-    val_out[off + i] = __fmul_rn((float)line[p], wgt);
-    rowid_out[off + i] = row;
-    if (nnz_count) atomicAdd(&nnz_count[p], 1);
+// What a line of the batch is: line l = ((b * ndc) + d) * nmc + k (station b of the batch, data component d, model
+// component k) -> matrix row, column shift and combined weight (sensitivity_gravmag.F90:837-843).
+struct BatchGeom {
+  int n;                       // cells per line
+  int ndc, nmc;
+  int idata0;                  // global 0-based index of the batch's first station
+  int dw0;                     // index of that station in dw (dw holds the rank's stations only)
+  int param_shift;
+  double problem_weight;
+  const double *dw;            // data weights [station][ndc]
+};
+
+static const int kSelBits = 12;
+static const int kSelBins = 1 << kSelBits;
+static const unsigned kCandCap = 16384;
+static const int kChunk = 4096;      // elements per compaction chunk: 256 threads x 16
+static const int kSumBlocks = 256;   // partial sums per line (fixed -> fixed summation order)
+
+__device__ __forceinline__ unsigned long long abs_bits(double x) {
+  return (unsigned long long)__double_as_longlong(x) & 0x7fffffffffffffffull;
+}
+
+// line *= column weight (apply_column_weight, :1042-1054), partial[line][block] = sum of the weighted x^2 (:234).
+__global__ void __launch_bounds__(256) k_cw_sumsq(double *__restrict__ lines, const double *__restrict__ cw, int n,
+                                                   double *__restrict__ partial) {
+  __shared__ double red[32];
+  double *line = lines + (size_t)blockIdx.y * n;
+  const int stride = gridDim.x * 256;
+  double s = 0.0;
+  int i = blockIdx.x * 256 + threadIdx.x;
+  for (; (long long)i + 3LL * stride < n; i += 4 * stride) {
+    double a0 = line[i], a1 = line[i + stride], a2 = line[i + 2 * stride], a3 = line[i + 3 * stride];
+    const double c0 = cw[i], c1 = cw[i + stride], c2 = cw[i + 2 * stride], c3 = cw[i + 3 * stride];
+    a0 = __dmul_rn(a0, c0); a1 = __dmul_rn(a1, c1); a2 = __dmul_rn(a2, c2); a3 = __dmul_rn(a3, c3);
+    line[i] = a0; line[i + stride] = a1; line[i + 2 * stride] = a2; line[i + 3 * stride] = a3;
+    s = fma(a0, a0, s); s = fma(a1, a1, s); s = fma(a2, a2, s); s = fma(a3, a3, s);
+  }
+  for (; i < n; i += stride) {
+    const double a = __dmul_rn(line[i], cw[i]);
+    line[i] = a;
+    s = fma(a, a, s);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+// out[line] = sum_b partial[line][b], b ascending per thread, fixed tree across threads.
+__global__ void __launch_bounds__(256) k_sum_partials(const double *__restrict__ partial, int nb, double *__restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) s += partial[(size_t)blockIdx.x * nb + i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+__global__ void k_sel_init(LineSel *sel, long long rank, int nlines, unsigned n) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < nlines) {
+    sel[l].prefix = 0ull;
+    sel[l].rank = rank;
+    sel[l].count = n;
+    sel[l].ncand = 0u;
+    sel[l].mode = 0;
   }
 }
-__global__ void k_advance(RowState *st, const double *cost_full, int nel_compressed, int64_t cap, long long *seg_end,
-                          int64_t iseg) {
-  if (st->nsel > nel_compressed || st->nnz + st->nsel > cap) st->bad = 1;
-  else st->nnz += st->nsel;
-  st->err_sum += sqrt(st->cost_disc / *cost_full);   // :283-285
-  seg_end[iseg] = st->nnz;
+
+// hist[line][digit] += members of the line's current bucket whose digit (bits [shift, shift + bits)) is `digit`.
+__global__ void __launch_bounds__(256) k_sel_hist(const double *__restrict__ lines, int n, const LineSel *__restrict__ sel,
+                                                   unsigned *__restrict__ hist, int shift, int bits) {
+  __shared__ unsigned sh[kSelBins];
+  const LineSel ls = sel[blockIdx.y];
+  if (ls.mode != 0) return;
+  const int bins = 1 << bits;
+  for (int i = threadIdx.x; i < bins; i += 256) sh[i] = 0u;
+  __syncthreads();
+  const double *line = lines + (size_t)blockIdx.y * n;
+  const unsigned long long himask = (shift + bits >= 63) ? 0ull : ((~0ull << (shift + bits)) & 0x7fffffffffffffffull);
+  const unsigned long long prefix = ls.prefix;
+  const unsigned bmask = (unsigned)bins - 1u;
+  const bool first = (himask == 0ull);
+  const int stride = gridDim.x * 256;
+  const long long step = 4LL * stride;
+  const long long nround = ((long long)n + step - 1) / step * step;   // whole warps stay together for the ballots
+  for (long long i0 = blockIdx.x * 256 + threadIdx.x; i0 < nround; i0 += step) {
+    unsigned long long b[4];
+    bool in[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = i0 + (long long)j * stride;
+      in[j] = i < n;
+      b[j] = in[j] ? abs_bits(line[i]) : ~0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool act = in[j] && ((b[j] & himask) == prefix);
+      const unsigned bin = (unsigned)(b[j] >> shift) & bmask;
+      if (first) {
+        // every element takes part and the digits cluster (exponents): the lanes that share lane 0's digit are
+        // counted with one ballot (a line of equal values would otherwise serialise 32-fold), the rest add singly
+        const unsigned b0 = __shfl_sync(0xffffffffu, bin, 0);
+        const unsigned same = __ballot_sync(0xffffffffu, act && bin == b0);
+        if ((threadIdx.x & 31) == 0 && same) atomicAdd(&sh[b0], __popc(same));
+        if (act && bin != b0) atomicAdd(&sh[bin], 1u);
+      } else if (act) {
+        atomicAdd(&sh[bin], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  unsigned *h = hist + (size_t)blockIdx.y * kSelBins;
+  for (int i = threadIdx.x; i < bins; i += 256)
+    if (sh[i]) atomicAdd(&h[i], sh[i]);
+}
+
+// One CTA per line: the digit that holds the wanted rank; the bucket shrinks to that digit. hist is zeroed for reuse.
+__global__ void __launch_bounds__(256) k_sel_pick(LineSel *sel, unsigned *__restrict__ hist, int shift, int bits) {
+  __shared__ unsigned sh[kSelBins];
+  __shared__ unsigned long long tsum[257];
+  LineSel *ls = &sel[blockIdx.x];
+  if (ls->mode != 0) return;
+  const int bins = 1 << bits;
+  unsigned *h = hist + (size_t)blockIdx.x * kSelBins;
+  for (int i = threadIdx.x; i < bins; i += 256) { sh[i] = h[i]; h[i] = 0u; }
+  __syncthreads();
+  const int per = (bins + 255) / 256;
+  unsigned long long mine = 0ull;
+  for (int j = 0; j < per; ++j) {
+    const int d = threadIdx.x * per + j;
+    if (d < bins) mine += sh[d];
+  }
+  tsum[threadIdx.x + 1] = mine;
+  if (threadIdx.x == 0) tsum[0] = 0ull;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int i = 1; i <= 256; ++i) tsum[i] += tsum[i - 1];
+  __syncthreads();
+  const unsigned long long r = (unsigned long long)ls->rank;   // every thread reads it before the owner rewrites it
+  __syncthreads();
+  if (r >= tsum[threadIdx.x] && r < tsum[threadIdx.x + 1]) {
+    // exactly one thread: its bins hold more than rr members, so the walk ends inside them
+    unsigned long long rr = r - tsum[threadIdx.x];
+    int d = threadIdx.x * per;
+    for (;; ++d) {
+      if (rr < (unsigned long long)sh[d]) break;
+      rr -= sh[d];
+    }
+    ls->prefix |= (unsigned long long)d << shift;
+    ls->rank = (long long)rr;
+    ls->count = sh[d];
+  }
+}
+
+// Members of the bucket fixed by the passes so far (all bits >= shift) -> cand[line][*] when they fit.
+__global__ void __launch_bounds__(256) k_sel_collect(const double *__restrict__ lines, int n, LineSel *sel,
+                                                      unsigned long long *__restrict__ cand, unsigned candcap, int shift) {
+  LineSel *ls = &sel[blockIdx.y];
+  if (ls->mode != 0 || ls->count > candcap) return;
+  const double *line = lines + (size_t)blockIdx.y * n;
+  const unsigned long long himask = (~0ull << shift) & 0x7fffffffffffffffull;
+  const unsigned long long prefix = ls->prefix;
+  unsigned long long *out = cand + (size_t)blockIdx.y * candcap;
+  const int stride = gridDim.x * 256;
+  int i = blockIdx.x * 256 + threadIdx.x;
+  for (; (long long)i + 3LL * stride < n; i += 4 * stride) {
+    unsigned long long b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = abs_bits(line[i + j * stride]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((b[j] & himask) == prefix) {
+        const unsigned pos = atomicAdd(&ls->ncand, 1u);
+        if (pos < candcap) out[pos] = b[j];
+      }
+  }
+  for (; i < n; i += stride) {
+    const unsigned long long b = abs_bits(line[i]);
+    if ((b & himask) == prefix) {
+      const unsigned pos = atomicAdd(&ls->ncand, 1u);
+      if (pos < candcap) out[pos] = b;
+    }
+  }
+}
+
+// One CTA per line: the remaining `shift` low bits of the k-th value, on the collected candidates (8-bit passes).
+__global__ void __launch_bounds__(256) k_sel_finish(LineSel *sel, const unsigned long long *__restrict__ cand,
+                                                     unsigned candcap, int shift) {
+  __shared__ unsigned sh[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ long long s_rank;
+  LineSel *ls = &sel[blockIdx.x];
+  if (ls->mode != 0 || ls->count > candcap) return;
+  const unsigned nc = ls->ncand;   // == count
+  const unsigned long long *c = cand + (size_t)blockIdx.x * candcap;
+  if (threadIdx.x == 0) { s_prefix = ls->prefix; s_rank = ls->rank; }
+  __syncthreads();
+  int sft = shift;
+  while (sft > 0) {
+    const int bits = min(8, sft);
+    sft -= bits;
+    const int bins = 1 << bits;
+    sh[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned long long himask = (~0ull << (sft + bits)) & 0x7fffffffffffffffull;
+    const unsigned long long prefix = s_prefix;
+    for (unsigned i = threadIdx.x; i < nc; i += 256) {
+      const unsigned long long b = c[i];
+      if ((b & himask) == prefix) atomicAdd(&sh[(unsigned)(b >> sft) & (unsigned)(bins - 1)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long r = s_rank;
+      int d = 0;
+      for (; d < bins - 1; ++d) {
+        if (r < (long long)sh[d]) break;
+        r -= sh[d];
+      }
+      s_prefix = prefix | ((unsigned long long)d << sft);
+      s_rank = r;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { ls->prefix = s_prefix; ls->rank = s_rank; ls->mode = 1; }
+}
+
+// thr[line] = |k-th value|, floored at 1e-30 (:252-256); no_select: every entry above the floor is kept.
+__global__ void k_sel_thr(const LineSel *sel, double *thr, int nlines, int no_select) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nlines) return;
+  double t = no_select ? -1.0 : __longlong_as_double((long long)sel[l].prefix);
+  if (t < 1.e-30) t = 1.e-30;
+  thr[l] = t;
+}
+
+// cnt[line][chunk] = kept entries of the chunk, disc[line][chunk] = sum of x^2 over its discarded entries (:283).
+__global__ void __launch_bounds__(256) k_cmp_count(const double *__restrict__ lines, int n, const double *__restrict__ thr,
+                                                    int *__restrict__ cnt, double *__restrict__ disc) {
+  __shared__ double red[32];
+  __shared__ int wc[8];
+  const double *line = lines + (size_t)blockIdx.y * n;
+  const double t = thr[blockIdx.y];
+  const long long c0 = (long long)blockIdx.x * kChunk;
+  double x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const long long i = c0 + j * 256 + threadIdx.x;
+    x[j] = (i < n) ? line[i] : 0.0;
+  }
+  int k = 0;
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (fabs(x[j]) > t) ++k;
+    else s = fma(x[j], x[j], s);
+  }
+  k = __reduce_add_sync(0xffffffffu, k);
+  s = block_sum(s, red);
+  if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = k;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += wc[w];
+    const size_t o = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    cnt[o] = tot;
+    disc[o] = s;
+  }
+}
+
+// One CTA per line: cnt -> exclusive offsets inside the line (in place), nsel[line], cost_disc[line].
+__global__ void __launch_bounds__(256) k_cmp_scan(int *__restrict__ cnt, const double *__restrict__ disc, int nchunks,
+                                                   int *__restrict__ nsel, double *__restrict__ cost_disc) {
+  __shared__ double red[32];
+  __shared__ int wsum[8];
+  __shared__ int carry_s;
+  int *c = cnt + (size_t)blockIdx.x * nchunks;
+  const double *d = disc + (size_t)blockIdx.x * nchunks;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  double s = 0.0;
+  for (int base = 0; base < nchunks; base += 256) {
+    const int i = base + threadIdx.x;
+    const int v = (i < nchunks) ? c[i] : 0;
+    if (i < nchunks) s += d[i];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    int woff = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < w) woff += wsum[j];
+    const int carry = carry_s;
+    if (i < nchunks) c[i] = carry + woff + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry_s = carry + woff + incl;
+    __syncthreads();
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    nsel[blockIdx.x] = carry_s;
+    cost_disc[blockIdx.x] = s;
+  }
+}
+
+// Sequential over the lines of the batch (segment order): running entry offset, the reference's element-count check
+// (:273-275), compression error terms (:283-285), seg_end.
+__global__ void k_batch_advance(RowState *st, const int *__restrict__ nsel, const double *__restrict__ cost_disc,
+                                const double *__restrict__ cost_full, long long *__restrict__ line_off,
+                                long long *__restrict__ seg_end, long long iseg0, int nlines, int nel_compressed,
+                                long long cap) {
+  long long nnz = st->nnz;
+  double err = st->err_sum;
+  int bad = st->bad;
+  for (int l = 0; l < nlines; ++l) {
+    const int k = nsel[l];
+    if (k > nel_compressed || nnz + k > cap) {
+      bad = 1;
+      line_off[l] = -1;
+    } else {
+      line_off[l] = nnz;
+      nnz += k;
+    }
+    err += sqrt(cost_disc[l] / cost_full[l]);
+    seg_end[iseg0 + l] = nnz;
+  }
+  st->nnz = nnz;
+  st->err_sum = err;
+  st->bad = bad;
+}
+
+// Ordered write of the kept entries: value = real(line(col), 4) * wgt in real(4) (:265 / :837-843), column = p + shift,
+// and the per-cell entry count sensit_nnz (:267).
+__global__ void __launch_bounds__(256) k_cmp_write(const double *__restrict__ lines, BatchGeom g,
+                                                    const double *__restrict__ thr, const int *__restrict__ chunk_off,
+                                                    const long long *__restrict__ line_off, int32_t *__restrict__ idx_out,
+                                                    float *__restrict__ val_out, int32_t *__restrict__ rowid_out,
+                                                    int32_t *__restrict__ nnz_count) {
+  __shared__ int wcnt[16 * 8];
+  const int l = blockIdx.y;
+  const long long loff = line_off[l];
+  if (loff < 0) return;
+  const int n = g.n;
+  const double *line = lines + (size_t)l * n;
+  const double t = thr[l];
+  const long long c0 = (long long)blockIdx.x * kChunk;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double x[16];
+  unsigned keep = 0u;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const long long i = c0 + j * 256 + threadIdx.x;
+    x[j] = (i < n) ? line[i] : 0.0;
+  }
+  int rank_in_warp[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const bool kp = fabs(x[j]) > t;
+    const unsigned m = __ballot_sync(0xffffffffu, kp);
+    if (kp) keep |= 1u << j;
+    rank_in_warp[j] = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) wcnt[j * 8 + w] = __popc(m);
+  }
+  __syncthreads();
+  if (w == 0) {
+    // exclusive scan of the 128 (row j, warp w) counts in element order: lane holds 4 consecutive entries
+    int v[4], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { v[q] = wcnt[lane * 4 + q]; sum += v[q]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    int run = incl - sum;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { wcnt[lane * 4 + q] = run; run += v[q]; }
+  }
+  __syncthreads();
+  if (!keep) return;
+  const int sgm_d = (l / g.nmc) % g.ndc, sgm_k = l % g.nmc, sgm_b = l / (g.nmc * g.ndc);
+  const int32_t row = (g.idata0 + sgm_b) * g.ndc + sgm_d;
+  const int32_t shift = g.param_shift + sgm_k * n;
+  // combined_weight = real(problem_weight * data_weight(d, idata), 4)
+  const float wgt = (float)(g.problem_weight * g.dw[(size_t)(g.dw0 + sgm_b) * g.ndc + sgm_d]);
+  const long long base = loff + chunk_off[(size_t)l * gridDim.x + blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (keep & (1u << j)) {
+      const int p = (int)(c0 + j * 256 + threadIdx.x);
+      const long long pos = base + wcnt[j * 8 + w] + rank_in_warp[j];
+      idx_out[pos] = p + shift;
+      val_out[pos] = __fmul_rn((float)x[j], wgt);
+      rowid_out[pos] = row;
+      atomicAdd(&nnz_count[p], 1);
+    }
+  }
 }
 __global__ void k_advance_dense(RowState *st, int n, long long *seg_end, int64_t iseg) {
   st->nnz += n;
@@ -281,89 +551,110 @@ int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const dou
   const int64_t cap = (int64_t)nel_compressed * nseg_lines;   // upper bound of nnz
   TFX_TRY(R.idx.alloc((size_t)cap)); TFX_TRY(R.val.alloc((size_t)cap)); TFX_TRY(R.rowid.alloc((size_t)cap));
   R.nnz = 0;
-  DevBuf<int32_t> dcols;
   DevBuf<int> derr;
-  TFX_TRY(dnnz.alloc(N)); TFX_TRY(dcols.alloc(N)); TFX_TRY(derr.alloc(1));
+  TFX_TRY(dnnz.alloc(N)); TFX_TRY(derr.alloc(1));
   TFX_CUDA(cudaMemsetAsync(dnnz.p, 0, (size_t)N * 4, st));
   TFX_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
   seg_end.assign((size_t)nseg_lines, 0);
   if (err_sum) *err_sum = 0.0;
   if (ndata_loc <= 0) return 0;
 
-  // batch of stations whose lines are resident at once (<= ~1 GiB)
+  // batch of stations whose lines are resident at once (<= ~1 GiB, <= 4096 lines: blockIdx.y = line)
   const size_t per_station = (size_t)N * nmc * ndc;
   int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)ndata_loc, ((size_t)1 << 27) / per_station));
+  B = std::max(1, std::min(B, 4096 / (ndc * nmc)));
   DevBuf<double> dl;
   TFX_TRY(dl.alloc(per_station * B));
   const int vgrid = c.num_sms * 8;
+  const int maxlines = B * ndc * nmc;
 
-  // device-resident state of the row pipeline (no host synchronisation per row)
-  DevBuf<RowState> dst;
-  DevBuf<unsigned> dhist;
-  DevBuf<double> dpartial;
-  DevBuf<long long> dsegend;
-  DevBuf<unsigned char> dtemp;
-  DevBuf<double> dcostfull;
-  TFX_TRY(dst.alloc(1)); TFX_TRY(dhist.alloc(256)); TFX_TRY(dpartial.alloc(kRedBlocks));
-  TFX_TRY(dsegend.alloc((size_t)nseg_lines));
-  TFX_CUDA(cudaMemsetAsync(dst.p, 0, sizeof(RowState), st));
-  size_t temp_bytes = 0;
-  {
-    KeepPredDev pred{dl.p, dst.p};
-    cub::DeviceSelect::If(nullptr, temp_bytes, thrust::counting_iterator<int>(0), dcols.p, &dst.p->nsel, N, pred, st);
-  }
-  TFX_TRY(dtemp.alloc(temp_bytes + 16));
+  // device-resident state of the row pipeline (no host synchronisation inside a batch)
+  const bool compressed = P.compression_type > 0;
   const long long rank = (long long)N - nel_compressed - 1;   // 0-based rank of sorted(N - nel_compressed), :240-251
   const bool no_select = nel_compressed >= N;
-  const int rgrid = std::min(kRedBlocks, (N + 255) / 256);
+  const int nchunks = (N + kChunk - 1) / kChunk;
+  const int gsum = std::min(kSumBlocks, (N + 1023) / 1024);
+  const unsigned candcap = std::min<unsigned>(g_opt_sensit_cand_cap > 0 ? (unsigned)g_opt_sensit_cand_cap : kCandCap, (unsigned)N);
+  DevBuf<RowState> dst;
+  DevBuf<long long> dsegend, dlineoff;
+  DevBuf<LineSel> dsel;
+  DevBuf<unsigned> dhist;
+  DevBuf<unsigned long long> dcand;
+  DevBuf<double> dpartial, dcostfull, dcostdisc, dthr, ddisc, ddw;
+  DevBuf<int> dcnt, dnsel;
+  TFX_TRY(dst.alloc(1));
+  TFX_TRY(dsegend.alloc((size_t)nseg_lines));
+  TFX_CUDA(cudaMemsetAsync(dst.p, 0, sizeof(RowState), st));
+  TFX_TRY(up(ddw, h_dw + (size_t)data0 * ndc, (size_t)ndata_loc * ndc));
+  if (compressed) {
+    TFX_TRY(dlineoff.alloc((size_t)maxlines)); TFX_TRY(dsel.alloc((size_t)maxlines));
+    TFX_TRY(dpartial.alloc((size_t)maxlines * gsum)); TFX_TRY(dcostfull.alloc((size_t)maxlines));
+    TFX_TRY(dcostdisc.alloc((size_t)maxlines)); TFX_TRY(dthr.alloc((size_t)maxlines)); TFX_TRY(dnsel.alloc((size_t)maxlines));
+    TFX_TRY(dcnt.alloc((size_t)maxlines * nchunks)); TFX_TRY(ddisc.alloc((size_t)maxlines * nchunks));
+    if (!no_select) {
+      TFX_TRY(dhist.alloc((size_t)maxlines * kSelBins)); TFX_TRY(dcand.alloc((size_t)maxlines * candcap));
+      TFX_CUDA(cudaMemsetAsync(dhist.p, 0, (size_t)maxlines * kSelBins * sizeof(unsigned), st));
+    }
+  }
 
   int64_t iseg = 0;
   for (int32_t b0 = 0; b0 < ndata_loc; b0 += B) {
     const int nb = std::min<int>(B, ndata_loc - b0);
     TFX_TRY(compute_lines(P, g, nb, d_dx + data0 + b0, d_dy + data0 + b0, d_dz + data0 + b0, dl.p, derr.p, st));
-    k_apply_cw<<<vgrid, 256, 0, st>>>(dl.p, d_cw, N, (int64_t)per_station * nb);
-    c.launches++;
     const int nseg_b = nb * ndc * nmc;   // segments (lines) of this batch, stored back to back in dl
-    if (P.compression_type > 0) {
-      // cost_full of every line (:234), then ONE batched wavelet transform of all lines of the batch (:237)
-      TFX_TRY(dcostfull.alloc((size_t)nseg_b));
-      for (int sgm = 0; sgm < nseg_b; ++sgm) {
-        k_row_sumsq<<<rgrid, 256, 0, st>>>(dl.p + (size_t)sgm * N, N, 0, dst.p, dpartial.p);
-        k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, dcostfull.p + sgm);
-      }
-      c.launches += 2 * nseg_b;
+    if (compressed) {
+      // column weight (:228) and cost_full (:234) in one pass, then ONE batched wavelet transform of all lines (:237)
+      k_cw_sumsq<<<dim3(gsum, nseg_b), 256, 0, st>>>(dl.p, d_cw, N, dpartial.p);
+      k_sum_partials<<<nseg_b, 256, 0, st>>>(dpartial.p, gsum, dcostfull.p);
+      c.launches += 2;
       TFX_TRY(wavelet3d_device_batch(dl.p, P.nx, P.ny, P.nz, nseg_b, P.compression_type, true, st));
-    }
-    for (int b = 0; b < nb; ++b) {
-      const int32_t idata = data0 + b0 + b;   // 0-based global station
-      for (int d = 0; d < ndc; ++d) {
-        const int32_t row = idata * ndc + d;
-        // combined_weight = real(problem_weight * data_weight(d, idata), 4)
-        const float wgt = (float)(P.problem_weight * h_dw[(size_t)idata * ndc + d]);
-        for (int k = 0; k < nmc; ++k, ++iseg) {
-          const int sgm = (b * ndc + d) * nmc + k;
-          double *line = dl.p + (size_t)sgm * N;
-          const int32_t shift = P.param_shift + k * N;   // 0-based column = p + shift
-          if (P.compression_type > 0) {
-            if (!no_select) {
-              k_select_begin<<<1, 256, 0, st>>>(dst.p, rank, dhist.p);
-              for (int pass = 0; pass < 8; ++pass) {
-                k_select_hist<<<vgrid, 256, 0, st>>>(line, N, dst.p, dhist.p);
-                k_select_pick<<<1, 256, 0, st>>>(dst.p, dhist.p);
-              }
-              c.launches += 17;
-            }
-            k_select_end<<<1, 1, 0, st>>>(dst.p, no_select ? 1 : 0);
-            KeepPredDev pred{line, dst.p};
-            size_t tb = temp_bytes;
-            TFX_CUDA(cub::DeviceSelect::If(dtemp.p, tb, thrust::counting_iterator<int>(0), dcols.p, &dst.p->nsel, N, pred, st));
-            k_row_sumsq<<<rgrid, 256, 0, st>>>(line, N, 1, dst.p, dpartial.p);                     // discarded cost, :283
-            k_row_sum_final<<<1, 256, 0, st>>>(dpartial.p, rgrid, &dst.p->cost_disc);
-            k_finish_segment_dev<<<std::min(vgrid, (nel_compressed + 255) / 256), 256, 0, st>>>(
-                dcols.p, line, wgt, shift, row, dst.p, cap, R.idx.p, R.val.p, R.rowid.p, dnnz.p);
-            k_advance<<<1, 1, 0, st>>>(dst.p, dcostfull.p + sgm, nel_compressed, cap, dsegend.p, iseg);
-            c.launches += 7;
-          } else {
+      // line-parallel grid of the passes over the lines: ~8 CTAs per SM in total, whole lines per blockIdx.y
+      const int gx = std::max(1, std::min((N + 1023) / 1024, (vgrid + nseg_b - 1) / nseg_b));
+      const dim3 glines(gx, nseg_b);
+      const int gl = (nseg_b + 255) / 256;
+      if (!no_select) {
+        k_sel_init<<<gl, 256, 0, st>>>(dsel.p, rank, nseg_b, (unsigned)N);
+        // top 24 bits with two passes over the line, candidates, the low 39 bits on the candidates
+        k_sel_hist<<<glines, 256, 0, st>>>(dl.p, N, dsel.p, dhist.p, 51, 12);
+        k_sel_pick<<<nseg_b, 256, 0, st>>>(dsel.p, dhist.p, 51, 12);
+        k_sel_hist<<<glines, 256, 0, st>>>(dl.p, N, dsel.p, dhist.p, 39, 12);
+        k_sel_pick<<<nseg_b, 256, 0, st>>>(dsel.p, dhist.p, 39, 12);
+        k_sel_collect<<<glines, 256, 0, st>>>(dl.p, N, dsel.p, dcand.p, candcap, 39);
+        k_sel_finish<<<nseg_b, 256, 0, st>>>(dsel.p, dcand.p, candcap, 39);
+        // lines whose bucket did not fit the candidate list (mode still 0) go on with passes over the line; the
+        // others leave these kernels at once
+        static const int kRest[4][2] = {{27, 12}, {15, 12}, {3, 12}, {0, 3}};
+        for (int q = 0; q < 4; ++q) {
+          k_sel_hist<<<glines, 256, 0, st>>>(dl.p, N, dsel.p, dhist.p, kRest[q][0], kRest[q][1]);
+          k_sel_pick<<<nseg_b, 256, 0, st>>>(dsel.p, dhist.p, kRest[q][0], kRest[q][1]);
+        }
+        c.launches += 15;
+      }
+      k_sel_thr<<<gl, 256, 0, st>>>(dsel.p, dthr.p, nseg_b, no_select ? 1 : 0);
+      BatchGeom bg;
+      bg.n = N; bg.ndc = ndc; bg.nmc = nmc; bg.idata0 = data0 + b0; bg.dw0 = b0; bg.param_shift = P.param_shift;
+      bg.problem_weight = P.problem_weight; bg.dw = ddw.p;
+      const dim3 gchunks(nchunks, nseg_b);
+      k_cmp_count<<<gchunks, 256, 0, st>>>(dl.p, N, dthr.p, dcnt.p, ddisc.p);
+      k_cmp_scan<<<nseg_b, 256, 0, st>>>(dcnt.p, ddisc.p, nchunks, dnsel.p, dcostdisc.p);
+      k_batch_advance<<<1, 1, 0, st>>>(dst.p, dnsel.p, dcostdisc.p, dcostfull.p, dlineoff.p, dsegend.p, iseg, nseg_b,
+                                       nel_compressed, cap);
+      k_cmp_write<<<gchunks, 256, 0, st>>>(dl.p, bg, dthr.p, dcnt.p, dlineoff.p, R.idx.p, R.val.p, R.rowid.p, dnnz.p);
+      c.launches += 5;
+      iseg += nseg_b;
+    } else {
+      k_apply_cw<<<vgrid, 256, 0, st>>>(dl.p, d_cw, N, (int64_t)per_station * nb);
+      c.launches++;
+      for (int b = 0; b < nb; ++b) {
+        const int32_t idata = data0 + b0 + b;   // 0-based global station
+        for (int d = 0; d < ndc; ++d) {
+          const int32_t row = idata * ndc + d;
+          // combined_weight = real(problem_weight * data_weight(d, idata), 4)
+          const float wgt = (float)(P.problem_weight * h_dw[(size_t)idata * ndc + d]);
+          for (int k = 0; k < nmc; ++k, ++iseg) {
+            const int sgm = (b * ndc + d) * nmc + k;
+            const double *line = dl.p + (size_t)sgm * N;
+            const int32_t shift = P.param_shift + k * N;   // 0-based column = p + shift
             // uncompressed general path: the offset is known on the host
             k_dense_segment<<<std::min(vgrid, (N + 255) / 256), 256, 0, st>>>(line, N, wgt, shift, row,
                                                                              R.idx.p + iseg * (int64_t)N, R.val.p + iseg * (int64_t)N,
@@ -377,6 +668,7 @@ int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const dou
     int e = 0;
     TFX_CUDA(cudaMemcpyAsync(&e, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     TFX_CUDA(cudaStreamSynchronize(st));
+    TFX_CUDA(cudaGetLastError());
     if (e) return kernel_error(e);
   }
   RowState hst;
@@ -476,6 +768,7 @@ int matrix_append_triplets(Matrix &M, RowTriplets &R, int32_t nrows, int32_t nco
   return 0;
 }
 
+int g_opt_sensit_cand_cap = 0;     // 0: kCandCap
 int g_opt_sensit_row_blocks = 0;   // 1: tfx_sensit_repartition_into / read_sensitivity_kernel_into build one row block per call
 
 // One more row block: the batch's rows become an independent finalized device matrix (T16 layouts when it is big
@@ -699,6 +992,19 @@ extern "C" int tfx_sensit_lines(const tfx_sensit_params *par, const double *X1, 
   TFX_CUDA(cudaMemcpyAsync(lines, dl.p, per * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
   TFX_CUDA(cudaStreamSynchronize(st));
   if (e) return kernel_error(e);
+  return 0;
+}
+
+extern "C" int tfx_debug_math(int64_t n, const double *y, const double *x, double *out) {
+  TFX_TRY(ensure_init());
+  cudaStream_t st = ctx().stream;
+  if (n <= 0) return 0;
+  DevBuf<double> dy, dx, dout;
+  TFX_TRY(up(dy, y, (size_t)n)); TFX_TRY(up(dx, x, (size_t)n));
+  TFX_TRY(dout.alloc((size_t)n * 4));
+  TFX_TRY(debug_math(n, dy.p, dx.p, dout.p, st));
+  TFX_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -265,14 +265,39 @@ __device__ __forceinline__ void haar_pair(double &lo, double &hi, const WaveCons
   }
 }
 
-template <int TYPE, bool FWD, bool TRANSPOSE>
-__global__ void __launch_bounds__(256, 4) wavelet_cols_kernel(double *__restrict__ s, int L, long long inner, long long nlines,
-                                                           int NC, int pitch, WaveConst k) {
+// Where the lines of a pass live. Line q (0 <= q < nlines), element l (0 <= l < L):
+//   TRANSPOSE (lines contiguous along l):  s[(q / per) * ostride + (q % per) * rstride + l]
+//   otherwise (lines strided):             s[(q / inner) * ostride + (q % inner) + l * rstride]
+// A whole-volume axis pass has per = 1, ostride = L (axis 1) or ostride = L * inner, rstride = inner (axes 2 / 3); the
+// other values address every 8th row of axis 2 (the Haar passes that go with the fused kernel, see run3d()).
+struct ColsGeom {
+  long long inner, nlines, per, ostride, rstride;
+  int L, NC, pitch;
+  int nscale;     // scales of this pass (the reference derives them from the FULL axis length)
+  // fused Haar axis-1 + axis-2 kernel: the tile's columns are NC consecutive axis-2 positions of ONE plane
+  int n2, tpp;    // axis-2 length, tiles per plane (0: not fused)
+  int nscale2;    // axis-2 scales done on the tile's groups of 8 columns (<= 3)
+  int skip0;      // inverse: columns j % 8 == 0 already went through the axis-1 pass (with the high axis-2 scales)
+};
+
+template <int TYPE, bool FWD, bool TRANSPOSE, bool FUSE>
+__global__ void __launch_bounds__(256, 4) wavelet_cols_kernel(double *__restrict__ s, ColsGeom G, WaveConst k) {
   extern __shared__ double tile[];
+  const int L = G.L, NC = G.NC, pitch = G.pitch;
+  const long long inner = G.inner;
   const int nt = (int)blockDim.x;
   const int c = (int)threadIdx.x % NC, rid = (int)threadIdx.x / NC, nrid = nt / NC;
-  const long long q0 = (long long)blockIdx.x * NC;
-  const int ncol = (int)min((long long)NC, nlines - q0);
+  long long q0;
+  int ncol;
+  if (FUSE) {
+    const long long plane = blockIdx.x / G.tpp;
+    const int jt = (int)(blockIdx.x - plane * G.tpp);
+    q0 = plane * G.n2 + (long long)jt * NC;
+    ncol = min(NC, G.n2 - jt * NC);
+  } else {
+    q0 = (long long)blockIdx.x * NC;
+    ncol = (int)min((long long)NC, G.nlines - q0);
+  }
   const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
 
   // ---- load
@@ -283,7 +308,8 @@ __global__ void __launch_bounds__(256, 4) wavelet_cols_kernel(double *__restrict
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nt >> 5;
     const uint32_t dstep = (uint32_t)(32 * pitch * (int)sizeof(double));
     for (int cc = w; cc < ncol; cc += nw) {
-      const double *src = s + (q0 + cc) * L + lane;
+      const long long q = q0 + cc, qo = q / G.per;
+      const double *src = s + qo * G.ostride + (q - qo * G.per) * G.rstride + lane;
       uint32_t dst = tile_s + (uint32_t)((lane * pitch + cc) * (int)sizeof(double));
 #pragma unroll 4
       for (int l = lane; l < L; l += 32) {
@@ -295,14 +321,14 @@ __global__ void __launch_bounds__(256, 4) wavelet_cols_kernel(double *__restrict
   } else {
     const long long q = q0 + c;
     const long long o = q / inner, i = q - o * inner;
-    colbase = o * L * inner + i;
+    colbase = o * G.ostride + i;
     if (c < ncol) {
-      const double *src = s + colbase + (long long)rid * inner;
+      const double *src = s + colbase + (long long)rid * G.rstride;
       uint32_t dst = tile_s + (uint32_t)((rid * pitch + c) * (int)sizeof(double));
 #pragma unroll 4
       for (int l = rid; l < L; l += nrid) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-        src += (long long)nrid * inner;
+        src += (long long)nrid * G.rstride;
         dst += (uint32_t)(nrid * pitch * (int)sizeof(double));
       }
     }
@@ -311,7 +337,7 @@ __global__ void __launch_bounds__(256, 4) wavelet_cols_kernel(double *__restrict
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
-  const int nscale = (L >= 2) ? ilog2_floor(L) : 0;
+  const int nscale = G.nscale;
   double *col = tile + c;
   if (TYPE == 1) {
     // ---- Haar: rounds of three scales in registers. Round t works on the rows that are multiples of B = 8^t.
@@ -323,7 +349,7 @@ __global__ void __launch_bounds__(256, 4) wavelet_cols_kernel(double *__restrict
       const int nchunk = (L + (8 << sh) - 1) >> (sh + 3);
       const size_t rs = (size_t)pitch << sh;       // distance of two rows of the chunk in the tile
       const bool sc2 = s1 + 1 <= nscale, sc3 = s1 + 2 <= nscale;
-      for (int g = rid; g < nchunk; g += nrid) {
+      for (int g = (FUSE && G.skip0 && (c & 7) == 0) ? nchunk : rid; g < nchunk; g += nrid) {
         const int r0 = g << (sh + 3);
         double *base = col + (size_t)r0 * pitch;
         double a[8];
@@ -377,6 +403,46 @@ __global__ void __launch_bounds__(256, 4) wavelet_cols_kernel(double *__restrict
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (in[j]) base[j * rs] = a[j];
+      }
+      __syncthreads();
+    }
+    if (FUSE && G.nscale2 > 0) {
+      // ---- the three lowest axis-2 scales on the tile's groups of 8 columns (8 consecutive axis-2 positions, the first
+      // a multiple of 8): rows of the tile are independent, a thread takes (row i, group g) with the lanes along i
+      // (odd pitch: conflict-free). A pair exists when its high element is inside the axis (npairs(), :97-101).
+      const int ngrp = (ncol + 7) >> 3;
+      const bool sc2 = G.nscale2 >= 2, sc3 = G.nscale2 >= 3;
+      for (int w = threadIdx.x; w < L * ngrp; w += nt) {
+        const int g = w / L, i = w - g * L;
+        double *base = tile + (size_t)i * pitch + g * 8;
+        const int nin = ncol - g * 8;   // columns of this group inside the axis (>= 1)
+        double a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = (j < nin) ? base[j] : 0.0;
+        if (FWD) {
+          if (nin > 1) haar_pair<true>(a[0], a[1], k);
+          if (nin > 3) haar_pair<true>(a[2], a[3], k);
+          if (nin > 5) haar_pair<true>(a[4], a[5], k);
+          if (nin > 7) haar_pair<true>(a[6], a[7], k);
+          if (sc2) {
+            if (nin > 2) haar_pair<true>(a[0], a[2], k);
+            if (nin > 6) haar_pair<true>(a[4], a[6], k);
+          }
+          if (sc3 && nin > 4) haar_pair<true>(a[0], a[4], k);
+        } else {
+          if (sc3 && nin > 4) haar_pair<false>(a[0], a[4], k);
+          if (sc2) {
+            if (nin > 2) haar_pair<false>(a[0], a[2], k);
+            if (nin > 6) haar_pair<false>(a[4], a[6], k);
+          }
+          if (nin > 1) haar_pair<false>(a[0], a[1], k);
+          if (nin > 3) haar_pair<false>(a[2], a[3], k);
+          if (nin > 5) haar_pair<false>(a[4], a[5], k);
+          if (nin > 7) haar_pair<false>(a[6], a[7], k);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nin) base[j] = a[j];
       }
       __syncthreads();
     }
@@ -442,7 +508,8 @@ __global__ void __launch_bounds__(256, 4) wavelet_cols_kernel(double *__restrict
   if (TRANSPOSE) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nt >> 5;
     for (int cc = w; cc < ncol; cc += nw) {
-      double *dst = s + (q0 + cc) * L + lane;
+      const long long q = q0 + cc, qo = q / G.per;
+      double *dst = s + qo * G.ostride + (q - qo * G.per) * G.rstride + lane;
       const double *src = tile + (size_t)lane * pitch + cc;
 #pragma unroll 4
       for (int l = lane; l < L; l += 32) {
@@ -452,12 +519,12 @@ __global__ void __launch_bounds__(256, 4) wavelet_cols_kernel(double *__restrict
       }
     }
   } else if (c < ncol) {
-    double *dst = s + colbase + (long long)rid * inner;
+    double *dst = s + colbase + (long long)rid * G.rstride;
     const double *src = col + (size_t)rid * pitch;
 #pragma unroll 4
     for (int l = rid; l < L; l += nrid) {
       *dst = *src;
-      dst += (long long)nrid * inner;
+      dst += (long long)nrid * G.rstride;
       src += (size_t)nrid * pitch;
     }
   }
@@ -466,37 +533,71 @@ __global__ void __launch_bounds__(256, 4) wavelet_cols_kernel(double *__restrict
 int g_opt_wavelet_cols = 1;   // 0: always the generic (line, pair) kernel
 int g_opt_wavelet_tile_kb = 0;   // 0: automatic (32 KB tiles, 64 KB for axes longer than 256)
 
-// Launches the column-layout kernel when the axis length fits its tile; returns 1 when it did, 0 to fall back.
-template <int TYPE, bool FWD>
-static int launch_cols(double *d_s, int L, long long inner, long long outer, cudaStream_t st, int *launched) {
-  *launched = 0;
+// Columns (lines) per CTA of the column-layout kernel for lines of length L; 0: the axis does not fit any tile.
+static int cols_tile(int L, bool transpose, long long inner) {
   if (!g_opt_wavelet_cols || L < 2) return 0;
-  const bool transpose = (inner == 1);
-  // columns per CTA: whole warps of lines while the tile stays <= 64 KB; half-warps for long lines (<= 1024 rows)
-  // columns (lines) per CTA: the largest power of two in [8, 256] whose tile stays within the budget (small tiles: many
-  // CTAs per SM in different phases -- load / lift / store -- keep the memory pipeline busy)
+  // the largest power of two in [8, 256] whose tile stays within the budget (small tiles: many CTAs per SM in different
+  // phases -- load / lift / store -- keep the memory pipeline busy)
   // measured (512x512x128 Haar): 16 KB tiles 0.51 ms, 32 KB 0.46 ms, 64 KB 0.39 ms; 256x256x64: 0.086 / 0.075 / 0.078 ms
   const size_t budget = (g_opt_wavelet_tile_kb > 0 ? (size_t)std::max(8, g_opt_wavelet_tile_kb) : (L > 256 ? 64 : 32)) * 1024;
   int NC = 256;
   while (NC > 8 && (size_t)L * NC * sizeof(double) > budget) NC >>= 1;
   if ((size_t)L * (NC + 1) * sizeof(double) > 140 * 1024) return 0;   // axis too long for any tile: generic kernel
   if (!transpose && inner < NC && inner < 16) return 0;   // tiny inner extents: lanes would not read contiguous memory
-  const long long nlines = inner * outer;
-  const int pitch = transpose ? NC + 1 : NC;
-  const size_t smem = (size_t)L * pitch * sizeof(double);
-  const long long grid = (nlines + NC - 1) / NC;
-  if (grid > 0x7fffffffLL) return 0;
-  if (transpose) {
-    auto kern = wavelet_cols_kernel<TYPE, FWD, true>;
-    TFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
-    kern<<<(unsigned)grid, 256, smem, st>>>(d_s, L, inner, nlines, NC, pitch, make_consts());
+  return NC;
+}
+
+// Launches the column-layout kernel on the lines described by G (L, inner, nlines, per, ostride, rstride, nscale and, for
+// the fused kernel, n2 / nscale2 / skip0 filled in by the caller; NC, pitch, tpp here).
+template <int TYPE, bool FWD>
+static int launch_cols_geom(double *d_s, ColsGeom G, bool transpose, bool fuse, long long nplanes, cudaStream_t st) {
+  const int NC = cols_tile(G.L, transpose, G.inner);
+  if (NC == 0) return fail(-23, "wavelet: internal error (column kernel launched on an axis that does not fit)");
+  G.NC = NC;
+  G.pitch = transpose ? NC + 1 : NC;
+  G.tpp = fuse ? (G.n2 + NC - 1) / NC : 0;
+  const size_t smem = (size_t)G.L * G.pitch * sizeof(double);
+  const long long grid = fuse ? nplanes * G.tpp : (G.nlines + NC - 1) / NC;
+  if (grid > 0x7fffffffLL) return fail(-23, "wavelet: volume too large for one launch");
+  if (grid <= 0) return 0;
+#define TFX_WCOLS(T, F)                                                                                     \
+  do {                                                                                                      \
+    auto kern = wavelet_cols_kernel<TYPE, FWD, T, F>;                                                       \
+    TFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));          \
+    kern<<<(unsigned)grid, 256, smem, st>>>(d_s, G, make_consts());                                         \
+  } while (0)
+  if (fuse) {
+    if (TYPE != 1 || !transpose) return fail(-23, "wavelet: internal error (fused kernel is Haar / axis 1 only)");
+    TFX_WCOLS(true, (TYPE == 1));
+  } else if (transpose) {
+    TFX_WCOLS(true, false);
   } else {
-    auto kern = wavelet_cols_kernel<TYPE, FWD, false>;
-    TFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
-    kern<<<(unsigned)grid, 256, smem, st>>>(d_s, L, inner, nlines, NC, pitch, make_consts());
+    TFX_WCOLS(false, false);
   }
+#undef TFX_WCOLS
   ctx().launches++;
   TFX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int host_ilog2(long long n) {
+  int k = 0;
+  while ((1LL << (k + 1)) <= n) ++k;
+  return k;
+}
+
+// One whole-volume axis pass with the column-layout kernel when the axis length fits its tile (*launched = 1).
+template <int TYPE, bool FWD>
+static int launch_cols(double *d_s, int L, long long inner, long long outer, cudaStream_t st, int *launched) {
+  *launched = 0;
+  const bool transpose = (inner == 1);
+  if (cols_tile(L, transpose, inner) == 0) return 0;
+  ColsGeom G = {};
+  G.L = L; G.inner = inner; G.nlines = inner * outer;
+  G.per = 1; G.ostride = transpose ? (long long)L : (long long)L * inner; G.rstride = transpose ? 0 : inner;
+  G.nscale = host_ilog2(L);
+  if ((G.nlines + 7) / 8 > 0x7fffffffLL) return 0;
+  TFX_TRY((launch_cols_geom<TYPE, FWD>(d_s, G, transpose, false, 0, st)));
   *launched = 1;
   return 0;
 }
@@ -578,6 +679,48 @@ static int launch_axis(double *d_s, int L, long long inner, long long outer, cud
 // 100 MB 0.441 ms -- the small launches lose more (partial waves, launch gaps) than the L2 hits win, so it stays off.
 int g_opt_wavelet_slab_mb = 0;
 
+int g_opt_wavelet_fuse12 = 1;   // 1: Haar axis-1 pass fused with the three lowest axis-2 scales (see run3d)
+
+// Haar, axes 1 and 2 of nplanes planes (n1 x n2 each) in 1 + 1/8 (forward) or 1 + 2/8 (inverse) passes over the data
+// instead of 2. The fused kernel holds NC complete axis-1 lines = NC consecutive axis-2 positions of one plane: after
+// the axis-1 scales it runs the three lowest axis-2 scales on the groups of 8 columns (a group of 8 starting at a
+// multiple of 8 is closed under scales 1-3). The remaining axis-2 scales only touch the rows j = 0 (mod 8) -- the
+// transform of the line (j / 8) of length ceil(n2 / 8) with nscale - 3 scales -- in a pass over 1/8 of the plane.
+// Every element goes through the reference's operations in the reference's order:
+//   forward (wavelet_transform.F90:75-153): axis 1, axis 2 scales 1..3 | axis 2 scales 4..nscale
+//   inverse (:158-236, same axis order, scales downwards): axis 1 on the rows j = 0 (mod 8) | axis 2 scales nscale..4 on
+//   them | axis 1 on the other rows, then axis 2 scales 3..1 on all of them (fused kernel, skip0)
+template <int TYPE, bool FWD>
+static int haar_axes12_fused(double *d_s, int n1, int n2, long long nplanes, cudaStream_t st, int *launched) {
+  *launched = 0;
+  if (TYPE != 1 || !g_opt_wavelet_fuse12 || n2 < 2 || n1 < 2) return 0;
+  if (cols_tile(n1, true, 1) == 0) return 0;
+  const int ns2 = host_ilog2(n2), m2 = (n2 + 7) / 8;
+  const bool high = ns2 > 3;
+  if (high && cols_tile(m2, false, n1) == 0) return 0;
+  ColsGeom F = {};   // fused kernel
+  F.L = n1; F.inner = 1; F.nlines = (long long)n2 * nplanes; F.per = 1; F.ostride = n1; F.rstride = 0;
+  F.nscale = host_ilog2(n1); F.n2 = n2; F.nscale2 = std::min(3, ns2); F.skip0 = (!FWD && high) ? 1 : 0;
+  ColsGeom H = {};   // axis-2 scales 4.. on the rows j = 0 (mod 8): lines of length m2, element stride 8 * n1
+  H.L = m2; H.inner = n1; H.nlines = (long long)n1 * nplanes; H.per = 1; H.ostride = (long long)n1 * n2;
+  H.rstride = 8LL * n1; H.nscale = ns2 - 3;
+  ColsGeom S = {};   // axis 1 on the rows j = 0 (mod 8): m2 lines per plane, 8 * n1 apart
+  S.L = n1; S.inner = 1; S.nlines = (long long)m2 * nplanes; S.per = m2; S.ostride = (long long)n1 * n2;
+  S.rstride = 8LL * n1; S.nscale = F.nscale;
+  if (FWD) {
+    TFX_TRY((launch_cols_geom<TYPE, FWD>(d_s, F, true, true, nplanes, st)));
+    if (high) TFX_TRY((launch_cols_geom<TYPE, FWD>(d_s, H, false, false, 0, st)));
+  } else {
+    if (high) {
+      TFX_TRY((launch_cols_geom<TYPE, FWD>(d_s, S, true, false, 0, st)));
+      TFX_TRY((launch_cols_geom<TYPE, FWD>(d_s, H, false, false, 0, st)));
+    }
+    TFX_TRY((launch_cols_geom<TYPE, FWD>(d_s, F, true, true, nplanes, st)));
+  }
+  *launched = 1;
+  return 0;
+}
+
 template <int TYPE, bool FWD>
 static int run3d(double *d_s, int n1, int n2, int n3, long long nvol, cudaStream_t st) {
   const long long plane = (long long)n1 * n2, nplanes = (long long)n3 * nvol;
@@ -588,6 +731,9 @@ static int run3d(double *d_s, int n1, int n2, int n3, long long nvol, cudaStream
   for (long long k0 = 0; k0 < nplanes; k0 += per) {
     const long long nk = std::min(per, nplanes - k0);
     double *slab = d_s + k0 * plane;
+    int fused = 0;
+    TFX_TRY((haar_axes12_fused<TYPE, FWD>(slab, n1, n2, nk, st, &fused)));
+    if (fused) continue;
     TFX_TRY((launch_axis<TYPE, FWD>(slab, n1, 1, (long long)n2 * nk, st)));
     TFX_TRY((launch_axis<TYPE, FWD>(slab, n2, n1, nk, st)));
   }
