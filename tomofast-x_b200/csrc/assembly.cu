@@ -312,8 +312,13 @@ __global__ void __launch_bounds__(256) grav_lines_nodes_kernel(double *__restric
                                                                const double *__restrict__ xn, const double *__restrict__ yn,
                                                                const double *__restrict__ zn, const double *__restrict__ xd,
                                                                const double *__restrict__ yd, const double *__restrict__ zd,
+                                                               const double *__restrict__ cw, double *__restrict__ partial,
                                                                int *err) {
+  // cw != nullptr: the line is stored already multiplied by the column weight (apply_column_weight,
+  // sensitivity_gravmag.F90:1042-1054); partial != nullptr: partial[station][tile] = this tile's share of the sum of the
+  // weighted squares (cost_full, :234) -- one pass over the line less in the row pipeline.
   __shared__ double T[kNTZ + 1][kNTY + 1][kNTX + 1];
+  __shared__ double red[32];
   const double twopi = 2.0 * TFX_PI;
   const int tiles_x = (nx + kNTX - 1) / kNTX, tiles_y = (ny + kNTY - 1) / kNTY;
   const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, tz = blockIdx.x / (tiles_x * tiles_y);
@@ -342,6 +347,7 @@ __global__ void __launch_bounds__(256) grav_lines_nodes_kernel(double *__restric
       T[c][bb][a] = term;
     }
     __syncthreads();
+    double ssq = 0.0;
     for (int idx = threadIdx.x; idx < kNTX * kNTY * kNTZ; idx += 256) {
       const int a = idx % kNTX, bb = (idx / kNTX) % kNTY, c = idx / (kNTX * kNTY);
       const int gi = i0 + a, gj = j0 + bb, gk = k0 + c;
@@ -356,8 +362,18 @@ __global__ void __launch_bounds__(256) grav_lines_nodes_kernel(double *__restric
               const double t = T[c + M][bb + L][a + K];
               gz = __dadd_rn(gz, ((K + L + M) & 1) ? t : -t);
             }
-        lines[(long long)b * n + gi + (long long)gj * nx + (long long)gk * nx * ny] = __dmul_rn(g_grav(), gz);
+        const long long p = gi + (long long)gj * nx + (long long)gk * nx * ny;
+        double v = __dmul_rn(g_grav(), gz);
+        if (cw) {
+          v = __dmul_rn(v, cw[p]);
+          ssq = fma(v, v, ssq);
+        }
+        lines[(long long)b * n + p] = v;
       }
+    }
+    if (partial) {
+      ssq = block_sum(ssq, red);   // (contains the barriers that separate this station's tile from the next one's)
+      if (threadIdx.x == 0) partial[(long long)b * gridDim.x + blockIdx.x] = ssq;
     }
     __syncthreads();
   }
@@ -394,16 +410,26 @@ int grav_full_lines(const GridDev &g, int32_t nb, const double *d_xd, const doub
   return 0;
 }
 
+// Number of per-line partial sums the fused column-weight path of grav_lines() writes; 0: that path does not apply (the
+// caller weights the lines and sums their squares itself).
+int grav_lines_fused_partials(const GridDev &g, int data_type) {
+  if (data_type == 1 && g.structured == 1 && g_opt_grav_shared_nodes)
+    return ((g.nx + kNTX - 1) / kNTX) * ((g.ny + kNTY - 1) / kNTY) * ((g.nz + kNTZ - 1) / kNTZ);
+  return 0;
+}
+
 int grav_lines(const GridDev &g, int32_t nb, const double *d_xd, const double *d_yd, const double *d_zd, int data_type,
-               double *d_lines, int *d_err, cudaStream_t st) {
+               double *d_lines, int *d_err, cudaStream_t st, const double *d_cw, double *d_partial) {
   if (data_type == 1 && g.structured == 1 && g_opt_grav_shared_nodes) {
     const int tiles = ((g.nx + kNTX - 1) / kNTX) * ((g.ny + kNTY - 1) / kNTY) * ((g.nz + kNTZ - 1) / kNTZ);
     dim3 grid(tiles, std::min(nb, 1024));
-    grav_lines_nodes_kernel<<<grid, 256, 0, st>>>(d_lines, g.nx, g.ny, g.nz, nb, g.xn.p, g.yn.p, g.zn.p, d_xd, d_yd, d_zd, d_err);
+    grav_lines_nodes_kernel<<<grid, 256, 0, st>>>(d_lines, g.nx, g.ny, g.nz, nb, g.xn.p, g.yn.p, g.zn.p, d_xd, d_yd, d_zd,
+                                                  d_cw, d_cw ? d_partial : nullptr, d_err);
     ctx().launches++;
     TFX_CUDA(cudaGetLastError());
     return 0;
   }
+  if (d_cw) return fail(-24, "grav_lines: the fused column weight needs the structured-grid kernel");
   dim3 grid((g.n + 255) / 256, std::min(nb, 1024));
   grav_lines_kernel<<<grid, 256, 0, st>>>(d_lines, g.n, nb, g.X1.p, g.X2.p, g.Y1.p, g.Y2.p, g.Z1.p, g.Z2.p, d_xd,
                                           d_yd, d_zd, data_type, d_err);

@@ -173,8 +173,12 @@ int assemble_grav_dense(DenseCM &S, const GridDev &g, int32_t cell0, int32_t nce
                         const double *d_dw, double problem_weight, int *d_err, cudaStream_t st);
 
 // Computes one gravity sensitivity line (all cells) per data point into d_lines[b*ncells + p].
+// d_cw != nullptr (only when grav_lines_fused_partials() > 0): the lines come out multiplied by the column weight and
+// d_partial[b * npartials + i] holds partial sums of their squares (cost_full, sensitivity_gravmag.F90:228-234).
 int grav_lines(const GridDev &g, int32_t ndata_batch, const double *d_xd, const double *d_yd, const double *d_zd,
-               int data_type, double *d_lines, int *d_err, cudaStream_t st);
+               int data_type, double *d_lines, int *d_err, cudaStream_t st, const double *d_cw = nullptr,
+               double *d_partial = nullptr);
+int grav_lines_fused_partials(const GridDev &g, int data_type);
 
 // Full-tensor gravity gradiometry lines (gradiprism_full): d_lines[(b*6 + d)*ncells + p], d = XX, YY, ZZ, XY, YZ, ZX.
 int grav_full_lines(const GridDev &g, int32_t ndata_batch, const double *d_xd, const double *d_yd, const double *d_zd,

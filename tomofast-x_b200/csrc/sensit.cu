@@ -509,11 +509,20 @@ int kernel_error(int e) {
   return fail(-70, "forward kernel error");
 }
 
+// d_cw / d_partial: see grav_lines() (only passed when lines_fused_partials() > 0).
+int lines_fused_partials(const tfx_sensit_params &P, const GridDev &g) {
+  if (P.problem_type == 1 && P.nmodel_components == 1 && P.data_type == 1 && P.ndata_components == 1)
+    return grav_lines_fused_partials(g, 1);
+  return 0;
+}
+
 int compute_lines(const tfx_sensit_params &P, const GridDev &g, int nb, const double *dx, const double *dy,
-                  const double *dz, double *d_lines, int *d_err, cudaStream_t st) {
+                  const double *dz, double *d_lines, int *d_err, cudaStream_t st, const double *d_cw = nullptr,
+                  double *d_partial = nullptr) {
   if (P.problem_type == 1) {
     if (P.nmodel_components != 1) return fail(-71, "gravity: nmodel_components must be 1");
-    if (P.data_type == 1 && P.ndata_components == 1) return grav_lines(g, nb, dx, dy, dz, 1, d_lines, d_err, st);
+    if (P.data_type == 1 && P.ndata_components == 1)
+      return grav_lines(g, nb, dx, dy, dz, 1, d_lines, d_err, st, d_cw, d_partial);
     if (P.data_type == 2 && P.ndata_components == 1) return grav_lines(g, nb, dx, dy, dz, 2, d_lines, d_err, st);
     if (P.data_type == 2 && P.ndata_components == 6) return grav_full_lines(g, nb, dx, dy, dz, d_lines, d_err, st);
     if (P.data_type == 2) return fail(-72, "Wrong number of gravity gradiometry data components!");   // :210-212
@@ -573,7 +582,9 @@ int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const dou
   const long long rank = (long long)N - nel_compressed - 1;   // 0-based rank of sorted(N - nel_compressed), :240-251
   const bool no_select = nel_compressed >= N;
   const int nchunks = (N + kChunk - 1) / kChunk;
-  const int gsum = std::min(kSumBlocks, (N + 1023) / 1024);
+  // structured-grid gravity: the line kernel applies the column weight and leaves partial sums of the squares
+  const int nfused = compressed ? lines_fused_partials(P, g) : 0;
+  const int gsum = nfused > 0 ? nfused : std::min(kSumBlocks, (N + 1023) / 1024);
   const unsigned candcap = std::min<unsigned>(g_opt_sensit_cand_cap > 0 ? (unsigned)g_opt_sensit_cand_cap : kCandCap, (unsigned)N);
   DevBuf<RowState> dst;
   DevBuf<long long> dsegend, dlineoff;
@@ -600,11 +611,13 @@ int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const dou
   int64_t iseg = 0;
   for (int32_t b0 = 0; b0 < ndata_loc; b0 += B) {
     const int nb = std::min<int>(B, ndata_loc - b0);
-    TFX_TRY(compute_lines(P, g, nb, d_dx + data0 + b0, d_dy + data0 + b0, d_dz + data0 + b0, dl.p, derr.p, st));
+    TFX_TRY(compute_lines(P, g, nb, d_dx + data0 + b0, d_dy + data0 + b0, d_dz + data0 + b0, dl.p, derr.p, st,
+                          nfused > 0 ? d_cw : nullptr, nfused > 0 ? dpartial.p : nullptr));
     const int nseg_b = nb * ndc * nmc;   // segments (lines) of this batch, stored back to back in dl
     if (compressed) {
-      // column weight (:228) and cost_full (:234) in one pass, then ONE batched wavelet transform of all lines (:237)
-      k_cw_sumsq<<<dim3(gsum, nseg_b), 256, 0, st>>>(dl.p, d_cw, N, dpartial.p);
+      // column weight (:228) and cost_full (:234) in one pass (inside the line kernel when it can), then ONE batched
+      // wavelet transform of all lines (:237)
+      if (nfused == 0) k_cw_sumsq<<<dim3(gsum, nseg_b), 256, 0, st>>>(dl.p, d_cw, N, dpartial.p);
       k_sum_partials<<<nseg_b, 256, 0, st>>>(dpartial.p, gsum, dcostfull.p);
       c.launches += 2;
       TFX_TRY(wavelet3d_device_batch(dl.p, P.nx, P.ny, P.nz, nseg_b, P.compression_type, true, st));
