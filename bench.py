@@ -507,6 +507,7 @@ def compressed_spmv(a, tfx, d):
     d.barrier()
     t0 = time.perf_counter()
     t_rows = t_part = None
+    grid = tfx.grid_pin(grid)      # one upload of the 48 B/cell grid for the sample and every row block (inside the timing)
     if a_comp_batch > 0:
         # Row-blocked assembly (bounded build memory, csrc/sensit.cu matrix_append_block): the column partition comes
         # from a strided sample of the stations (the reference balances on the nnz counts of ALL rows, which it has on
@@ -558,6 +559,7 @@ def compressed_spmv(a, tfx, d):
         ncl, cell0, nnz_loc = int(nel_at[d.rank]), int(nel_at[:d.rank].sum()), int(nnz_at[d.rank])
         slabs = [int(v) for v in nel_at]
         del rows
+    tfx.grid_unpin()
     tfx.synchronize()
     t_asm = d.max(time.perf_counter() - t0)
     if t_rows is not None:

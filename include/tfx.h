@@ -374,6 +374,14 @@ int tfx_sensit_lines(const tfx_sensit_params *par, const double *X1, const doubl
                      const double *Y2, const double *Z1, const double *Z2, int32_t ndata_batch,
                      const double *data_X, const double *data_Y, const double *data_Z, double *lines);
 
+/* Keeps a device copy of the model grid (grid_type: X1..Z2 of the ncells cells, src/model/grid.F90) for the following
+ * tfx_calculate_sensit / tfx_sensit_assemble_rows / tfx_sensit_lines calls that pass THE SAME six host arrays, instead of
+ * uploading 48 B per cell on every call (row blocks, the two problems of a joint inversion). The caller must not change
+ * the arrays while they are pinned. tfx_grid_unpin releases the copy. */
+int tfx_grid_pin(int32_t ncells, const double *X1, const double *X2, const double *Y1, const double *Y2,
+                 const double *Z1, const double *Z2);
+int tfx_grid_unpin(void);
+
 /* Diagnostics for tests/test_gpu_mathx.py: the forward kernels' own log / atan2 (csrc/mathx.cuh: CUDA's algorithms with
  * the polynomial coefficients read from the constant bank) next to the CUDA library's, element by element (host arrays):
  * out = [tfx_log(x) | log(x) | tfx_atan2(y, x) | atan2(y, x)], 4 * n doubles. */

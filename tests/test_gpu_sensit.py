@@ -192,6 +192,25 @@ def test_kth_select_fallback_passes_give_the_same_rows():
     assert tot_a <= nel * pb.ndata and tot_a >= (nel - 2) * pb.ndata
 
 
+def test_pinned_grid_gives_the_same_rows():
+    """tfx_grid_pin keeps the device copy of the grid for calls that pass the same host arrays; other arrays (even with
+    equal content) are uploaded as before."""
+    pb = make_problem(nx=20, ny=12, nz=8, ndata=7, compression_type=1, rate=0.1)
+    S0, nnz0, cerr0, tot0 = tfx.calculate_sensit(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+    try:
+        pinned = tfx.grid_pin(pb.grid)
+        S1, nnz1, cerr1, tot1 = tfx.calculate_sensit(pb.par, pinned, pb.data_xyz, pb.cw, pb.dw)
+        rows, nnz2, cerr2, tot2 = tfx.sensit_assemble_rows(pb.par, pinned, pb.data_xyz, pb.cw, pb.dw)
+        other = tuple(np.array(a, copy=True) for a in pb.grid)
+        S3, nnz3, cerr3, tot3 = tfx.calculate_sensit(pb.par, other, pb.data_xyz, pb.cw, pb.dw)
+    finally:
+        tfx.grid_unpin()
+    assert tot0 == tot1 == tot2 == tot3 and cerr0 == cerr1 == cerr2 == cerr3
+    assert np.array_equal(nnz0, nnz1) and np.array_equal(nnz0, nnz2) and np.array_equal(nnz0, nnz3)
+    for x, y, z in zip(S0.export(), S1.export(), S3.export()):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+
+
 def test_magnetic_compressed_assembly_three_components(oracle):
     # config D shape in miniature: magnetisation model (3 comps), TMI data, columns shifted to problem 2
     pb = make_problem(nx=8, ny=7, nz=4, ndata=6, compression_type=2, rate=0.3, problem_type=2, nmodel_components=3)

@@ -108,6 +108,7 @@ def lib():
     L.tfx_sensit_repartition.argtypes = [C.POINTER(vp), vp, i32, vp, i32, i32]
     L.tfx_sensit_lines.argtypes = [C.POINTER(SensitParams)] + [vp] * 6 + [i32] + [vp] * 4
     L.tfx_debug_math.argtypes = [i64, vp, vp, vp]
+    L.tfx_grid_pin.argtypes = [i32] + [vp] * 6
     _lib = L
     return L
 
@@ -524,6 +525,17 @@ def sensit_lines(par, grid, data_xyz):
     _check(lib().tfx_sensit_lines(C.byref(par), *gp, dx.size, dx.ctypes.data, dy.ctypes.data, dz.ctypes.data,
                                   out.ctypes.data))
     return out
+
+
+def grid_pin(grid):
+    """Keeps a device copy of `grid` for the following assembly calls that pass the same arrays (tfx_grid_pin)."""
+    arrs, gp = _grid_ptrs(grid)
+    _check(lib().tfx_grid_pin(arrs[0].size, *gp))
+    return arrs
+
+
+def grid_unpin():
+    _check(lib().tfx_grid_unpin())
 
 
 def debug_math(y, x):

@@ -199,10 +199,12 @@ def run_config_e(tfx, nx, ny, nz, nd1, nd2, rate=0.002, niter=20, warmup=3, rank
 
     # ---- (III) both kernels: rows sharded by station, then ONE nnz-balanced column partition for the joint matrix
     tfx.synchronize(); barrier(); t0 = wall()
+    grid = tfx.grid_pin(grid)      # both problems share the grid: one upload
     rows, nnz_col, tot = [], np.zeros(N, dtype=np.int64), []
     for i in range(2):
         r, nc, cerr, t = tfx.sensit_assemble_rows(params(i), grid, xyz[i], cw_full[i], np.ones((nds[i], 1)), rank, world)
         rows.append(r); nnz_col += nc; tot.append(int(t))
+    tfx.grid_unpin()
     tfx.synchronize(); barrier(); out["assemble_rows_s"] = wall() - t0
     _, nel_at = tfx.get_load_balancing_nelements(np.minimum(nnz_col, 2**31 - 1).astype(np.int32), world)
     ncl, cell0 = int(nel_at[rank]), int(nel_at[:rank].sum())

@@ -420,6 +420,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_sensit_row_blocks = value;
     return 0;
   }
+  if (name && strcmp(name, "trace") == 0) {
+    g_opt_trace = value;
+    return 0;
+  }
   if (name && strcmp(name, "sensit_cand_cap") == 0) {
     g_opt_sensit_cand_cap = value;
     return 0;

@@ -77,6 +77,8 @@ int matrix_trans(Matrix &m, const double *d_u, double *d_y, bool accumulate, con
 // Appends the rows held as device triplets (row ids relative to the batch) as one more row block.
 int matrix_append_block(Matrix &M, RowTriplets &R, int32_t nrows, int32_t ncolumns);
 extern int g_opt_sensit_row_blocks;
+extern int g_opt_trace;
+void trace(const char *label);
 extern int g_opt_sensit_cand_cap;   // > 0: candidate-list capacity of the k-th select (tests force the fallback passes with 1)
 
 int matrix_upload(Matrix &m, bool allow_dense);
@@ -96,6 +98,13 @@ int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R
 int matrix_append_triplets(Matrix &M, RowTriplets &R, int32_t nrows, int32_t ncolumns);
 // Moves the rows built on the host so far into the pending device rows (see sensit.cu).
 int matrix_flush_host_rows(Matrix &M);
+// The device copy of a grid for one call: the pinned one (tfx_grid_pin, same host arrays) or a fresh upload.
+struct GridHold {
+  GridDev own;
+  GridDev *g = nullptr;
+};
+int grid_acquire(GridHold &h, int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
+                 const double *Z1, const double *Z2, int32_t nx, int32_t ny, int32_t nz);
 int upload_grid(GridDev &g, int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
                 const double *Z1, const double *Z2);
 

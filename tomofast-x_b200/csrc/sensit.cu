@@ -22,6 +22,7 @@
 #include <thrust/unique.h>
 
 #include <algorithm>
+#include <time.h>
 #include <vector>
 
 #include "common.cuh"
@@ -541,6 +542,40 @@ int upload_grid(GridDev &g, int32_t n, const double *X1, const double *X2, const
   return upload_grid_impl(g, n, X1, X2, Y1, Y2, Z1, Z2);
 }
 
+// ---- pinned grid (tfx_grid_pin): the six cell-box arrays of a 512x512x128 grid are 1.6 GB of pageable host memory,
+// 0.3-0.5 s per upload; an application that assembles several row sets on the same grid (row blocks, the two problems of
+// a joint inversion) uploads it once.
+static GridDev *g_pin = nullptr;
+static const double *g_pin_ptr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+int grid_acquire(GridHold &h, int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
+                 const double *Z1, const double *Z2, int32_t nx, int32_t ny, int32_t nz) {
+  const double *ptr[6] = {X1, X2, Y1, Y2, Z1, Z2};
+  bool same = g_pin != nullptr && g_pin->n == n;
+  for (int i = 0; i < 6 && same; ++i) same = (g_pin_ptr[i] == ptr[i]);
+  if (same) {
+    h.g = g_pin;
+  } else {
+    TFX_TRY(upload_grid_impl(h.own, n, X1, X2, Y1, Y2, Z1, Z2));
+    h.g = &h.own;
+  }
+  TFX_TRY(grid_detect_structured(*h.g, nx, ny, nz, ctx().stream));
+  return 0;
+}
+
+// ---- phase timing on stderr (option "trace"): where the wall-clock time of an assembly goes
+int g_opt_trace = 0;
+void trace(const char *label) {
+  static double last = 0.0;
+  if (!g_opt_trace) return;
+  cudaStreamSynchronize(ctx().stream);
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  const double now = ts.tv_sec + 1e-9 * ts.tv_nsec;
+  fprintf(stderr, "[tfx trace] %-44s +%8.1f ms\n", label, last > 0.0 ? 1e3 * (now - last) : 0.0);
+  last = now;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Row pipeline for the stations [data0, data0 + ndata_loc) (the reference's data loop,
 // sensitivity_gravmag.F90:189-318, for one rank's share of the data). Entries come out sorted by
@@ -678,10 +713,13 @@ int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const dou
         }
       }
     }
+    TFX_CUDA(cudaGetLastError());
+  }
+  {
+    // forward-kernel errors (a station on a grid boundary ...) are fatal: one look at the flag after the last batch
     int e = 0;
     TFX_CUDA(cudaMemcpyAsync(&e, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     TFX_CUDA(cudaStreamSynchronize(st));
-    TFX_CUDA(cudaGetLastError());
     if (e) return kernel_error(e);
   }
   RowState hst;
@@ -885,6 +923,7 @@ int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R
   M.nl = nl; M.nl_current_all = nl; M.ncolumns = ncolumns;
   M.device_only = true;
 
+  trace("from_triplets: begin");
   // ---- forward representation: runs of equal row ids
   SegMatrix &F = M.fwd;
   F.nnz = nnz; F.nout = nl; F.nin = ncolumns;
@@ -902,6 +941,7 @@ int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R
     TFX_TRY(seg_build_items(F, ptr.data()));
   }
 
+  trace("from_triplets: forward segments");
   // ---- transpose on the device: stable sort by column keeps the row order inside each column.
   // (r2) The sort moves (column, position) pairs only -- a CUB radix sort over the significant column bits with double
   // buffers -- and the row ids / values are gathered through the permutation afterwards, one array at a time: 28 B per
@@ -970,7 +1010,9 @@ int matrix_from_triplets(Matrix &M, int32_t nl, int32_t ncolumns, RowTriplets &R
   }
 
   M.has_seg = true;
+  trace("from_triplets: transposed copy (sort + gathers)");
   TFX_TRY(matrix_build_t16(M));
+  trace("from_triplets: T16 layouts");
   if (M.nnz < nnz) M.nnz = nnz;   // a matrix created by initialize() keeps its capacity (reset() + rebuild)
   M.nel = nnz;
   M.nl_nonempty = F.nseg;
@@ -989,9 +1031,9 @@ extern "C" int tfx_sensit_lines(const tfx_sensit_params *par, const double *X1, 
   cudaStream_t st = ctx().stream;
   const tfx_sensit_params &P = *par;
   const int32_t N = P.nx * P.ny * P.nz;
-  GridDev g;
-  TFX_TRY(upload_grid(g, N, X1, X2, Y1, Y2, Z1, Z2));
-  TFX_TRY(grid_detect_structured(g, P.nx, P.ny, P.nz, st));
+  GridHold gh;
+  TFX_TRY(grid_acquire(gh, N, X1, X2, Y1, Y2, Z1, Z2, P.nx, P.ny, P.nz));
+  GridDev &g = *gh.g;
   DevBuf<double> dx, dy, dz, dl;
   DevBuf<int> derr;
   TFX_TRY(up(dx, data_X, nb)); TFX_TRY(up(dy, data_Y, nb)); TFX_TRY(up(dz, data_Z, nb));
@@ -1005,6 +1047,26 @@ extern "C" int tfx_sensit_lines(const tfx_sensit_params *par, const double *X1, 
   TFX_CUDA(cudaMemcpyAsync(lines, dl.p, per * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
   TFX_CUDA(cudaStreamSynchronize(st));
   if (e) return kernel_error(e);
+  return 0;
+}
+
+extern "C" int tfx_grid_pin(int32_t n, const double *X1, const double *X2, const double *Y1, const double *Y2,
+                            const double *Z1, const double *Z2) {
+  TFX_TRY(ensure_init());
+  if (n <= 0 || !X1 || !X2 || !Y1 || !Y2 || !Z1 || !Z2) return fail(-88, "grid_pin: wrong arguments");
+  if (g_pin) { delete g_pin; g_pin = nullptr; }
+  GridDev *g = new GridDev();
+  int rc = upload_grid_impl(*g, n, X1, X2, Y1, Y2, Z1, Z2);
+  if (!rc && cudaStreamSynchronize(ctx().stream) != cudaSuccess) rc = fail(-100, "grid_pin: upload failed");
+  if (rc) { delete g; return rc; }
+  g_pin = g;
+  const double *ptr[6] = {X1, X2, Y1, Y2, Z1, Z2};
+  for (int i = 0; i < 6; ++i) g_pin_ptr[i] = ptr[i];
+  return 0;
+}
+extern "C" int tfx_grid_unpin(void) {
+  if (g_pin) { delete g_pin; g_pin = nullptr; }
+  for (int i = 0; i < 6; ++i) g_pin_ptr[i] = nullptr;
   return 0;
 }
 
@@ -1041,9 +1103,9 @@ extern "C" int tfx_calculate_sensit(tfx_matrix **out, const tfx_sensit_params *p
   const int32_t nel_compressed = (P.compression_type > 0) ? (int32_t)(P.compression_rate * (double)N) : N;
   const int32_t nl = P.ndata * ndc;
 
-  GridDev g;
-  TFX_TRY(upload_grid(g, N, X1, X2, Y1, Y2, Z1, Z2));
-  TFX_TRY(grid_detect_structured(g, P.nx, P.ny, P.nz, ctx().stream));
+  GridHold gh;
+  TFX_TRY(grid_acquire(gh, N, X1, X2, Y1, Y2, Z1, Z2, P.nx, P.ny, P.nz));
+  GridDev &g = *gh.g;
   DevBuf<double> dx, dy, dz, dcw, ddw;
   DevBuf<int> derr;
   TFX_TRY(up(dx, data_X, P.ndata)); TFX_TRY(up(dy, data_Y, P.ndata)); TFX_TRY(up(dz, data_Z, P.ndata));

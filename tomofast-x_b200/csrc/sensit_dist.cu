@@ -221,19 +221,22 @@ extern "C" int tfx_sensit_assemble_rows(tfx_sensit_rows **out, const tfx_sensit_
   h->ndata_loc = nelements_at_cpu_even(par->ndata, myrank, nbproc);   // sensitivity_gravmag.F90:179-180
   h->data0 = nsmaller_even(par->ndata, myrank, nbproc);
 
-  GridDev g;
+  GridHold gh;
   DevBuf<double> dx, dy, dz, dcw;
   DevBuf<int32_t> dnnz;
   double err_sum = 0.0;
-  int rc = upload_grid(g, N, X1, X2, Y1, Y2, Z1, Z2);
-  if (!rc) rc = grid_detect_structured(g, par->nx, par->ny, par->nz, ctx().stream);
+  trace("assemble_rows: begin");
+  int rc = grid_acquire(gh, N, X1, X2, Y1, Y2, Z1, Z2, par->nx, par->ny, par->nz);
+  trace("assemble_rows: grid on the device");
   if (!rc) rc = up(dx, data_X, par->ndata);
   if (!rc) rc = up(dy, data_Y, par->ndata);
   if (!rc) rc = up(dz, data_Z, par->ndata);
   if (!rc) rc = up(dcw, column_weight_full, N);
+  trace("assemble_rows: stations + column weight");
   if (!rc)
-    rc = assemble_rows_device(h->par, g, dx.p, dy.p, dz.p, dcw.p, data_weight, h->data0, h->ndata_loc, h->R, dnnz,
+    rc = assemble_rows_device(h->par, *gh.g, dx.p, dy.p, dz.p, dcw.p, data_weight, h->data0, h->ndata_loc, h->R, dnnz,
                               h->seg_end, &err_sum);
+  trace("assemble_rows: row pipeline");
   if (rc) { delete h; return rc; }
 
   // reductions over ranks: sensit_nnz (:322), nnz_total (:327), compression error (:346-353)
@@ -257,6 +260,7 @@ extern "C" int tfx_sensit_assemble_rows(tfx_sensit_rows **out, const tfx_sensit_
   if (comp_error)
     *comp_error = (par->compression_type > 0) ? err_sum / ((double)par->ndata * ndc * nmc) : 0.0;
   *out = h;
+  trace("assemble_rows: reductions + sensit_nnz");
   return 0;
 }
 
@@ -264,6 +268,7 @@ extern "C" int tfx_sensit_assemble_rows(tfx_sensit_rows **out, const tfx_sensit_
 static int repartition_core(tfx_sensit_rows *rows, int32_t problem_slot, const int32_t *nelements_at_cpu, int32_t myrank,
                             int32_t nbproc, RowTriplets &Rx, int32_t *nl_out, int32_t *ncolumns_out) {
   TFX_TRY(ensure_init());
+  trace("repartition: begin");
   Context &c = ctx();
   cudaStream_t st = c.stream;
   if (!rows) return fail(-82, "sensit_repartition: null handle");
