@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turns an .ncu-rep (ncu --set full --import-source on) into the small CSV summaries kept under profiles/.
 
-    python profiles/make_summary.py gpurun_out/x.ncu-rep "comment line" > profiles/r1_x_ncu_summary.csv
+    python profiles/make_summary.py gpurun_out/x.ncu-rep "comment line" [launch index] > profiles/r1_x_ncu_summary.csv
 """
 import csv
 import io
@@ -22,15 +22,17 @@ METRICS = [
 ]
 
 
-def ncu_csv(rep, page):
-    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+def ncu_csv(rep, page, launch=None):
+    sel = ["--launch-skip", str(launch), "--launch-count", "1"] if (launch is not None and page == "source") else []
+    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"] + sel, capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
 def main():
     rep, comment = sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else ""
+    launch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     rows = ncu_csv(rep, "raw")
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units, vals = rows[0], rows[1], rows[2 + launch]
     col = {h: i for i, h in enumerate(hdr)}
     print("# " + comment)
     print("Kernel Name,%s," % vals[col["Kernel Name"]])
@@ -47,7 +49,7 @@ def main():
     tot = sum(v for v, _ in stalls) or 1.0
     for v, n in sorted(stalls, reverse=True)[:10]:
         print("stall_%s,%.2f,%%" % (n, 100.0 * v / tot))
-    src = ncu_csv(rep, "source")
+    src = ncu_csv(rep, "source", launch if len(rows) > 3 else None)
     h = next(i for i, r in enumerate(src) if r and r[0] == "Address")
     idx = {n: j for j, n in enumerate(src[h])}
     ops = {}

@@ -308,7 +308,7 @@ int grid_detect_structured(GridDev &g, int32_t nx, int32_t ny, int32_t nz, cudaS
 namespace {
 constexpr int kNTX = 32, kNTY = 8, kNTZ = 8;
 }
-__global__ void __launch_bounds__(256) grav_lines_nodes_kernel(double *__restrict__ lines, int nx, int ny, int nz, int nb,
+__global__ void __launch_bounds__(256, 4) grav_lines_nodes_kernel(double *__restrict__ lines, int nx, int ny, int nz, int nb,
                                                                const double *__restrict__ xn, const double *__restrict__ yn,
                                                                const double *__restrict__ zn, const double *__restrict__ xd,
                                                                const double *__restrict__ yd, const double *__restrict__ zd,
@@ -348,10 +348,26 @@ __global__ void __launch_bounds__(256) grav_lines_nodes_kernel(double *__restric
     }
     __syncthreads();
     double ssq = 0.0;
-    for (int idx = threadIdx.x; idx < kNTX * kNTY * kNTZ; idx += 256) {
+    constexpr int kCellsPerThread = kNTX * kNTY * kNTZ / 256;
+    static_assert(kCellsPerThread * 256 == kNTX * kNTY * kNTZ, "tile cells must be a multiple of the block size");
+    // the column weights of this thread's cells first (independent loads in flight together: the weight is streamed from
+    // HBM once per station and there is little arithmetic in this phase to hide its latency behind)
+    double cwv[kCellsPerThread];
+    long long pv[kCellsPerThread];
+#pragma unroll
+    for (int it = 0; it < kCellsPerThread; ++it) {
+      const int idx = threadIdx.x + it * 256;
       const int a = idx % kNTX, bb = (idx / kNTX) % kNTY, c = idx / (kNTX * kNTY);
       const int gi = i0 + a, gj = j0 + bb, gk = k0 + c;
-      if (gi < nx && gj < ny && gk < nz) {
+      const bool in = gi < nx && gj < ny && gk < nz;
+      pv[it] = in ? gi + (long long)gj * nx + (long long)gk * nx * ny : -1;
+      cwv[it] = (in && cw) ? cw[pv[it]] : 1.0;
+    }
+#pragma unroll
+    for (int it = 0; it < kCellsPerThread; ++it) {
+      const int idx = threadIdx.x + it * 256;
+      const int a = idx % kNTX, bb = (idx / kNTX) % kNTY, c = idx / (kNTX * kNTY);
+      if (pv[it] >= 0) {
         double gz = 0.0;
 #pragma unroll
         for (int K = 0; K < 2; ++K)
@@ -362,13 +378,12 @@ __global__ void __launch_bounds__(256) grav_lines_nodes_kernel(double *__restric
               const double t = T[c + M][bb + L][a + K];
               gz = __dadd_rn(gz, ((K + L + M) & 1) ? t : -t);
             }
-        const long long p = gi + (long long)gj * nx + (long long)gk * nx * ny;
         double v = __dmul_rn(g_grav(), gz);
         if (cw) {
-          v = __dmul_rn(v, cw[p]);
+          v = __dmul_rn(v, cwv[it]);
           ssq = fma(v, v, ssq);
         }
-        lines[(long long)b * n + p] = v;
+        lines[(long long)b * n + pv[it]] = v;
       }
     }
     if (partial) {
