@@ -279,6 +279,20 @@ module tfx_c_api
       integer(c_int) :: rc
     end function
 
+    ! Keeps the grid on the device for the following assembly calls that pass the same arrays (both problems of a joint
+    ! inversion read the same grid_full, sensitivity_gravmag.F90:82-177).
+    function tfx_grid_pin(ncells, X1, X2, Y1, Y2, Z1, Z2) bind(C, name="tfx_grid_pin") result(rc)
+      import :: c_int, c_int32_t, c_double
+      integer(c_int32_t), value :: ncells
+      real(c_double), intent(in) :: X1(*), X2(*), Y1(*), Y2(*), Z1(*), Z2(*)
+      integer(c_int) :: rc
+    end function
+
+    function tfx_grid_unpin() bind(C, name="tfx_grid_unpin") result(rc)
+      import :: c_int
+      integer(c_int) :: rc
+    end function
+
     function tfx_sensit_assemble_rows(rows, par, X1, X2, Y1, Y2, Z1, Z2, data_X, data_Y, data_Z, &
                                       column_weight_full, data_weight, myrank, nbproc, sensit_nnz, comp_error, nnz_total) &
         bind(C, name="tfx_sensit_assemble_rows") result(rc)

@@ -191,6 +191,52 @@ __global__ void __launch_bounds__(256) k_sel_hist(const double *__restrict__ lin
     if (sh[i]) atomicAdd(&h[i], sh[i]);
 }
 
+// The two passes every line goes through (digits = bits 62..51 and 50..39), specialised: both digits and the prefix
+// test live in the HIGH word of the double, and the first pass needs no prefix test at all (ncu on the generic kernel:
+// issue slots 72 % busy, 64-bit shifts and compares). Same histogram as k_sel_hist(shift = 51 / 39, bits = 12).
+template <int PASS>
+__global__ void __launch_bounds__(256) k_sel_hist12(const double *__restrict__ lines, int n, const LineSel *__restrict__ sel,
+                                                     unsigned *__restrict__ hist) {
+  __shared__ unsigned sh[kSelBins];
+  const LineSel ls = sel[blockIdx.y];
+  if (ls.mode != 0) return;
+  for (int i = threadIdx.x; i < kSelBins; i += 256) sh[i] = 0u;
+  __syncthreads();
+  const double *line = lines + (size_t)blockIdx.y * n;
+  const unsigned p12 = (unsigned)(ls.prefix >> 51);
+  const int stride = gridDim.x * 256;
+  const long long step = 4LL * stride;
+  const long long nround = ((long long)n + step - 1) / step * step;   // whole warps stay together for the ballots
+  for (long long i0 = blockIdx.x * 256 + threadIdx.x; i0 < nround; i0 += step) {
+    unsigned hi[4];
+    bool in[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = i0 + (long long)j * stride;
+      in[j] = i < n;
+      hi[j] = in[j] ? ((unsigned)__double2hiint(line[i]) & 0x7fffffffu) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (PASS == 1) {
+        // the digits cluster (exponents): the lanes that share lane 0's digit are counted with one ballot (a line of
+        // equal values would otherwise serialise 32-fold), the rest add singly
+        const unsigned bin = hi[j] >> 19;
+        const unsigned b0 = __shfl_sync(0xffffffffu, bin, 0);
+        const unsigned same = __ballot_sync(0xffffffffu, in[j] && bin == b0);
+        if ((threadIdx.x & 31) == 0 && same) atomicAdd(&sh[b0], __popc(same));
+        if (in[j] && bin != b0) atomicAdd(&sh[bin], 1u);
+      } else {
+        if (in[j] && (hi[j] >> 19) == p12) atomicAdd(&sh[(hi[j] >> 7) & 0xfffu], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  unsigned *h = hist + (size_t)blockIdx.y * kSelBins;
+  for (int i = threadIdx.x; i < kSelBins; i += 256)
+    if (sh[i]) atomicAdd(&h[i], sh[i]);
+}
+
 // One CTA per line: the digit that holds the wanted rank; the bucket shrinks to that digit. hist is zeroed for reuse.
 __global__ void __launch_bounds__(256) k_sel_pick(LineSel *sel, unsigned *__restrict__ hist, int shift, int bits) {
   __shared__ unsigned sh[kSelBins];
@@ -663,9 +709,9 @@ int assemble_rows_device(const tfx_sensit_params &P, const GridDev &g, const dou
       if (!no_select) {
         k_sel_init<<<gl, 256, 0, st>>>(dsel.p, rank, nseg_b, (unsigned)N);
         // top 24 bits with two passes over the line, candidates, the low 39 bits on the candidates
-        k_sel_hist<<<glines, 256, 0, st>>>(dl.p, N, dsel.p, dhist.p, 51, 12);
+        k_sel_hist12<1><<<glines, 256, 0, st>>>(dl.p, N, dsel.p, dhist.p);
         k_sel_pick<<<nseg_b, 256, 0, st>>>(dsel.p, dhist.p, 51, 12);
-        k_sel_hist<<<glines, 256, 0, st>>>(dl.p, N, dsel.p, dhist.p, 39, 12);
+        k_sel_hist12<2><<<glines, 256, 0, st>>>(dl.p, N, dsel.p, dhist.p);
         k_sel_pick<<<nseg_b, 256, 0, st>>>(dsel.p, dhist.p, 39, 12);
         k_sel_collect<<<glines, 256, 0, st>>>(dl.p, N, dsel.p, dcand.p, candcap, 39);
         k_sel_finish<<<nseg_b, 256, 0, st>>>(dsel.p, dcand.p, candcap, 39);
