@@ -10,12 +10,12 @@ for (nx, ny, nz) in ((256, 256, 64), (512, 512, 128), (1024, 1024, 128)):
     N = nx * ny * nz
     vol = tfx.Buffer(N)
     tfx.copy(vol, rng.uniform(-1, 1, N), N)
-    for slab, tile, fuse in ((0, 0, 0), (0, 0, 1)):
+    for slab, tile, fuse in ((0, 0, 0), (0, 0, 1), (0, 32, 1), (0, 128, 1)):
         tfx.set_option("wavelet_slab_mb", slab)
         tfx.set_option("wavelet_tile_kb", tile)
         tfx.set_option("wavelet_fuse12", fuse)
         for wname, wtype in (("haar", 1), ("d4", 2)):
-            if wtype == 2 and fuse == 0:
+            if wtype == 2 and (fuse == 0 or tile != 0):
                 continue
             for _ in range(2):
                 tfx.forward_wavelet(vol, nx, ny, nz, wtype); tfx.inverse_wavelet(vol, nx, ny, nz, wtype)

@@ -145,3 +145,55 @@ def test_joint_blocked_matrix_part_products(blocks_on, t16):
         # a window that spans both problems cannot be served from one nelements-sized x: loud error, no wild read
         with pytest.raises(tfx.TfxError, match="outside"):
             Sb.part_mult_vector(rng.standard_normal(N), g.ndata + 2, 1, 0)
+
+
+def test_dense_row_blocks_match_single_dense_block(oracle):
+    """Uncompressed gravity kernels with more data rows than the register-resident sweep holds (kDenseMaxRows = 10 240)
+    are stored as several dense row blocks (4 B per entry). Option dense_block_rows lowers the block size so that a small
+    problem exercises the path: products, part_mult_vector, calculate_data and the LSQR solve (split path over the blocks)
+    against the single block (fused path) and the oracle."""
+    pb = make_problem(nx=10, ny=9, nz=5, ndata=50, compression_type=0)
+    S1, nnz1, _, tot1 = tfx.calculate_sensit(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+    try:
+        tfx.set_option("dense_block_rows", 16)
+        Sb, nnzb, _, totb = tfx.calculate_sensit(pb.par, pb.grid, pb.data_xyz, pb.cw, pb.dw)
+    finally:
+        tfx.set_option("dense_block_rows", 0)
+    assert S1.storage_kind() == 1 and Sb.storage_kind() == 1
+    assert tot1 == totb == pb.ndata * pb.N and np.array_equal(nnz1, nnzb)
+    assert Sb.device_bytes() >= 4 * pb.ndata * pb.N
+    So = pb.oracle_matrix(oracle)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(pb.ncolumns); u = rng.standard_normal(pb.ndata)
+    want = So.mult_vector(x)
+    assert np.array_equal(Sb.mult_vector(x), S1.mult_vector(x))          # same columns per CTA, same order per row
+    assert np.allclose(Sb.mult_vector(x), want, rtol=1e-6, atol=1e-7 * np.abs(want).max())   # f32 values vs the oracle's
+    t1 = S1.trans_mult_vector(u)
+    assert np.allclose(Sb.trans_mult_vector(u), t1, rtol=1e-12, atol=1e-13 * np.abs(t1).max())
+    acc = rng.standard_normal(pb.ncolumns)
+    a1, ab = acc.copy(), acc.copy()
+    S1.add_trans_mult_vector(u, a1); Sb.add_trans_mult_vector(u, ab)
+    assert np.allclose(ab, a1, rtol=1e-12, atol=1e-13 * np.abs(a1).max())
+    accd = rng.standard_normal(pb.ndata)
+    d1, db = accd.copy(), accd.copy()
+    S1.add_mult_vector(x, d1); Sb.add_mult_vector(x, db)
+    assert np.allclose(db, d1, rtol=1e-13, atol=1e-300)
+    xm = rng.standard_normal(pb.N)
+    assert np.allclose(Sb.part_mult_vector(xm, 9, 12, 0), So.part_mult_vector(xm, 9, 12, 0), rtol=1e-6,
+                       atol=1e-7 * np.abs(want).max())
+    d1 = tfx.calculate_data(S1, pb.m_true, pb.ndata, pb.ndc, 1.0, pb.cw, pb.dw, 0, pb.nx, pb.ny, pb.nz)
+    db = tfx.calculate_data(Sb, pb.m_true, pb.ndata, pb.ndc, 1.0, pb.cw, pb.dw, 0, pb.nx, pb.ny, pb.nz)
+    assert np.allclose(db, d1, rtol=1e-13, atol=1e-300)
+    b = S1.mult_vector(rng.standard_normal(pb.ncolumns))
+    out = []
+    for S in (S1, Sb):
+        uu = b.copy(); xx = np.zeros(pb.ncolumns)
+        tfx.lsqr_solve(len(uu), pb.ncolumns, 25, 1e-13, 0.0, S, uu, xx)
+        h, it, fused = tfx.last_history()
+        out.append((h, it, xx, fused))
+    assert out[0][3] == 1 and out[1][3] == 0                              # fused sweep vs split path over the blocks
+    assert out[0][1] == out[1][1]
+    n = min(10, len(out[0][0]))
+    assert np.allclose(out[1][0][:n], out[0][0][:n], rtol=1e-9)
+    # (25 LSQR iterations amplify the last-bit differences of the two summation orders)
+    assert np.allclose(out[1][2], out[0][2], rtol=1e-4, atol=1e-5 * np.abs(out[0][2]).max())

@@ -262,6 +262,19 @@ int matrix_fwd(Matrix &m, const double *d_x, double *d_y, bool accumulate, int32
   }
   if (m.has_t16) return t16_spmv(m.t16f, d_x, d_y, accumulate, xshift, d_done, st);
   if (m.has_seg) return seg_spmv(m.fwd, d_x, d_y, accumulate, 0, m.nl, xshift, d_done, st);
+  if (m.has_dense) {
+    // a dense row block (uncompressed kernels with more than kDenseMaxRows data rows are stored as several):
+    // the forward-only mode of the sweep, x read at column - xshift
+    if (!accumulate)
+      return dense_sweep(m.dense, DENSE_F_ONLY, nullptr, d_x - xshift, nullptr, nullptr, nullptr, d_y + m.dense_row0, nullptr,
+                         d_done, st);
+    DevBuf<double> tmp;   // (add_mult_vector through the API: never inside the LSQR loop)
+    TFX_TRY(tmp.alloc((size_t)m.dense.nrows));
+    TFX_TRY(dense_sweep(m.dense, DENSE_F_ONLY, nullptr, d_x - xshift, nullptr, nullptr, nullptr, tmp.p, nullptr, d_done, st));
+    TFX_TRY(vec_add_inplace(d_y + m.dense_row0, tmp.p, (size_t)m.dense.nrows, st));
+    TFX_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
   return fail(-21, "sparse_matrix: no compressed device representation");
 }
 int matrix_trans(Matrix &m, const double *d_u, double *d_y, bool accumulate, const int *d_done, cudaStream_t st) {
@@ -273,6 +286,12 @@ int matrix_trans(Matrix &m, const double *d_u, double *d_y, bool accumulate, con
   }
   if (m.has_t16) return t16_spmv(m.t16t, d_u, d_y, accumulate, 0, d_done, st);
   if (m.has_seg) return seg_spmv(m.trn, d_u, d_y, accumulate, 0, m.ncolumns, 0, d_done, st);
+  if (m.has_dense) {
+    // the sweep writes the block's own columns only: the others are zero unless accumulating
+    if (!accumulate) TFX_CUDA(cudaMemsetAsync(d_y, 0, (size_t)m.ncolumns * 8, st));
+    return dense_sweep(m.dense, DENSE_T_ONLY, d_u + m.dense_row0, nullptr, nullptr, d_y, nullptr, nullptr, nullptr, d_done, st,
+                       true);
+  }
   return fail(-21, "sparse_matrix: no compressed device representation");
 }
 
@@ -326,6 +345,7 @@ int64_t tfx_sparse_matrix_device_bytes(const tfx_matrix *h) {
     for (const Matrix *blk : m.blocks) {
       if (blk->has_seg) b += (blk->fwd.nnz + blk->trn.nnz) * 8 + ((int64_t)blk->fwd.nseg + blk->trn.nseg) * 12;
       if (blk->has_t16) b += blk->t16f.bytes() + blk->t16t.bytes();
+      if (blk->has_dense) b += (int64_t)blk->dense.ld * blk->dense.ncols * 4;
     }
     return b;
   }
@@ -418,6 +438,11 @@ int tfx_set_option(const char *name, int value) {
   }
   if (name && strcmp(name, "sensit_row_blocks") == 0) {
     g_opt_sensit_row_blocks = value;
+    return 0;
+  }
+  if (name && strcmp(name, "dense_block_rows") == 0) {
+    if (value < 0 || value > kDenseMaxRows) return fail(-4, "dense_block_rows must be in [0, kDenseMaxRows] (0: kDenseMaxRows)");
+    g_opt_dense_block_rows = value;
     return 0;
   }
   if (name && strcmp(name, "trace") == 0) {
@@ -662,6 +687,9 @@ int64_t tfx_sparse_matrix_get_nnz(const tfx_matrix *h) { return h->m.nnz; }
 int tfx_sparse_matrix_storage_kind(const tfx_matrix *h) {
   const Matrix &m = h->m;
   if (m.has_blocks) {
+    bool all_dense = !m.blocks.empty();
+    for (const Matrix *b : m.blocks) all_dense = all_dense && b->has_dense;
+    if (all_dense) return 1;
     for (const Matrix *b : m.blocks) if (!b->has_t16) return 0;
     return m.blocks.empty() ? 0 : 2;
   }
@@ -804,6 +832,14 @@ int tfx_sparse_matrix_part_mult_vector(tfx_matrix *h, int32_t nelements, const d
         TFX_CUDA(cudaMemcpyAsync(dst, full.p + (lo - r0), (size_t)(hi - lo) * 8, cudaMemcpyDeviceToDevice, st));
       } else if (B.has_seg) {
         TFX_TRY(seg_spmv(B.fwd, vx.dev, dst, false, lo - r0, hi - r0, param_shift, nullptr, st));
+      } else if (B.has_dense) {
+        if (B.dense.col0 < param_shift || (int64_t)B.dense.col0 - param_shift + B.dense.ncols > nelements)
+          return fail(-24, "part_mult_vector: a row block inside the requested lines holds columns outside "
+                           "[param_shift, param_shift + nelements)");
+        TFX_TRY(full.alloc((size_t)B.nl));
+        TFX_TRY(dense_sweep(B.dense, DENSE_F_ONLY, nullptr, vx.dev - param_shift, nullptr, nullptr, nullptr, full.p, nullptr,
+                            nullptr, st));
+        TFX_CUDA(cudaMemcpyAsync(dst, full.p + (lo - r0), (size_t)(hi - lo) * 8, cudaMemcpyDeviceToDevice, st));
       } else {
         return fail(-21, "sparse_matrix: row block without a device representation");
       }

@@ -93,6 +93,7 @@ struct DenseArgs {
   unsigned col_bytes;    // bytes of one column in global memory and in a ring slot (ld * 4)
   unsigned ring_bytes;   // ns * col_bytes + zeroed guard so that row index K*1024-1 is always readable
   const int *done;
+  int accumulate;        // DENSE_T_ONLY: out[j] += t_j (row blocks after the first one) instead of out[j] = t_j
 };
 
 // Sum of `a` over the warp for column 0 and of `b` for column 1 with ONE transposed butterfly:
@@ -267,8 +268,14 @@ __global__ void __launch_bounds__(NT, 1) dense_sweep_kernel(DenseArgs a) {
         x1 = t1;
       }
       if (t == 0) {
-        a.out[a.col0 + c_lo + j0] = x0;
-        if (two) a.out[a.col0 + c_lo + j0 + 1] = x1;
+        double *o = a.out + a.col0 + c_lo + j0;
+        if (MODE == DENSE_T_ONLY && a.accumulate) {
+          o[0] += x0;
+          if (two) o[1] += x1;
+        } else {
+          o[0] = x0;
+          if (two) o[1] = x1;
+        }
       }
     }
 
@@ -420,7 +427,7 @@ static int launch_kf(DenseMode mode, const DenseArgs &a, int grid, size_t smem, 
 int g_opt_dense_vec4 = 1;
 
 int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v, const double *d_g, double *d_out,
-                const double *d_nbeta, double *d_q, double *d_n2, const int *d_done, cudaStream_t st) {
+                const double *d_nbeta, double *d_q, double *d_n2, const int *d_done, cudaStream_t st, bool accumulate) {
   Context &c = ctx();
   if (S.empty()) return 0;
   if (S.nrows > kDenseMaxRows)
@@ -451,6 +458,7 @@ int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v
   a.u = d_u; a.v = d_v; a.g = d_g; a.out = d_out; a.nbeta = d_nbeta;
   a.partial_q = S.partial_q.p; a.partial_n2 = S.partial_n2.p;
   a.ns = ns; a.col_bytes = col_bytes; a.ring_bytes = (unsigned)ring_bytes; a.done = d_done;
+  a.accumulate = (mode == DENSE_T_ONLY && accumulate) ? 1 : 0;
   const bool fast = S.fastcvt_ok == 1;
   int rc;
   if (wide) {

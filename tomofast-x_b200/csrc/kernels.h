@@ -146,7 +146,8 @@ static const int kDenseMaxRows = 10240;  // register-resident u / q: 20 rows per
 // q (nrows) and n2 (1) are written (not accumulated) by the trailing reduction kernel.
 int dense_sweep(DenseCM &S, DenseMode mode, const double *d_u, const double *d_v, const double *d_g,
                 double *d_out, const double *d_nbeta, double *d_q, double *d_n2, const int *d_done,
-                cudaStream_t st);
+                cudaStream_t st, bool accumulate = false);   // accumulate: DENSE_T_ONLY adds to d_out
+extern int g_opt_dense_block_rows;   // rows per dense row block (<= kDenseMaxRows; tests lower it)
 
 // ---- assembly.cu ------------------------------------------------------------------------------
 struct GridDev {

@@ -865,6 +865,7 @@ int matrix_append_triplets(Matrix &M, RowTriplets &R, int32_t nrows, int32_t nco
   return 0;
 }
 
+int g_opt_dense_block_rows = 0;    // 0: kDenseMaxRows
 int g_opt_sensit_cand_cap = 0;     // 0: kCandCap
 int g_opt_sensit_row_blocks = 0;   // 1: tfx_sensit_repartition_into / read_sensitivity_kernel_into build one row block per call
 
@@ -1165,20 +1166,41 @@ extern "C" int tfx_calculate_sensit(tfx_matrix **out, const tfx_sensit_params *p
   M.device_only = true;
   M.nl = nl; M.nl_current_all = nl; M.ncolumns = P.ncolumns;
 
-  // ------------------------------------------------------------------ uncompressed gravity: dense block
-  if (P.compression_type == 0 && P.problem_type == 1 && P.data_type == 1 && ndc == 1 && nmc == 1 &&
-      P.ndata <= kDenseMaxRows) {
+  // ------------------------------------------------------------------ uncompressed gravity: dense block(s)
+  if (P.compression_type == 0 && P.problem_type == 1 && P.data_type == 1 && ndc == 1 && nmc == 1) {
     const int32_t ncl = P.ncells_local > 0 ? P.ncells_local : N;
     if (P.cell0 < 0 || P.cell0 + ncl > N) { delete h; return fail(-77, "calculate_sensit: wrong local cell range"); }
-    int rc = assemble_grav_dense(M.dense, g, P.cell0, ncl, P.ndata, dx.p, dy.p, dz.p, dcw.p, ddw.p, P.problem_weight,
-                                 derr.p, st);
-    if (rc) { delete h; return rc; }
-    int e = 0;
-    TFX_CUDA(cudaMemcpyAsync(&e, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    TFX_CUDA(cudaStreamSynchronize(st));
-    if (e) { delete h; return kernel_error(e); }
-    M.dense.col0 = P.param_shift;   // local columns 1..nelements of this rank, shifted for the problem
-    M.has_dense = true; M.dense_row0 = 0;
+    // One block of <= kDenseMaxRows stations feeds the fused single-sweep LSQR path; more stations become several dense
+    // row blocks (4 B per entry each, split-path LSQR: one transposed and one forward sweep per block and iteration).
+    const int32_t brows = (g_opt_dense_block_rows > 0) ? g_opt_dense_block_rows : kDenseMaxRows;
+    const int32_t nblk = (P.ndata + brows - 1) / brows;
+    for (int32_t bi = 0; bi < nblk; ++bi) {
+      const int32_t r0 = bi * brows, nr = std::min(brows, P.ndata - r0);
+      Matrix *B = (nblk == 1) ? &M : new Matrix();
+      int rc = assemble_grav_dense(B->dense, g, P.cell0, ncl, nr, dx.p + r0, dy.p + r0, dz.p + r0, dcw.p, ddw.p + r0,
+                                   P.problem_weight, derr.p, st);
+      int e = 0;
+      if (!rc && cudaMemcpyAsync(&e, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -100;
+      if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(-100, "calculate_sensit: dense assembly failed");
+      if (!rc && e) rc = kernel_error(e);
+      if (rc) {
+        if (nblk > 1) delete B;
+        delete h;
+        return rc;
+      }
+      B->dense.col0 = P.param_shift;   // local columns 1..nelements of this rank, shifted for the problem
+      B->has_dense = true; B->dense_row0 = 0;
+      B->nnz = B->nel = (int64_t)nr * ncl;
+      B->finalized = true;
+      if (nblk > 1) {
+        B->device_only = true;
+        B->nl = B->nl_current_all = B->nl_nonempty = nr;
+        B->ncolumns = P.ncolumns;
+        M.blocks.push_back(B);
+        M.block_row0.push_back(r0);
+        M.has_blocks = true;
+      }
+    }
     M.nnz = M.nel = (int64_t)P.ndata * ncl;
     M.nl_nonempty = nl;
     M.finalized = true;

@@ -534,12 +534,13 @@ int g_opt_wavelet_cols = 1;   // 0: always the generic (line, pair) kernel
 int g_opt_wavelet_tile_kb = 0;   // 0: automatic (32 KB tiles, 64 KB for axes longer than 256)
 
 // Columns (lines) per CTA of the column-layout kernel for lines of length L; 0: the axis does not fit any tile.
-static int cols_tile(int L, bool transpose, long long inner) {
+static int cols_tile(int L, bool transpose, long long inner, bool fuse = false) {
   if (!g_opt_wavelet_cols || L < 2) return 0;
   // the largest power of two in [8, 256] whose tile stays within the budget (small tiles: many CTAs per SM in different
   // phases -- load / lift / store -- keep the memory pipeline busy)
   // measured (512x512x128 Haar): 16 KB tiles 0.51 ms, 32 KB 0.46 ms, 64 KB 0.39 ms; 256x256x64: 0.086 / 0.075 / 0.078 ms
-  const size_t budget = (g_opt_wavelet_tile_kb > 0 ? (size_t)std::max(8, g_opt_wavelet_tile_kb) : (L > 256 ? 64 : 32)) * 1024;
+  // fused Haar kernel (512x512x128): 64 KB tiles 0.295 ms per transform, 32 KB 0.281 ms, 128 KB 0.50 ms
+  const size_t budget = (g_opt_wavelet_tile_kb > 0 ? (size_t)std::max(8, g_opt_wavelet_tile_kb) : ((L > 256 && !fuse) ? 64 : 32)) * 1024;
   int NC = 256;
   while (NC > 8 && (size_t)L * NC * sizeof(double) > budget) NC >>= 1;
   if ((size_t)L * (NC + 1) * sizeof(double) > 140 * 1024) return 0;   // axis too long for any tile: generic kernel
@@ -551,7 +552,7 @@ static int cols_tile(int L, bool transpose, long long inner) {
 // the fused kernel, n2 / nscale2 / skip0 filled in by the caller; NC, pitch, tpp here).
 template <int TYPE, bool FWD>
 static int launch_cols_geom(double *d_s, ColsGeom G, bool transpose, bool fuse, long long nplanes, cudaStream_t st) {
-  const int NC = cols_tile(G.L, transpose, G.inner);
+  const int NC = cols_tile(G.L, transpose, G.inner, fuse);
   if (NC == 0) return fail(-23, "wavelet: internal error (column kernel launched on an axis that does not fit)");
   G.NC = NC;
   G.pitch = transpose ? NC + 1 : NC;
