@@ -294,11 +294,18 @@ def dist_sensit_case(rank, world, td, niter):
     rng = np.random.default_rng(11)
     vol = rng.standard_normal(N)
     mine = vol[cell0:cell0 + ncl].copy()
-    tfx.apply_wavelet_transform(ncl, pb.nx, pb.ny, pb.nz, 1, mine, True, 1, 1, [1], rank, world)
     want_w = orc.forward_wavelet(vol.copy(), pb.nx, pb.ny, pb.nz, 1)
-    assert np.array_equal(mine, want_w[cell0:cell0 + ncl]), "distributed Haar must be bit-identical to the serial one"
-    tfx.apply_wavelet_transform(ncl, pb.nx, pb.ny, pb.nz, 1, mine, False, 1, 1, [1], rank, world)
-    assert np.array_equal(mine, orc.inverse_wavelet(want_w.copy(), pb.nx, pb.ny, pb.nz, 1)[cell0:cell0 + ncl])
+    want_i = orc.inverse_wavelet(want_w.copy(), pb.nx, pb.ny, pb.nz, 1)
+    # the layout changes through peer memory (cudaIpc, default), through NCCL send/recv, and the all-gather fallback;
+    # twice each (the second transform re-uses the mapped buffers: ordering between consecutive transforms)
+    for p2p, dist in ((1, 1), (1, 1), (0, 1), (0, 0), (1, 1)):
+        tfx.set_option("wavelet_p2p", p2p); tfx.set_option("wavelet_dist", dist)
+        mine = vol[cell0:cell0 + ncl].copy()
+        tfx.apply_wavelet_transform(ncl, pb.nx, pb.ny, pb.nz, 1, mine, True, 1, 1, [1], rank, world)
+        assert np.array_equal(mine, want_w[cell0:cell0 + ncl]), "distributed Haar must be bit-identical to the serial one"
+        tfx.apply_wavelet_transform(ncl, pb.nx, pb.ny, pb.nz, 1, mine, False, 1, 1, [1], rank, world)
+        assert np.array_equal(mine, want_i[cell0:cell0 + ncl])
+    tfx.set_option("wavelet_p2p", 1); tfx.set_option("wavelet_dist", 1)
     dwt = np.linspace(0.5, 1.5, ndata).reshape(ndata, 1)
     d_got = tfx.calculate_data(S, pb.m_true[:, cell0:cell0 + ncl], ndata, 1, 1.0, pb.cw[cell0:cell0 + ncl], dwt, 1,
                                pb.nx, pb.ny, pb.nz, 1, 0, rank, world)

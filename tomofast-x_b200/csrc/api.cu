@@ -400,6 +400,10 @@ int tfx_set_option(const char *name, int value) {
     g_opt_wavelet_cols = value;
     return 0;
   }
+  if (name && strcmp(name, "wavelet_p2p") == 0) {
+    g_opt_wavelet_p2p = value;
+    return 0;
+  }
   if (name && strcmp(name, "wavelet_fuse12") == 0) {
     g_opt_wavelet_fuse12 = value;
     return 0;
@@ -481,7 +485,10 @@ int tfx_set_option(const char *name, int value) {
 // ---- communicator -------------------------------------------------------------------------------
 int tfx_comm_unique_id(char id[128]) { return comm_unique_id(id); }
 int tfx_comm_init(int nranks, int rank, const char id[128]) { return comm_init(nranks, rank, id); }
-int tfx_comm_finalize(void) { return comm_finalize(); }
+int tfx_comm_finalize(void) {
+  wavelet_peer_reset();
+  return comm_finalize();
+}
 int tfx_comm_allreduce_sum(double *buf, int64_t count) {
   TFX_TRY(ensure_init());
   VecIO v;

@@ -3,6 +3,8 @@
 // the device so the model never leaves HBM between solves.
 #include "../../include/tfx.h"
 
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -58,6 +60,171 @@ DistBufs &dist_bufs() {
 inline int64_t clampi(int64_t v, int64_t lo, int64_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Peer-memory exchange (r2). The two layout changes of the distributed transform move ~V/N doubles per GPU each; through
+// grouped ncclSend/ncclRecv they went pack (strided copy into a staging buffer) -> NCCL -> unpack. Here every rank's A, B
+// and staging buffers are mapped into all the other processes (cudaIpc over NVLink / NVSwitch peer access) and ONE kernel
+// per layout change reads the local layout and stores straight into the peers' buffers at their final places -- pack,
+// transfer and unpack in the same pass, all NVLinks busy at once. Ordering between the ranks: a one-element all-reduce on
+// the stream after each exchange (every rank's stores are complete when its kernel is, and nobody leaves the collective
+// before everybody entered it). Falls back to the NCCL path when IPC mapping is not available.
+// ---------------------------------------------------------------------------------------------------------------------
+int g_opt_wavelet_p2p = 1;
+
+namespace {
+const int kMaxPeers = 16;
+struct PeerPtrs {
+  double *p[kMaxPeers];
+};
+struct PeerState {
+  bool failed = false;                 // IPC not available: NCCL path from now on
+  int nr = 0;
+  std::vector<size_t> capA, capB, capS; // capacities (doubles) of EVERY rank's buffers: the same numbers on all ranks
+  DevBuf<double> A, B, S, flag;
+  PeerPtrs pA, pB, pS;                  // pX.p[r]: rank r's buffer in this process (own buffer for r == me)
+  bool mapped = false;
+};
+PeerState &peer_state() {
+  static PeerState s;
+  return s;
+}
+
+void peer_unmap(PeerState &P, int me) {
+  if (!P.mapped) return;
+  for (int r = 0; r < P.nr; ++r) {
+    if (r == me) continue;
+    if (P.pA.p[r]) cudaIpcCloseMemHandle(P.pA.p[r]);
+    if (P.pB.p[r]) cudaIpcCloseMemHandle(P.pB.p[r]);
+    if (P.pS.p[r]) cudaIpcCloseMemHandle(P.pS.p[r]);
+    P.pA.p[r] = P.pB.p[r] = P.pS.p[r] = nullptr;
+  }
+  P.mapped = false;
+}
+
+// Makes sure every rank's buffers hold needX[r] doubles and are mapped everywhere. All ranks call this with the same
+// arguments (they all know the whole plan), so they agree on when buffers are re-allocated and handles re-exchanged.
+int peer_ensure(PeerState &P, const std::vector<size_t> &needA, const std::vector<size_t> &needB,
+                const std::vector<size_t> &needS, int me, int nr, cudaStream_t st) {
+  if (P.failed || nr > kMaxPeers) return 1;
+  if (P.nr != nr) {
+    peer_unmap(P, me);
+    P.nr = nr;
+    P.capA.assign((size_t)nr, 0); P.capB.assign((size_t)nr, 0); P.capS.assign((size_t)nr, 0);
+  }
+  bool grow = !P.mapped;
+  for (int r = 0; r < nr; ++r)
+    if (needA[r] > P.capA[r] || needB[r] > P.capB[r] || needS[r] > P.capS[r]) grow = true;
+  if (!grow) return 0;
+  TFX_CUDA(cudaStreamSynchronize(st));
+  peer_unmap(P, me);
+  for (int r = 0; r < nr; ++r) {
+    P.capA[r] = std::max(P.capA[r], needA[r]); P.capB[r] = std::max(P.capB[r], needB[r]);
+    P.capS[r] = std::max(P.capS[r], needS[r]);
+  }
+  // every rank has passed its last use of the old buffers before any of them is freed
+  TFX_TRY(P.flag.alloc(8));
+  TFX_CUDA(cudaMemsetAsync(P.flag.p, 0, 64, st));
+  TFX_TRY(comm_allreduce_sum(P.flag.p, 1, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  P.A.release(); P.B.release(); P.S.release();
+  TFX_TRY(P.A.alloc(P.capA[me])); TFX_TRY(P.B.alloc(P.capB[me])); TFX_TRY(P.S.alloc(P.capS[me]));
+  // handles: 3 x 64 bytes per rank, all-gathered as int64
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  int64_t mine[24];
+  cudaIpcMemHandle_t h[3];
+  int bad = 0;
+  if (cudaIpcGetMemHandle(&h[0], P.A.p) != cudaSuccess || cudaIpcGetMemHandle(&h[1], P.B.p) != cudaSuccess ||
+      cudaIpcGetMemHandle(&h[2], P.S.p) != cudaSuccess) {
+    cudaGetLastError();
+    bad = 1;
+    memset(h, 0, sizeof(h));
+  }
+  memcpy(mine, h, sizeof(h));
+  DevBuf<int64_t> dmine, dall;
+  TFX_TRY(dmine.alloc(24)); TFX_TRY(dall.alloc((size_t)24 * nr));
+  TFX_CUDA(cudaMemcpyAsync(dmine.p, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  TFX_TRY(comm_allgather_i64(dmine.p, dall.p, 24, st));
+  std::vector<int64_t> all((size_t)24 * nr);
+  TFX_CUDA(cudaMemcpyAsync(all.data(), dall.p, all.size() * 8, cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r < nr; ++r) P.pA.p[r] = P.pB.p[r] = P.pS.p[r] = nullptr;
+  P.pA.p[me] = P.A.p; P.pB.p[me] = P.B.p; P.pS.p[me] = P.S.p;
+  for (int r = 0; r < nr && !bad; ++r) {
+    if (r == me) continue;
+    cudaIpcMemHandle_t hr[3];
+    memcpy(hr, all.data() + (size_t)24 * r, sizeof(hr));
+    void *a = nullptr, *b = nullptr, *c = nullptr;
+    if (cudaIpcOpenMemHandle(&a, hr[0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&b, hr[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&c, hr[2], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      bad = 1;
+    }
+    P.pA.p[r] = (double *)a; P.pB.p[r] = (double *)b; P.pS.p[r] = (double *)c;
+  }
+  P.mapped = true;
+  // everybody maps or nobody uses the path
+  double hb = bad ? 1.0 : 0.0;
+  TFX_CUDA(cudaMemcpyAsync(P.flag.p, &hb, 8, cudaMemcpyHostToDevice, st));
+  TFX_TRY(comm_allreduce_sum(P.flag.p, 1, st));
+  TFX_CUDA(cudaMemcpyAsync(&hb, P.flag.p, 8, cudaMemcpyDeviceToHost, st));
+  TFX_CUDA(cudaStreamSynchronize(st));
+  if (hb != 0.0) {
+    peer_unmap(P, me);
+    P.failed = true;
+    return 1;
+  }
+  return 0;
+}
+
+}  // namespace
+// Drops the mappings of the other processes' buffers (before the communicator goes away).
+void wavelet_peer_reset() {
+  PeerState &P = peer_state();
+  peer_unmap(P, comm_rank());
+  P.A.release(); P.B.release(); P.S.release();
+  P.nr = 0;
+  P.failed = false;
+}
+namespace {
+int peer_barrier(PeerState &P, cudaStream_t st) { return comm_allreduce_sum(P.flag.p + 1, 1, st); }
+
+// Layout A -> layout B of every rank: rank q receives the columns [pa[q], pa[q+1]) of my nk planes as the rows
+// ka_me .. ka_me + nk of its B (row length W_q). blockIdx.z = q, blockIdx.y = plane, x over the columns.
+struct ScatterArgs {
+  PeerPtrs dst;
+  long long pa[kMaxPeers + 1];
+  long long plane, ka_me;
+  int nk, nr;
+};
+__global__ void __launch_bounds__(256) k_scatter_columns(const double *__restrict__ A, ScatterArgs a) {
+  const int q = blockIdx.z;
+  const long long p0 = a.pa[q], W = a.pa[q + 1] - p0;
+  double *dst = a.dst.p[q];
+  for (long long k = blockIdx.y; k < a.nk; k += gridDim.y) {
+    const double *src = A + k * a.plane + p0;
+    double *d = dst + (a.ka_me + k) * W;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < W; i += 256LL * gridDim.x) d[i] = src[i];
+  }
+}
+// Layout B -> the slabs: the cells of slab q inside my columns are one contiguous range [b0[q], b1[q]) of my B; they go
+// to rank q's staging buffer at offset roff[q] (where rank q's unpack expects what comes from me). q == me is skipped
+// (unpacked straight from B).
+struct RangeArgs {
+  PeerPtrs dst;
+  long long b0[kMaxPeers], cnt[kMaxPeers], roff[kMaxPeers];
+  int nr, me;
+};
+__global__ void __launch_bounds__(256) k_scatter_ranges(const double *__restrict__ B, RangeArgs a) {
+  const int q = blockIdx.y;
+  if (q == a.me) return;
+  const double *src = B + a.b0[q];
+  double *d = a.dst.p[q] + a.roff[q];
+  const long long n = a.cnt[q];
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) d[i] = src[i];
+}
+}  // namespace
+
 // Distributed 3-D transform of a volume held as contiguous cell slabs (i fastest, then j, then k; slab r = cells
 // [off[r], off[r+1])), WITHOUT assembling the volume anywhere:
 //   layout A: rank r holds the complete k-planes whose first cell lies in its slab -> the axis-1 and axis-2 passes are
@@ -89,48 +256,6 @@ static int wavelet_slab_dist(double *d_slab, const std::vector<int64_t> &off, in
   const int64_t own = off[me + 1] - ka[me] * plane;                // cells of my planes I hold myself
   const int64_t trail = ka[me + 1] * plane - off[me + 1];          // ... and the rest comes from rank me+1
   const int64_t W = pa[me + 1] - pa[me];
-  DistBufs &D = dist_bufs();
-  TFX_TRY(D.A.alloc((size_t)(nk * plane)));
-  TFX_TRY(D.B.alloc((size_t)(n3 * W)));
-  TFX_TRY(D.stage.alloc((size_t)std::max<int64_t>(nk * plane, off[me + 1] - off[me])));
-  std::vector<int64_t> soff((size_t)nr, 0), scnt((size_t)nr, 0), roff((size_t)nr, 0), rcnt((size_t)nr, 0);
-
-  // ---- slabs -> layout A
-  TFX_CUDA(cudaMemcpyAsync(D.A.p, d_slab + lead, (size_t)own * 8, cudaMemcpyDeviceToDevice, st));
-  if (me > 0) { soff[me - 1] = 0; scnt[me - 1] = lead; }
-  if (me + 1 < nr) { roff[me + 1] = own; rcnt[me + 1] = trail; }
-  TFX_TRY(comm_exchange_f64(d_slab, soff.data(), scnt.data(), D.A.p, roff.data(), rcnt.data(), st));
-
-  // ---- axes 1 and 2 on my planes
-  TFX_TRY(wavelet_axis_device(D.A.p, nx, 1, (long long)ny * nk, wavelet_type, forward, st));
-  TFX_TRY(wavelet_axis_device(D.A.p, ny, nx, nk, wavelet_type, forward, st));
-
-  // ---- A -> B: to rank q the columns [pa[q], pa[q+1]) of my planes (packed); what arrives from rank r are the rows
-  // [ka[r], ka[r+1]) of B, already in place
-  {
-    int64_t pos = 0;
-    for (int q = 0; q < nr; ++q) {
-      const int64_t Wq = pa[q + 1] - pa[q];
-      if (q == me) {
-        TFX_CUDA(cudaMemcpy2DAsync(D.B.p + ka[me] * W, (size_t)W * 8, D.A.p + pa[me], (size_t)plane * 8, (size_t)W * 8,
-                                   (size_t)nk, cudaMemcpyDeviceToDevice, st));
-        scnt[q] = rcnt[q] = 0;
-        continue;
-      }
-      TFX_CUDA(cudaMemcpy2DAsync(D.stage.p + pos, (size_t)Wq * 8, D.A.p + pa[q], (size_t)plane * 8, (size_t)Wq * 8,
-                                 (size_t)nk, cudaMemcpyDeviceToDevice, st));
-      soff[q] = pos; scnt[q] = nk * Wq;
-      pos += nk * Wq;
-      roff[q] = ka[q] * W; rcnt[q] = (ka[q + 1] - ka[q]) * W;
-    }
-    TFX_TRY(comm_exchange_f64(D.stage.p, soff.data(), scnt.data(), D.B.p, roff.data(), rcnt.data(), st));
-  }
-
-  // ---- axis 3 on my columns
-  TFX_TRY(wavelet_axis_device(D.B.p, nz, W, 1, wavelet_type, forward, st));
-
-  // ---- B -> slabs: the cells of slab r inside my columns are ONE contiguous range of B (suffix of the first row, whole
-  // rows, prefix of the last row); the receiver unpacks rows of width W_q at stride `plane`.
   auto range_in = [&](int q, int r, int64_t *b0, int64_t *b1) {     // range of rank q's B that belongs to slab r
     const int64_t Wq = pa[q + 1] - pa[q];
     const int64_t k0 = off[r] / plane, s0 = off[r] - k0 * plane;
@@ -139,6 +264,87 @@ static int wavelet_slab_dist(double *d_slab, const std::vector<int64_t> &off, in
     *b1 = k1 * Wq + clampi(e1, pa[q], pa[q + 1]) - pa[q];
     if (*b1 < *b0) *b1 = *b0;
   };
+  // ---- buffers: mapped into every process (peer-memory exchange) or private (NCCL exchange)
+  PeerState &P = peer_state();
+  bool p2p = false;
+  if (g_opt_wavelet_p2p) {
+    std::vector<size_t> needA((size_t)nr), needB((size_t)nr), needS((size_t)nr);
+    for (int r = 0; r < nr; ++r) {
+      const int64_t nkr = ka[r + 1] - ka[r];
+      needA[r] = (size_t)(nkr * plane);
+      needB[r] = (size_t)(n3 * (pa[r + 1] - pa[r]));
+      needS[r] = (size_t)std::max<int64_t>(nkr * plane, off[r + 1] - off[r]);
+    }
+    const int rc = peer_ensure(P, needA, needB, needS, me, nr, st);
+    if (rc < 0) return rc;
+    p2p = (rc == 0);
+  }
+  DistBufs &D = dist_bufs();
+  if (!p2p) {
+    TFX_TRY(D.A.alloc((size_t)(nk * plane)));
+    TFX_TRY(D.B.alloc((size_t)(n3 * W)));
+    TFX_TRY(D.stage.alloc((size_t)std::max<int64_t>(nk * plane, off[me + 1] - off[me])));
+  }
+  double *const bufA = p2p ? P.A.p : D.A.p, *const bufB = p2p ? P.B.p : D.B.p, *const bufS = p2p ? P.S.p : D.stage.p;
+  std::vector<int64_t> soff((size_t)nr, 0), scnt((size_t)nr, 0), roff((size_t)nr, 0), rcnt((size_t)nr, 0);
+
+  // ---- slabs -> layout A
+  TFX_CUDA(cudaMemcpyAsync(bufA, d_slab + lead, (size_t)own * 8, cudaMemcpyDeviceToDevice, st));
+  if (p2p) {
+    if (me > 0 && lead > 0) {
+      const int64_t own_prev = off[me] - ka[me - 1] * plane;          // cells of rank me-1's planes it holds itself
+      TFX_CUDA(cudaMemcpyAsync(P.pA.p[me - 1] + own_prev, d_slab, (size_t)lead * 8, cudaMemcpyDefault, st));
+    }
+    TFX_TRY(peer_barrier(P, st));
+  } else {
+    if (me > 0) { soff[me - 1] = 0; scnt[me - 1] = lead; }
+    if (me + 1 < nr) { roff[me + 1] = own; rcnt[me + 1] = trail; }
+    TFX_TRY(comm_exchange_f64(d_slab, soff.data(), scnt.data(), bufA, roff.data(), rcnt.data(), st));
+  }
+
+  // ---- axes 1 and 2 on my planes
+  TFX_TRY(wavelet_axis_device(bufA, nx, 1, (long long)ny * nk, wavelet_type, forward, st));
+  TFX_TRY(wavelet_axis_device(bufA, ny, nx, nk, wavelet_type, forward, st));
+
+  // ---- A -> B: to rank q the columns [pa[q], pa[q+1]) of my planes; what arrives from rank r are the rows
+  // [ka[r], ka[r+1]) of B, already in place
+  if (p2p) {
+    ScatterArgs sa;
+    sa.dst = P.pB;
+    int64_t wmax = 0;
+    for (int q = 0; q <= nr; ++q) sa.pa[q] = pa[q];
+    for (int q = 0; q < nr; ++q) wmax = std::max(wmax, pa[q + 1] - pa[q]);
+    sa.plane = plane; sa.ka_me = ka[me]; sa.nk = (int)nk; sa.nr = nr;
+    const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((wmax + 1023) / 1024, 64)),
+                    (unsigned)std::min<int64_t>(nk, 1024), (unsigned)nr);
+    k_scatter_columns<<<grid, 256, 0, st>>>(bufA, sa);
+    ctx().launches++;
+    TFX_CUDA(cudaGetLastError());
+    TFX_TRY(peer_barrier(P, st));
+  } else {
+    int64_t pos = 0;
+    for (int q = 0; q < nr; ++q) {
+      const int64_t Wq = pa[q + 1] - pa[q];
+      if (q == me) {
+        TFX_CUDA(cudaMemcpy2DAsync(bufB + ka[me] * W, (size_t)W * 8, bufA + pa[me], (size_t)plane * 8, (size_t)W * 8,
+                                   (size_t)nk, cudaMemcpyDeviceToDevice, st));
+        scnt[q] = rcnt[q] = 0;
+        continue;
+      }
+      TFX_CUDA(cudaMemcpy2DAsync(bufS + pos, (size_t)Wq * 8, bufA + pa[q], (size_t)plane * 8, (size_t)Wq * 8,
+                                 (size_t)nk, cudaMemcpyDeviceToDevice, st));
+      soff[q] = pos; scnt[q] = nk * Wq;
+      pos += nk * Wq;
+      roff[q] = ka[q] * W; rcnt[q] = (ka[q + 1] - ka[q]) * W;
+    }
+    TFX_TRY(comm_exchange_f64(bufS, soff.data(), scnt.data(), bufB, roff.data(), rcnt.data(), st));
+  }
+
+  // ---- axis 3 on my columns
+  TFX_TRY(wavelet_axis_device(bufB, nz, W, 1, wavelet_type, forward, st));
+
+  // ---- B -> slabs: the cells of slab r inside my columns are ONE contiguous range of B (suffix of the first row, whole
+  // rows, prefix of the last row); the receiver unpacks rows of width W_q at stride `plane`.
   {
     int64_t pos = 0;
     for (int q = 0; q < nr; ++q) {
@@ -149,7 +355,31 @@ static int wavelet_slab_dist(double *d_slab, const std::vector<int64_t> &off, in
       roff[q] = pos; rcnt[q] = (q == me) ? 0 : b1 - b0;
       if (q != me) pos += b1 - b0;
     }
-    TFX_TRY(comm_exchange_f64(D.B.p, soff.data(), scnt.data(), D.stage.p, roff.data(), rcnt.data(), st));
+    if (p2p) {
+      RangeArgs ra;
+      ra.dst = P.pS; ra.nr = nr; ra.me = me;
+      int64_t cmax = 0;
+      for (int q = 0; q < nr; ++q) {
+        ra.b0[q] = soff[q]; ra.cnt[q] = scnt[q];
+        // where rank q expects my piece: behind the pieces of the ranks before me (rank q itself sends nothing)
+        int64_t o = 0;
+        for (int sidx = 0; sidx < me; ++sidx) {
+          if (sidx == q) continue;
+          int64_t b0, b1;
+          range_in(sidx, q, &b0, &b1);
+          o += b1 - b0;
+        }
+        ra.roff[q] = o;
+        cmax = std::max(cmax, scnt[q]);
+      }
+      const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((cmax + 1023) / 1024, 512)), (unsigned)nr);
+      k_scatter_ranges<<<grid, 256, 0, st>>>(bufB, ra);
+      ctx().launches++;
+      TFX_CUDA(cudaGetLastError());
+      TFX_TRY(peer_barrier(P, st));
+    } else {
+      TFX_TRY(comm_exchange_f64(bufB, soff.data(), scnt.data(), bufS, roff.data(), rcnt.data(), st));
+    }
     // unpack (the own block straight from B)
     const int64_t k0 = off[me] / plane, s0 = off[me] - k0 * plane;
     const int64_t k1 = (off[me + 1] - 1) / plane, e1 = off[me + 1] - k1 * plane;
@@ -158,7 +388,7 @@ static int wavelet_slab_dist(double *d_slab, const std::vector<int64_t> &off, in
       int64_t b0, b1;
       range_in(q, me, &b0, &b1);
       if (b1 <= b0) continue;
-      const double *src = (q == me) ? D.B.p + b0 : D.stage.p + roff[q];
+      const double *src = (q == me) ? bufB + b0 : bufS + roff[q];
       int64_t consumed = 0;
       for (int part = 0; part < 3; ++part) {
         // part 0: row k0 (partial), part 1: rows k0+1 .. k1-1 (whole), part 2: row k1 (partial, when k1 > k0)
@@ -176,6 +406,8 @@ static int wavelet_slab_dist(double *d_slab, const std::vector<int64_t> &off, in
         consumed += (nrows > 1 || part == 1) ? nrows * Wq : w;
       }
     }
+    // (peer-memory path: B and the staging buffer are overwritten by the peers' next exchanges only after the barrier
+    // that follows the NEXT transform's first exchange, which every rank enters after this unpack)
   }
   *done = 1;
   g_wavelet_last_dist = 1;

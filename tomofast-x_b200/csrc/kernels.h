@@ -23,6 +23,8 @@ extern int g_opt_wavelet_tile_kb;
 int wavelet_axis_device(double *d_s, int L, long long inner, long long outer, int wavelet_type, bool forward,
                         cudaStream_t st);
 extern int g_opt_wavelet_dist;
+extern int g_opt_wavelet_p2p;   // 1: layout changes of the distributed transform through peer memory (cudaIpc), 0: NCCL
+void wavelet_peer_reset();
 
 // ---- csr.cu -----------------------------------------------------------------------------------
 // A compressed-segment matrix view on the device. For the forward product it is the CSR of A
