@@ -492,8 +492,6 @@ def compressed_spmv(a, tfx, d):
         nb = max(32, fit) * d.world
         if rows_left - nb < 64 * d.world:                          # no crumbs at the end
             nb = rows_left
-        elif rows_left - nb < nb // 2:                             # two blocks left and the last would be small: halve
-            nb = ((rows_left + 1) // 2 + d.world - 1) // d.world * d.world
         return min(nb, rows_left)
     grid = regular_grid(nx, ny, nz)
     xyz = station_lattice(nd, 100.0 * nx, 100.0 * ny, z=-0.1)
