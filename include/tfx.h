@@ -158,7 +158,10 @@ int tfx_wavelet_last_distributed(void);
  * tfx_comm_init) the volume is transformed in place across the GPUs -- axis-1/2 passes on the k-planes a rank owns, one
  * NVLink all-to-all, the axis-3 pass on its share of the k-lines, one all-to-all back (or, when a slab is thinner than a
  * plane: slabs all-gathered on every GPU, transformed, own slab kept) -- the reference's gather to rank 0 / serial
- * transform / scatter (:57-67) without the serial section, bit-identical; model_full is not needed. */
+ * transform / scatter (:57-67) without the serial section, bit-identical; model_full is not needed. The two all-to-all
+ * layout changes go through peer memory when the ranks' buffers can be mapped into each other (cudaIpc over NVLink: one
+ * kernel per exchange stores straight into the peers' buffers), else through grouped ncclSend/ncclRecv (option
+ * "wavelet_p2p" = 0 forces that path). */
 int tfx_apply_wavelet_transform(int32_t nelements, int32_t nx, int32_t ny, int32_t nz, int32_t ncomponents,
                                 double *v, int32_t fwd, int32_t compression_type, int32_t nproblems,
                                 const int32_t *solve_problem, int32_t myrank, int32_t nbproc);

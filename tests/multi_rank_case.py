@@ -488,6 +488,15 @@ def dist_wavelet_model(rank, world, td):
                 return b0, max(b0, b1)
             send = [Bf[slice(*rng_in(me, r))].copy() for r in range(world)]
             td.all_gather_object(allsend, send)
+            # peer-memory path (csrc/data.cu k_scatter_ranges): the SENDER computes where its piece starts in rank r's
+            # staging buffer -- behind the pieces of the ranks before it, rank r itself sending nothing; the receiver
+            # unpacks the pieces in rank order. Both views must agree.
+            for r in range(world):
+                if r == me:
+                    continue
+                sender_off = sum(rng_in(s_, r)[1] - rng_in(s_, r)[0] for s_ in range(me) if s_ != r)
+                recv_off = sum(allsend[s_][r].size for s_ in range(me) if s_ != r)
+                assert sender_off == recv_off, (sender_off, recv_off)
             out = np.full(off[me + 1] - off[me], np.nan)
             k0, k1 = int(off[me]) // plane, (int(off[me + 1]) - 1) // plane
             for q in range(world):
