@@ -177,6 +177,32 @@ int peer_ensure(PeerState &P, const std::vector<size_t> &needA, const std::vecto
   return 0;
 }
 
+// Unpack of the B -> slabs exchange in one launch: the piece of source rank q (blockIdx.y) is the contiguous run
+// [first row from column c0, then whole rows of width W_q from column pa_q, the last row cut short]; element e of it is
+// cell (row, column) of the volume and lands at d_slab[row * plane + column - off_me].
+struct UnpackArgs {
+  const double *src[kMaxPeers];
+  long long cnt[kMaxPeers], w0[kMaxPeers], c0[kMaxPeers], paq[kMaxPeers], Wq[kMaxPeers];
+  long long k0, plane, off_me;
+  int nr;
+};
+__global__ void __launch_bounds__(256) k_unpack_slab(double *__restrict__ slab, UnpackArgs a) {
+  const int q = blockIdx.y;
+  const long long n = a.cnt[q];
+  if (n <= 0) return;
+  const double *src = a.src[q];
+  const long long w0 = a.w0[q], c0 = a.c0[q], paq = a.paq[q], Wq = a.Wq[q];
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += 256LL * gridDim.x) {
+    long long row, col;
+    if (e < w0) {
+      row = a.k0; col = c0 + e;
+    } else {
+      const long long r = (e - w0) / Wq;
+      row = a.k0 + 1 + r; col = paq + (e - w0) - r * Wq;
+    }
+    slab[row * a.plane + col - a.off_me] = src[e];
+  }
+}
 }  // namespace
 // Drops the mappings of the other processes' buffers (before the communicator goes away).
 void wavelet_peer_reset() {
@@ -303,8 +329,7 @@ static int wavelet_slab_dist(double *d_slab, const std::vector<int64_t> &off, in
   }
 
   // ---- axes 1 and 2 on my planes
-  TFX_TRY(wavelet_axis_device(bufA, nx, 1, (long long)ny * nk, wavelet_type, forward, st));
-  TFX_TRY(wavelet_axis_device(bufA, ny, nx, nk, wavelet_type, forward, st));
+  TFX_TRY(wavelet_axes12_device(bufA, nx, ny, nk, wavelet_type, forward, st));
 
   // ---- A -> B: to rank q the columns [pa[q], pa[q+1]) of my planes; what arrives from rank r are the rows
   // [ka[r], ka[r+1]) of B, already in place
@@ -380,31 +405,28 @@ static int wavelet_slab_dist(double *d_slab, const std::vector<int64_t> &off, in
     } else {
       TFX_TRY(comm_exchange_f64(bufB, soff.data(), scnt.data(), bufS, roff.data(), rcnt.data(), st));
     }
-    // unpack (the own block straight from B)
+    // unpack (the own block straight from B): one launch for all the sources
     const int64_t k0 = off[me] / plane, s0 = off[me] - k0 * plane;
     const int64_t k1 = (off[me + 1] - 1) / plane, e1 = off[me + 1] - k1 * plane;
+    UnpackArgs ua;
+    ua.k0 = k0; ua.plane = plane; ua.off_me = off[me]; ua.nr = nr;
+    int64_t cmax = 0;
     for (int q = 0; q < nr; ++q) {
-      const int64_t Wq = pa[q + 1] - pa[q];
       int64_t b0, b1;
       range_in(q, me, &b0, &b1);
-      if (b1 <= b0) continue;
-      const double *src = (q == me) ? bufB + b0 : bufS + roff[q];
-      int64_t consumed = 0;
-      for (int part = 0; part < 3; ++part) {
-        // part 0: row k0 (partial), part 1: rows k0+1 .. k1-1 (whole), part 2: row k1 (partial, when k1 > k0)
-        int64_t ka_ = 0, nrows = 0, plo = 0, phi = 0;
-        if (part == 0) { ka_ = k0; nrows = 1; plo = clampi(s0, pa[q], pa[q + 1]); phi = (k1 == k0) ? clampi(e1, pa[q], pa[q + 1]) : pa[q + 1]; }
-        else if (part == 1) { ka_ = k0 + 1; nrows = k1 - k0 - 1; plo = pa[q]; phi = pa[q + 1]; }
-        else { if (k1 == k0) break; ka_ = k1; nrows = 1; plo = pa[q]; phi = clampi(e1, pa[q], pa[q + 1]); }
-        const int64_t w = phi - plo;
-        if (nrows <= 0 || w <= 0) continue;
-        double *dst = d_slab + (ka_ * plane + plo - off[me]);
-        // inside the source range the rows keep B's pitch W_q except that the first / last row are shortened
-        const size_t spitch = (size_t)Wq * 8;
-        TFX_CUDA(cudaMemcpy2DAsync(dst, (size_t)plane * 8, src + consumed, nrows > 1 ? spitch : (size_t)w * 8, (size_t)w * 8,
-                                   (size_t)nrows, cudaMemcpyDeviceToDevice, st));
-        consumed += (nrows > 1 || part == 1) ? nrows * Wq : w;
-      }
+      ua.src[q] = (q == me) ? bufB + b0 : bufS + roff[q];
+      ua.cnt[q] = b1 - b0;
+      ua.paq[q] = pa[q]; ua.Wq[q] = pa[q + 1] - pa[q];
+      ua.c0[q] = clampi(s0, pa[q], pa[q + 1]);
+      // elements of the first row: up to the end of the column range, or up to e1 when the slab ends in that row
+      ua.w0[q] = ((k1 == k0) ? clampi(e1, pa[q], pa[q + 1]) : pa[q + 1]) - ua.c0[q];
+      cmax = std::max<int64_t>(cmax, ua.cnt[q]);
+    }
+    if (cmax > 0) {
+      const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((cmax + 1023) / 1024, 512)), (unsigned)nr);
+      k_unpack_slab<<<grid, 256, 0, st>>>(d_slab, ua);
+      ctx().launches++;
+      TFX_CUDA(cudaGetLastError());
     }
     // (peer-memory path: B and the staging buffer are overwritten by the peers' next exchanges only after the barrier
     // that follows the NEXT transform's first exchange, which every rank enters after this unpack)

@@ -22,6 +22,7 @@ extern int g_opt_wavelet_tile_kb;
 
 int wavelet_axis_device(double *d_s, int L, long long inner, long long outer, int wavelet_type, bool forward,
                         cudaStream_t st);
+int wavelet_axes12_device(double *d_s, int n1, int n2, long long nplanes, int wavelet_type, bool forward, cudaStream_t st);
 extern int g_opt_wavelet_dist;
 extern int g_opt_wavelet_p2p;   // 1: layout changes of the distributed transform through peer memory (cudaIpc), 0: NCCL
 void wavelet_peer_reset();

@@ -768,4 +768,19 @@ int wavelet_axis_device(double *d_s, int L, long long inner, long long outer, in
   return fail(-22, "Unknown wavelet type!");
 }
 
+// Axes 1 and 2 of nplanes independent n1 x n2 planes stored back to back (layout A of the distributed transform): the
+// fused Haar scheme when it applies, else the two axis passes.
+int wavelet_axes12_device(double *d_s, int n1, int n2, long long nplanes, int wavelet_type, bool forward, cudaStream_t st) {
+  if (n1 < 1 || n2 < 1 || nplanes < 1) return 0;
+  if (wavelet_type != 1 && wavelet_type != 2) return fail(-22, "Unknown wavelet type!");
+  int fused = 0;
+  if (wavelet_type == 1) {
+    if (forward) TFX_TRY((haar_axes12_fused<1, true>(d_s, n1, n2, nplanes, st, &fused)));
+    else TFX_TRY((haar_axes12_fused<1, false>(d_s, n1, n2, nplanes, st, &fused)));
+  }
+  if (fused) return 0;
+  TFX_TRY(wavelet_axis_device(d_s, n1, 1, (long long)n2 * nplanes, wavelet_type, forward, st));
+  return wavelet_axis_device(d_s, n2, n1, nplanes, wavelet_type, forward, st);
+}
+
 }  // namespace tfx
