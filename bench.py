@@ -435,6 +435,7 @@ def config_e_extra(a, tfx, d):
             "residual_last": float(r["history"][-1]) if len(r["history"]) else None,
             "S_fwd_ms": fwd, "S_trans_ms": trn, "wavelet_transform_ms": wav,
             "wavelet_share": 4.0 * wav / ms_it, "wavelet_distributed": r.get("wavelet_distributed"),
+            "wavelet_exchange": r.get("wavelet_exchange"),
             "non_product_ms_per_it": non_product,
             "projected_full_config_e": {"nnz": full_nnz, "ms_per_it": projected, "it_per_s": 1e3 / projected,
                                         "note": "measured non-product part of the iteration (wavelets, constraint block, vectors, "

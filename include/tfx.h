@@ -150,8 +150,9 @@ int tfx_Haar3D(double *s, int32_t n1, int32_t n2, int32_t n3);                  
 int tfx_iHaar3D(double *s, int32_t n1, int32_t n2, int32_t n3);                                 /* :158-236 */
 int tfx_DaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3);                                /* :243-367 */
 int tfx_iDaubD43D(double *s, int32_t n1, int32_t n2, int32_t n3);                               /* :374-498 */
-/* Diagnostic: 1 when the last transform of a distributed vector ran on the plane-owner / column-owner layouts (two
- * all-to-all exchanges), 0 when it gathered the slabs into a full volume on every GPU (slab layout did not qualify). */
+/* Diagnostic: non-zero when the last transform of a distributed vector ran on the plane-owner / column-owner layouts (two
+ * all-to-all exchanges: 1 through ncclSend/ncclRecv, 2 through peer memory), 0 when it gathered the slabs into a full
+ * volume on every GPU (slab layout did not qualify). */
 int tfx_wavelet_last_distributed(void);
 /* module wavelet_utils: apply_wavelet_transform (src/inversion/wavelet_utils.F90:37-72):
  * v(nelements, ncomponents, nproblems) holds this rank's cell slab of every volume. With nbproc > 1 (needs

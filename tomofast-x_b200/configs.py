@@ -276,6 +276,8 @@ def run_config_e(tfx, nx, ny, nz, nd1, nd2, rate=0.002, niter=20, warmup=3, rank
     for _ in range(4):
         tfx.apply_wavelet_transform(ncl, nx, ny, nz, 1, vol, True, compression_type, 1, [1], rank, world)
     tfx.synchronize(); barrier(); out["wavelet_slab_ms"] = (wall() - t0) / 4 * 1e3
-    out["wavelet_distributed"] = bool(tfx.lib().tfx_wavelet_last_distributed())
+    mode = int(tfx.lib().tfx_wavelet_last_distributed())
+    out["wavelet_distributed"] = bool(mode)
+    out["wavelet_exchange"] = {0: "all-gather (fallback)", 1: "ncclSend/ncclRecv", 2: "peer memory (cudaIpc)"}.get(mode, str(mode))
     out["ncl"], out["cell0"], out["nlines"], out["ncolumns_local"] = ncl, cell0, nlines, ncol
     return out

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) k_model_update(double *__restrict__ v, co
 }  // namespace
 
 int g_opt_wavelet_dist = 1;   // 1: plane-owner / column-owner transform when the slabs allow it, 0: always gather
-int g_wavelet_last_dist = 0;  // diagnostic: 1 when the last slab transform ran distributed (tfx_wavelet_last_distributed)
+int g_wavelet_last_dist = 0;  // diagnostic: 1 / 2 when the last slab transform ran distributed with NCCL / peer-memory exchanges
 
 namespace {
 struct DistBufs {
@@ -432,7 +432,7 @@ static int wavelet_slab_dist(double *d_slab, const std::vector<int64_t> &off, in
     // that follows the NEXT transform's first exchange, which every rank enters after this unpack)
   }
   *done = 1;
-  g_wavelet_last_dist = 1;
+  g_wavelet_last_dist = p2p ? 2 : 1;
   return 0;
 }
 
