@@ -66,7 +66,16 @@ int         tfx_timer_stop(double *ms);
  *   corner terms once per grid node -- and the magnetic edge terms once per grid edge -- instead of once per cell);
  * "dense_vec4" (1, default: 512 threads x float4 rows; 0: 1024 threads x float2 rows), "dense_f2f_rows" (row vectors
  *   per thread whose second use converts with F2F; default 2), "dense_stream_only" (diagnostic: the sweep's TMA ring
- *   without the products -- results are meaningless, only the time is). */
+ *   without the products -- results are meaningless, only the time is);
+ * "dense_block_rows" (0, default: 10240; data rows per dense block of an uncompressed kernel -- more rows become several
+ *   dense row blocks on the split LSQR path; tests lower it);
+ * "wavelet_fuse12" (1, default: Haar axis-1 pass fused with the three lowest axis-2 scales), "wavelet_dist" (1, default:
+ *   distributed transform on plane-owner / column-owner layouts; 0: all-gather), "wavelet_p2p" (1, default: its layout
+ *   changes through cudaIpc peer memory; 0: ncclSend/ncclRecv), "wavelet_tile_kb" (0: automatic tile size);
+ * "sensit_cand_cap" (0, default: 16384; candidate-list capacity of the k-th select of the row pipeline -- tests force
+ *   the fallback passes with 1);
+ * "t16_tma" (1: long segments through the cp.async.bulk + mbarrier ring; measured slower, default 0);
+ * "trace" (1: wall-clock phases of the assembly on stderr). */
 int         tfx_set_option(const char *name, int value);
 
 /* Memory helpers for callers that keep their vectors on the device (or in pinned host memory)
